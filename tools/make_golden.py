@@ -1,0 +1,225 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the REFERENCE's own code on CPU.
+
+Runs only where /root/reference is mounted (the build container).  The GPU box
+has no reference tree, so the vectors produced here are committed and the tests
+read only them.  Nothing is copied out of the reference: its modules are
+imported by path and called.
+
+Stubs: lifelines / tensorboardX / matplotlib / sksurv are absent from the image
+and only needed for the scripts' top-level imports.
+
+    python tools/make_golden.py            # writes tests/golden/*.npz
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("MMBS_REFERENCE", "/root/reference")
+OUT = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+
+def _stub_third_party():
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    mod("lifelines")
+    mod("lifelines.utils", concordance_index=lambda *a, **k: float("nan"))
+    mod("sksurv")
+    mod("sksurv.metrics", concordance_index_censored=lambda *a, **k: (float("nan"),))
+    mod("tensorboardX", SummaryWriter=object)
+    plt = mod("matplotlib.pyplot", switch_backend=lambda *a, **k: None)
+    mod("matplotlib", pyplot=plt)
+
+
+def load_ref(relpath, name):
+    """Import a reference file by path with its own directory first on sys.path
+    (the scripts import ``resnet`` / ``models`` by bare name)."""
+    path = os.path.join(REF, relpath)
+    d = os.path.dirname(path)
+    for k in ("resnet", "models", "datasets"):
+        sys.modules.pop(k, None)
+    sys.path.insert(0, d)
+    try:
+        spec = importlib.util.spec_from_file_location(name, path)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+    finally:
+        sys.path.remove(d)
+    return m
+
+
+def det_input(shape, a=0.37, b=1.3):
+    """RNG-free deterministic tensor (reproducible on any box)."""
+    n = int(np.prod(shape))
+    i = np.arange(n, dtype=np.float64)
+    return (np.sin(i * a) + 0.5 * np.cos(i * b * 0.01)).astype(np.float32).reshape(shape)
+
+
+# ----------------------------------------------------------------------------- cox
+def cox_cases():
+    rng = np.random.default_rng(20261018)
+    cases = {}
+    cases["kat"] = (np.array([0.5, -1, 2, 0, 1.5, -0.5, 0.25, -2], np.float32),
+                    np.array([5, 3, 5, 1, 3, 5, 0, 0], np.float32),
+                    np.array([1, 0, 1, 1, 0, 1, 1, 0], np.float32))
+    cases["n1_event"] = (np.array([0.3], np.float32), np.array([2.0], np.float32), np.array([1.0], np.float32))
+    cases["n2"] = (np.array([0.3, -0.2], np.float32), np.array([2.0, 7.5], np.float32), np.array([1.0, 1.0], np.float32))
+    for n in (22, 128, 1000, 4099):
+        s = rng.standard_normal(n).astype(np.float32)
+        t = rng.uniform(0, 200, n).astype(np.float32)
+        e = (rng.uniform(size=n) < 0.6).astype(np.float32)
+        cases[f"rand_{n}"] = (s, t, e)
+    n = 1000
+    cases["ties_1000"] = (rng.standard_normal(n).astype(np.float32) * 3,
+                          rng.integers(0, 50, n).astype(np.float32),
+                          (rng.uniform(size=n) < 0.6).astype(np.float32))
+    cases["all_censored"] = (rng.standard_normal(64).astype(np.float32),
+                             rng.uniform(0, 200, 64).astype(np.float32), np.zeros(64, np.float32))
+    s = rng.standard_normal(300).astype(np.float32)
+    s[[3, 77, 200]] = s.max() + 1.0  # tied maximum: max-backward splits evenly
+    cases["tied_max"] = (s, rng.integers(0, 20, 300).astype(np.float32),
+                         (rng.uniform(size=300) < 0.7).astype(np.float32))
+    cases["wide_scores"] = (rng.standard_normal(512).astype(np.float32) * 30,
+                            rng.uniform(0, 200, 512).astype(np.float32),
+                            (rng.uniform(size=512) < 0.6).astype(np.float32))
+    cases["neg_zero_times"] = (rng.standard_normal(16).astype(np.float32),
+                               np.array([0.0, -0.0, 1, 0.0, -0.0, 2, 1, 0, 3, -0.0, 0, 1, 2, 3, 0, -0.0], np.float32),
+                               np.ones(16, np.float32))
+    return cases
+
+
+def gen_cox():
+    ref = load_ref("5_JointFusion/models.py", "ref_joint_models")
+    real_sort = torch.sort
+    out = {}
+    for name, (s, t, e) in cox_cases().items():
+        # the reference calls torch.sort(-times) (unstable); the only well-defined
+        # tie order is the stable one (SURVEY.md §7 hard part 4) -> force stable.
+        torch.sort = lambda x, *a, **k: real_sort(x, *a, stable=True, **k)
+        try:
+            sc = torch.tensor(s, requires_grad=True)
+            loss = ref.cox_loss(sc, torch.tensor(t), torch.tensor(e))
+            loss.backward()
+            perm = real_sort(-torch.tensor(t), stable=True)[1].numpy()
+        finally:
+            torch.sort = real_sort
+        out[name + "/scores"] = s
+        out[name + "/times"] = t
+        out[name + "/status"] = e
+        out[name + "/loss"] = loss.detach().numpy()
+        out[name + "/grad"] = sc.grad.numpy()
+        out[name + "/perm"] = perm.astype(np.int64)
+    np.savez_compressed(os.path.join(OUT, "cox_reference.npz"), **out)
+    print("cox:", len(cox_cases()), "cases")
+
+
+# ----------------------------------------------------------------------- aggregation
+def gen_aggregate():
+    _stub_third_party()
+    rng = np.random.default_rng(7)
+    ext = load_ref("1_HistoPathology/4_HistoPath_extractfeatures.py", "ref_extract")
+    sav = load_ref("1_HistoPathology/3_HistoPath_savescore.py", "ref_savescore")
+
+    n, d, n_case = 57, 96, 9
+    cases = [f"TCGA-{rng.integers(0, n_case):02d}" for _ in range(n)]
+    feats = rng.standard_normal((n, d)).astype(np.float32)
+
+    class FakeModel:
+        def eval(self):
+            pass
+
+        def extract(self, x):
+            return x, None
+
+    bs = 8
+    loader = [{"patch_bag": torch.tensor(feats[i:i + bs]), "WSI": cases[i:i + bs], "case": cases[i:i + bs]}
+              for i in range(0, n, bs)]
+    case_uniques, features_final = ext.extract_features(FakeModel(), loader, torch.device("cpu"))
+
+    outputs = rng.standard_normal((n, 1)).astype(np.float32)
+    surv = rng.uniform(1, 100, n).astype(np.float32)
+    vital = (rng.uniform(size=n) < 0.5).astype(np.float32)
+    _, df = sav.get_survival_CI(outputs, cases, surv, vital)
+    np.savez_compressed(
+        os.path.join(OUT, "aggregate_reference.npz"),
+        cases=np.array(cases), features=feats,
+        case_uniques=np.array(case_uniques), features_final=np.asarray(features_final),
+        outputs=outputs, survival=surv, vital=vital,
+        ci_ids=np.array(df["id"]).astype(str), ci_score=np.array(df["score"]),
+        ci_survival=np.array(df["survival_months"]), ci_vital=np.array(df["vital_status"]))
+    print("aggregate: features_final", np.asarray(features_final).shape, np.asarray(features_final).dtype,
+          "score dtype", np.array(df["score"]).dtype)
+
+
+# ---------------------------------------------------------------------------- resnet
+def gen_resnet():
+    from oracle import resnet_oracle
+    refnet = load_ref("5_JointFusion/resnet.py", "ref_resnet")
+    sd = resnet_oracle.init_state_dict(seed=1111)
+    net = refnet.resnet50(pretrained=False)
+    missing = net.load_state_dict(sd, strict=True)
+    net.eval()
+    x = torch.tensor(det_input((2, 3, 224, 224)))
+    with torch.no_grad():
+        f = net.forward_extract(x)
+    fp = {k: float(v.double().abs().sum()) for k, v in sd.items() if k in
+          ("conv1.weight", "layer2.1.conv2.weight", "layer4.2.bn3.running_var", "fc.weight")}
+    np.savez_compressed(os.path.join(OUT, "resnet_reference.npz"), features=f.numpy(),
+                        fp_keys=np.array(list(fp.keys())), fp_vals=np.array(list(fp.values())))
+    print("resnet: features", tuple(f.shape), "mean", float(f.mean()), missing)
+
+
+# ------------------------------------------------------------------------------- mlp
+def gen_mlp():
+    import torch.nn as nn
+    rna_models = load_ref("2_GeneExpression/models.py", "ref_rna_models")
+    joint_models = load_ref("5_JointFusion/models.py", "ref_joint_models2")
+    torch.manual_seed(1111)
+    model_rna = nn.Sequential(nn.Dropout(), nn.Linear(12778, 4096), nn.ReLU(), nn.Dropout(), nn.Linear(4096, 2048))
+    head = nn.Sequential(nn.Linear(2048, 1))
+    model = rna_models.RNAOnlyModel(model_rna, head).eval()
+    x = torch.tensor(det_input((6, 12778), a=0.11))
+    with torch.no_grad():
+        y = model(x)
+        feat = model.extract(x)
+    torch.manual_seed(2222)
+    early = nn.Sequential(nn.Dropout(), nn.Linear(4096, 2048), nn.ReLU(), nn.Dropout(), nn.Linear(2048, 200),
+                          nn.ReLU(), nn.Dropout(), nn.Linear(200, 1)).eval()
+    xe = torch.tensor(det_input((5, 4096), a=0.23))
+    with torch.no_grad():
+        ye = early(xe)
+    # joint head on cat([img, rna]) with a stand-in "resnet" that returns given features
+    torch.manual_seed(3333)
+
+    class FakeResnet(nn.Module):
+        def forward_extract(self, p):
+            return p.flatten(1)[:, :2048]
+
+    jhead = nn.Sequential(nn.Dropout(0.8), nn.Linear(4096, 1))
+    jm = joint_models.BagHistopathologyRNAModel(FakeResnet(), model_rna, jhead).eval()
+    bag = torch.tensor(det_input((6, 2, 1, 32, 64), a=0.05))  # 2048 values per patch
+    with torch.no_grad():
+        yj = jm(bag, x)
+    np.savez_compressed(os.path.join(OUT, "mlp_reference.npz"),
+                        rna_out=y.numpy(), rna_feat_head=feat[:, :64].numpy(), rna_feat_sum=feat.sum(1).numpy(),
+                        early_out=ye.numpy(), joint_out=yj.numpy())
+    print("mlp: rna", tuple(y.shape), "early", tuple(ye.shape), "joint", tuple(yj.shape))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ["cox", "aggregate", "resnet", "mlp"]
+    for w in which:
+        globals()["gen_" + w]()
