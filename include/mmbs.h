@@ -1,0 +1,164 @@
+/*
+ * mmbs.h - C ABI of libmmbs.so: the B200 (sm_100a) kernels behind the Cox-loss
+ * survival hot path of gevaertlab/MultiModalBrainSurvival.
+ *
+ * The reference has no FFI of its own (it is pure PyTorch); its boundary for
+ * this path is the set of Python callables listed below.  Each entry point
+ * cites the reference interface whose arithmetic it replaces.  The host-side
+ * mirror in multimodalbrainsurvival_b200/ keeps those Python names/signatures
+ * and calls these functions through ctypes.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host;
+ *  - the library never allocates, frees or retains device memory: all scratch
+ *    is a caller-provided workspace sized by the matching *_workspace_bytes();
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call
+ *    synchronises the device;
+ *  - return value: 0 = OK, <0 = error (mmbs_last_error() describes it);
+ *    nothing throws across this boundary;
+ *  - there is NO CPU fallback: on a machine without an sm_100 device every
+ *    compute entry point returns MMBS_ERR_DEVICE.
+ */
+#ifndef MMBS_H_
+#define MMBS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMBS_OK 0
+#define MMBS_ERR_ARG (-1)
+#define MMBS_ERR_WORKSPACE (-2)
+#define MMBS_ERR_CUDA (-3)
+#define MMBS_ERR_DEVICE (-4)
+#define MMBS_ERR_UNSUPPORTED (-5)
+
+/* ------------------------------------------------------------------ misc */
+const char* mmbs_last_error(void);
+int mmbs_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t mmbs_launch_count(void);
+/* 0 when the current device is sm_100 and the driver entry points resolved */
+int mmbs_device_check(void);
+
+/* ------------------------------------------------------------------ Cox loss
+ * Replaces cox_loss(cox_scores, times, status)
+ *   /root/reference/1_HistoPathology/models.py:90-111   (CoxLoss.forward :113-118)
+ *   /root/reference/5_JointFusion/models.py:119-140     (CoxLoss.forward :142-147)
+ *   /root/reference/2_GeneExpression/models.py:24-45
+ *   /root/reference/3_EarlyFusion/models.py:24-45
+ *
+ * forward:  perm = stable argsort(-times) (u32 radix sort, key-transformed);
+ *           s~ = scores[perm]-max(scores); C = cumsum(exp(s~));
+ *           loss = -(1/n) sum status[perm]*(s~ - log(C+1e-5)).
+ *   perm_out   [n] int32  : sorted order (original indices), bit-exact vs torch.sort(stable)
+ *   saved_e    [n] float  : exp(s~) in sorted order          (saved for backward)
+ *   saved_w    [n] float  : status[perm]/(C+1e-5)            (saved for backward)
+ *   loss_out   [1] float
+ *   flags_out  [1] int32  : bit0 = a NaN term was produced (the reference traps
+ *                           into pdb at models.py:107-109; we report instead)
+ * backward: grad_scores[perm[k]] = -(status_k - e_k * sum_{i>=k} w_i) * grad_loss / n,
+ *           minus the gradient through max(scores) shared by all argmax positions.
+ *   grad_loss  [1] float (device scalar: upstream gradient)
+ */
+size_t mmbs_cox_workspace_bytes(int64_t n);
+int mmbs_cox_forward(const float* scores, const float* times, const float* status, int64_t n,
+                     int32_t* perm_out, float* saved_e, float* saved_w, float* loss_out,
+                     int32_t* flags_out, void* workspace, size_t workspace_bytes, void* stream);
+int mmbs_cox_backward(const float* scores, const float* status, const int32_t* perm,
+                      const float* saved_e, const float* saved_w, const float* grad_loss,
+                      int64_t n, float* grad_scores, void* workspace, size_t workspace_bytes,
+                      void* stream);
+/* stable argsort(-times) only (the permutation/risk-set order), for parity tests and
+ * the multi-GPU all-gathered risk set. */
+int mmbs_risk_order(const float* times, int64_t n, int32_t* perm_out, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------- per-patient aggregation
+ * Replaces the aggregation tails of
+ *   extract_features   /root/reference/1_HistoPathology/4_HistoPath_extractfeatures.py:75-89
+ *                      /root/reference/2_GeneExpression/3_GeneExpress_extractfeatures.py:70-82
+ *   get_survival_CI    /root/reference/1_HistoPathology/3_HistoPath_savescore.py:126-152 (+7 copies)
+ * values [n,d] float, seg_ids [n] int32 in [0,n_seg): out[g,:] = mean of rows with
+ * seg_ids==g (fp32 accumulation in ascending row order), counts[g] = number of rows;
+ * last_row[g] = largest row index of segment g ("last row seen", savescore.py:137-138), -1 if empty.
+ */
+size_t mmbs_segmented_mean_workspace_bytes(int64_t n, int64_t n_seg);
+int mmbs_segmented_mean(const float* values, const int32_t* seg_ids, int64_t n, int64_t d,
+                        int64_t n_seg, float* out, int32_t* counts, int32_t* last_row,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------ implicit-GEMM conv / linear
+ * One tcgen05/TMEM kernel, TMA-fed, serves both
+ *   nn.Conv2d + BatchNorm2d(eval) + ReLU (+ residual)  of Bottleneck.forward
+ *       /root/reference/5_JointFusion/resnet.py:70-90, stem :151-155
+ *   nn.Linear (+ ReLU)                                  of the MLPs
+ *       /root/reference/2_GeneExpression/1_GeneExpress_train.py:247-257 etc.
+ *
+ * Activations are NHWC bf16; weights are [Cout][kh][kw][Cin] bf16 (K-major).
+ * out[m, n] = act( scale[n] * sum_k A[m,k] W[n,k] + shift[n] (+ residual[m,n]) )
+ *
+ * A conv is described once by mmbs_conv_plan_create() (host struct holding the
+ * TMA descriptors for fixed pointers/shapes) and launched by mmbs_conv_run().
+ */
+typedef struct mmbs_conv_plan mmbs_conv_plan; /* opaque, host memory */
+
+typedef struct {
+  int32_t batch;          /* B */
+  int32_t in_h, in_w;     /* input spatial size  */
+  int32_t c_in;           /* multiple of 64 (stem: see mmbs_stem_*) */
+  int32_t c_out;          /* multiple of 32 */
+  int32_t ksize;          /* 1 or 3 (4 = the space-to-depth stem, internal) */
+  int32_t stride;         /* 1 or 2 */
+  int32_t relu;           /* apply ReLU in the epilogue */
+  int32_t out_f32;        /* 1: out is float32 (row stride c_out), else bf16 */
+  const void* in;         /* bf16 NHWC [B, in_h, in_w, c_in] */
+  const void* weight;     /* bf16 [c_out, ksize*ksize*c_in] */
+  const float* scale;     /* [c_out] or NULL (=1) */
+  const float* shift;     /* [c_out] or NULL (=0) */
+  const void* residual;   /* bf16 NHWC like out, or NULL */
+  void* out;              /* NHWC [B, out_h, out_w, c_out] */
+} mmbs_conv_desc;
+
+int mmbs_conv_plan_create(const mmbs_conv_desc* desc, mmbs_conv_plan** plan_out);
+void mmbs_conv_plan_destroy(mmbs_conv_plan* plan);
+int mmbs_conv_run(const mmbs_conv_plan* plan, void* stream);
+
+/* Linear: y[M,N] = act(x[M,K] W[N,K]^T + bias[N]); x/W bf16 with K % 64 == 0 (pad
+ * with zeros), N % 32 == 0.  Same kernel as the 1x1 conv. */
+int mmbs_linear_plan_create(const void* x_bf16, const void* w_bf16, const float* bias,
+                            void* y, int64_t m, int64_t n, int64_t k, int32_t relu,
+                            int32_t out_f32, mmbs_conv_plan** plan_out);
+
+/* ------------------------------------------------ ResNet glue kernels (HBM-bound)
+ * stem input: NCHW fp32 [B,3,224,224] -> space-to-depth, zero-padded NHWC bf16
+ *   [B,116,116,16] (channel = (row parity, col parity, rgb), 12 used) so that the
+ *   7x7/2 stem conv (resnet.py:97,152) becomes 4 K=64 taps of the GEMM kernel. */
+int mmbs_stem_pack_input(const float* x_nchw, void* out_s2d_bf16, int64_t batch, void* stream);
+/* stem weight: [64,3,7,7] fp32 -> bf16 [64, 4*64] in the matching (a, b, p, q, c) order */
+int mmbs_stem_pack_weight(const float* w_oihw, void* out_bf16, void* stream);
+/* conv weight OIHW fp32 -> [O][kh][kw][I] bf16 */
+int mmbs_pack_conv_weight(const float* w_oihw, void* out_bf16, int64_t c_out, int64_t c_in,
+                          int64_t ksize, void* stream);
+/* eval BatchNorm fold: scale = gamma/sqrt(var+eps), shift = beta - mean*scale (resnet.py:60..) */
+int mmbs_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var,
+                 float eps, int64_t c, float* scale, float* shift, void* stream);
+/* MaxPool2d(3,2,1) NHWC bf16 (resnet.py:101,155) */
+int mmbs_maxpool_3x3s2(const void* in_bf16, void* out_bf16, int64_t batch, int64_t h, int64_t w,
+                       int64_t c, void* stream);
+/* AvgPool2d(7)+flatten NHWC bf16 [B,7,7,C] -> fp32 [B,C] (resnet.py:106,162-163) */
+int mmbs_avgpool_global(const void* in_bf16, float* out, int64_t batch, int64_t hw, int64_t c,
+                        void* stream);
+int mmbs_avgpool_global_f32(const float* in, float* out, int64_t batch, int64_t hw, int64_t c,
+                            void* stream);
+/* fp32 [rows, cols] -> bf16 [rows, cols_padded] (zero pad), optional transposed copy */
+int mmbs_cast_pad_bf16(const float* in, void* out_bf16, int64_t rows, int64_t cols,
+                       int64_t cols_padded, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMBS_H_ */

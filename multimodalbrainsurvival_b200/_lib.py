@@ -1,0 +1,120 @@
+"""ctypes binding of libmmbs.so (the C ABI declared in include/mmbs.h).
+
+The shared library is built in-tree (``multimodalbrainsurvival_b200/libmmbs.so``)
+by ``csrc/Makefile`` for sm_100a only.  There is no CPU fallback: if the library
+is missing, or no sm_100 device is present, every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmmbs.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+_lock = threading.Lock()
+_lib = None
+
+c_void_p = ctypes.c_void_p
+c_i64 = ctypes.c_int64
+c_i32 = ctypes.c_int32
+c_size = ctypes.c_size_t
+c_float = ctypes.c_float
+
+
+class ConvDesc(ctypes.Structure):
+    """mmbs_conv_desc (include/mmbs.h)."""
+    _fields_ = [
+        ("batch", c_i32), ("in_h", c_i32), ("in_w", c_i32), ("c_in", c_i32), ("c_out", c_i32),
+        ("ksize", c_i32), ("stride", c_i32), ("relu", c_i32), ("out_f32", c_i32),
+        ("in_", c_void_p), ("weight", c_void_p), ("scale", c_void_p), ("shift", c_void_p),
+        ("residual", c_void_p), ("out", c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/mmbs.h declares
+SIGNATURES = {
+    "mmbs_last_error": (ctypes.c_char_p, []),
+    "mmbs_version": (ctypes.c_int, []),
+    "mmbs_launch_count": (c_i64, []),
+    "mmbs_device_check": (ctypes.c_int, []),
+    "mmbs_cox_workspace_bytes": (c_size, [c_i64]),
+    "mmbs_cox_forward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_size, c_void_p]),
+    "mmbs_cox_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64,
+                                         c_void_p, c_void_p, c_size, c_void_p]),
+    "mmbs_risk_order": (ctypes.c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_size, c_void_p]),
+    "mmbs_segmented_mean_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "mmbs_segmented_mean": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_size, c_void_p]),
+    "mmbs_conv_plan_create": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(c_void_p)]),
+    "mmbs_conv_plan_destroy": (None, [c_void_p]),
+    "mmbs_conv_run": (ctypes.c_int, [c_void_p, c_void_p]),
+    "mmbs_linear_plan_create": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64,
+                                               c_i32, c_i32, ctypes.POINTER(c_void_p)]),
+    "mmbs_stem_pack_input": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
+    "mmbs_stem_pack_weight": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
+    "mmbs_pack_conv_weight": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
+    "mmbs_bn_fold": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_i64, c_void_p,
+                                    c_void_p, c_void_p]),
+    "mmbs_maxpool_3x3s2": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p]),
+    "mmbs_avgpool_global": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
+    "mmbs_avgpool_global_f32": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
+    "mmbs_cast_pad_bf16": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
+}
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libmmbs.so in-tree with nvcc (sm_100a).  Cross-compiles without a GPU."""
+    r = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libmmbs.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+    if verbose:
+        print(r.stdout[-2000:])
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded library (loads on first use; raises if it was never built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "or `make -C multimodalbrainsurvival_b200/csrc` (there is no CPU/PyTorch fallback)")
+            l = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(l, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = l
+    return _lib
+
+
+class MMBSError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().mmbs_last_error().decode("utf-8", "replace")
+        raise MMBSError(f"libmmbs {what} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().mmbs_launch_count())
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)

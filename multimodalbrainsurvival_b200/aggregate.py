@@ -1,0 +1,103 @@
+"""Per-patient aggregation on the GPU (csrc/segmean.cu), mirroring the reference's tails.
+
+* ``aggregate_case_features``  <->  the per-case mean at the end of ``extract_features``
+  (/root/reference/1_HistoPathology/4_HistoPath_extractfeatures.py:75-89,
+   /root/reference/2_GeneExpression/3_GeneExpress_extractfeatures.py:70-82)
+* ``survival_grouping`` / ``get_survival_CI``  <->  ``get_survival_CI``
+  (/root/reference/1_HistoPathology/3_HistoPath_savescore.py:126-152 and its 7 copies)
+
+The id -> segment mapping (string handling) is host logic and bit-exact with the
+reference (``set`` / ``sorted(set)``); the means are computed by the segmented-mean
+kernel.  No CPU fallback: the value tensors must be CUDA tensors (or are moved to
+the current CUDA device when given as numpy arrays).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def segmented_mean(values: torch.Tensor, seg_ids: torch.Tensor, n_seg: int):
+    """values [n, ...] fp32 CUDA, seg_ids [n] int32 CUDA in [0, n_seg) ->
+    (mean [n_seg, ...] fp32, counts [n_seg] int32, last_row [n_seg] int32)."""
+    if not values.is_cuda or not seg_ids.is_cuda:
+        raise RuntimeError("segmented_mean: CUDA tensors required (no CPU fallback in this build)")
+    n = values.shape[0]
+    if seg_ids.numel() != n:
+        raise ValueError(f"segmented_mean: {n} rows but {seg_ids.numel()} segment ids")
+    v = values.detach().reshape(n, -1).float().contiguous()
+    s = seg_ids.detach().reshape(-1).to(torch.int32).contiguous()
+    d = v.shape[1]
+    dev = v.device
+    out = torch.empty((n_seg, d), dtype=torch.float32, device=dev)
+    counts = torch.empty(n_seg, dtype=torch.int32, device=dev)
+    last = torch.empty(n_seg, dtype=torch.int32, device=dev)
+    if n == 0 or n_seg == 0:
+        return out.fill_(float("nan")).reshape((n_seg,) + tuple(values.shape[1:])), counts.zero_(), last.fill_(-1)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        nbytes = L.mmbs_segmented_mean_workspace_bytes(n, n_seg)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.check(L.mmbs_segmented_mean(_lib.ptr(v), _lib.ptr(s), n, d, n_seg, _lib.ptr(out), _lib.ptr(counts),
+                                         _lib.ptr(last), _lib.ptr(ws), nbytes, _lib.stream_ptr()),
+                   "mmbs_segmented_mean")
+    return out.reshape((n_seg,) + tuple(values.shape[1:])), counts, last
+
+
+def _segments(ids, uniq):
+    lut = {k: i for i, k in enumerate(uniq)}
+    return np.fromiter((lut[i] for i in ids), dtype=np.int32, count=len(ids))
+
+
+def _to_cuda(x, device=None):
+    if isinstance(x, torch.Tensor):
+        if not x.is_cuda:
+            x = x.cuda(device) if device is not None else x.cuda()
+        return x
+    return torch.as_tensor(np.asarray(x)).cuda(device) if device is not None else torch.as_tensor(np.asarray(x)).cuda()
+
+
+def aggregate_case_features(features, case_list, case_order=None):
+    """Per-case mean of feature rows.
+
+    features: (N, D) CUDA tensor or numpy array; case_list: N hashable ids.
+    Returns (case_uniques: list, features_final: np.ndarray float64 (n_cases, D)) exactly
+    like the tail of the reference's ``extract_features``; the case order is the
+    reference's ``set(case_list)`` iteration order unless ``case_order`` is given.
+    """
+    case_list = list(case_list)
+    case_uniques = list(set(case_list)) if case_order is None else list(case_order)
+    feats = _to_cuda(features)
+    seg = torch.from_numpy(_segments(case_list, case_uniques)).to(feats.device)
+    mean, _, _ = segmented_mean(feats, seg, len(case_uniques))
+    return case_uniques, mean.double().cpu().numpy()
+
+
+def survival_grouping(output_list, ids_list, survival_months, vital_status):
+    """The grouping part of ``get_survival_CI``: (ids_unique, score float32[n_ids],
+    survival_months[n_ids], vital_status[n_ids]) with the "last row seen" rule."""
+    ids_list = list(ids_list)
+    ids_unique = sorted(list(set(ids_list)))
+    out = _to_cuda(output_list)
+    seg = torch.from_numpy(_segments(ids_list, ids_unique)).to(out.device)
+    mean, _, last = segmented_mean(out.reshape(len(ids_list), -1)[:, :1], seg, len(ids_unique))
+    last = last.cpu().numpy().astype(np.int64)
+    sm = np.asarray(survival_months.cpu() if isinstance(survival_months, torch.Tensor) else survival_months)[last]
+    vs = np.asarray(vital_status.cpu() if isinstance(vital_status, torch.Tensor) else vital_status)[last]
+    return ids_unique, mean[:, 0].cpu().numpy(), sm, vs
+
+
+def get_survival_CI(output_list, ids_list, survival_months, vital_status, concordance_index=None):
+    """Same contract as the reference's ``get_survival_CI``: returns (CI, DataFrame with
+    columns id, score, survival_months, vital_status).  ``concordance_index`` defaults to
+    ``lifelines.utils.concordance_index`` (third-party, as in the reference)."""
+    import pandas as pd
+    if concordance_index is None:
+        from lifelines.utils import concordance_index  # noqa: PLC0415 (same dependency as the reference)
+    ids_unique, score_list, sm, vs = survival_grouping(output_list, ids_list, survival_months, vital_status)
+    CI = concordance_index(sm, -score_list, vs)
+    pandas_output = pd.DataFrame({'id': ids_unique, 'score': score_list, 'survival_months': sm,
+                                  'vital_status': vs})
+    return CI, pandas_output

@@ -1,0 +1,148 @@
+"""Drop-in ``cox_loss`` / ``CoxLoss`` backed by the sm_100a kernels in csrc/cox.cu.
+
+Mirrors the reference's interface (same name, argument meaning, 0-d tensor result,
+differentiable w.r.t. ``cox_scores`` only):
+
+    cox_loss(cox_scores, times, status)
+        /root/reference/1_HistoPathology/models.py:90-111
+        /root/reference/5_JointFusion/models.py:119-140
+        /root/reference/2_GeneExpression/models.py:24-45
+        /root/reference/3_EarlyFusion/models.py:24-45
+    CoxLoss().forward(cox_scores, times, status)
+        /root/reference/1_HistoPathology/models.py:113-118, 5_JointFusion/models.py:142-147
+
+Differences, all deliberate:
+  * tie order is the stable one (``torch.sort(-times, stable=True)``);
+  * a NaN term does not drop into ``pdb`` (models.py:107-109); the device-side flag
+    is checked only when ``MMBS_COX_CHECK_NAN=1`` (it costs a host sync);
+  * tensors must live on a CUDA device: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def _pad64(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
+def _prep(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"cox_loss: `{name}` must be a CUDA tensor (no CPU fallback in this build)")
+    t = t.detach().reshape(-1)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def risk_order(times: torch.Tensor) -> torch.Tensor:
+    """Stable argsort(-times) as int32 (the risk-set order), via the radix sort."""
+    t = _prep(times, "times")
+    n = t.numel()
+    perm = torch.empty(n, dtype=torch.int32, device=t.device)
+    if n == 0:
+        return perm
+    L = _lib.lib()
+    with torch.cuda.device(t.device):
+        nbytes = L.mmbs_cox_workspace_bytes(n)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=t.device)
+        _lib.check(L.mmbs_risk_order(_lib.ptr(t), n, _lib.ptr(perm), _lib.ptr(ws), nbytes, _lib.stream_ptr()),
+                   "mmbs_risk_order")
+    return perm
+
+
+class _CoxLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cox_scores, times, status):
+        s = _prep(cox_scores, "cox_scores")
+        t = _prep(times, "times")
+        d = _prep(status, "status")
+        n = s.numel()
+        if t.numel() != n or d.numel() != n:
+            raise ValueError(f"cox_loss: size mismatch scores={tuple(cox_scores.shape)} "
+                             f"times={tuple(times.shape)} status={tuple(status.shape)}")
+        dev = s.device
+        if n == 0:  # mean over an empty batch
+            ctx.n = 0
+            ctx.in_shape = cox_scores.shape
+            ctx.in_dtype = cox_scores.dtype
+            return torch.full((), float("nan"), device=dev)
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            nbytes = L.mmbs_cox_workspace_bytes(n)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            perm = torch.empty(n, dtype=torch.int32, device=dev)
+            saved = torch.empty(2, _pad64(n), dtype=torch.float32, device=dev)  # e, w (sorted order)
+            out = torch.empty(2, dtype=torch.float32, device=dev)       # loss, flags(bits)
+            flags = out[1:].view(torch.int32)
+            _lib.check(L.mmbs_cox_forward(_lib.ptr(s), _lib.ptr(t), _lib.ptr(d), n, _lib.ptr(perm),
+                                          _lib.ptr(saved[0]), _lib.ptr(saved[1]), _lib.ptr(out),
+                                          _lib.ptr(flags), _lib.ptr(ws), nbytes, _lib.stream_ptr()),
+                       "mmbs_cox_forward")
+        if os.environ.get("MMBS_COX_CHECK_NAN", "0") == "1" and int(flags.item()) != 0:
+            raise FloatingPointError(f"cox_loss: NaN in the loss terms (n={n})")
+        ctx.n = n
+        ctx.in_shape = cox_scores.shape
+        ctx.in_dtype = cox_scores.dtype
+        ctx.ws_bytes = nbytes
+        ctx.save_for_backward(s, d, perm, saved, ws)
+        return out[0].clone().reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        if ctx.n == 0:
+            return torch.zeros(ctx.in_shape, dtype=ctx.in_dtype, device=grad_loss.device), None, None
+        s, d, perm, saved, ws = ctx.saved_tensors
+        n = ctx.n
+        g = grad_loss.detach().reshape(1).float().contiguous()
+        grad = torch.empty(n, dtype=torch.float32, device=s.device)
+        L = _lib.lib()
+        with torch.cuda.device(s.device):
+            _lib.check(L.mmbs_cox_backward(_lib.ptr(s), _lib.ptr(d), _lib.ptr(perm), _lib.ptr(saved[0]),
+                                           _lib.ptr(saved[1]), _lib.ptr(g), n, _lib.ptr(grad), _lib.ptr(ws),
+                                           ctx.ws_bytes, _lib.stream_ptr()),
+                       "mmbs_cox_backward")
+        return grad.reshape(ctx.in_shape).to(ctx.in_dtype), None, None
+
+
+def cox_loss(cox_scores, times, status):
+    """
+    :param cox_scores: cox scores, size (batch_size)
+    :param times: event times (either death or censor), size batch_size
+    :param status: event status (1 for death, 0 for censor), size batch_size
+    :return: 0-d loss tensor: mean over the batch of the negative log partial likelihood terms
+    """
+    return _CoxLossFn.apply(cox_scores, times, status)
+
+
+class CoxLoss(nn.Module):
+    def __init__(self):
+        super(CoxLoss, self).__init__()
+
+    def forward(self, cox_scores, times, status):
+        return cox_loss(cox_scores, times, status)
+
+
+def cox_loss_with_order(cox_scores, times, status):
+    """(loss, perm int32) - the loss plus the risk-set order the kernel used (parity tests)."""
+    s = _prep(cox_scores, "cox_scores")
+    t = _prep(times, "times")
+    d = _prep(status, "status")
+    n = s.numel()
+    L = _lib.lib()
+    with torch.cuda.device(s.device):
+        nbytes = L.mmbs_cox_workspace_bytes(n)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=s.device)
+        perm = torch.empty(n, dtype=torch.int32, device=s.device)
+        saved = torch.empty(2, _pad64(n), dtype=torch.float32, device=s.device)
+        out = torch.empty(2, dtype=torch.float32, device=s.device)
+        _lib.check(L.mmbs_cox_forward(_lib.ptr(s), _lib.ptr(t), _lib.ptr(d), n, _lib.ptr(perm),
+                                      _lib.ptr(saved[0]), _lib.ptr(saved[1]), _lib.ptr(out),
+                                      _lib.ptr(out[1:]), _lib.ptr(ws), nbytes, _lib.stream_ptr()),
+                   "mmbs_cox_forward")
+    return out[0].clone(), perm

@@ -1,0 +1,102 @@
+// Shared host/device helpers for libmmbs (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mmbs.h"
+
+namespace mmbs {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define MMBS_CUDA_TRY(expr)                                                        \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      ::mmbs::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,              \
+                        cudaGetErrorString(_e));                                   \
+      return MMBS_ERR_CUDA;                                                        \
+    }                                                                              \
+  } while (0)
+
+#define MMBS_LAUNCH_CHECK()                                                        \
+  do {                                                                             \
+    ::mmbs::count_launch();                                                        \
+    cudaError_t _e = cudaPeekAtLastError();                                        \
+    if (_e != cudaSuccess) {                                                       \
+      ::mmbs::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__,          \
+                        cudaGetErrorString(_e));                                   \
+      return MMBS_ERR_CUDA;                                                        \
+    }                                                                              \
+  } while (0)
+
+#define MMBS_REQUIRE(cond, ...)                                                    \
+  do {                                                                             \
+    if (!(cond)) {                                                                 \
+      ::mmbs::set_error(__VA_ARGS__);                                              \
+      return MMBS_ERR_ARG;                                                         \
+    }                                                                              \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+int sm_count();
+
+// Bump allocator over the caller's workspace.
+struct Carver {
+  char* base;
+  size_t off;
+  explicit Carver(void* p) : base(static_cast<char*>(p)), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = align_up(off, 256);
+    T* r = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return r;
+  }
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Order-preserving u32 image of (0 - t): ascending key == descending time; +0/-0 tie.
+__device__ __forceinline__ uint32_t time_key(float t) {
+  uint32_t b = __float_as_uint(__fsub_rn(0.0f, t));
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_volatile_f64(double* p, double v) {
+  asm volatile("st.volatile.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+#endif
+
+}  // namespace mmbs

@@ -1,0 +1,235 @@
+// Onesweep-style stable radix sort for sm_100a.  See radix_sort.cuh.
+#include <algorithm>
+
+#include "radix_sort.cuh"
+
+namespace mmbs {
+
+// ---------------------------------------------------------------- histogram
+// One pass over the source: per-digit counts for every radix pass.  Counting is
+// warp-aggregated with match.any so that a skewed byte (survival times cluster in
+// a few exponent values) does not serialise on one shared-memory counter.
+// Optionally fused: max over `scores` (order-encoded u32 atomicMax) + NaN flag.
+__global__ void __launch_bounds__(256) rs_histogram_kernel(
+    const void* __restrict__ src, int kind, int64_t n, int num_passes, uint32_t* __restrict__ hist,
+    const float* __restrict__ scores, uint32_t* __restrict__ max_enc, int32_t* __restrict__ nan_flag) {
+  __shared__ uint32_t s_hist[4][RS_RADIX];
+  __shared__ uint32_t s_max[8];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  for (int i = tid; i < 4 * RS_RADIX; i += 256) (&s_hist[0][0])[i] = 0;
+  __syncthreads();
+
+  float vmax = -INFINITY;
+  bool has_nan = false;
+  const int64_t n_round = (n + 31) / 32 * 32;  // keep warps converged for match.any
+  for (int64_t i = int64_t(blockIdx.x) * 256 + tid; i < n_round; i += int64_t(gridDim.x) * 256) {
+    const bool valid = i < n;
+    const uint32_t key = valid ? rs_load_key(src, kind, i) : 0u;
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    if (scores != nullptr && valid) {
+      const float s = __ldg(scores + i);
+      has_nan |= (s != s);
+      vmax = fmaxf(vmax, s);
+    }
+    if (valid) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        if (p < num_passes) {
+          const uint32_t d = (key >> (8 * p)) & 0xffu;
+          const unsigned m = __match_any_sync(vmask, d);
+          if (lane == __ffs(m) - 1) atomicAdd(&s_hist[p][d], __popc(m));
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < num_passes * RS_RADIX; i += 256) {
+    const uint32_t c = (&s_hist[0][0])[i];
+    if (c) atomicAdd(hist + i, c);
+  }
+  if (scores != nullptr) {
+    vmax = warp_max(vmax);
+    if (lane == 0) s_max[tid >> 5] = float_order_enc(vmax);
+    const unsigned any_nan = __ballot_sync(0xffffffffu, has_nan);
+    if (lane == 0 && any_nan) atomicOr(nan_flag, 1);
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t m = s_max[0];
+      for (int w = 1; w < 8; ++w) m = max(m, s_max[w]);
+      atomicMax(max_enc, m);
+    }
+  }
+}
+
+// Exclusive scan of each pass's 256 counters -> first global slot of every digit.
+__global__ void __launch_bounds__(RS_RADIX) rs_digit_base_kernel(const uint32_t* __restrict__ hist,
+                                                                 uint32_t* __restrict__ digit_base) {
+  __shared__ uint32_t s_w[8];
+  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t c = hist[p * RS_RADIX + tid];
+  uint32_t incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  uint32_t off = 0;
+  for (int w = 0; w < warp; ++w) off += s_w[w];
+  digit_base[p * RS_RADIX + tid] = off + incl - c;
+}
+
+// ---------------------------------------------------------------- one radix pass
+__global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(
+    const void* __restrict__ src, int kind, const uint32_t* __restrict__ keys_in,
+    const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
+    uint32_t* __restrict__ vals_out, int64_t n, int shift, const uint32_t* __restrict__ digit_base,
+    uint32_t* lookback, uint32_t* tile_counter, int first, int last) {
+  __shared__ uint32_t s_warp_hist[RS_WARPS][RS_RADIX];
+  __shared__ uint32_t s_digit_start[RS_RADIX];
+  __shared__ uint32_t s_global_base[RS_RADIX];
+  __shared__ uint32_t s_keys[RS_TILE];
+  __shared__ uint32_t s_vals[RS_TILE];
+  __shared__ uint32_t s_wsum[RS_WARPS];
+  __shared__ uint32_t s_tile;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // tiles are numbered in the order blocks start running: a tile only ever waits
+  // on tiles that already hold an SM, so the look-back cannot deadlock.
+  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+  for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&s_warp_hist[0][0])[i] = 0;
+  __syncthreads();
+  const int64_t tile = s_tile;
+  const int64_t tile_base = tile * RS_TILE;
+  const int n_valid = int(min((long long)RS_TILE, (long long)(n - tile_base)));
+
+  uint32_t key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS];
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    const int it = warp * (32 * RS_ITEMS) + j * 32 + lane;
+    const int64_t g = tile_base + it;
+    if (it < n_valid) {
+      key[j] = first ? rs_load_key(src, kind, g) : __ldg(keys_in + g);
+      val[j] = first ? uint32_t(g) : __ldg(vals_in + g);
+    } else {
+      key[j] = 0xffffffffu;  // padding sorts to the very end of the (last) tile
+      val[j] = 0xffffffffu;
+    }
+  }
+
+  // stable rank of every key among equal digits inside its warp
+  const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    const uint32_t d = (key[j] >> shift) & 0xffu;
+    const unsigned m = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(m) - 1;
+    uint32_t prev = 0;
+    if (lane == leader) {
+      prev = s_warp_hist[warp][d];
+      s_warp_hist[warp][d] = prev + __popc(m);
+    }
+    prev = __shfl_sync(0xffffffffu, prev, leader);
+    rank[j] = prev + __popc(m & lt_mask);
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // thread `tid` owns digit `tid`: exclusive scan over warps, tile total
+  uint32_t total = 0;
+#pragma unroll
+  for (int w = 0; w < RS_WARPS; ++w) {
+    const uint32_t c = s_warp_hist[w][tid];
+    s_warp_hist[w][tid] = total;
+    total += c;
+  }
+  uint32_t* lb = lookback + tile * RS_RADIX;
+  st_volatile_u32(lb + tid, (tile == 0 ? RS_FLAG_INCL : RS_FLAG_AGG) | total);
+
+  // tile-local exclusive scan over digits
+  uint32_t incl = total;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (int w = 0; w < warp; ++w) woff += s_wsum[w];
+  s_digit_start[tid] = woff + incl - total;
+
+  // decoupled look-back: sum this digit's counts over all earlier tiles
+  uint32_t excl = 0;
+  if (tile > 0) {
+    int64_t p = tile - 1;
+    while (true) {
+      uint32_t v;
+      do {
+        v = ld_volatile_u32(lookback + p * RS_RADIX + tid);
+      } while ((v & RS_FLAG_MASK) == 0);
+      excl += v & RS_VALUE_MASK;
+      if (v & RS_FLAG_INCL) break;
+      --p;
+    }
+    st_volatile_u32(lb + tid, RS_FLAG_INCL | (excl + total));
+  }
+  s_global_base[tid] = digit_base[tid] + excl;
+  __syncthreads();
+
+  // bring the tile into digit order in shared memory, then stream it out: equal
+  // digits leave as contiguous runs (coalesced stores)
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    const uint32_t d = (key[j] >> shift) & 0xffu;
+    const uint32_t pos = s_digit_start[d] + s_warp_hist[warp][d] + rank[j];
+    s_keys[pos] = key[j];
+    s_vals[pos] = val[j];
+  }
+  __syncthreads();
+  for (int i = tid; i < n_valid; i += RS_THREADS) {
+    const uint32_t k = s_keys[i];
+    const uint32_t d = (k >> shift) & 0xffu;
+    const uint32_t dst = s_global_base[d] + (uint32_t(i) - s_digit_start[d]);
+    if (!last) keys_out[dst] = k;
+    vals_out[dst] = s_vals[i];
+  }
+}
+
+int rs_histogram_enqueue(const void* src, KeyKind kind, int64_t n, int num_passes, uint32_t* hist,
+                         uint32_t* digit_base, const float* scores, uint32_t* max_enc,
+                         int32_t* nan_flag, cudaStream_t stream) {
+  const int64_t want = ceil_div(n, 256 * 8);
+  const int grid = int(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(sm_count()) * 8)));
+  rs_histogram_kernel<<<grid, 256, 0, stream>>>(src, int(kind), n, num_passes, hist, scores, max_enc,
+                                                nan_flag);
+  MMBS_LAUNCH_CHECK();
+  rs_digit_base_kernel<<<num_passes, RS_RADIX, 0, stream>>>(hist, digit_base);
+  MMBS_LAUNCH_CHECK();
+  return MMBS_OK;
+}
+
+int rs_sort_enqueue(const void* src, KeyKind kind, int64_t n, int num_passes,
+                    const SortWorkspace& ws, int32_t* perm_out, cudaStream_t stream) {
+  MMBS_REQUIRE(n >= 1 && n <= RS_MAX_N, "radix sort: n=%lld out of range [1, 2^30)", (long long)n);
+  MMBS_REQUIRE(num_passes >= 1 && num_passes <= 4, "radix sort: num_passes=%d", num_passes);
+  const int64_t tiles = rs_tiles(n);
+  const uint32_t* kin = nullptr;
+  const uint32_t* vin = nullptr;
+  for (int p = 0; p < num_passes; ++p) {
+    const bool first = (p == 0), last = (p == num_passes - 1);
+    uint32_t* kout = (p & 1) ? ws.keys_b : ws.keys_a;
+    uint32_t* vout = last ? reinterpret_cast<uint32_t*>(perm_out) : ((p & 1) ? ws.vals_b : ws.vals_a);
+    rs_onesweep_kernel<<<unsigned(tiles), RS_THREADS, 0, stream>>>(
+        src, int(kind), kin, vin, kout, vout, n, 8 * p, ws.digit_base + p * RS_RADIX,
+        ws.lookback + int64_t(p) * tiles * RS_RADIX, ws.counters + p, first ? 1 : 0, last ? 1 : 0);
+    MMBS_LAUNCH_CHECK();
+    kin = kout;
+    vin = vout;
+  }
+  return MMBS_OK;
+}
+
+}  // namespace mmbs

@@ -1,0 +1,68 @@
+// Stable LSD radix sort of (u32 key, u32 index) pairs, Onesweep style: one global
+// histogram pass, then one read+write pass per 8-bit digit in which every tile
+// resolves its global digit offsets by decoupled look-back over its predecessors
+// (no separate scan kernel between passes, 16 B/pair/pass of HBM traffic).
+//
+// Used by the Cox loss (key = order-preserving image of -time, reference
+// torch.sort(-times) at /root/reference/1_HistoPathology/models.py:99) and by the
+// per-patient aggregation (key = segment id).
+#pragma once
+
+#include "common.cuh"
+
+namespace mmbs {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 pairs per tile
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_RADIX = 256;
+constexpr uint32_t RS_FLAG_AGG = 1u << 30;
+constexpr uint32_t RS_FLAG_INCL = 2u << 30;
+constexpr uint32_t RS_FLAG_MASK = 3u << 30;
+constexpr uint32_t RS_VALUE_MASK = (1u << 30) - 1;
+constexpr int64_t RS_MAX_N = (int64_t(1) << 30) - 1;
+
+enum KeyKind : int { KEY_NEG_TIME_F32 = 0, KEY_U32 = 1 };
+
+struct SortWorkspace {
+  uint32_t* keys_a;
+  uint32_t* keys_b;
+  uint32_t* vals_a;
+  uint32_t* vals_b;
+  uint32_t* hist;        // [4][256]    (zeroed by caller)
+  uint32_t* digit_base;  // [4][256]
+  uint32_t* counters;    // [4]         (zeroed by caller)
+  uint32_t* lookback;    // [4][tiles][256] (zeroed by caller)
+};
+
+static inline int64_t rs_tiles(int64_t n) { return n > 0 ? (n + RS_TILE - 1) / RS_TILE : 1; }
+
+// Enqueue the sort.  `src` holds n floats (times) or n u32 keys.  The histogram
+// must already be in ws.hist (see cox.cu / segmean.cu: the histogram kernel is
+// fused with other per-element work there).  Writes the sorted original indices
+// to perm_out.  num_passes in [1,4]: number of low bytes that can differ.
+int rs_sort_enqueue(const void* src, KeyKind kind, int64_t n, int num_passes,
+                    const SortWorkspace& ws, int32_t* perm_out, cudaStream_t stream);
+
+// Plain histogram (+ optional fused max / NaN flag over `scores`).
+int rs_histogram_enqueue(const void* src, KeyKind kind, int64_t n, int num_passes, uint32_t* hist,
+                         uint32_t* digit_base, const float* scores, uint32_t* max_enc,
+                         int32_t* nan_flag, cudaStream_t stream);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t rs_load_key(const void* src, int kind, int64_t i) {
+  if (kind == KEY_NEG_TIME_F32) return time_key(__ldg(static_cast<const float*>(src) + i));
+  return __ldg(static_cast<const uint32_t*>(src) + i);
+}
+// order-preserving u32 image of a float (for atomicMax over floats)
+__device__ __forceinline__ uint32_t float_order_enc(float f) {
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float float_order_dec(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+#endif
+
+}  // namespace mmbs

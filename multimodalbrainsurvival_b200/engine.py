@@ -1,0 +1,211 @@
+"""Host-side execution engine over libmmbs: conv/linear plans and the ResNet-50
+inference pipeline (NHWC bf16 activations, folded eval BatchNorm, fused ReLU/residual).
+
+Replaces the arithmetic of ``ResNet.forward_extract``
+(/root/reference/5_JointFusion/resnet.py:151-165 == 1_HistoPathology/resnet.py:151-165)
+while reading the weights from the stock ``nn.Conv2d`` / ``nn.BatchNorm2d`` parameters
+(state_dict stays byte-compatible).  PyTorch is used for device
+memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, c_void_p
+
+
+class ConvPlan:
+    """Owns one mmbs_conv_plan (TMA descriptors bound to fixed device buffers)."""
+
+    def __init__(self, handle, keep):
+        self._h = handle
+        self._keep = keep  # tensors whose storage the descriptors point at
+
+    def run(self):
+        _lib.check(_lib.lib().mmbs_conv_run(self._h, _lib.stream_ptr()), "mmbs_conv_run")
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib().mmbs_conv_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def conv_plan(x, w, out, *, ksize, stride, c_in, scale=None, shift=None, residual=None, relu=False,
+              in_hw=None):
+    """x: bf16 NHWC [B,H,W,Cin] (ksize 4 = stem: the [B,116,116,16] space-to-depth buffer);
+    w: bf16 [Cout, k*k*Cin]; out: NHWC bf16 or fp32."""
+    B = x.shape[0]
+    H, W = (x.shape[1], x.shape[2]) if in_hw is None else in_hw
+    d = ConvDesc()
+    d.batch, d.in_h, d.in_w, d.c_in, d.c_out = B, H, W, c_in, w.shape[0]
+    d.ksize, d.stride, d.relu = ksize, stride, int(relu)
+    d.out_f32 = int(out.dtype == torch.float32)
+    d.in_ = x.data_ptr()
+    d.weight = w.data_ptr()
+    d.scale = scale.data_ptr() if scale is not None else None
+    d.shift = shift.data_ptr() if shift is not None else None
+    d.residual = residual.data_ptr() if residual is not None else None
+    d.out = out.data_ptr()
+    h = c_void_p()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().mmbs_conv_plan_create(ctypes.byref(d), ctypes.byref(h)), "mmbs_conv_plan_create")
+    return ConvPlan(h, (x, w, out, scale, shift, residual))
+
+
+def linear_plan(x, w, bias, out, relu=False):
+    """x bf16 [M,K], w bf16 [N,K] (K % 64 == 0, N % 32 == 0), out bf16/fp32 [M,N]."""
+    M, K = x.shape
+    N = w.shape[0]
+    h = c_void_p()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().mmbs_linear_plan_create(
+            _lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(out), M, N, K, int(relu),
+            int(out.dtype == torch.float32), ctypes.byref(h)), "mmbs_linear_plan_create")
+    return ConvPlan(h, (x, w, bias, out))
+
+
+# ------------------------------------------------------------------ small wrappers
+def pack_conv_weight(w_oihw: torch.Tensor) -> torch.Tensor:
+    O, I, k, _ = w_oihw.shape
+    w = w_oihw.detach().float().contiguous()
+    out = torch.empty((O, k * k * I), dtype=torch.bfloat16, device=w.device)
+    _lib.check(_lib.lib().mmbs_pack_conv_weight(_lib.ptr(w), _lib.ptr(out), O, I, k, _lib.stream_ptr()),
+               "mmbs_pack_conv_weight")
+    return out
+
+
+def pack_stem_weight(w_oihw: torch.Tensor) -> torch.Tensor:
+    assert tuple(w_oihw.shape) == (64, 3, 7, 7), "stem conv must be Conv2d(3, 64, 7, stride 2, pad 3)"
+    w = w_oihw.detach().float().contiguous()
+    out = torch.empty((64, 256), dtype=torch.bfloat16, device=w.device)
+    _lib.check(_lib.lib().mmbs_stem_pack_weight(_lib.ptr(w), _lib.ptr(out), _lib.stream_ptr()),
+               "mmbs_stem_pack_weight")
+    return out
+
+
+def bn_fold(bn: torch.nn.BatchNorm2d):
+    c = bn.num_features
+    dev = bn.running_mean.device
+    g = (bn.weight if bn.weight is not None else torch.ones(c, device=dev)).detach().float().contiguous()
+    b = (bn.bias if bn.bias is not None else torch.zeros(c, device=dev)).detach().float().contiguous()
+    m = bn.running_mean.detach().float().contiguous()
+    v = bn.running_var.detach().float().contiguous()
+    out = torch.empty((2, c), dtype=torch.float32, device=dev)
+    _lib.check(_lib.lib().mmbs_bn_fold(_lib.ptr(g), _lib.ptr(b), _lib.ptr(m), _lib.ptr(v), float(bn.eps), c,
+                                       _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.stream_ptr()), "mmbs_bn_fold")
+    return out[0], out[1]
+
+
+def cast_pad_bf16(x: torch.Tensor, cols_padded: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    x = x.detach().float().contiguous()
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty((rows, cols_padded), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().mmbs_cast_pad_bf16(_lib.ptr(x), _lib.ptr(out), rows, cols, cols_padded,
+                                             _lib.stream_ptr()), "mmbs_cast_pad_bf16")
+    return out
+
+
+# ------------------------------------------------------------------ ResNet-50 pipeline
+class ResNetEngine:
+    """Inference pipeline for one (ResNet module, chunk size).  `chunk` patches are pushed
+    through all 53 convs at a time so the inter-layer activations of a chunk stay L2-resident."""
+
+    def __init__(self, resnet, chunk: int):
+        p = next(resnet.parameters())
+        if not p.is_cuda:
+            raise RuntimeError("ResNetEngine: the module must live on a CUDA device (no CPU fallback)")
+        self.device = p.device
+        self.chunk = int(chunk)
+        self._steps = []
+        self._keep = []
+        self._weights_version = None
+        self._build(resnet)
+
+    @staticmethod
+    def weights_version(resnet):
+        return tuple((t.data_ptr(), t._version) for t in list(resnet.parameters()) + list(resnet.buffers()))
+
+    def _buf(self, *shape, dtype=torch.bfloat16):
+        t = torch.empty(shape, dtype=dtype, device=self.device)
+        self._keep.append(t)
+        return t
+
+    def _build(self, net):
+        B = self.chunk
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            self.x_s2d = self._buf(B, 116, 116, 16)
+            stem_out = self._buf(B, 112, 112, 64)
+            pool_out = self._buf(B, 56, 56, 64)
+            w = pack_stem_weight(net.conv1.weight)
+            sc, sh = bn_fold(net.bn1)
+            stem = conv_plan(self.x_s2d, w, stem_out, ksize=4, stride=1, c_in=16, scale=sc, shift=sh, relu=True,
+                             in_hw=(116, 116))
+            self._steps.append(stem.run)
+            self._steps.append(lambda: _lib.check(L.mmbs_maxpool_3x3s2(
+                _lib.ptr(stem_out), _lib.ptr(pool_out), B, 112, 112, 64, _lib.stream_ptr()), "mmbs_maxpool_3x3s2"))
+            x = pool_out
+            layers = [net.layer1, net.layer2, net.layer3, net.layer4]
+            n_blocks = sum(len(l) for l in layers)
+            bi = 0
+            for layer in layers:
+                for blk in layer:
+                    bi += 1
+                    last = bi == n_blocks
+                    Bx, H, W, Cin = x.shape
+                    planes = blk.conv1.out_channels
+                    s = blk.conv2.stride[0]
+                    Ho, Wo = H // s, W // s
+                    t1 = self._buf(B, H, W, planes)
+                    t2 = self._buf(B, Ho, Wo, planes)
+                    out = self._buf(B, Ho, Wo, planes * 4, dtype=torch.float32 if last else torch.bfloat16)
+                    sc1, sh1 = bn_fold(blk.bn1)
+                    sc2, sh2 = bn_fold(blk.bn2)
+                    sc3, sh3 = bn_fold(blk.bn3)
+                    c1 = conv_plan(x, pack_conv_weight(blk.conv1.weight), t1, ksize=1, stride=1, c_in=Cin,
+                                   scale=sc1, shift=sh1, relu=True)
+                    c2 = conv_plan(t1, pack_conv_weight(blk.conv2.weight), t2, ksize=3, stride=s, c_in=planes,
+                                   scale=sc2, shift=sh2, relu=True)
+                    if blk.downsample is not None:
+                        res = self._buf(B, Ho, Wo, planes * 4)
+                        scd, shd = bn_fold(blk.downsample[1])
+                        ds = conv_plan(x, pack_conv_weight(blk.downsample[0].weight), res, ksize=1,
+                                       stride=blk.downsample[0].stride[0], c_in=Cin, scale=scd, shift=shd, relu=False)
+                        self._steps.append(ds.run)
+                    else:
+                        res = x
+                    c3 = conv_plan(t2, pack_conv_weight(blk.conv3.weight), out, ksize=1, stride=1, c_in=planes,
+                                   scale=sc3, shift=sh3, residual=res, relu=True)
+                    self._steps += [c1.run, c2.run, c3.run]
+                    self._keep += [c1, c2, c3]
+                    x = out
+            self.final = x  # [B,7,7,2048] fp32
+            self._keep.append(stem)
+        self._weights_version = self.weights_version(net)
+        self.n_kernels = len(self._steps) + 2
+
+    def run_chunk(self, x_nchw: torch.Tensor, out: torch.Tensor):
+        """x_nchw: fp32 [chunk,3,224,224] contiguous; out: fp32 [chunk,2048]."""
+        L = _lib.lib()
+        B = self.chunk
+        _lib.check(L.mmbs_stem_pack_input(_lib.ptr(x_nchw), _lib.ptr(self.x_s2d), B, _lib.stream_ptr()),
+                   "mmbs_stem_pack_input")
+        for step in self._steps:
+            step()
+        _lib.check(L.mmbs_avgpool_global_f32(_lib.ptr(self.final), _lib.ptr(out), B, 49, 2048, _lib.stream_ptr()),
+                   "mmbs_avgpool_global_f32")
+
+
+def default_chunk(batch: int) -> int:
+    env = os.environ.get("MMBS_RESNET_CHUNK")
+    if env:
+        return max(1, min(int(env), batch))
+    return batch if batch <= 128 else 128

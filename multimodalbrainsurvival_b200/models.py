@@ -1,0 +1,176 @@
+"""Drop-in superset of the reference's four ``models.py`` files (same names, signatures,
+return conventions and ``state_dict`` keys):
+
+  1_HistoPathology/models.py : Identity :13, TanhAttention :22, AggregationModel :35-57,
+                               AggregationProjectModel :59, cox_loss :90, CoxLoss :113,
+                               NLLSurvLoss :121, nll_loss :155, PatchBagDataset :234
+  5_JointFusion/models.py    : BagHistopathologyRNAModel :87-104, HistopathologyRNAModel :106
+  2_GeneExpression/models.py = 3_EarlyFusion/models.py : RNAOnlyModel :8-21, cox_loss :24
+
+The wrappers are thin: the arithmetic lives in the kernels reached through
+``resnet.forward_extract`` (engine.ResNetEngine), ``mlp.run_mlp`` (tcgen05 GEMMs reading the
+stock ``nn.Linear`` parameters in place) and ``cox.cox_loss``.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .cox import CoxLoss, cox_loss  # noqa: F401  (re-exported under the reference's names)
+from .datasets import PatchBagDataset  # noqa: F401
+from . import mlp as _mlp
+
+__all__ = ["Identity", "TanhAttention", "AggregationModel", "AggregationProjectModel", "cox_loss", "CoxLoss",
+           "NLLSurvLoss", "nll_loss", "PatchBagDataset", "BagHistopathologyRNAModel", "HistopathologyRNAModel",
+           "RNAOnlyModel", "accelerate"]
+
+
+class Identity(nn.Module):
+    """Aggregator that keeps every patch feature; attention weights are all ones."""
+
+    def forward(self, x):
+        return x, torch.ones(x.shape[0], x.shape[1], device=x.device)
+
+
+class TanhAttention(nn.Module):
+    def __init__(self, dim=2048):
+        super().__init__()
+        self.dim = dim
+        self.vector = torch.nn.Parameter(torch.zeros(dim))
+        self.linear = nn.Linear(dim, dim, bias=False)
+
+    def forward(self, x):
+        logits = torch.tanh(self.linear(x)).matmul(self.vector.unsqueeze(-1))
+        attention_weights = F.softmax(logits, dim=1)
+        return x * attention_weights * x.shape[1], attention_weights
+
+
+def _bag_features(resnet, x, resnet_dim):
+    """(B, bag, C, H, W) -> per-patch features (B, bag, resnet_dim) through forward_extract."""
+    batch_size, bag_size = x.shape[0], x.shape[1]
+    feats = resnet.forward_extract(x.reshape(-1, *x.shape[2:]))
+    return feats.view(batch_size, bag_size, resnet_dim)
+
+
+class AggregationModel(nn.Module):
+    def __init__(self, resnet, aggregator, aggregator_dim, resnet_dim=2048, out_features=1):
+        super().__init__()
+        self.resnet = resnet
+        self.aggregator = aggregator
+        self.fc = nn.Linear(aggregator_dim, out_features)
+        self.aggregator_dim = aggregator_dim
+        self.resnet_dim = resnet_dim
+
+    def extract(self, x):
+        features = _bag_features(self.resnet, x, self.resnet_dim)
+        features, attention_weights = self.aggregator(features)
+        return features.mean(dim=1), attention_weights
+
+    def forward(self, x):
+        features, attention_weights = self.extract(x)
+        return self.fc(features), attention_weights
+
+
+class AggregationProjectModel(nn.Module):
+    def __init__(self, resnet, aggregator, aggregator_dim, resnet_dim=2048, out_features=1, hdim=200, dropout=.3):
+        super().__init__()
+        self.resnet = resnet
+        self.aggregator = aggregator
+        self.aggregator_dim = aggregator_dim
+        self.resnet_dim = resnet_dim
+        self.hdim = hdim
+        self.dropout = nn.Dropout(p=dropout)
+        self.project = nn.Linear(aggregator_dim, hdim)
+        self.fc = nn.Linear(hdim, out_features)
+
+    def extract(self, x):
+        features = _bag_features(self.resnet, x, self.resnet_dim)
+        features, attention_weights = self.aggregator(features)
+        features = self.dropout(torch.tanh(self.project(features.mean(dim=1))))
+        return features, attention_weights
+
+    def forward(self, x):
+        features, attention_weights = self.extract(x)
+        return self.fc(features), attention_weights
+
+
+class BagHistopathologyRNAModel(nn.Module):
+    def __init__(self, resnet, rna_mlp, final_mlp):
+        super().__init__()
+        self.resnet = resnet
+        self.rna_mlp = rna_mlp
+        self.final_mlp = final_mlp
+
+    def forward(self, patch_bag, rna, resnet_dim=2048):
+        image_features = _bag_features(self.resnet, patch_bag, resnet_dim).mean(dim=1)
+        rna_features = _mlp.run_mlp(self.rna_mlp, rna)
+        return _mlp.run_mlp(self.final_mlp, torch.cat([image_features, rna_features], dim=1))
+
+
+class HistopathologyRNAModel(nn.Module):
+    def __init__(self, resnet, rna_mlp, final_mlp):
+        super().__init__()
+        self.resnet = resnet
+        self.rna_mlp = rna_mlp
+        self.final_mlp = final_mlp
+
+    def forward(self, patch, rna):
+        image_features = self.resnet.forward_extract(patch)
+        rna_features = _mlp.run_mlp(self.rna_mlp, rna)
+        return _mlp.run_mlp(self.final_mlp, torch.cat([image_features, rna_features], dim=1))
+
+
+class RNAOnlyModel(nn.Module):
+    def __init__(self, rna_mlp, final_mlp):
+        super().__init__()
+        self.rna_mlp = rna_mlp
+        self.final_mlp = final_mlp
+
+    def forward(self, rna):
+        return _mlp.run_mlp(self.final_mlp, _mlp.run_mlp(self.rna_mlp, rna))
+
+    def extract(self, rna):
+        return _mlp.run_mlp(self.rna_mlp, rna)
+
+
+def accelerate(module: nn.Module) -> nn.Module:
+    """Route a bare ``nn.Sequential`` MLP (the early-fusion script uses one as its whole
+    model, 3_EarlyFusion/2_EarlyFusion_train.py:242-253) through the fused kernels.
+    Parameters, ``state_dict`` keys and optimizer bindings are untouched."""
+    return _mlp.AcceleratedSequential.wrap(module)
+
+
+# --------------------------------------------------------------------------- NLL survival loss
+def nll_loss(h, y, c, alpha=0.0, eps=1e-7, reduction='mean'):
+    """Discrete-time survival negative log-likelihood (Zadeh & Schmid 2020); ``survival_bin``
+    task of the histopathology scripts - not on the Cox hot path, kept as plain torch.
+    h: (n, n_bins) logits; y: (n, 1) int64 bin; c: (n, 1) censoring indicator (1 = censored)."""
+    n = len(y)
+    y = y.view(n, 1)
+    c = c.view(n, 1).float()
+    hazards = torch.sigmoid(h)
+    surv = torch.cat([torch.ones_like(c), torch.cumprod(1 - hazards, dim=1)], 1)  # S(-1) = 1
+    log_s_prev = torch.log(torch.gather(surv, 1, y).clamp(min=eps))
+    log_h_this = torch.log(torch.gather(hazards, 1, y).clamp(min=eps))
+    log_s_this = torch.log(torch.gather(surv, 1, y + 1).clamp(min=eps))
+    uncensored = -(1 - c) * (log_s_prev + log_h_this)
+    censored = -c * log_s_this
+    loss = (1 - alpha) * censored + uncensored
+    if reduction == 'mean':
+        return loss.mean()
+    if reduction == 'sum':
+        return loss.sum()
+    raise ValueError("Bad input for reduction: {}".format(reduction))
+
+
+class NLLSurvLoss(nn.Module):
+    def __init__(self, alpha=0.0, eps=1e-7, reduction='mean'):
+        super().__init__()
+        self.alpha = alpha
+        self.eps = eps
+        self.reduction = reduction
+
+    def __call__(self, h, y, c):
+        return nll_loss(h=h, y=y.unsqueeze(dim=1), c=c.unsqueeze(dim=1), alpha=self.alpha, eps=self.eps,
+                        reduction=self.reduction)

@@ -1,0 +1,243 @@
+"""Drop-in for the reference's ``resnet.py`` (import surface, module tree and
+``state_dict`` keys identical):
+
+    from resnet import resnet50            /root/reference/1_HistoPathology/2_HistoPath_train.py:41
+    model.forward(x), model.forward_extract(x), .conv1/.bn1/.layer1..4/.fc
+        /root/reference/5_JointFusion/resnet.py:92-165 (ResNet), :54-90 (Bottleneck)
+
+What differs is what runs underneath ``forward_extract``: for CUDA tensors in
+eval mode without autograd the patches go through ``engine.ResNetEngine`` - NHWC
+bf16 activations, tcgen05 implicit-GEMM convolutions with the eval BatchNorm,
+ReLU and residual add fused into the epilogue (csrc/gemm_tcgen05.cu).  The
+weights stay in the stock ``nn.Conv2d`` / ``nn.BatchNorm2d`` parameters; packed bf16
+copies are caches rebuilt when a parameter's version counter moves.
+
+Training mode (batch-statistics BatchNorm + autograd through layer4) is not yet
+served by the kernels: it runs the module graph below on the tensor's own device.
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+__all__ = ['ResNet', 'resnet18', 'resnet34', 'resnet50', 'resnet101', 'resnet152']
+
+model_urls = {
+    'resnet18': 'https://download.pytorch.org/models/resnet18-5c106cde.pth',
+    'resnet34': 'https://download.pytorch.org/models/resnet34-333f7ec4.pth',
+    'resnet50': 'https://download.pytorch.org/models/resnet50-19c8e357.pth',
+    'resnet101': 'https://download.pytorch.org/models/resnet101-5d3b4d8f.pth',
+    'resnet152': 'https://download.pytorch.org/models/resnet152-b121ed2d.pth',
+}
+
+
+def conv3x3(in_planes, out_planes, stride=1):
+    return nn.Conv2d(in_planes, out_planes, 3, stride=stride, padding=1, bias=False)
+
+
+def _conv1x1(cin, cout, stride=1):
+    return nn.Conv2d(cin, cout, 1, stride=stride, bias=False)
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1, self.bn1 = conv3x3(inplanes, planes, stride), nn.BatchNorm2d(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2, self.bn2 = conv3x3(planes, planes), nn.BatchNorm2d(planes)
+        self.downsample, self.stride = downsample, stride
+
+    def forward(self, x):
+        shortcut = x if self.downsample is None else self.downsample(x)
+        y = self.relu(self.bn1(self.conv1(x)))
+        y = self.bn2(self.conv2(y))
+        return self.relu(y + shortcut)
+
+
+class Bottleneck(nn.Module):
+    """1x1 -> 3x3 (carries the stride) -> 1x1 (x4), residual add, ReLU."""
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1, self.bn1 = _conv1x1(inplanes, planes), nn.BatchNorm2d(planes)
+        self.conv2, self.bn2 = conv3x3(planes, planes, stride), nn.BatchNorm2d(planes)
+        self.conv3, self.bn3 = _conv1x1(planes, planes * 4), nn.BatchNorm2d(planes * 4)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample, self.stride = downsample, stride
+
+    def forward(self, x):
+        shortcut = x if self.downsample is None else self.downsample(x)
+        y = self.relu(self.bn1(self.conv1(x)))
+        y = self.relu(self.bn2(self.conv2(y)))
+        y = self.bn3(self.conv3(y))
+        return self.relu(y + shortcut)
+
+
+class _Trunk(nn.Module):
+    """Shared body of ResNet / RNfour / RNone (they differ in the stem's input channels)."""
+    _in_channels = 3
+
+    def __init__(self, block, layers, num_classes=1000):
+        super().__init__()
+        self.inplanes = 64
+        self.conv1 = nn.Conv2d(self._in_channels, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        self.layer1 = self._make_layer(block, 64, layers[0])
+        self.layer2 = self._make_layer(block, 128, layers[1], stride=2)
+        self.layer3 = self._make_layer(block, 256, layers[2], stride=2)
+        self.layer4 = self._make_layer(block, 512, layers[3], stride=2)
+        self.avgpool = nn.AvgPool2d(7, stride=1)
+        self.fc = nn.Linear(512 * block.expansion, num_classes)
+        for m in self.modules():  # He-normal convs, unit BatchNorm (reference resnet.py:109-115)
+            if isinstance(m, nn.Conv2d):
+                fan = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+                m.weight.data.normal_(0, math.sqrt(2. / fan))
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+        self._engines = {}
+
+    def _make_layer(self, block, planes, blocks, stride=1):
+        width = planes * block.expansion
+        downsample = None
+        if stride != 1 or self.inplanes != width:
+            downsample = nn.Sequential(_conv1x1(self.inplanes, width, stride), nn.BatchNorm2d(width))
+        stages = [block(self.inplanes, planes, stride, downsample)]
+        self.inplanes = width
+        stages += [block(width, planes) for _ in range(1, blocks)]
+        return nn.Sequential(*stages)
+
+    # ---- module-graph path (training mode / autograd / non-accelerated variants)
+    def _features_torch(self, x):
+        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        x = self.avgpool(x)
+        return x.view(x.size(0), -1)
+
+    def _can_accelerate(self, x):
+        return False
+
+    def forward_extract(self, x):
+        if self._can_accelerate(x):
+            return self._features_b200(x)
+        return self._features_torch(x)
+
+    def forward(self, x):
+        return self.fc(self.forward_extract(x))
+
+
+class ResNet(_Trunk):
+    _in_channels = 3
+
+    def _can_accelerate(self, x):
+        if os.environ.get("MMBS_DISABLE_KERNELS", "0") == "1":
+            return False
+        return (x.is_cuda and not self.training and not torch.is_grad_enabled()
+                and x.dim() == 4 and tuple(x.shape[1:]) == (3, 224, 224)
+                and isinstance(self.layer1[0], Bottleneck) and self.fc.in_features == 2048)
+
+    def _features_b200(self, x):
+        from . import engine
+        B = x.shape[0]
+        x = x.float().contiguous()
+        out = torch.empty((B, 2048), dtype=torch.float32, device=x.device)
+        done = 0
+        while done < B:
+            chunk = engine.default_chunk(B - done)
+            key = (x.device.index, chunk)
+            eng = self._engines.get(key)
+            ver = engine.ResNetEngine.weights_version(self)
+            if eng is None or eng._weights_version != ver:
+                eng = engine.ResNetEngine(self, chunk)
+                self._engines[key] = eng
+            eng.run_chunk(x[done:done + chunk], out[done:done + chunk])
+            done += chunk
+        return out
+
+    def __getstate__(self):  # engines hold ctypes handles: never pickle / deepcopy them
+        d = self.__dict__.copy()
+        d["_engines"] = {}
+        return d
+
+
+class RNfour(_Trunk):
+    _in_channels = 4
+
+
+class RNone(_Trunk):
+    _in_channels = 1
+
+
+class ResNetProject(nn.Module):
+    def __init__(self, resnet, hdim=200, input_dim=2048, dropout=.3):
+        super().__init__()
+        self.resnet = resnet
+        self.hdim = hdim
+        self.dropout = nn.Dropout(p=dropout)
+        self.project = nn.Linear(input_dim, hdim)
+        self.fc = nn.Linear(hdim, 1)
+
+    def forward_extract(self, x):
+        return self.dropout(torch.tanh(self.project(self.resnet.forward_extract(x))))
+
+    def forward(self, x):
+        return self.fc(self.forward_extract(x))
+
+
+_CONFIGS = {
+    'resnet18': (BasicBlock, [2, 2, 2, 2]), 'resnet34': (BasicBlock, [3, 4, 6, 3]),
+    'resnet50': (Bottleneck, [3, 4, 6, 3]), 'resnet101': (Bottleneck, [3, 4, 23, 3]),
+    'resnet152': (Bottleneck, [3, 8, 36, 3]),
+}
+
+
+def _build(name, pretrained, cls=ResNet, **kwargs):
+    block, layers = _CONFIGS[name]
+    model = cls(block, layers, **kwargs)
+    if pretrained:
+        import torch.utils.model_zoo as model_zoo
+        state = model_zoo.load_url(model_urls[name])
+        if cls is not ResNet:  # 1-/4-channel stems keep their own random conv1
+            state = {k: v for k, v in state.items() if not k.startswith('conv1.')}
+            model.load_state_dict(state, strict=False)
+        else:
+            model.load_state_dict(state)
+    return model
+
+
+def resnet18(pretrained=False, **kwargs):
+    return _build('resnet18', pretrained, **kwargs)
+
+
+def resnet34(pretrained=False, **kwargs):
+    return _build('resnet34', pretrained, **kwargs)
+
+
+def resnet50(pretrained=False, **kwargs):
+    """ResNet-50; pretrained=True downloads the ImageNet weights (needs network)."""
+    return _build('resnet50', pretrained, **kwargs)
+
+
+def resnet50_4channel(pretrained=False, **kwargs):
+    return _build('resnet50', pretrained, cls=RNfour, **kwargs)
+
+
+def resnet50_1channel(pretrained=False, **kwargs):
+    return _build('resnet50', pretrained, cls=RNone, **kwargs)
+
+
+def resnet101(pretrained=False, **kwargs):
+    return _build('resnet101', pretrained, **kwargs)
+
+
+def resnet152(pretrained=False, **kwargs):
+    return _build('resnet152', pretrained, **kwargs)

@@ -1,0 +1,114 @@
+"""GPU numerics: the tcgen05 implicit-GEMM kernel (csrc/gemm_tcgen05.cu) vs a plain torch
+fp32 reference of the same op on bf16-rounded operands.  Tolerance: bf16 output rounding
+(2^-8 relative) + fp32 accumulation-order noise."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def _ref_conv(x_nhwc, w_oihw, scale, shift, res_nhwc, relu, stride, pad):
+    x = _bf(x_nhwc).permute(0, 3, 1, 2).double().cpu()
+    w = _bf(w_oihw).double().cpu()
+    y = F.conv2d(x, w, stride=stride, padding=pad)
+    y = y * scale.double().cpu().view(1, -1, 1, 1) + shift.double().cpu().view(1, -1, 1, 1)
+    if res_nhwc is not None:
+        y = y + _bf(res_nhwc).permute(0, 3, 1, 2).double().cpu()
+    if relu:
+        y = torch.relu(y)
+    return y.permute(0, 2, 3, 1).float()
+
+
+def _assert_close(got, ref, tol, name):
+    got = got.float().cpu()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= tol * scale + 1e-6, f"{name}: max err {err:.4g} vs scale {scale:.4g}"
+
+
+CASES = [
+    # B, H, W, Cin, Cout, k, stride, residual, relu, out_f32
+    (2, 56, 56, 64, 64, 1, 1, False, True, False),
+    (2, 56, 56, 64, 256, 1, 1, True, True, False),
+    (2, 56, 56, 64, 64, 3, 1, False, True, False),
+    (3, 56, 56, 128, 128, 3, 2, False, True, False),
+    (2, 56, 56, 256, 512, 1, 2, False, False, False),
+    (4, 28, 28, 128, 128, 3, 1, False, True, False),
+    (5, 14, 14, 256, 256, 3, 1, False, True, False),
+    (3, 14, 14, 512, 512, 3, 2, False, True, False),
+    (130, 7, 7, 512, 512, 3, 1, False, True, False),
+    (2, 7, 7, 512, 2048, 1, 1, True, True, True),
+    (2, 14, 14, 1024, 256, 1, 1, False, True, False),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "B{}_{}x{}_c{}-{}_k{}s{}".format(*c[:7]))
+def test_conv_matches_torch(case):
+    from multimodalbrainsurvival_b200 import engine
+    B, H, W, Cin, Cout, k, s, use_res, relu, out_f32 = case
+    torch.manual_seed(hash(case) % 1000)
+    x = torch.randn(B, H, W, Cin, device=DEV)
+    w = torch.randn(Cout, Cin, k, k, device=DEV) / (k * k * Cin) ** 0.5
+    scale = torch.rand(Cout, device=DEV) + 0.5
+    shift = torch.randn(Cout, device=DEV) * 0.1
+    Ho, Wo = H // s, W // s
+    res = torch.randn(B, Ho, Wo, Cout, device=DEV).to(torch.bfloat16) if use_res else None
+    xb = x.to(torch.bfloat16).contiguous()
+    out = torch.full((B, Ho, Wo, Cout), float("nan"), device=DEV,
+                     dtype=torch.float32 if out_f32 else torch.bfloat16)
+    plan = engine.conv_plan(xb, engine.pack_conv_weight(w), out, ksize=k, stride=s, c_in=Cin, scale=scale,
+                            shift=shift, residual=res, relu=relu)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = _ref_conv(x, w, scale, shift, res.float() if use_res else None, relu, s, k // 2)
+    _assert_close(out, ref, 1e-5 if out_f32 else 6e-3, str(case))
+
+
+@pytest.mark.parametrize("M,N,K,relu", [(128, 4096, 12800, True), (6, 2048, 4096, False), (300, 224, 2048, True),
+                                        (1000, 32, 64, False)])
+def test_linear_matches_torch(M, N, K, relu):
+    from multimodalbrainsurvival_b200 import engine
+    torch.manual_seed(M + N)
+    x = torch.randn(M, K, device=DEV)
+    w = torch.randn(N, K, device=DEV) / K ** 0.5
+    b = torch.randn(N, device=DEV)
+    xb, wb = x.to(torch.bfloat16).contiguous(), w.to(torch.bfloat16).contiguous()
+    out = torch.full((M, N), float("nan"), device=DEV)
+    engine.linear_plan(xb, wb, b, out, relu=relu).run()
+    torch.cuda.synchronize()
+    ref = xb.double() @ wb.double().t() + b.double()
+    if relu:
+        ref = torch.relu(ref)
+    _assert_close(out, ref.float().cpu(), 2e-5, f"linear {M}x{N}x{K}")
+
+
+def test_stem_matches_torch():
+    """7x7/2 stem conv + BN + ReLU through the space-to-depth GEMM, then MaxPool(3,2,1)."""
+    from multimodalbrainsurvival_b200 import _lib, engine
+    torch.manual_seed(3)
+    B = 3
+    x = torch.randn(B, 3, 224, 224, device=DEV)
+    w = torch.randn(64, 3, 7, 7, device=DEV) * 0.1
+    scale = torch.rand(64, device=DEV) + 0.5
+    shift = torch.randn(64, device=DEV) * 0.1
+    L = _lib.lib()
+    s2d = torch.empty(B, 116, 116, 16, device=DEV, dtype=torch.bfloat16)
+    _lib.check(L.mmbs_stem_pack_input(_lib.ptr(x), _lib.ptr(s2d), B, _lib.stream_ptr()))
+    out = torch.full((B, 112, 112, 64), float("nan"), device=DEV, dtype=torch.bfloat16)
+    engine.conv_plan(s2d, engine.pack_stem_weight(w), out, ksize=4, stride=1, c_in=16, scale=scale, shift=shift,
+                     relu=True, in_hw=(116, 116)).run()
+    pooled = torch.empty(B, 56, 56, 64, device=DEV, dtype=torch.bfloat16)
+    _lib.check(L.mmbs_maxpool_3x3s2(_lib.ptr(out), _lib.ptr(pooled), B, 112, 112, 64, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = F.conv2d(_bf(x).double().cpu(), _bf(w).double().cpu(), stride=2, padding=3)
+    ref = torch.relu(ref * scale.double().cpu().view(1, -1, 1, 1) + shift.double().cpu().view(1, -1, 1, 1))
+    _assert_close(out, ref.permute(0, 2, 3, 1).float(), 6e-3, "stem")
+    ref_pool = F.max_pool2d(out.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).cpu()
+    assert torch.equal(pooled.float().cpu(), ref_pool)

@@ -1,0 +1,69 @@
+"""GPU parity: ResNet-50 forward_extract through the drop-in module (engine + tcgen05 kernels)
+vs the reference's features (golden) and the fp32 / bf16-emulating oracle.
+Tolerance (north_star): bf16 patch features within 1e-2 relative."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import det_input
+from oracle import resnet_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(sd):
+    from multimodalbrainsurvival_b200 import resnet
+    net = resnet.resnet50(pretrained=False)
+    net.load_state_dict(sd, strict=True)
+    return net.cuda().eval()
+
+
+def test_features_match_reference_golden(golden):
+    g = golden("resnet_reference.npz")
+    sd = resnet_oracle.init_state_dict(seed=1111)
+    for k, v in zip(g["fp_keys"], g["fp_vals"]):
+        if abs(float(sd[str(k)].double().abs().sum()) - float(v)) > 1e-6 * abs(float(v)):
+            pytest.skip("torch CPU RNG stream differs from the one that produced the golden weights")
+    net = _model(sd)
+    x = torch.tensor(det_input((2, 3, 224, 224))).cuda()
+    with torch.no_grad():
+        f = net.forward_extract(x)
+    torch.cuda.synchronize()
+    assert net._engines, "the CUDA engine did not run"
+    f = f.cpu().numpy()
+    ref = g["features"]
+    rel = np.linalg.norm(f - ref) / np.linalg.norm(ref)
+    assert rel < 1e-2, f"relative L2 error {rel}"
+    assert np.abs(f - ref).max() < 2e-2 * np.abs(ref).max()
+
+
+def test_features_match_bf16_oracle_tightly():
+    sd = resnet_oracle.init_state_dict(seed=7)
+    net = _model(sd)
+    torch.manual_seed(0)
+    x = torch.randn(3, 3, 224, 224)
+    with torch.no_grad():
+        f = net.forward_extract(x.cuda()).cpu()
+    ref = resnet_oracle.forward_extract(sd, x, emulate_bf16=True)
+    rel = float((f - ref).norm() / ref.norm())
+    assert rel < 3e-3, f"relative L2 error vs bf16-emulating oracle {rel}"
+
+
+def test_aggregation_model_extract_and_chunking(monkeypatch):
+    """AggregationModel.extract over bags, odd batch sizes and chunked execution agree."""
+    from multimodalbrainsurvival_b200 import models
+    sd = resnet_oracle.init_state_dict(seed=11)
+    net = _model(sd)
+    model = models.AggregationModel(net, models.Identity(), 2048, 2048, 1).cuda().eval()
+    torch.manual_seed(1)
+    x = torch.randn(5, 2, 3, 224, 224, device="cuda")
+    with torch.no_grad():
+        feats, att = model.extract(x)
+        out, _ = model(x)
+        monkeypatch.setenv("MMBS_RESNET_CHUNK", "3")
+        feats2, _ = model.extract(x)
+    assert feats.shape == (5, 2048) and att.shape == (5, 2) and out.shape == (5, 1)
+    assert float((feats - feats2).abs().max()) <= 1e-3 * float(feats.abs().max())
+    ref = resnet_oracle.forward_extract(sd, x.reshape(-1, 3, 224, 224).cpu(), emulate_bf16=True)
+    ref = ref.view(5, 2, 2048).mean(1)
+    assert float((feats.cpu() - ref).norm() / ref.norm()) < 3e-3
