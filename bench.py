@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json configs[1]): ResNet-50 patch feature extraction,
+224x224 synthetic patches, batch 512 per GPU, bf16 storage / fp32 accumulate, followed by
+the per-case aggregation of that batch's features.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one batch of 512 patches per GPU through AggregationModel.extract (the
+reference's extract_features hot loop, 1_HistoPathology/4_HistoPath_extractfeatures.py:60-71)
+plus the segmented per-case mean of the batch's features (:80-88).  Prints ONE JSON line.
+
+* value      patches/s over all GPUs, inputs resident in HBM (CUDA events, max over ranks)
+* e2e        same metric through the public API with HOST (pinned) inputs: H2D copy of the
+             fp32 batch and D2H of the features inside the timed region
+* roofline   the tcgen05 conv kernel: 8.174 GFLOP/patch over the summed
+             device time of its launches, against MEASURED_PEAKS.json (sustained bf16)
+* cpu_baseline / --impl reference: the oracle port of the reference's CPU path
+             (oracle/resnet_oracle.py, fp32 torch on all host cores), bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GFLOP_PER_PATCH = 8.174          # 2*MAC over the 53 convs at 224x224
+BATCH = 512
+PATCHES_PER_CASE = 100
+CPU_SAMPLE = 32                  # patches per CPU-baseline pass (bounded sample)
+METRIC = "resnet50_patch_feature_extraction_throughput"
+UNIT = "patches/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"tensor": float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))),
+                "tensor_burst": float(d.get("bf16_tflops", 1590.0)),
+                "hbm": float(d.get("hbm_gbs", 6650.0)), "source": "measured"}
+    return {"tensor": 1400.0, "tensor_burst": 1590.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def make_state_dict():
+    from oracle import resnet_oracle  # weights only: a seeded init with the reference's key names
+    return resnet_oracle.init_state_dict(seed=1111)
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_reference_pass(sd, x):
+    from oracle import resnet_oracle
+    return resnet_oracle.forward_extract(sd, x)
+
+
+def time_cpu(steps, warmup, sample=CPU_SAMPLE):
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = make_state_dict()
+    x = torch.randn(sample, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    for _ in range(warmup):
+        cpu_reference_pass(sd, x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_pass(sd, x)
+    dt = time.perf_counter() - t0
+    return {"value": sample * steps / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} passes of {sample} patches (fp32 torch CPU, oracle/resnet_oracle.py)",
+            "ms_per_step": 1e3 * dt / steps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 4))
+    r = time_cpu(steps, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "resnet50_extract_224_b512_bf16 (CPU sample of %d patches per step)" % CPU_SAMPLE},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+def cox_secondary(torch, dev, peaks):
+    """Cox fwd+bwd on the 10 M-sample cohort (BASELINE config 4): ms and fraction of HBM peak
+    on the 112 B/sample algorithmic traffic."""
+    from multimodalbrainsurvival_b200 import cox
+    n = 10_000_000
+    g = torch.Generator(device=dev).manual_seed(1111)
+    s = torch.randn(n, device=dev, generator=g).requires_grad_(True)
+    t = torch.rand(n, device=dev, generator=g) * 200
+    e = (torch.rand(n, device=dev, generator=g) < 0.6).float()
+    times = []
+    for i in range(6):
+        s.grad = None
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        loss = cox.cox_loss(s, t, e)
+        loss.backward()
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            times.append(a.elapsed_time(b))
+    ms = statistics.median(times)
+    gbs = n * 112 / (ms * 1e-3) / 1e9
+    return {"workload": "cox_fwd_bwd_10M", "ms": ms, "alg_bytes_per_sample": 112, "achieved_gbs": gbs,
+            "frac_of_hbm_peak": gbs / peaks["hbm"], "loss": float(loss)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from multimodalbrainsurvival_b200 import _lib, aggregate, models, resnet
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this framework has no CPU fallback; use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+
+    net = resnet.resnet50()
+    net.load_state_dict(make_state_dict())
+    model = models.AggregationModel(net, models.Identity(), 2048, 2048, 1).to(dev).eval()
+
+    B = BATCH
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    # two resident input batches (2 x 308 MB > L2) alternated between steps
+    xs = [torch.randn(B, 1, 3, 224, 224, device=dev, generator=gen) for _ in range(2)]
+    n_cases = (B + PATCHES_PER_CASE - 1) // PATCHES_PER_CASE
+    seg = (torch.arange(B, device=dev) // PATCHES_PER_CASE).to(torch.int32)
+    host = [torch.randn(B, 1, 3, 224, 224).pin_memory() for _ in range(2)]
+    host_out = torch.empty(B, 2048).pin_memory()
+
+    def step(i):
+        with torch.no_grad():
+            feats, _ = model.extract(xs[i % 2])
+        return aggregate.segmented_mean(feats, seg, n_cases)[0]
+
+    def step_e2e(i):
+        x = host[i % 2].to(dev, non_blocking=True)
+        with torch.no_grad():
+            feats, _ = model.extract(x)
+        host_out.copy_(feats, non_blocking=True)
+        return aggregate.segmented_mean(feats, seg, n_cases)[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        l0 = _lib.launch_count()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as cs:
+            a.record()
+            for i in range(steps):
+                fn(i)
+            b.record()
+            barrier()
+        ms = a.elapsed_time(b)
+        launches = _lib.launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, cs.summary()
+
+    warmup = max(args.warmup, 3)
+    ms, launches, clocks = timed(step, args.steps, warmup)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, 2)
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+
+    line = None
+    if rank == 0:
+        # per-kernel device time of one step (events around every launch of the conv kernel)
+        conv_ms = conv_kernel_time(torch, model, xs[0])
+        achieved = B * GFLOP_PER_PATCH / (conv_ms * 1e-3) / 1e3 if conv_ms else None  # TFLOP/s
+        roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, 53 launches/chunk)",
+                    "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s",
+                    "frac": (achieved / peaks["tensor"]) if achieved else None, "traffic": None,
+                    "peak_source": peaks["source"] + " (sustained bf16; burst %.1f)" % peaks["tensor_burst"],
+                    "conv_ms_per_step": conv_ms}
+        cpu = time_cpu(2, 1)
+        try:
+            cox_sec = cox_secondary(torch, dev, peaks)
+        except Exception as ex:  # secondary metric must never kill the headline line
+            cox_sec = {"error": repr(ex)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "resnet50_extract_224_b512_bf16", "batch_per_gpu": B,
+                           "patches_per_case": PATCHES_PER_CASE, "chunk": int(os.environ.get("MMBS_RESNET_CHUNK", 0)) or "default",
+                           "l2": "two alternating 308 MB input batches (> L2)", "parallelism": f"dp{world} (patches sharded, no collective)"},
+                "roofline": roofline,
+                "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * 224 * 224 * 4,
+                        "d2h_bytes_per_step": B * 2048 * 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks, "secondary": {"cox": cox_sec}}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def conv_kernel_time(torch, model, x):
+    """Sum of the device time of every conv_gemm_kernel launch in one step (CUDA events on the
+    launching stream around each launch)."""
+    from multimodalbrainsurvival_b200 import engine
+    net = model.resnet
+    total = 0.0
+    evs = []
+    orig = engine.ConvPlan.run
+
+    def timed_run(self):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        orig(self)
+        b.record()
+        evs.append((a, b))
+
+    engine.ConvPlan.run = timed_run
+    try:
+        for eng in net._engines.values():   # plans captured bound methods: rebind
+            eng._steps = [(lambda p=s.__self__: timed_run(p)) if getattr(s, "__self__", None).__class__ is engine.ConvPlan
+                          else s for s in eng._steps]
+        with torch.no_grad():
+            model.extract(x)
+        torch.cuda.synchronize()
+        total = sum(a.elapsed_time(b) for a, b in evs)
+    finally:
+        engine.ConvPlan.run = orig
+        for eng in net._engines.values():
+            eng._steps = [s for s in eng._steps]
+        net._engines.clear()  # drop the instrumented engines
+    return total
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,7 +21,7 @@ def _run(s, t, e, grad_loss=1.0):
     (loss * grad_loss).backward()
     perm = cox.risk_order(tt)
     torch.cuda.synchronize()
-    return float(loss), sc.grad.cpu().numpy().astype(np.float64), perm.cpu().numpy().astype(np.int64)
+    return float(loss.detach()), sc.grad.cpu().numpy().astype(np.float64), perm.cpu().numpy().astype(np.int64)
 
 
 def _check(s, t, e, name="", ref_loss=None, ref_grad=None, ref_perm=None, grad_loss=1.0):
