@@ -170,13 +170,13 @@ def cox_secondary(torch, dev, peaks):
     ms = statistics.median(times)
     gbs = n * 112 / (ms * 1e-3) / 1e9
     return {"workload": "cox_fwd_bwd_10M", "ms": ms, "alg_bytes_per_sample": 112, "achieved_gbs": gbs,
-            "frac_of_hbm_peak": gbs / peaks["hbm"], "loss": float(loss)}
+            "frac_of_hbm_peak": gbs / peaks["hbm"], "loss": float(loss.detach())}
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from multimodalbrainsurvival_b200 import _lib, aggregate, models, resnet
+    from multimodalbrainsurvival_b200 import _lib, aggregate, engine, models, resnet
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -223,7 +223,7 @@ def run_ours(args):
         for i in range(warmup):
             fn(i)
         barrier()
-        l0 = _lib.launch_count()
+        l0 = _lib.launch_count() + engine.GRAPH_LAUNCHES
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local) as cs:
             a.record()
@@ -232,7 +232,7 @@ def run_ours(args):
             b.record()
             barrier()
         ms = a.elapsed_time(b)
-        launches = _lib.launch_count() - l0
+        launches = _lib.launch_count() + engine.GRAPH_LAUNCHES - l0
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -280,10 +280,9 @@ def run_ours(args):
 
 def conv_kernel_time(torch, model, x):
     """Sum of the device time of every conv_gemm_kernel launch in one step (CUDA events on the
-    launching stream around each launch)."""
+    launching stream around each launch; CUDA-graph replay disabled for this instrumented pass)."""
     from multimodalbrainsurvival_b200 import engine
     net = model.resnet
-    total = 0.0
     evs = []
     orig = engine.ConvPlan.run
 
@@ -294,20 +293,27 @@ def conv_kernel_time(torch, model, x):
         b.record()
         evs.append((a, b))
 
+    saved_engines = dict(net._engines)
+    old_env = os.environ.get("MMBS_CUDA_GRAPH")
+    net._engines.clear()
+    os.environ["MMBS_CUDA_GRAPH"] = "0"
     engine.ConvPlan.run = timed_run
     try:
-        for eng in net._engines.values():   # plans captured bound methods: rebind
-            eng._steps = [(lambda p=s.__self__: timed_run(p)) if getattr(s, "__self__", None).__class__ is engine.ConvPlan
-                          else s for s in eng._steps]
         with torch.no_grad():
+            model.extract(x)          # builds instrumented engines, warm
+            torch.cuda.synchronize()
+            evs.clear()
             model.extract(x)
         torch.cuda.synchronize()
         total = sum(a.elapsed_time(b) for a, b in evs)
     finally:
         engine.ConvPlan.run = orig
-        for eng in net._engines.values():
-            eng._steps = [s for s in eng._steps]
-        net._engines.clear()  # drop the instrumented engines
+        if old_env is None:
+            os.environ.pop("MMBS_CUDA_GRAPH", None)
+        else:
+            os.environ["MMBS_CUDA_GRAPH"] = old_env
+        net._engines.clear()
+        net._engines.update(saved_engines)
     return total
 
 

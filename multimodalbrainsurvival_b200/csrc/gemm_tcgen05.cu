@@ -27,18 +27,23 @@ namespace mmbs {
 constexpr int GM_TILE_M = 128;
 constexpr int GM_CHUNK_K = 64;                       // bf16 elements = 128 B = one swizzle row
 constexpr int GM_A_BYTES = GM_TILE_M * GM_CHUNK_K * 2;  // 16 KB
-constexpr int GM_THREADS = 192;
+constexpr int GM_THREADS = 192;                      // producer, MMA, 4 epilogue warps
+constexpr int GM_EPI_THREADS = 128;
 constexpr int GM_MAX_TAPS = 16;
+constexpr int GM_OUT_BLK_BYTES = GM_TILE_M * 128;    // one 64-channel column block of a bf16 tile
 
 struct ConvParams {
   CUtensorMap a_map[4];
   CUtensorMap b_map;
+  CUtensorMap out_map;   // bf16 output, box (64, tw, th, tn)      (TMA-store path)
+  CUtensorMap res_map;   // bf16 residual, same geometry           (TMA-load into the staging tile)
   int32_t tw, th, tn;
   int32_t tiles_w, tiles_h, tiles_n;
   int32_t out_w, out_h, batch;
   int32_t c_out;
   int32_t num_taps, k_chunks;
   int32_t relu, out_f32;
+  int32_t total_tiles;
   uint32_t idesc;
   int8_t tap_map[GM_MAX_TAPS];
   int8_t tap_dw[GM_MAX_TAPS];
@@ -49,16 +54,36 @@ struct ConvParams {
   void* out;
 };
 
+// Shared-memory carve-up (offsets from a 1024-B aligned base):
+//   [ring: STAGES x (A 16 KB | B N_TILE*128 B)] [staging: N_TILE/64 x 16 KB] [barriers] [tmem slot] [scale|shift]
 template <int N_TILE, int STAGES>
 struct GemmSmem {
   static constexpr int B_BYTES = N_TILE * GM_CHUNK_K * 2;
   static constexpr int STAGE_BYTES = GM_A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;            // full[S], empty[S], accum
-  static constexpr int TMEM_SLOT_OFFSET = BAR_OFFSET + (2 * STAGES + 1) * 8;
+  static constexpr int OUT_BLKS = (N_TILE + 63) / 64;
+  static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int STAGING_BYTES = OUT_BLKS * GM_OUT_BLK_BYTES;
+  static constexpr int BAR_OFFSET = STAGING_OFFSET + STAGING_BYTES;  // full[S] empty[S] tfull[2] tempty[2] res
+  static constexpr int NUM_BARS = 2 * STAGES + 5;
+  static constexpr int TMEM_SLOT_OFFSET = BAR_OFFSET + NUM_BARS * 8;
   static constexpr int SCALE_OFFSET = (TMEM_SLOT_OFFSET + 4 + 15) / 16 * 16;
   static constexpr int TOTAL = SCALE_OFFSET + 2 * N_TILE * 4;
-  static constexpr int DYNAMIC = TOTAL + 1024;  // slack for 1024-B alignment of the ring
+  static constexpr int DYNAMIC = TOTAL + 1024;  // slack for the 1024-B alignment of the ring
+  static constexpr int TMEM_COLS = 2 * N_TILE;  // double-buffered fp32 accumulator
 };
+
+struct TileCoord {
+  int nt, w0, h0, n0;
+};
+__device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int tile, int n_tiles) {
+  TileCoord c;
+  c.nt = tile % n_tiles;  // n-tile fastest: CTAs that share an A tile run back to back (L2 reuse)
+  const int mt = tile / n_tiles;
+  c.w0 = (mt % p.tiles_w) * p.tw;
+  c.h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
+  c.n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
+  return c;
+}
 
 template <int N_TILE, int STAGES>
 __global__ void __launch_bounds__(GM_THREADS, 1)
@@ -72,41 +97,36 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full_bar = base_u32 + L::BAR_OFFSET;
   const uint32_t empty_bar = full_bar + STAGES * 8;
-  const uint32_t accum_bar = empty_bar + STAGES * 8;
+  const uint32_t tfull_bar = empty_bar + STAGES * 8;   // [2] accumulator ready   (MMA -> epilogue)
+  const uint32_t tempty_bar = tfull_bar + 16;          // [2] accumulator drained (epilogue -> MMA)
+  const uint32_t res_bar = tempty_bar + 16;            // residual tile landed in the staging buffer
   const uint32_t tmem_slot = base_u32 + L::TMEM_SLOT_OFFSET;
+  const uint32_t staging_u32 = base_u32 + L::STAGING_OFFSET;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + L::TMEM_SLOT_OFFSET);
   float* s_scale = reinterpret_cast<float*>(base_ptr + L::SCALE_OFFSET);
   float* s_shift = s_scale + N_TILE;
 
-  // tile coordinates: n-tile fastest so CTAs that share an A tile run together (L2 reuse)
   const int n_tiles = p.c_out / N_TILE;
-  const int nt = blockIdx.x % n_tiles;
-  const int mt = blockIdx.x / n_tiles;
-  const int w0 = (mt % p.tiles_w) * p.tw;
-  const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
-  const int n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
-  const int total_iters = p.num_taps * p.k_chunks;
+  const int k_iters = p.num_taps * p.k_chunks;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tc::tma_prefetch_desc(&p.a_map[i]);
     tc::tma_prefetch_desc(&p.b_map);
+    if (N_TILE >= 64 && !p.out_f32) tc::tma_prefetch_desc(&p.out_map);
     for (int s = 0; s < STAGES; ++s) {
       tc::mbar_init(full_bar + 8 * s, 1);
       tc::mbar_init(empty_bar + 8 * s, 1);
     }
-    tc::mbar_init(accum_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      tc::mbar_init(tfull_bar + 8 * a, 1);
+      tc::mbar_init(tempty_bar + 8 * a, 4);  // one arrive per epilogue warp
+    }
+    tc::mbar_init(res_bar, 1);
     tc::fence_mbar_init();
   }
   if (warp == 1) {
-    tc::tmem_alloc(tmem_slot, N_TILE);
+    tc::tmem_alloc(tmem_slot, L::TMEM_COLS);
     tc::tmem_relinquish();
-  }
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < N_TILE; i += GM_THREADS - 64) {
-      const int n = nt * N_TILE + i;
-      s_scale[i] = p.scale ? __ldg(p.scale + n) : 1.0f;
-      s_shift[i] = p.shift ? __ldg(p.shift + n) : 0.0f;
-    }
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -115,106 +135,198 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer =====
-      int it = 0;
-      for (int t = 0; t < p.num_taps; ++t) {
-        const CUtensorMap* amap = &p.a_map[p.tap_map[t]];
-        const int cw = w0 + p.tap_dw[t], ch = h0 + p.tap_dh[t];
-        for (int c = 0; c < p.k_chunks; ++c, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          tc::mbar_wait(empty_bar + 8 * s, ph ^ 1u);
-          tc::mbar_expect_tx(full_bar + 8 * s, L::STAGE_BYTES);
-          const uint32_t a_dst = base_u32 + s * L::STAGE_BYTES;
-          tc::tma_load_4d(amap, full_bar + 8 * s, a_dst, c * GM_CHUNK_K, cw, ch, n0);
-          tc::tma_load_2d(&p.b_map, full_bar + 8 * s, a_dst + GM_A_BYTES,
-                          (t * p.k_chunks + c) * GM_CHUNK_K, nt * N_TILE);
+      // ===== TMA producer: runs ahead across tile boundaries =====
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord tcd = tile_coord(p, tile, n_tiles);
+        for (int t = 0; t < p.num_taps; ++t) {
+          const CUtensorMap* amap = &p.a_map[p.tap_map[t]];
+          const int cw = tcd.w0 + p.tap_dw[t], ch = tcd.h0 + p.tap_dh[t];
+          for (int c = 0; c < p.k_chunks; ++c, ++it) {
+            const uint32_t s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1u;
+            tc::mbar_wait(empty_bar + 8 * s, ph ^ 1u);
+            tc::mbar_expect_tx(full_bar + 8 * s, L::STAGE_BYTES);
+            const uint32_t a_dst = base_u32 + s * L::STAGE_BYTES;
+            tc::tma_load_4d(amap, full_bar + 8 * s, a_dst, c * GM_CHUNK_K, cw, ch, tcd.n0);
+            tc::tma_load_2d(&p.b_map, full_bar + 8 * s, a_dst + GM_A_BYTES,
+                            (t * p.k_chunks + c) * GM_CHUNK_K, tcd.nt * N_TILE);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ===== MMA issuer (single thread) =====
-      for (int it = 0; it < total_iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        tc::mbar_wait(full_bar + 8 * s, ph);
+      // ===== MMA issuer (single thread), accumulators ping-pong in TMEM =====
+      uint32_t it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+        const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+        tc::mbar_wait(tempty_bar + 8 * acc, aph ^ 1u);  // epilogue has drained this accumulator
         tc::tc_fence_after();
-        const uint32_t a_addr = base_u32 + s * L::STAGE_BYTES;
-        const uint64_t da = tc::make_sw128_desc(a_addr);
-        const uint64_t db = tc::make_sw128_desc(a_addr + GM_A_BYTES);
+        const uint32_t d_tmem = tmem_base + acc * N_TILE;
+        for (int ki = 0; ki < k_iters; ++ki, ++it) {
+          const uint32_t s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          tc::mbar_wait(full_bar + 8 * s, ph);
+          tc::tc_fence_after();
+          const uint32_t a_addr = base_u32 + s * L::STAGE_BYTES;
+          const uint64_t da = tc::make_sw128_desc(a_addr);
+          const uint64_t db = tc::make_sw128_desc(a_addr + GM_A_BYTES);
 #pragma unroll
-        for (int k = 0; k < GM_CHUNK_K / 16; ++k) {
-          // +32 B per K=16 step inside the 128-B swizzle row (start-address field is >>4)
-          tc::umma_bf16(tmem_base, da + uint64_t(2 * k), db + uint64_t(2 * k), p.idesc,
-                        (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < GM_CHUNK_K / 16; ++k) {
+            // +32 B per K=16 step inside the 128-B swizzle row (start-address field is >>4)
+            tc::umma_bf16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), p.idesc,
+                          (ki | k) != 0 ? 1u : 0u);
+          }
+          tc::umma_commit(empty_bar + 8 * s);  // frees the smem stage when these MMAs retire
         }
-        tc::umma_commit(empty_bar + 8 * s);  // frees the smem stage when these MMAs retire
+        tc::umma_commit(tfull_bar + 8 * acc);  // accumulator complete
       }
-      tc::umma_commit(accum_bar);  // accumulator complete
     }
   } else {
-    // ===== epilogue: TMEM lane quarter (warp % 4) <-> tile rows =====
+    // ===== epilogue warps: TMEM lane quarter (warp % 4) <-> tile rows =====
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    const int pw = w0 + (r % p.tw);
-    const int phh = h0 + ((r / p.tw) % p.th);
-    const int pn = n0 + (r / (p.tw * p.th));
-    const bool row_ok = (pw < p.out_w) && (phh < p.out_h) && (pn < p.batch);
-    const int64_t row = (int64_t(pn) * p.out_h + phh) * p.out_w + pw;
-    const int64_t row_off = row * p.c_out + int64_t(nt) * N_TILE;
-    tc::mbar_wait(accum_bar, 0);
-    tc::tc_fence_after();
+    const int et = threadIdx.x - 64;  // 0..127
+    const bool use_tma_store = (N_TILE >= 64) && !p.out_f32;
+    const bool tma_res = use_tma_store && (p.residual != nullptr);
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+      const TileCoord tcd = tile_coord(p, tile, n_tiles);
+      const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+      // the previous tile's TMA store must have finished READING the staging tile
+      if (use_tma_store && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      for (int i = et; i < N_TILE; i += GM_EPI_THREADS) {
+        const int n = tcd.nt * N_TILE + i;
+        s_scale[i] = p.scale ? __ldg(p.scale + n) : 1.0f;
+        s_shift[i] = p.shift ? __ldg(p.shift + n) : 0.0f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tma_res && et == 0) {
+        tc::mbar_expect_tx(res_bar, L::OUT_BLKS * GM_OUT_BLK_BYTES);
+        for (int b = 0; b < L::OUT_BLKS; ++b)
+          tc::tma_load_4d(&p.res_map, res_bar, staging_u32 + b * GM_OUT_BLK_BYTES,
+                          tcd.nt * N_TILE + b * 64, tcd.w0, tcd.h0, tcd.n0);
+      }
+      const int pw = tcd.w0 + (r % p.tw);
+      const int phh = tcd.h0 + ((r / p.tw) % p.th);
+      const int pn = tcd.n0 + (r / (p.tw * p.th));
+      const bool row_ok = (pw < p.out_w) && (phh < p.out_h) && (pn < p.batch);
+      const int64_t row = (int64_t(pn) * p.out_h + phh) * p.out_w + pw;
+      const int64_t row_off = row * p.c_out + int64_t(tcd.nt) * N_TILE;
+
+      tc::mbar_wait(tfull_bar + 8 * acc, aph);
+      tc::tc_fence_after();
+      if (tma_res) tc::mbar_wait(res_bar, tl & 1u);
+      const uint32_t t_addr = tmem_base + acc * N_TILE + (uint32_t(q * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-      uint32_t acc[32];
-      tc::tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0), acc);
-      tc::tmem_ld_wait();
-      if (row_ok) {
+      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        uint32_t accr[32];
+        tc::tmem_ld_32x32(t_addr + uint32_t(c0), accr);
+        tc::tmem_ld_wait();
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * s_scale[c0 + j] + s_shift[c0 + j];
-        if (p.residual) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + c0);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + j);
+          const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + j);
+          v[j] = __uint_as_float(accr[j]) * sc.x + sh.x;
+          v[j + 1] = __uint_as_float(accr[j + 1]) * sc.y + sh.y;
+          v[j + 2] = __uint_as_float(accr[j + 2]) * sc.z + sh.z;
+          v[j + 3] = __uint_as_float(accr[j + 3]) * sc.w + sh.w;
+        }
+        if (use_tma_store) {
+          // staging tile: column block (c0/64), row r, 16-B chunk index XOR-swizzled by (r & 7)
+          const uint32_t blk = staging_u32 + uint32_t(c0 >> 6) * GM_OUT_BLK_BYTES + uint32_t(r) * 128u;
+          const uint32_t ch0 = uint32_t((c0 & 63) >> 3);  // first 16-B chunk of these 32 columns (0 or 4)
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const uint4 rv = __ldg(rp + g);
-            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+            const uint32_t addr = blk + (((ch0 + g) ^ uint32_t(r & 7)) << 4);
+            if (tma_res) {
+              uint32_t rw[4];
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]) : "r"(addr));
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[h]);
-              v[g * 8 + h * 2] += __bfloat162float(b2.x);
-              v[g * 8 + h * 2 + 1] += __bfloat162float(b2.y);
+              for (int h = 0; h < 4; ++h) {
+                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[h]);
+                v[g * 8 + h * 2] += __bfloat162float(b2.x);
+                v[g * 8 + h * 2 + 1] += __bfloat162float(b2.y);
+              }
             }
-          }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-        }
-        if (p.out_f32) {
-          float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + row_off + c0);
-#pragma unroll
-          for (int g = 0; g < 8; ++g) op[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-        } else {
-          uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row_off + c0);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
             uint32_t w[4];
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-              const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[g * 8 + h * 2], v[g * 8 + h * 2 + 1]);
+              float a = v[g * 8 + h * 2], b = v[g * 8 + h * 2 + 1];
+              if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+              const __nv_bfloat162 b2 = __floats2bfloat162_rn(a, b);
               w[h] = *reinterpret_cast<const uint32_t*>(&b2);
             }
-            op[g] = make_uint4(w[0], w[1], w[2], w[3]);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]),
+                         "r"(w[2]), "r"(w[3]) : "memory");
+          }
+        } else if (row_ok) {
+          // fp32 output (final block / MLP head): direct, row-predicated 128-bit stores
+          if (p.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + c0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 rv = __ldg(rp + g);
+              const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[h]);
+                v[g * 8 + h * 2] += __bfloat162float(b2.x);
+                v[g * 8 + h * 2 + 1] += __bfloat162float(b2.y);
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+          }
+          if (p.out_f32) {
+            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + row_off + c0);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) op[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row_off + c0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t w[4];
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[g * 8 + h * 2], v[g * 8 + h * 2 + 1]);
+                w[h] = *reinterpret_cast<const uint32_t*>(&b2);
+              }
+              op[g] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
           }
         }
       }
+      // accumulator fully read: hand it back to the MMA warp before the stores drain
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tempty_bar + 8 * acc);
+      if (use_tma_store) {
+        tc::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA engine
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          for (int b = 0; b < L::OUT_BLKS; ++b) {
+            asm volatile(
+                "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                    reinterpret_cast<uint64_t>(&p.out_map)),
+                "r"(staging_u32 + b * GM_OUT_BLK_BYTES), "r"(tcd.nt * N_TILE + b * 64), "r"(tcd.w0),
+                "r"(tcd.h0), "r"(tcd.n0)
+                : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
     }
+    if (use_tma_store && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, N_TILE);
+  if (warp == 1) tc::tmem_dealloc(tmem_base, L::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------ host side
@@ -296,10 +408,10 @@ extern "C" int mmbs_conv_run(const mmbs_conv_plan* plan, void* stream_) {
   MMBS_REQUIRE(plan != nullptr, "mmbs_conv_run: null plan");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   switch (plan->n_tile) {
-    case 256: return launch_conv<256, 4>(plan, stream);
-    case 128: return launch_conv<128, 6>(plan, stream);
-    case 64: return launch_conv<64, 8>(plan, stream);
-    case 32: return launch_conv<32, 8>(plan, stream);
+    case 256: return launch_conv<256, 3>(plan, stream);
+    case 128: return launch_conv<128, 5>(plan, stream);
+    case 64: return launch_conv<64, 6>(plan, stream);
+    case 32: return launch_conv<32, 6>(plan, stream);
     default: set_error("mmbs_conv_run: bad n_tile %d", plan->n_tile); return MMBS_ERR_ARG;
   }
 }
@@ -386,7 +498,8 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
   plan->n_tile = pick_n_tile(d->c_out, m_tiles);
   plan->stages = 0;
   MMBS_REQUIRE(m_tiles * (d->c_out / plan->n_tile) < (int64_t(1) << 31), "conv plan: grid too large");
-  plan->grid = unsigned(m_tiles * (d->c_out / plan->n_tile));
+  p.total_tiles = int32_t(m_tiles * (d->c_out / plan->n_tile));
+  plan->grid = unsigned(std::min<int64_t>(p.total_tiles, sm_count()));  // persistent: <= one CTA per SM
   p.idesc = make_idesc_bf16(GM_TILE_M, plan->n_tile);
 
   const uint32_t box_a[4] = {64u, uint32_t(p.tw), uint32_t(p.th), uint32_t(p.tn)};
@@ -416,6 +529,17 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
     const uint64_t str[1] = {uint64_t(k_total) * 2};
     const uint32_t box_b[2] = {64u, uint32_t(plan->n_tile)};
     rc = encode_map(&p.b_map, d->weight, 2, dims, str, box_b);
+  }
+  if (!rc && !d->out_f32 && plan->n_tile >= 64) {
+    // TMA-store view of the bf16 output (and TMA-load view of the residual): same pixel box as A
+    const uint64_t C = uint64_t(d->c_out), W = uint64_t(out_w), H = uint64_t(out_h);
+    const uint64_t dims[4] = {C, W, H, uint64_t(d->batch)};
+    const uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
+    rc = encode_map(&p.out_map, d->out, 4, dims, str, box_a);
+    if (!rc && d->residual) {
+      MMBS_REQUIRE(reinterpret_cast<uintptr_t>(d->residual) % 16 == 0, "conv plan: residual must be 16-byte aligned");
+      rc = encode_map(&p.res_map, d->residual, 4, dims, str, box_a);
+    }
   }
   if (rc) {
     delete plan;

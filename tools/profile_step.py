@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""One warm + one measured pass of each hot-path piece, for `ncu` launch lists.
+    python tools/profile_step.py [resnet|cox|agg] [batch]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from multimodalbrainsurvival_b200 import aggregate, cox, models, resnet  # noqa: E402
+from oracle import resnet_oracle  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else "resnet"
+dev = torch.device("cuda:0")
+if what == "resnet":
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+    net = resnet.resnet50()
+    net.load_state_dict(resnet_oracle.init_state_dict(seed=1111))
+    model = models.AggregationModel(net, models.Identity(), 2048, 2048, 1).to(dev).eval()
+    x = torch.randn(B, 1, 3, 224, 224, device=dev)
+    with torch.no_grad():
+        for _ in range(2):
+            f, _ = model.extract(x)
+    torch.cuda.synchronize()
+    print("features", tuple(f.shape), float(f.mean()))
+elif what == "cox":
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 10_000_000
+    s = torch.randn(n, device=dev, requires_grad=True)
+    t = torch.rand(n, device=dev) * 200
+    e = (torch.rand(n, device=dev) < 0.6).float()
+    for _ in range(2):
+        s.grad = None
+        loss = cox.cox_loss(s, t, e)
+        loss.backward()
+    torch.cuda.synchronize()
+    print("loss", float(loss.detach()))
+elif what == "agg":
+    n, d, g = 100_000, 2048, 1000
+    v = torch.randn(n, d, device=dev)
+    seg = (torch.arange(n, device=dev) % g).to(torch.int32)
+    for _ in range(2):
+        m, c, l = aggregate.segmented_mean(v, seg, g)
+    torch.cuda.synchronize()
+    print("mean", float(m.mean()))
