@@ -54,7 +54,8 @@ int mmbs_device_check(void);
  * forward:  perm = stable argsort(-times) (u32 radix sort, key-transformed);
  *           s~ = scores[perm]-max(scores); C = cumsum(exp(s~));
  *           loss = -(1/n) sum status[perm]*(s~ - log(C+1e-5)).
- *   perm_out   [n] int32  : sorted order (original indices), bit-exact vs torch.sort(stable)
+ *   perm_out   [n] int32  : sorted order: bits 0-30 = original index (bit-exact vs
+ *                           torch.sort(stable)), bit 31 = (status[index] != 0)
  *   saved_e    [n] float  : exp(s~) in sorted order          (saved for backward)
  *   saved_w    [n] float  : status[perm]/(C+1e-5)            (saved for backward)
  *   loss_out   [1] float

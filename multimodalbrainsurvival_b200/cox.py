@@ -145,4 +145,4 @@ def cox_loss_with_order(cox_scores, times, status):
                                       _lib.ptr(saved[0]), _lib.ptr(saved[1]), _lib.ptr(out),
                                       _lib.ptr(out[1:]), _lib.ptr(ws), nbytes, _lib.stream_ptr()),
                    "mmbs_cox_forward")
-    return out[0].clone(), perm
+    return out[0].clone(), perm & 0x7FFFFFFF  # bit 31 carries the event indicator

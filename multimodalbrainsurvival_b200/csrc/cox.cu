@@ -25,11 +25,24 @@ constexpr float COX_EPS = 1e-5f;
 
 static inline int64_t cs_tiles(int64_t n) { return n > 0 ? (n + CS_TILE - 1) / CS_TILE : 1; }
 
+// Chained-scan tile status: ONE 64-bit word per tile = a double whose two mantissa LSBs are
+// replaced by the state (0 = empty, 1 = tile aggregate, 2 = inclusive prefix).  Value and flag
+// travel in a single atomic 8-byte store/load, so the look-back needs no memory fences; the
+// carry keeps 50 mantissa bits.
 struct ScanState {
-  uint32_t* flags;  // 0 = empty, 1 = aggregate ready, 2 = inclusive ready
-  double* aggr;
-  double* incl;
+  unsigned long long* status;
 };
+__device__ __forceinline__ unsigned long long pack_status(double v, unsigned flag) {
+  return (static_cast<unsigned long long>(__double_as_longlong(v)) & ~3ull) | flag;
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 // Warp-parallel decoupled look-back: returns the sum of all earlier tiles' totals.
 __device__ __forceinline__ double lookback_sum(const ScanState& st, int64_t tile, int lane) {
@@ -37,17 +50,15 @@ __device__ __forceinline__ double lookback_sum(const ScanState& st, int64_t tile
   int64_t pred = tile - 1;
   while (true) {
     const int64_t idx = pred - lane;
-    uint32_t f = 2u;  // tiles before tile 0: inclusive prefix 0
+    unsigned long long w = 2ull;  // tiles before tile 0: inclusive prefix 0
     if (idx >= 0) {
       do {
-        f = ld_volatile_u32(st.flags + idx);
-      } while (f == 0u);
+        w = ld_volatile_u64(st.status + idx);
+      } while ((w & 3ull) == 0ull);
     }
-    __threadfence();
-    const unsigned incl_mask = __ballot_sync(0xffffffffu, f == 2u);
+    const unsigned incl_mask = __ballot_sync(0xffffffffu, (w & 3ull) == 2ull);
     const int first_incl = incl_mask ? (__ffs(incl_mask) - 1) : 32;
-    double v = 0.0;
-    if (idx >= 0 && lane <= first_incl) v = ld_volatile_f64((f == 2u ? st.incl : st.aggr) + idx);
+    const double v = (lane <= first_incl) ? __longlong_as_double(static_cast<long long>(w & ~3ull)) : 0.0;
     excl += warp_sum(v);
     if (incl_mask) break;
     pred -= 32;
@@ -61,7 +72,7 @@ __global__ void __launch_bounds__(CS_THREADS) cox_scan_fwd_kernel(
     const float* __restrict__ status, const uint32_t* __restrict__ max_enc, int64_t n,
     float* __restrict__ saved_e, float* __restrict__ saved_w, ScanState st, uint32_t* tile_counter,
     double* __restrict__ loss_partial, int32_t* nan_flag, int32_t* max_count,
-    int32_t* __restrict__ max_list) {
+    int32_t* __restrict__ max_list, const int32_t* __restrict__ nonbinary) {
   __shared__ double s_warp_tot[CS_WARPS];
   __shared__ double s_red[CS_WARPS];
   __shared__ double s_block_excl;
@@ -81,22 +92,33 @@ __global__ void __launch_bounds__(CS_THREADS) cox_scan_fwd_kernel(
     p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
   } else {
 #pragma unroll
-    for (int j = 0; j < CS_ITEMS; ++j) p[j] = (base + j < n) ? __ldg(perm + base + j) : -1;
+    for (int j = 0; j < CS_ITEMS; ++j) p[j] = (base + j < n) ? __ldg(perm + base + j) : 0;
   }
+  // perm words: bits 0-30 original index, bit 31 = event indicator (binary status)
+  const bool gather_status = (*nonbinary != 0);
+  const uint64_t pol = make_evict_last_policy();
+  bool valid[CS_ITEMS];
   float sc[CS_ITEMS], dl[CS_ITEMS], e[CS_ITEMS], c[CS_ITEMS];
 #pragma unroll
-  for (int j = 0; j < CS_ITEMS; ++j) {  // the two random 4-byte gathers
-    sc[j] = (p[j] >= 0) ? __ldg(scores + p[j]) : 0.f;
-    dl[j] = (p[j] >= 0) ? __ldg(status + p[j]) : 0.f;
+  for (int j = 0; j < CS_ITEMS; ++j) {
+    valid[j] = (base + j < n);
+    const uint32_t word = uint32_t(p[j]);
+    p[j] = int32_t(word & 0x7fffffffu);
+    dl[j] = (valid[j] && (word >> 31)) ? 1.f : 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < CS_ITEMS; ++j) {  // the random 4-byte gather (scores stay L2-resident: evict_last)
+    sc[j] = valid[j] ? ld_f32_hint(scores + p[j], pol) : 0.f;
+    if (gather_status) dl[j] = valid[j] ? __ldg(status + p[j]) : 0.f;
   }
   float run = 0.f;
 #pragma unroll
   for (int j = 0; j < CS_ITEMS; ++j) {
     sc[j] -= smax;                                  // s~ (models.py:102)
-    e[j] = (p[j] >= 0) ? expf(sc[j]) : 0.f;         // models.py:103
+    e[j] = valid[j] ? expf(sc[j]) : 0.f;            // models.py:103
     run += e[j];
     c[j] = run;
-    if (p[j] >= 0 && sc[j] == 0.f) {                // an argmax position (for backward)
+    if (valid[j] && sc[j] == 0.f) {                 // an argmax position (for backward)
       const int pos = atomicAdd(max_count, 1);
       if (pos < COX_MAX_LIST) max_list[pos] = p[j];
     }
@@ -119,25 +141,11 @@ __global__ void __launch_bounds__(CS_THREADS) cox_scan_fwd_kernel(
     block_total += t;
   }
   if (warp == 0) {
-    if (lane == 0) {
-      if (tile == 0) {
-        st_volatile_f64(st.incl + tile, block_total);
-        __threadfence();
-        st_volatile_u32(st.flags + tile, 2u);
-      } else {
-        st_volatile_f64(st.aggr + tile, block_total);
-        __threadfence();
-        st_volatile_u32(st.flags + tile, 1u);
-      }
-    }
+    if (lane == 0) st_volatile_u64(st.status + tile, pack_status(block_total, tile == 0 ? 2u : 1u));
     double excl = 0.0;
     if (tile > 0) {
       excl = lookback_sum(st, tile, lane);
-      if (lane == 0) {
-        st_volatile_f64(st.incl + tile, excl + block_total);
-        __threadfence();
-        st_volatile_u32(st.flags + tile, 2u);
-      }
+      if (lane == 0) st_volatile_u64(st.status + tile, pack_status(excl + block_total, 2u));
     }
     if (lane == 0) s_block_excl = excl;
   }
@@ -153,7 +161,7 @@ __global__ void __launch_bounds__(CS_THREADS) cox_scan_fwd_kernel(
     const float den = cj + COX_EPS;
     const float term = -(sc[j] - logf(den)) * dl[j];  // models.py:104-105
     w[j] = dl[j] / den;
-    if (p[j] >= 0) {
+    if (valid[j]) {
       lsum += term;
       bad |= (term != term);
     }
@@ -213,7 +221,8 @@ __global__ void __launch_bounds__(CS_THREADS) cox_scan_bwd_kernel(
     const int32_t* __restrict__ perm, const float* __restrict__ status,
     const float* __restrict__ saved_e, const float* __restrict__ saved_w,
     const float* __restrict__ grad_loss, int64_t n, int64_t n_pad, float* __restrict__ grad_scores,
-    ScanState st, uint32_t* tile_counter, double* __restrict__ gsum_partial) {
+    ScanState st, uint32_t* tile_counter, double* __restrict__ gsum_partial,
+    const int32_t* __restrict__ nonbinary) {
   __shared__ double s_warp_tot[CS_WARPS];
   __shared__ double s_red[CS_WARPS];
   __shared__ double s_block_excl;
@@ -244,12 +253,20 @@ __global__ void __launch_bounds__(CS_THREADS) cox_scan_bwd_kernel(
       const bool v = base + j < n;
       e[j] = v ? __ldg(saved_e + base + j) : 0.f;
       w[j] = v ? __ldg(saved_w + base + j) : 0.f;
-      p[j] = v ? __ldg(perm + base + j) : -1;
+      p[j] = v ? __ldg(perm + base + j) : 0;
     }
   }
+  const bool gather_status = (*nonbinary != 0);
+  bool valid[CS_ITEMS];
   float dl[CS_ITEMS];
 #pragma unroll
-  for (int j = 0; j < CS_ITEMS; ++j) dl[j] = (p[j] >= 0) ? __ldg(status + p[j]) : 0.f;
+  for (int j = 0; j < CS_ITEMS; ++j) {
+    valid[j] = (base + j < n);
+    const uint32_t word = uint32_t(p[j]);
+    p[j] = int32_t(word & 0x7fffffffu);
+    dl[j] = (valid[j] && (word >> 31)) ? 1.f : 0.f;
+    if (gather_status) dl[j] = valid[j] ? __ldg(status + p[j]) : 0.f;
+  }
 
   float suf[CS_ITEMS];  // inclusive suffix sums inside the thread (descending k)
   float run = 0.f;
@@ -275,25 +292,11 @@ __global__ void __launch_bounds__(CS_THREADS) cox_scan_bwd_kernel(
     block_total += t;
   }
   if (warp == 0) {
-    if (lane == 0) {
-      if (tile == 0) {
-        st_volatile_f64(st.incl + tile, block_total);
-        __threadfence();
-        st_volatile_u32(st.flags + tile, 2u);
-      } else {
-        st_volatile_f64(st.aggr + tile, block_total);
-        __threadfence();
-        st_volatile_u32(st.flags + tile, 1u);
-      }
-    }
+    if (lane == 0) st_volatile_u64(st.status + tile, pack_status(block_total, tile == 0 ? 2u : 1u));
     double excl = 0.0;
     if (tile > 0) {
       excl = lookback_sum(st, tile, lane);
-      if (lane == 0) {
-        st_volatile_f64(st.incl + tile, excl + block_total);
-        __threadfence();
-        st_volatile_u32(st.flags + tile, 2u);
-      }
+      if (lane == 0) st_volatile_u64(st.status + tile, pack_status(excl + block_total, 2u));
     }
     if (lane == 0) s_block_excl = excl;
   }
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(CS_THREADS) cox_scan_bwd_kernel(
   float gs = 0.f;
 #pragma unroll
   for (int j = 0; j < CS_ITEMS; ++j) {
-    if (p[j] >= 0) {
+    if (valid[j]) {
       const float W = float(off + double(suf[j]));      // sum_{i>=k} status_i/(C_i+eps)
       const float g = -(dl[j] - e[j] * W) * scale;
       grad_scores[p[j]] = g;                            // un-permute
@@ -368,17 +371,18 @@ struct CoxWorkspace {
   uint32_t* max_enc;       // [1]
   int32_t* nan_flag;       // [1]
   int32_t* max_count;      // [1]
+  int32_t* nonbinary;      // [1] some status value is neither 0 nor 1
   uint32_t* lookback;      // [4][rs_tiles][256]
-  uint32_t* flags_fwd;     // [cs_tiles]
+  unsigned long long* status_fwd;  // [cs_tiles]
   size_t zero_bytes;
   // zeroed at the start of backward
-  uint32_t* flags_bwd;     // [cs_tiles]
+  unsigned long long* status_bwd;  // [cs_tiles]
   // not zeroed
   uint32_t* digit_base;    // [4][256]
   int32_t* max_list;       // [COX_MAX_LIST]
   double* gsum_total;      // [1]
-  double* aggr_fwd; double* incl_fwd; double* loss_partial;
-  double* aggr_bwd; double* incl_bwd; double* gsum_partial;
+  double* loss_partial;
+  double* gsum_partial;
   uint32_t* keys_a; uint32_t* keys_b; uint32_t* vals_a; uint32_t* vals_b;
   size_t total_bytes;
 };
@@ -392,18 +396,15 @@ static CoxWorkspace carve_cox(void* base, int64_t n) {
   w.max_enc = c.take<uint32_t>(1);
   w.nan_flag = c.take<int32_t>(1);
   w.max_count = c.take<int32_t>(1);
+  w.nonbinary = c.take<int32_t>(1);
   w.lookback = c.take<uint32_t>(size_t(4) * rt * RS_RADIX);
-  w.flags_fwd = c.take<uint32_t>(ct);
+  w.status_fwd = c.take<unsigned long long>(ct);
   w.zero_bytes = align_up(c.off, 256);
-  w.flags_bwd = c.take<uint32_t>(ct);
+  w.status_bwd = c.take<unsigned long long>(ct);
   w.digit_base = c.take<uint32_t>(4 * RS_RADIX);
   w.max_list = c.take<int32_t>(COX_MAX_LIST);
   w.gsum_total = c.take<double>(1);
-  w.aggr_fwd = c.take<double>(ct);
-  w.incl_fwd = c.take<double>(ct);
   w.loss_partial = c.take<double>(ct);
-  w.aggr_bwd = c.take<double>(ct);
-  w.incl_bwd = c.take<double>(ct);
   w.gsum_partial = c.take<double>(ct);
   w.keys_a = c.take<uint32_t>(n);
   w.keys_b = c.take<uint32_t>(n);
@@ -429,13 +430,13 @@ extern "C" size_t mmbs_cox_workspace_bytes(int64_t n) {
   return carve_cox(nullptr, n).total_bytes;
 }
 
-static int cox_sort_common(const float* scores, const float* times, int64_t n, int32_t* perm_out,
-                           const CoxWorkspace& w, cudaStream_t stream) {
+static int cox_sort_common(const float* scores, const float* times, const float* status, int64_t n,
+                           int32_t* perm_out, const CoxWorkspace& w, cudaStream_t stream) {
   MMBS_CUDA_TRY(cudaMemsetAsync(w.hist, 0, w.zero_bytes, stream));
   int rc = rs_histogram_enqueue(times, KEY_NEG_TIME_F32, n, 4, w.hist, w.digit_base, scores,
                                 w.max_enc, w.nan_flag, stream);
   if (rc) return rc;
-  return rs_sort_enqueue(times, KEY_NEG_TIME_F32, n, 4, sort_ws(w), perm_out, stream);
+  return rs_sort_enqueue(times, KEY_NEG_TIME_F32, n, 4, sort_ws(w), perm_out, stream, status, w.nonbinary);
 }
 
 extern "C" int mmbs_risk_order(const float* times, int64_t n, int32_t* perm_out, void* workspace,
@@ -448,7 +449,7 @@ extern "C" int mmbs_risk_order(const float* times, int64_t n, int32_t* perm_out,
     set_error("mmbs_risk_order: workspace %zu < %zu bytes", workspace_bytes, w.total_bytes);
     return MMBS_ERR_WORKSPACE;
   }
-  return cox_sort_common(nullptr, times, n, perm_out, w, static_cast<cudaStream_t>(stream));
+  return cox_sort_common(nullptr, times, nullptr, n, perm_out, w, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mmbs_cox_forward(const float* scores, const float* times, const float* status,
@@ -469,12 +470,12 @@ extern "C" int mmbs_cox_forward(const float* scores, const float* times, const f
     set_error("mmbs_cox_forward: workspace %zu < %zu bytes", workspace_bytes, w.total_bytes);
     return MMBS_ERR_WORKSPACE;
   }
-  if (int rc = cox_sort_common(scores, times, n, perm_out, w, stream)) return rc;
+  if (int rc = cox_sort_common(scores, times, status, n, perm_out, w, stream)) return rc;
   const int64_t tiles = cs_tiles(n);
-  ScanState st{w.flags_fwd, w.aggr_fwd, w.incl_fwd};
+  ScanState st{w.status_fwd};
   cox_scan_fwd_kernel<<<unsigned(tiles), CS_THREADS, 0, stream>>>(
       perm_out, scores, status, w.max_enc, n, saved_e, saved_w, st, w.counters + 4, w.loss_partial,
-      w.nan_flag, w.max_count, w.max_list);
+      w.nan_flag, w.max_count, w.max_list, w.nonbinary);
   MMBS_LAUNCH_CHECK();
   cox_finalize_kernel<<<1, 256, 0, stream>>>(w.loss_partial, tiles, n, w.nan_flag, loss_out, flags_out);
   MMBS_LAUNCH_CHECK();
@@ -496,12 +497,12 @@ extern "C" int mmbs_cox_backward(const float* scores, const float* status, const
     return MMBS_ERR_WORKSPACE;
   }
   const int64_t tiles = cs_tiles(n);
-  MMBS_CUDA_TRY(cudaMemsetAsync(w.flags_bwd, 0, size_t(tiles) * sizeof(uint32_t), stream));
+  MMBS_CUDA_TRY(cudaMemsetAsync(w.status_bwd, 0, size_t(tiles) * sizeof(unsigned long long), stream));
   MMBS_CUDA_TRY(cudaMemsetAsync(w.counters + 5, 0, sizeof(uint32_t), stream));
-  ScanState st{w.flags_bwd, w.aggr_bwd, w.incl_bwd};
+  ScanState st{w.status_bwd};
   cox_scan_bwd_kernel<<<unsigned(tiles), CS_THREADS, 0, stream>>>(
       perm, status, saved_e, saved_w, grad_loss, n, tiles * CS_TILE, grad_scores, st, w.counters + 5,
-      w.gsum_partial);
+      w.gsum_partial, w.nonbinary);
   MMBS_LAUNCH_CHECK();
   cox_maxfix_list_kernel<<<1, 256, 0, stream>>>(w.gsum_partial, tiles, w.max_count, w.max_list,
                                                w.gsum_total, grad_scores);

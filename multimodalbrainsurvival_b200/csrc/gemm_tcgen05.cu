@@ -27,8 +27,9 @@ namespace mmbs {
 constexpr int GM_TILE_M = 128;
 constexpr int GM_CHUNK_K = 64;                       // bf16 elements = 128 B = one swizzle row
 constexpr int GM_A_BYTES = GM_TILE_M * GM_CHUNK_K * 2;  // 16 KB
-constexpr int GM_THREADS = 192;                      // producer, MMA, 4 epilogue warps
-constexpr int GM_EPI_THREADS = 128;
+constexpr int GM_EPI_WARPS = 8;
+constexpr int GM_EPI_THREADS = GM_EPI_WARPS * 32;    // 256
+constexpr int GM_THREADS = 64 + GM_EPI_THREADS;      // producer warp, MMA warp, 8 epilogue warps
 constexpr int GM_MAX_TAPS = 16;
 constexpr int GM_OUT_BLK_BYTES = GM_TILE_M * 128;    // one 64-channel column block of a bf16 tile
 
@@ -55,21 +56,22 @@ struct ConvParams {
 };
 
 // Shared-memory carve-up (offsets from a 1024-B aligned base):
-//   [ring: STAGES x (A 16 KB | B N_TILE*128 B)] [staging: N_TILE/64 x 16 KB] [barriers] [tmem slot] [scale|shift]
-template <int N_TILE, int STAGES>
+//   [ring: STAGES x (A 16 KB | B N_TILE*128 B)] [staging: NSTG x N_TILE/64 x 16 KB] [barriers] [tmem slot] [scale|shift]
+template <int N_TILE, int STAGES, int NSTG>
 struct GemmSmem {
   static constexpr int B_BYTES = N_TILE * GM_CHUNK_K * 2;
   static constexpr int STAGE_BYTES = GM_A_BYTES + B_BYTES;
   static constexpr int OUT_BLKS = (N_TILE + 63) / 64;
   static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int STAGING_BYTES = OUT_BLKS * GM_OUT_BLK_BYTES;
-  static constexpr int BAR_OFFSET = STAGING_OFFSET + STAGING_BYTES;  // full[S] empty[S] tfull[2] tempty[2] res
-  static constexpr int NUM_BARS = 2 * STAGES + 5;
+  static constexpr int STAGING_BYTES = OUT_BLKS * GM_OUT_BLK_BYTES;    // one staging tile
+  static constexpr int BAR_OFFSET = STAGING_OFFSET + NSTG * STAGING_BYTES;
+  static constexpr int NUM_BARS = 2 * STAGES + 6;   // full[S] empty[S] tfull[2] tempty[2] res[2]
   static constexpr int TMEM_SLOT_OFFSET = BAR_OFFSET + NUM_BARS * 8;
   static constexpr int SCALE_OFFSET = (TMEM_SLOT_OFFSET + 4 + 15) / 16 * 16;
   static constexpr int TOTAL = SCALE_OFFSET + 2 * N_TILE * 4;
   static constexpr int DYNAMIC = TOTAL + 1024;  // slack for the 1024-B alignment of the ring
   static constexpr int TMEM_COLS = 2 * N_TILE;  // double-buffered fp32 accumulator
+  static_assert(DYNAMIC <= 227 * 1024, "shared memory budget exceeded");
 };
 
 struct TileCoord {
@@ -85,10 +87,10 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int tile, i
   return c;
 }
 
-template <int N_TILE, int STAGES>
+template <int N_TILE, int STAGES, int NSTG>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ ConvParams p) {
-  using L = GemmSmem<N_TILE, STAGES>;
+  using L = GemmSmem<N_TILE, STAGES, NSTG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = tc::smem_u32(smem_raw);
   const uint32_t base_u32 = (raw_u32 + 1023u) & ~1023u;
@@ -99,7 +101,7 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   const uint32_t empty_bar = full_bar + STAGES * 8;
   const uint32_t tfull_bar = empty_bar + STAGES * 8;   // [2] accumulator ready   (MMA -> epilogue)
   const uint32_t tempty_bar = tfull_bar + 16;          // [2] accumulator drained (epilogue -> MMA)
-  const uint32_t res_bar = tempty_bar + 16;            // residual tile landed in the staging buffer
+  const uint32_t res_bar = tempty_bar + 16;            // [2] residual tile landed in staging[i]
   const uint32_t tmem_slot = base_u32 + L::TMEM_SLOT_OFFSET;
   const uint32_t staging_u32 = base_u32 + L::STAGING_OFFSET;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + L::TMEM_SLOT_OFFSET);
@@ -119,9 +121,9 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       tc::mbar_init(tfull_bar + 8 * a, 1);
-      tc::mbar_init(tempty_bar + 8 * a, 4);  // one arrive per epilogue warp
+      tc::mbar_init(tempty_bar + 8 * a, GM_EPI_WARPS);  // one arrive per epilogue warp
+      tc::mbar_init(res_bar + 8 * a, 1);
     }
-    tc::mbar_init(res_bar, 1);
     tc::fence_mbar_init();
   }
   if (warp == 1) {
@@ -184,29 +186,53 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
       }
     }
   } else {
-    // ===== epilogue warps: TMEM lane quarter (warp % 4) <-> tile rows =====
+    // ===== 8 epilogue warps: TMEM lane quarter = warp % 4 (rows), column half = (warp-2)/4 =====
+    constexpr int COLS_PER_HALF = (N_TILE / 2 >= 32) ? N_TILE / 2 : 32;
+    constexpr int ACTIVE_HALVES = N_TILE / COLS_PER_HALF;  // 2, or 1 when N_TILE == 32
     const int q = warp & 3;
+    const int hh = (warp - 2) >> 2;
     const int r = q * 32 + lane;
-    const int et = threadIdx.x - 64;  // 0..127
+    const int et = threadIdx.x - 64;  // 0..255
     const bool use_tma_store = (N_TILE >= 64) && !p.out_f32;
     const bool tma_res = use_tma_store && (p.residual != nullptr);
+    const bool active = hh < ACTIVE_HALVES;
+    const int col_lo = hh * COLS_PER_HALF;
+
+    auto issue_residual = [&](int tile, uint32_t sb) {
+      const TileCoord t2 = tile_coord(p, tile, n_tiles);
+      tc::mbar_expect_tx(res_bar + 8 * sb, L::OUT_BLKS * GM_OUT_BLK_BYTES);
+      for (int b = 0; b < L::OUT_BLKS; ++b)
+        tc::tma_load_4d(&p.res_map, res_bar + 8 * sb, staging_u32 + sb * L::STAGING_BYTES + b * GM_OUT_BLK_BYTES,
+                        t2.nt * N_TILE + b * 64, t2.w0, t2.h0, t2.n0);
+    };
+    if (NSTG == 2 && tma_res && et == 0 && int(blockIdx.x) < p.total_tiles) issue_residual(blockIdx.x, 0);
+
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
       const TileCoord tcd = tile_coord(p, tile, n_tiles);
       const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
-      // the previous tile's TMA store must have finished READING the staging tile
-      if (use_tma_store && et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      const uint32_t sb = (NSTG == 2) ? (tl & 1u) : 0u;            // staging buffer of this tile
+      const uint32_t res_parity = (NSTG == 2) ? ((tl >> 1) & 1u) : (tl & 1u);
+      const uint32_t stg = staging_u32 + sb * L::STAGING_BYTES;
+      // staging[sb] was last read by the TMA store of tile (tl - NSTG): it must be done reading
+      if (use_tma_store && et == 0) {
+        if (NSTG == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
       for (int i = et; i < N_TILE; i += GM_EPI_THREADS) {
         const int n = tcd.nt * N_TILE + i;
         s_scale[i] = p.scale ? __ldg(p.scale + n) : 1.0f;
         s_shift[i] = p.shift ? __ldg(p.shift + n) : 0.0f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (tma_res && et == 0) {
-        tc::mbar_expect_tx(res_bar, L::OUT_BLKS * GM_OUT_BLK_BYTES);
-        for (int b = 0; b < L::OUT_BLKS; ++b)
-          tc::tma_load_4d(&p.res_map, res_bar, staging_u32 + b * GM_OUT_BLK_BYTES,
-                          tcd.nt * N_TILE + b * 64, tcd.w0, tcd.h0, tcd.n0);
+        if (NSTG == 2) {
+          // prefetch the NEXT tile's residual into the other staging tile (its last store must be read out)
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (tile + int(gridDim.x) < p.total_tiles) issue_residual(tile + gridDim.x, sb ^ 1u);
+        } else {
+          issue_residual(tile, 0);
+        }
       }
       const int pw = tcd.w0 + (r % p.tw);
       const int phh = tcd.h0 + ((r / p.tw) % p.th);
@@ -217,87 +243,89 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
 
       tc::mbar_wait(tfull_bar + 8 * acc, aph);
       tc::tc_fence_after();
-      if (tma_res) tc::mbar_wait(res_bar, tl & 1u);
+      if (tma_res) tc::mbar_wait(res_bar + 8 * sb, res_parity);
       const uint32_t t_addr = tmem_base + acc * N_TILE + (uint32_t(q * 32) << 16);
+      if (active) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-        uint32_t accr[32];
-        tc::tmem_ld_32x32(t_addr + uint32_t(c0), accr);
-        tc::tmem_ld_wait();
-        float v[32];
+        for (int c0 = col_lo; c0 < col_lo + COLS_PER_HALF; c0 += 32) {
+          uint32_t accr[32];
+          tc::tmem_ld_32x32(t_addr + uint32_t(c0), accr);
+          tc::tmem_ld_wait();
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + j);
-          const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + j);
-          v[j] = __uint_as_float(accr[j]) * sc.x + sh.x;
-          v[j + 1] = __uint_as_float(accr[j + 1]) * sc.y + sh.y;
-          v[j + 2] = __uint_as_float(accr[j + 2]) * sc.z + sh.z;
-          v[j + 3] = __uint_as_float(accr[j + 3]) * sc.w + sh.w;
-        }
-        if (use_tma_store) {
-          // staging tile: column block (c0/64), row r, 16-B chunk index XOR-swizzled by (r & 7)
-          const uint32_t blk = staging_u32 + uint32_t(c0 >> 6) * GM_OUT_BLK_BYTES + uint32_t(r) * 128u;
-          const uint32_t ch0 = uint32_t((c0 & 63) >> 3);  // first 16-B chunk of these 32 columns (0 or 4)
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t addr = blk + (((ch0 + g) ^ uint32_t(r & 7)) << 4);
-            if (tma_res) {
-              uint32_t rw[4];
-              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]) : "r"(addr));
-#pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[h]);
-                v[g * 8 + h * 2] += __bfloat162float(b2.x);
-                v[g * 8 + h * 2 + 1] += __bfloat162float(b2.y);
-              }
-            }
-            uint32_t w[4];
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              float a = v[g * 8 + h * 2], b = v[g * 8 + h * 2 + 1];
-              if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
-              const __nv_bfloat162 b2 = __floats2bfloat162_rn(a, b);
-              w[h] = *reinterpret_cast<const uint32_t*>(&b2);
-            }
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]),
-                         "r"(w[2]), "r"(w[3]) : "memory");
+          for (int j = 0; j < 32; j += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + j);
+            const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + j);
+            v[j] = __uint_as_float(accr[j]) * sc.x + sh.x;
+            v[j + 1] = __uint_as_float(accr[j + 1]) * sc.y + sh.y;
+            v[j + 2] = __uint_as_float(accr[j + 2]) * sc.z + sh.z;
+            v[j + 3] = __uint_as_float(accr[j + 3]) * sc.w + sh.w;
           }
-        } else if (row_ok) {
-          // fp32 output (final block / MLP head): direct, row-predicated 128-bit stores
-          if (p.residual) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + c0);
+          if (use_tma_store) {
+            // staging tile: column block (c0/64), row r, 16-B chunk index XOR-swizzled by (r & 7)
+            const uint32_t blk = stg + uint32_t(c0 >> 6) * GM_OUT_BLK_BYTES + uint32_t(r) * 128u;
+            const uint32_t ch0 = uint32_t((c0 & 63) >> 3);  // first 16-B chunk of these 32 columns (0 or 4)
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              const uint4 rv = __ldg(rp + g);
-              const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+              const uint32_t addr = blk + (((ch0 + g) ^ uint32_t(r & 7)) << 4);
+              if (tma_res) {
+                uint32_t rw[4];
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]) : "r"(addr));
 #pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[h]);
-                v[g * 8 + h * 2] += __bfloat162float(b2.x);
-                v[g * 8 + h * 2 + 1] += __bfloat162float(b2.y);
+                for (int h = 0; h < 4; ++h) {
+                  const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[h]);
+                  v[g * 8 + h * 2] += __bfloat162float(b2.x);
+                  v[g * 8 + h * 2 + 1] += __bfloat162float(b2.y);
+                }
               }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-          }
-          if (p.out_f32) {
-            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + row_off + c0);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) op[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-          } else {
-            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row_off + c0);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
               uint32_t w[4];
 #pragma unroll
               for (int h = 0; h < 4; ++h) {
-                const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[g * 8 + h * 2], v[g * 8 + h * 2 + 1]);
+                float a = v[g * 8 + h * 2], b = v[g * 8 + h * 2 + 1];
+                if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+                const __nv_bfloat162 b2 = __floats2bfloat162_rn(a, b);
                 w[h] = *reinterpret_cast<const uint32_t*>(&b2);
               }
-              op[g] = make_uint4(w[0], w[1], w[2], w[3]);
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]),
+                           "r"(w[2]), "r"(w[3]) : "memory");
+            }
+          } else if (row_ok) {
+            // fp32 output (final block / MLP head) or narrow tiles: direct, row-predicated 128-bit stores
+            if (p.residual) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + c0);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint4 rv = __ldg(rp + g);
+                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[h]);
+                  v[g * 8 + h * 2] += __bfloat162float(b2.x);
+                  v[g * 8 + h * 2 + 1] += __bfloat162float(b2.y);
+                }
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+            }
+            if (p.out_f32) {
+              float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + row_off + c0);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) op[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row_off + c0);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint32_t w[4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[g * 8 + h * 2], v[g * 8 + h * 2 + 1]);
+                  w[h] = *reinterpret_cast<const uint32_t*>(&b2);
+                }
+                op[g] = make_uint4(w[0], w[1], w[2], w[3]);
+              }
             }
           }
         }
@@ -308,18 +336,20 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
       if (lane == 0) tc::mbar_arrive(tempty_bar + 8 * acc);
       if (use_tma_store) {
         tc::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA engine
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 2, 256;" ::: "memory");
         if (et == 0) {
           for (int b = 0; b < L::OUT_BLKS; ++b) {
             asm volatile(
                 "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                     reinterpret_cast<uint64_t>(&p.out_map)),
-                "r"(staging_u32 + b * GM_OUT_BLK_BYTES), "r"(tcd.nt * N_TILE + b * 64), "r"(tcd.w0),
+                "r"(stg + b * GM_OUT_BLK_BYTES), "r"(tcd.nt * N_TILE + b * 64), "r"(tcd.w0),
                 "r"(tcd.h0), "r"(tcd.n0)
                 : "memory");
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+      } else {
+        asm volatile("bar.sync 2, 256;" ::: "memory");  // s_scale/s_shift are reloaded by the next tile
       }
     }
     if (use_tma_store && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -389,16 +419,16 @@ struct mmbs_conv_plan {
   unsigned grid;
 };
 
-template <int N_TILE, int STAGES>
+template <int N_TILE, int STAGES, int NSTG>
 static int launch_conv(const mmbs_conv_plan* plan, cudaStream_t stream) {
-  using L = GemmSmem<N_TILE, STAGES>;
+  using L = GemmSmem<N_TILE, STAGES, NSTG>;
   static bool configured = false;
   if (!configured) {
-    MMBS_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE, STAGES>,
+    MMBS_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE, STAGES, NSTG>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYNAMIC));
     configured = true;
   }
-  conv_gemm_kernel<N_TILE, STAGES><<<plan->grid, GM_THREADS, L::DYNAMIC, stream>>>(plan->p);
+  conv_gemm_kernel<N_TILE, STAGES, NSTG><<<plan->grid, GM_THREADS, L::DYNAMIC, stream>>>(plan->p);
   MMBS_LAUNCH_CHECK();
   return MMBS_OK;
 }
@@ -408,10 +438,10 @@ extern "C" int mmbs_conv_run(const mmbs_conv_plan* plan, void* stream_) {
   MMBS_REQUIRE(plan != nullptr, "mmbs_conv_run: null plan");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   switch (plan->n_tile) {
-    case 256: return launch_conv<256, 3>(plan, stream);
-    case 128: return launch_conv<128, 5>(plan, stream);
-    case 64: return launch_conv<64, 6>(plan, stream);
-    case 32: return launch_conv<32, 6>(plan, stream);
+    case 256: return launch_conv<256, 3, 1>(plan, stream);
+    case 128: return launch_conv<128, 4, 2>(plan, stream);
+    case 64: return launch_conv<64, 6, 2>(plan, stream);
+    case 32: return launch_conv<32, 6, 1>(plan, stream);
     default: set_error("mmbs_conv_run: bad n_tile %d", plan->n_tile); return MMBS_ERR_ARG;
   }
 }
@@ -496,6 +526,9 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
   p.tiles_w = int(ceil_div(out_w, p.tw)); p.tiles_h = int(ceil_div(out_h, p.th)); p.tiles_n = int(ceil_div(d->batch, p.tn));
   const int64_t m_tiles = int64_t(p.tiles_w) * p.tiles_h * p.tiles_n;
   plan->n_tile = pick_n_tile(d->c_out, m_tiles);
+  // epilogue-bound residual layers (short K loop): 128-wide tile = double-staged epilogue with the
+  // residual prefetched one tile ahead; long K loops keep the 256-wide tile (operand-feed bound)
+  if (d->residual && !d->out_f32 && plan->n_tile > 128 && p.num_taps * p.k_chunks <= 4) plan->n_tile = 128;
   plan->stages = 0;
   MMBS_REQUIRE(m_tiles * (d->c_out / plan->n_tile) < (int64_t(1) << 31), "conv plan: grid too large");
   p.total_tiles = int32_t(m_tiles * (d->c_out / plan->n_tile));

@@ -6,10 +6,13 @@
 namespace mmbs {
 
 // ---------------------------------------------------------------- histogram
-// One pass over the source: per-digit counts for every radix pass.  Counting is
-// warp-aggregated with match.any so that a skewed byte (survival times cluster in
-// a few exponent values) does not serialise on one shared-memory counter.
-// Optionally fused: max over `scores` (order-encoded u32 atomicMax) + NaN flag.
+// One pass over the source: per-digit counts for every radix pass, 4 keys per thread
+// (128-bit loads).  Shared-memory atomics, with two guards against skewed bytes
+// (survival times share a few exponent values; integer-valued months share zero low
+// bytes): a thread whose 4 digits agree adds 4 at once, and a warp whose 128 digits
+// agree adds 128 from one lane.  Optionally fused: max over `scores` (order-encoded u32
+// atomicMax, loaded with an L2 evict_last policy because the forward scan gathers from
+// `scores` again after the sort has streamed through L2) and a NaN flag.
 __global__ void __launch_bounds__(256) rs_histogram_kernel(
     const void* __restrict__ src, int kind, int64_t n, int num_passes, uint32_t* __restrict__ hist,
     const float* __restrict__ scores, uint32_t* __restrict__ max_enc, int32_t* __restrict__ nan_flag) {
@@ -20,25 +23,56 @@ __global__ void __launch_bounds__(256) rs_histogram_kernel(
   for (int i = tid; i < 4 * RS_RADIX; i += 256) (&s_hist[0][0])[i] = 0;
   __syncthreads();
 
+  const uint64_t pol = make_evict_last_policy();
+  const bool vec_src = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  const bool vec_sc = (reinterpret_cast<uintptr_t>(scores) & 15) == 0;
   float vmax = -INFINITY;
   bool has_nan = false;
-  const int64_t n_round = (n + 31) / 32 * 32;  // keep warps converged for match.any
-  for (int64_t i = int64_t(blockIdx.x) * 256 + tid; i < n_round; i += int64_t(gridDim.x) * 256) {
-    const bool valid = i < n;
-    const uint32_t key = valid ? rs_load_key(src, kind, i) : 0u;
-    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-    if (scores != nullptr && valid) {
-      const float s = __ldg(scores + i);
-      has_nan |= (s != s);
-      vmax = fmaxf(vmax, s);
-    }
-    if (valid) {
+  // warp-uniform trip count: every lane runs the same number of iterations
+  for (int64_t blk = blockIdx.x; blk * 1024 < n; blk += gridDim.x) {
+    const int64_t base = blk * 1024 + int64_t(tid) * 4;
+    const int cnt = int(max((long long)0, min((long long)4, (long long)(n - base))));
+    uint32_t k[4] = {0u, 0u, 0u, 0u};
+    if (cnt == 4 && vec_src) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint32_t*>(src) + base));
+      k[0] = raw.x; k[1] = raw.y; k[2] = raw.z; k[3] = raw.w;
+      if (kind == KEY_NEG_TIME_F32) {
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        if (p < num_passes) {
-          const uint32_t d = (key >> (8 * p)) & 0xffu;
-          const unsigned m = __match_any_sync(vmask, d);
-          if (lane == __ffs(m) - 1) atomicAdd(&s_hist[p][d], __popc(m));
+        for (int i = 0; i < 4; ++i) k[i] = time_key(__uint_as_float(k[i]));
+      }
+    } else {
+      for (int i = 0; i < cnt; ++i) k[i] = rs_load_key(src, kind, base + i);
+    }
+    if (scores != nullptr) {
+      float s4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (cnt == 4 && vec_sc) {
+        const float4 v = ld_f32x4_hint(scores + base, pol);
+        s4[0] = v.x; s4[1] = v.y; s4[2] = v.z; s4[3] = v.w;
+      } else {
+        for (int i = 0; i < cnt; ++i) s4[i] = ld_f32_hint(scores + base + i, pol);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        has_nan |= (s4[i] != s4[i]);
+        vmax = fmaxf(vmax, s4[i]);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      if (p < num_passes) {
+        const uint32_t d0 = (k[0] >> (8 * p)) & 0xffu, d1 = (k[1] >> (8 * p)) & 0xffu;
+        const uint32_t d2 = (k[2] >> (8 * p)) & 0xffu, d3 = (k[3] >> (8 * p)) & 0xffu;
+        const bool same4 = (cnt == 4) && d0 == d1 && d1 == d2 && d2 == d3;
+        const uint32_t dl = __shfl_sync(0xffffffffu, d0, 0);
+        if (__all_sync(0xffffffffu, same4 && d0 == dl)) {
+          if (lane == 0) atomicAdd(&s_hist[p][dl], 128u);
+        } else if (same4) {
+          atomicAdd(&s_hist[p][d0], 4u);
+        } else {
+          if (cnt > 0) atomicAdd(&s_hist[p][d0], 1u);
+          if (cnt > 1) atomicAdd(&s_hist[p][d1], 1u);
+          if (cnt > 2) atomicAdd(&s_hist[p][d2], 1u);
+          if (cnt > 3) atomicAdd(&s_hist[p][d3], 1u);
         }
       }
     }
@@ -86,7 +120,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(
     const void* __restrict__ src, int kind, const uint32_t* __restrict__ keys_in,
     const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, int64_t n, int shift, const uint32_t* __restrict__ digit_base,
-    uint32_t* lookback, uint32_t* tile_counter, int first, int last) {
+    uint32_t* lookback, uint32_t* tile_counter, int first, int last,
+    const float* __restrict__ status, int32_t* __restrict__ nonbinary_flag) {
   __shared__ uint32_t s_warp_hist[RS_WARPS][RS_RADIX];
   __shared__ uint32_t s_digit_start[RS_RADIX];
   __shared__ uint32_t s_global_base[RS_RADIX];
@@ -106,6 +141,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(
   const int n_valid = int(min((long long)RS_TILE, (long long)(n - tile_base)));
 
   uint32_t key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS];
+  bool nonbinary = false;
 #pragma unroll
   for (int j = 0; j < RS_ITEMS; ++j) {
     const int it = warp * (32 * RS_ITEMS) + j * 32 + lane;
@@ -113,18 +149,39 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(
     if (it < n_valid) {
       key[j] = first ? rs_load_key(src, kind, g) : __ldg(keys_in + g);
       val[j] = first ? uint32_t(g) : __ldg(vals_in + g);
+      if (first && status != nullptr) {
+        // carry the (binary) event indicator in bit 31 of the payload: the scans then never
+        // gather `status` through the permutation
+        const float st = __ldg(status + g);
+        if (st != 0.0f) val[j] |= 0x80000000u;
+        if (st != 0.0f && st != 1.0f) nonbinary = true;
+      }
     } else {
       key[j] = 0xffffffffu;  // padding sorts to the very end of the (last) tile
       val[j] = 0xffffffffu;
     }
   }
 
-  // stable rank of every key among equal digits inside its warp
+  if (nonbinary) atomicOr(nonbinary_flag, 1);
+  // stable rank of every key among equal digits inside its warp.  The peer mask is built
+  // from 8 ballots (one per digit bit): MATCH.ANY issues ~50x slower than VOTE on sm_100.
   const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
   for (int j = 0; j < RS_ITEMS; ++j) {
     const uint32_t d = (key[j] >> shift) & 0xffu;
-    const unsigned m = __match_any_sync(0xffffffffu, d);
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const bool bit = (d >> b) & 1u;
+      const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? bal : ~bal;
+    }
+    rank[j] = peers;  // parked here until the counter pass below
+  }
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    const uint32_t d = (key[j] >> shift) & 0xffu;
+    const unsigned m = rank[j];
     const int leader = __ffs(m) - 1;
     uint32_t prev = 0;
     if (lane == leader) {
@@ -162,17 +219,26 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(
   s_digit_start[tid] = woff + incl - total;
 
   // decoupled look-back: sum this digit's counts over all earlier tiles
+  // (8 predecessors are fetched per round trip: the loads of a round are independent, so a walk
+  //  over w tiles costs ~w/8 L2 latencies instead of w)
   uint32_t excl = 0;
   if (tile > 0) {
     int64_t p = tile - 1;
-    while (true) {
-      uint32_t v;
-      do {
-        v = ld_volatile_u32(lookback + p * RS_RADIX + tid);
-      } while ((v & RS_FLAG_MASK) == 0);
-      excl += v & RS_VALUE_MASK;
-      if (v & RS_FLAG_INCL) break;
-      --p;
+    bool done = false;
+    while (!done) {
+      uint32_t v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        v[u] = (p - u >= 0) ? ld_volatile_u32(lookback + (p - u) * RS_RADIX + tid) : RS_FLAG_INCL;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (!done) {
+          while ((v[u] & RS_FLAG_MASK) == 0) v[u] = ld_volatile_u32(lookback + (p - u) * RS_RADIX + tid);
+          excl += v[u] & RS_VALUE_MASK;
+          if (v[u] & RS_FLAG_INCL) done = true;
+        }
+      }
+      p -= 8;
     }
     st_volatile_u32(lb + tid, RS_FLAG_INCL | (excl + total));
   }
@@ -212,7 +278,8 @@ int rs_histogram_enqueue(const void* src, KeyKind kind, int64_t n, int num_passe
 }
 
 int rs_sort_enqueue(const void* src, KeyKind kind, int64_t n, int num_passes,
-                    const SortWorkspace& ws, int32_t* perm_out, cudaStream_t stream) {
+                    const SortWorkspace& ws, int32_t* perm_out, cudaStream_t stream,
+                    const float* status, int32_t* nonbinary_flag) {
   MMBS_REQUIRE(n >= 1 && n <= RS_MAX_N, "radix sort: n=%lld out of range [1, 2^30)", (long long)n);
   MMBS_REQUIRE(num_passes >= 1 && num_passes <= 4, "radix sort: num_passes=%d", num_passes);
   const int64_t tiles = rs_tiles(n);
@@ -224,7 +291,8 @@ int rs_sort_enqueue(const void* src, KeyKind kind, int64_t n, int num_passes,
     uint32_t* vout = last ? reinterpret_cast<uint32_t*>(perm_out) : ((p & 1) ? ws.vals_b : ws.vals_a);
     rs_onesweep_kernel<<<unsigned(tiles), RS_THREADS, 0, stream>>>(
         src, int(kind), kin, vin, kout, vout, n, 8 * p, ws.digit_base + p * RS_RADIX,
-        ws.lookback + int64_t(p) * tiles * RS_RADIX, ws.counters + p, first ? 1 : 0, last ? 1 : 0);
+        ws.lookback + int64_t(p) * tiles * RS_RADIX, ws.counters + p, first ? 1 : 0, last ? 1 : 0,
+        first ? status : nullptr, nonbinary_flag);
     MMBS_LAUNCH_CHECK();
     kin = kout;
     vin = vout;

@@ -42,8 +42,11 @@ static inline int64_t rs_tiles(int64_t n) { return n > 0 ? (n + RS_TILE - 1) / R
 // must already be in ws.hist (see cox.cu / segmean.cu: the histogram kernel is
 // fused with other per-element work there).  Writes the sorted original indices
 // to perm_out.  num_passes in [1,4]: number of low bytes that can differ.
+// When `status` is given, bit 31 of every output word carries (status[idx] != 0) and
+// *nonbinary_flag is set if some status value is neither 0 nor 1.
 int rs_sort_enqueue(const void* src, KeyKind kind, int64_t n, int num_passes,
-                    const SortWorkspace& ws, int32_t* perm_out, cudaStream_t stream);
+                    const SortWorkspace& ws, int32_t* perm_out, cudaStream_t stream,
+                    const float* status = nullptr, int32_t* nonbinary_flag = nullptr);
 
 // Plain histogram (+ optional fused max / NaN flag over `scores`).
 int rs_histogram_enqueue(const void* src, KeyKind kind, int64_t n, int num_passes, uint32_t* hist,
@@ -63,6 +66,25 @@ __device__ __forceinline__ uint32_t float_order_enc(float f) {
 __device__ __forceinline__ float float_order_dec(uint32_t u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
+// L2 evict_last loads: keep a gathered-from array resident while streams pass through L2
+__device__ __forceinline__ uint64_t make_evict_last_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float ld_f32_hint(const float* p, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float4 ld_f32x4_hint(const float* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+
 #endif
 
 }  // namespace mmbs

@@ -114,9 +114,23 @@ def cast_pad_bf16(x: torch.Tensor, cols_padded: int, out: torch.Tensor | None = 
 
 
 # ------------------------------------------------------------------ ResNet-50 pipeline
+def front_chunk(chunk: int) -> int:
+    """Sub-chunk for stem .. layer2 (big activations).  Small sub-chunks keep a bottleneck's
+    tensors inside the 126 MB L2, but measured on B200 (profiles/r01_chunk_sweep.md) the extra
+    launches cost more than the saved HBM traffic, so the default is the whole chunk."""
+    f = int(os.environ.get("MMBS_RESNET_FRONT_CHUNK", "0")) or chunk
+    f = max(1, min(f, chunk))
+    return f if chunk % f == 0 else chunk
+
+
 class ResNetEngine:
-    """Inference pipeline for one (ResNet module, chunk size).  `chunk` patches are pushed
-    through all 53 convs at a time so the inter-layer activations of a chunk stay L2-resident."""
+    """Inference pipeline for one (ResNet module, chunk size).
+
+    A chunk of `chunk` patches is packed once, then stem / maxpool / layer1 / layer2 run in
+    sub-chunks of `front` patches on reused scratch buffers (L2-resident), writing layer2's output
+    for the whole chunk; layer3 / layer4 (small activations, compute-bound) run once on the whole
+    chunk so their grids fill the 148 SMs.  Everything between the input pack and the final
+    average pool is one CUDA graph."""
 
     def __init__(self, resnet, chunk: int):
         p = next(resnet.parameters())
@@ -124,6 +138,7 @@ class ResNetEngine:
             raise RuntimeError("ResNetEngine: the module must live on a CUDA device (no CPU fallback)")
         self.device = p.device
         self.chunk = int(chunk)
+        self.front = front_chunk(self.chunk)
         self._steps = []
         self._keep = []
         self._weights_version = None
@@ -141,57 +156,91 @@ class ResNetEngine:
         self._keep.append(t)
         return t
 
+    def _plan(self, *a, **k):
+        pl = conv_plan(*a, **k)
+        self._keep.append(pl)
+        return pl
+
+    def _block_steps(self, blk, w, x, out):
+        """Steps of one Bottleneck on input buffer x writing `out` (scratch allocated here)."""
+        B, H, W, Cin = x.shape
+        planes = blk.conv1.out_channels
+        s = blk.conv2.stride[0]
+        Ho, Wo = H // s, W // s
+        t1 = self._buf(B, H, W, planes)
+        t2 = self._buf(B, Ho, Wo, planes)
+        steps = []
+        if blk.downsample is not None:
+            res = self._buf(B, Ho, Wo, planes * 4)
+            steps.append(self._plan(x, w["wd"], res, ksize=1, stride=blk.downsample[0].stride[0], c_in=Cin,
+                                    scale=w["scd"], shift=w["shd"], relu=False).run)
+        else:
+            res = x
+        steps.append(self._plan(x, w["w1"], t1, ksize=1, stride=1, c_in=Cin, scale=w["sc1"], shift=w["sh1"],
+                                relu=True).run)
+        steps.append(self._plan(t1, w["w2"], t2, ksize=3, stride=s, c_in=planes, scale=w["sc2"], shift=w["sh2"],
+                                relu=True).run)
+        steps.append(self._plan(t2, w["w3"], out, ksize=1, stride=1, c_in=planes, scale=w["sc3"], shift=w["sh3"],
+                                residual=res, relu=True).run)
+        return steps
+
+    @staticmethod
+    def _block_weights(blk):
+        w = {"w1": pack_conv_weight(blk.conv1.weight), "w2": pack_conv_weight(blk.conv2.weight),
+             "w3": pack_conv_weight(blk.conv3.weight)}
+        w["sc1"], w["sh1"] = bn_fold(blk.bn1)
+        w["sc2"], w["sh2"] = bn_fold(blk.bn2)
+        w["sc3"], w["sh3"] = bn_fold(blk.bn3)
+        if blk.downsample is not None:
+            w["wd"] = pack_conv_weight(blk.downsample[0].weight)
+            w["scd"], w["shd"] = bn_fold(blk.downsample[1])
+        return w
+
     def _build(self, net):
-        B = self.chunk
+        B, F = self.chunk, self.front
         L = _lib.lib()
         with torch.cuda.device(self.device):
+            w_stem = pack_stem_weight(net.conv1.weight)
+            sc0, sh0 = bn_fold(net.bn1)
+            front_blocks = list(net.layer1) + list(net.layer2)
+            back_blocks = list(net.layer3) + list(net.layer4)
+            fw = [self._block_weights(b) for b in front_blocks]
+            bw = [self._block_weights(b) for b in back_blocks]
+            self._keep += [w_stem, sc0, sh0, fw, bw]
+
             self.x_s2d = self._buf(B, 116, 116, 16)
-            stem_out = self._buf(B, 112, 112, 64)
-            pool_out = self._buf(B, 56, 56, 64)
-            w = pack_stem_weight(net.conv1.weight)
-            sc, sh = bn_fold(net.bn1)
-            stem = conv_plan(self.x_s2d, w, stem_out, ksize=4, stride=1, c_in=16, scale=sc, shift=sh, relu=True,
-                             in_hw=(116, 116))
-            self._steps.append(stem.run)
-            self._steps.append(lambda: _lib.check(L.mmbs_maxpool_3x3s2(
-                _lib.ptr(stem_out), _lib.ptr(pool_out), B, 112, 112, 64, _lib.stream_ptr()), "mmbs_maxpool_3x3s2"))
-            x = pool_out
-            layers = [net.layer1, net.layer2, net.layer3, net.layer4]
-            n_blocks = sum(len(l) for l in layers)
-            bi = 0
-            for layer in layers:
-                for blk in layer:
-                    bi += 1
-                    last = bi == n_blocks
-                    Bx, H, W, Cin = x.shape
-                    planes = blk.conv1.out_channels
-                    s = blk.conv2.stride[0]
-                    Ho, Wo = H // s, W // s
-                    t1 = self._buf(B, H, W, planes)
-                    t2 = self._buf(B, Ho, Wo, planes)
-                    out = self._buf(B, Ho, Wo, planes * 4, dtype=torch.float32 if last else torch.bfloat16)
-                    sc1, sh1 = bn_fold(blk.bn1)
-                    sc2, sh2 = bn_fold(blk.bn2)
-                    sc3, sh3 = bn_fold(blk.bn3)
-                    c1 = conv_plan(x, pack_conv_weight(blk.conv1.weight), t1, ksize=1, stride=1, c_in=Cin,
-                                   scale=sc1, shift=sh1, relu=True)
-                    c2 = conv_plan(t1, pack_conv_weight(blk.conv2.weight), t2, ksize=3, stride=s, c_in=planes,
-                                   scale=sc2, shift=sh2, relu=True)
-                    if blk.downsample is not None:
-                        res = self._buf(B, Ho, Wo, planes * 4)
-                        scd, shd = bn_fold(blk.downsample[1])
-                        ds = conv_plan(x, pack_conv_weight(blk.downsample[0].weight), res, ksize=1,
-                                       stride=blk.downsample[0].stride[0], c_in=Cin, scale=scd, shift=shd, relu=False)
-                        self._steps.append(ds.run)
-                    else:
-                        res = x
-                    c3 = conv_plan(t2, pack_conv_weight(blk.conv3.weight), out, ksize=1, stride=1, c_in=planes,
-                                   scale=sc3, shift=sh3, residual=res, relu=True)
-                    self._steps += [c1.run, c2.run, c3.run]
-                    self._keep += [c1, c2, c3]
-                    x = out
+            mid = self._buf(B, 28, 28, front_blocks[-1].conv3.out_channels)  # layer2 output, whole chunk
+            # ---- front: per sub-chunk, on scratch buffers shared by all sub-chunks
+            stem_out = self._buf(F, 112, 112, 64)
+            pool_out = self._buf(F, 56, 56, 64)
+            scratch_steps = None
+            for j in range(B // F):
+                xs = self.x_s2d[j * F:(j + 1) * F]
+                self._steps.append(self._plan(xs, w_stem, stem_out, ksize=4, stride=1, c_in=16, scale=sc0, shift=sh0,
+                                              relu=True, in_hw=(116, 116)).run)
+                self._steps.append(lambda: _lib.check(L.mmbs_maxpool_3x3s2(
+                    _lib.ptr(stem_out), _lib.ptr(pool_out), F, 112, 112, 64, _lib.stream_ptr()), "mmbs_maxpool_3x3s2"))
+                if scratch_steps is None:  # plans between pool_out and the last front block are sub-chunk independent
+                    scratch_steps = []
+                    x = pool_out
+                    for blk, w in zip(front_blocks[:-1], fw[:-1]):
+                        s = blk.conv2.stride[0]
+                        out = self._buf(F, x.shape[1] // s, x.shape[2] // s, blk.conv3.out_channels)
+                        scratch_steps += self._block_steps(blk, w, x, out)
+                        x = out
+                    self._front_last_in = x
+                self._steps += scratch_steps
+                self._steps += self._block_steps(front_blocks[-1], fw[-1], self._front_last_in, mid[j * F:(j + 1) * F])
+            # ---- back: whole chunk
+            x = mid
+            for bi, (blk, w) in enumerate(zip(back_blocks, bw)):
+                last = bi == len(back_blocks) - 1
+                s = blk.conv2.stride[0]
+                out = self._buf(B, x.shape[1] // s, x.shape[2] // s, blk.conv3.out_channels,
+                                dtype=torch.float32 if last else torch.bfloat16)
+                self._steps += self._block_steps(blk, w, x, out)
+                x = out
             self.final = x  # [B,7,7,2048] fp32
-            self._keep.append(stem)
         self._weights_version = self.weights_version(net)
         self.n_kernels = len(self._steps) + 2
 
@@ -210,8 +259,8 @@ GRAPH_LAUNCHES = 0  # kernels launched through CUDA-graph replays (not seen by m
 
 
 def _engine_run_body(self):
-    """The 53 convs + maxpool of one chunk: eager on the first call (kernel attributes are set
-    lazily), captured into a CUDA graph on the second, replayed afterwards."""
+    """Everything between the input pack and the final pool: eager on the first call (kernel
+    attributes are set lazily), captured into a CUDA graph on the second, replayed afterwards."""
     self._runs += 1
     if not self.use_graph or self._runs == 1:
         for step in self._steps:

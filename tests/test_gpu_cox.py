@@ -138,3 +138,14 @@ def test_large_cohort_properties():
     cs = s.detach()[idx] - s.detach().max()
     ref = (-(cs - torch.log(torch.cumsum(torch.exp(cs).double(), 0).float() + 1e-5)) * e[idx]).double().mean()
     assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+
+
+def test_non_binary_status_weights():
+    """The reference multiplies by `status`, whatever its values: general float weights must
+    take the gather path (the kernel only packs a bit when every status is 0 or 1)."""
+    rng = np.random.default_rng(77)
+    n = 6000
+    s = rng.standard_normal(n).astype(np.float32)
+    t = rng.integers(0, 40, n).astype(np.float32)
+    e = rng.choice(np.array([0.0, 0.5, 1.0, 2.0], np.float32), n)
+    _check(s, t, e, "non-binary status")
