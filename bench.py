@@ -176,7 +176,7 @@ def cox_secondary(torch, dev, peaks):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from multimodalbrainsurvival_b200 import _lib, aggregate, engine, models, resnet
+    from multimodalbrainsurvival_b200 import _lib, aggregate, engine, models, pipeline, resnet
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -207,12 +207,18 @@ def run_ours(args):
             feats, _ = model.extract(xs[i % 2])
         return aggregate.segmented_mean(feats, seg, n_cases)[0]
 
-    def step_e2e(i):
-        x = host[i % 2].to(dev, non_blocking=True)
-        with torch.no_grad():
-            feats, _ = model.extract(x)
-        host_out.copy_(feats, non_blocking=True)
-        return aggregate.segmented_mean(feats, seg, n_cases)[0]
+    def run_e2e(steps):
+        """Public-API loop with HOST inputs: pinned fp32 batches are staged by
+        pipeline.prefetch_to_device (H2D of batch i+1 overlaps the kernels of batch i), features
+        are read back to pinned host memory every step."""
+        outs = None
+        batches = (host[i % 2] for i in range(steps))
+        for x in pipeline.prefetch_to_device(batches, dev, depth=2):
+            with torch.no_grad():
+                feats, _ = model.extract(x)
+            host_out.copy_(feats, non_blocking=True)
+            outs = aggregate.segmented_mean(feats, seg, n_cases)[0]
+        return outs
 
     def barrier():
         if world > 1:
@@ -241,7 +247,18 @@ def run_ours(args):
 
     warmup = max(args.warmup, 3)
     ms, launches, clocks = timed(step, args.steps, warmup)
-    ms_e2e, _, _ = timed(step_e2e, args.steps, 2)
+    run_e2e(2)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    run_e2e(args.steps)
+    b.record()
+    barrier()
+    ms_e2e = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
     value = world * B * args.steps / (ms * 1e-3)
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
 

@@ -56,7 +56,7 @@ int mmbs_device_check(void);
  *           loss = -(1/n) sum status[perm]*(s~ - log(C+1e-5)).
  *   perm_out   [n] int32  : sorted order: bits 0-30 = original index (bit-exact vs
  *                           torch.sort(stable)), bit 31 = (status[index] != 0)
- *   saved_e    [n] float  : exp(s~) in sorted order          (saved for backward)
+ *   saved_e    [n] float  : s~ = scores[perm]-max in sorted order (saved for backward)
  *   saved_w    [n] float  : status[perm]/(C+1e-5)            (saved for backward)
  *   loss_out   [1] float
  *   flags_out  [1] int32  : bit0 = a NaN term was produced (the reference traps
@@ -116,6 +116,7 @@ typedef struct {
   int32_t stride;         /* 1 or 2 */
   int32_t relu;           /* apply ReLU in the epilogue */
   int32_t out_f32;        /* 1: out is float32 (row stride c_out), else bf16 */
+  int32_t flags;          /* bit0: 3x3 weights are [c_out][kw][c_in/64][kh][64] (halo variant) */
   const void* in;         /* bf16 NHWC [B, in_h, in_w, c_in] */
   const void* weight;     /* bf16 [c_out, ksize*ksize*c_in] */
   const float* scale;     /* [c_out] or NULL (=1) */

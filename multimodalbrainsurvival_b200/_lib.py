@@ -29,7 +29,7 @@ class ConvDesc(ctypes.Structure):
     """mmbs_conv_desc (include/mmbs.h)."""
     _fields_ = [
         ("batch", c_i32), ("in_h", c_i32), ("in_w", c_i32), ("c_in", c_i32), ("c_out", c_i32),
-        ("ksize", c_i32), ("stride", c_i32), ("relu", c_i32), ("out_f32", c_i32),
+        ("ksize", c_i32), ("stride", c_i32), ("relu", c_i32), ("out_f32", c_i32), ("flags", c_i32),
         ("in_", c_void_p), ("weight", c_void_p), ("scale", c_void_p), ("shift", c_void_p),
         ("residual", c_void_p), ("out", c_void_p),
     ]

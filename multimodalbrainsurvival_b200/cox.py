@@ -27,6 +27,9 @@ import torch.nn as nn
 from . import _lib
 
 
+SMALL_N = 2048  # csrc/cox.cu SM_MAX: one fused block, no workspace
+
+
 def _pad64(n: int) -> int:
     return (n + 63) // 64 * 64
 
@@ -73,13 +76,19 @@ class _CoxLossFn(torch.autograd.Function):
             ctx.in_dtype = cox_scores.dtype
             return torch.full((), float("nan"), device=dev)
         L = _lib.lib()
+        npad = _pad64(n)
         with torch.cuda.device(dev):
-            nbytes = L.mmbs_cox_workspace_bytes(n)
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            perm = torch.empty(n, dtype=torch.int32, device=dev)
-            saved = torch.empty(2, _pad64(n), dtype=torch.float32, device=dev)  # e, w (sorted order)
-            out = torch.empty(2, dtype=torch.float32, device=dev)       # loss, flags(bits)
+            # one allocation: [perm | saved s~ | saved w | loss, flags]  (all 4-byte words)
+            buf = torch.empty(3 * npad + 64, dtype=torch.float32, device=dev)
+            perm = buf[:npad].view(torch.int32)[:n]
+            saved = buf[npad:3 * npad].view(2, npad)
+            out = buf[3 * npad:3 * npad + 2]
             flags = out[1:].view(torch.int32)
+            if n <= SMALL_N:
+                ws, nbytes = None, 0
+            else:
+                nbytes = L.mmbs_cox_workspace_bytes(n)
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             _lib.check(L.mmbs_cox_forward(_lib.ptr(s), _lib.ptr(t), _lib.ptr(d), n, _lib.ptr(perm),
                                           _lib.ptr(saved[0]), _lib.ptr(saved[1]), _lib.ptr(out),
                                           _lib.ptr(flags), _lib.ptr(ws), nbytes, _lib.stream_ptr()),
@@ -90,15 +99,19 @@ class _CoxLossFn(torch.autograd.Function):
         ctx.in_shape = cox_scores.shape
         ctx.in_dtype = cox_scores.dtype
         ctx.ws_bytes = nbytes
-        ctx.save_for_backward(s, d, perm, saved, ws)
+        ctx.save_for_backward(s, d, buf, *([ws] if ws is not None else []))
+        ctx.npad = npad
         return out[0].clone().reshape(())
 
     @staticmethod
     def backward(ctx, grad_loss):
         if ctx.n == 0:
             return torch.zeros(ctx.in_shape, dtype=ctx.in_dtype, device=grad_loss.device), None, None
-        s, d, perm, saved, ws = ctx.saved_tensors
-        n = ctx.n
+        s, d, buf = ctx.saved_tensors[:3]
+        ws = ctx.saved_tensors[3] if len(ctx.saved_tensors) > 3 else None
+        n, npad = ctx.n, ctx.npad
+        perm = buf[:npad].view(torch.int32)
+        saved = buf[npad:3 * npad].view(2, npad)
         g = grad_loss.detach().reshape(1).float().contiguous()
         grad = torch.empty(n, dtype=torch.float32, device=s.device)
         L = _lib.lib()

@@ -4,12 +4,17 @@
 // and its three textual copies):
 //   sort(-times) -> gather -> subtract max -> exp -> cumsum -> log(.+1e-5) -> mask -> mean.
 //
-// Forward  = histogram(+max of scores)  ->  4 Onesweep radix passes  ->  one chained
-//            scan pass over the sorted order (decoupled look-back, fp64 carries).
-// Backward = one reverse chained scan pass (suffix sums of status/(C+eps)) that
-//            scatters the gradient, + the gradient through max(scores).
-// All passes are HBM-bound: coalesced 128-bit loads/stores on the streamed
-// arrays, the only random accesses are the 4-byte gathers through the permutation.
+// Forward  = histogram(+max of scores) -> 4 Onesweep radix passes (payload = index | event bit)
+//            -> reduce-then-scan over the sorted order:
+//               cox_gather_kernel  : s~ = scores[perm]-max, tile sums of exp(s~)      (1 gather)
+//               cox_tile_scan_kernel: exclusive scan of the 2048-element tile sums (fp64)
+//               cox_loss_kernel    : C = cumsum, log, mask, loss partials; saves w = status/(C+eps)
+//                                    and the tile sums of w for the backward pass
+// Backward = cox_tile_scan_kernel (suffix) -> cox_grad_kernel (suffix sums of w, gradient
+//            scatter) -> the gradient through max(scores).
+// Every pass streams with 128-bit accesses and has no inter-block dependency (an earlier
+// chained-scan version with decoupled look-back spent >40 % of its time waiting on predecessor
+// tiles: profiles/r01_ncu_stalls_cox_scan_fwd.txt); fp32 inside a tile, fp64 across tiles.
 #include <algorithm>
 
 #include "radix_sort.cuh"
@@ -25,105 +30,142 @@ constexpr float COX_EPS = 1e-5f;
 
 static inline int64_t cs_tiles(int64_t n) { return n > 0 ? (n + CS_TILE - 1) / CS_TILE : 1; }
 
-// Chained-scan tile status: ONE 64-bit word per tile = a double whose two mantissa LSBs are
-// replaced by the state (0 = empty, 1 = tile aggregate, 2 = inclusive prefix).  Value and flag
-// travel in a single atomic 8-byte store/load, so the look-back needs no memory fences; the
-// carry keeps 50 mantissa bits.
-struct ScanState {
-  unsigned long long* status;
-};
-__device__ __forceinline__ unsigned long long pack_status(double v, unsigned flag) {
-  return (static_cast<unsigned long long>(__double_as_longlong(v)) & ~3ull) | flag;
-}
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// Warp-parallel decoupled look-back: returns the sum of all earlier tiles' totals.
-__device__ __forceinline__ double lookback_sum(const ScanState& st, int64_t tile, int lane) {
-  double excl = 0.0;
-  int64_t pred = tile - 1;
-  while (true) {
-    const int64_t idx = pred - lane;
-    unsigned long long w = 2ull;  // tiles before tile 0: inclusive prefix 0
-    if (idx >= 0) {
-      do {
-        w = ld_volatile_u64(st.status + idx);
-      } while ((w & 3ull) == 0ull);
-    }
-    const unsigned incl_mask = __ballot_sync(0xffffffffu, (w & 3ull) == 2ull);
-    const int first_incl = incl_mask ? (__ffs(incl_mask) - 1) : 32;
-    const double v = (lane <= first_incl) ? __longlong_as_double(static_cast<long long>(w & ~3ull)) : 0.0;
-    excl += warp_sum(v);
-    if (incl_mask) break;
-    pred -= 32;
-  }
-  return excl;
-}
-
-// ------------------------------------------------------------------ forward scan
-__global__ void __launch_bounds__(CS_THREADS) cox_scan_fwd_kernel(
-    const int32_t* __restrict__ perm, const float* __restrict__ scores,
-    const float* __restrict__ status, const uint32_t* __restrict__ max_enc, int64_t n,
-    float* __restrict__ saved_e, float* __restrict__ saved_w, ScanState st, uint32_t* tile_counter,
-    double* __restrict__ loss_partial, int32_t* nan_flag, int32_t* max_count,
-    int32_t* __restrict__ max_list, const int32_t* __restrict__ nonbinary) {
-  __shared__ double s_warp_tot[CS_WARPS];
-  __shared__ double s_red[CS_WARPS];
-  __shared__ double s_block_excl;
-  __shared__ uint32_t s_tile;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-  __syncthreads();
-  const int64_t tile = s_tile;
-  const int64_t base = tile * CS_TILE + int64_t(tid) * CS_ITEMS;
-  const float smax = float_order_dec(*max_enc);
-
-  int32_t p[CS_ITEMS];
-  if (base + CS_ITEMS <= n) {
-    const int4 a = __ldg(reinterpret_cast<const int4*>(perm + base));
-    const int4 b = __ldg(reinterpret_cast<const int4*>(perm + base) + 1);
-    p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w;
-    p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
+__device__ __forceinline__ void load8_i32(const int32_t* p, int64_t base, int64_t n, int32_t (&v)[8]) {
+  if (base + 8 <= n) {
+    const int4 a = __ldg(reinterpret_cast<const int4*>(p + base));
+    const int4 b = __ldg(reinterpret_cast<const int4*>(p + base) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   } else {
 #pragma unroll
-    for (int j = 0; j < CS_ITEMS; ++j) p[j] = (base + j < n) ? __ldg(perm + base + j) : 0;
+    for (int j = 0; j < 8; ++j) v[j] = (base + j < n) ? __ldg(p + base + j) : 0;
   }
-  // perm words: bits 0-30 original index, bit 31 = event indicator (binary status)
-  const bool gather_status = (*nonbinary != 0);
+}
+__device__ __forceinline__ void load8_f32(const float* p, int64_t base, int64_t n, float (&v)[8]) {
+  if (base + 8 <= n) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p + base));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p + base) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (base + j < n) ? __ldg(p + base + j) : 0.f;
+  }
+}
+__device__ __forceinline__ void store8_f32(float* p, int64_t base, int64_t n, const float (&v)[8]) {
+  if (base + 8 <= n) {
+    float4* q = reinterpret_cast<float4*>(p + base);
+    q[0] = make_float4(v[0], v[1], v[2], v[3]);
+    q[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (base + j < n) p[base + j] = v[j];
+  }
+}
+// sum over the block, returned to thread 0 (other threads get 0); s_red has CS_WARPS slots
+__device__ __forceinline__ double block_sum_to_t0(double v, double* s_red, int lane, int warp) {
+  v = warp_sum(v);
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (warp == 0 && lane == 0) {
+#pragma unroll
+    for (int w = 0; w < CS_WARPS; ++w) t += s_red[w];
+  }
+  return t;
+}
+
+// ------------------------------------------------------------------ forward, pass A
+// perm words: bits 0-30 original index, bit 31 = event indicator (binary status).
+__global__ void __launch_bounds__(CS_THREADS) cox_gather_kernel(
+    const int32_t* __restrict__ perm, const float* __restrict__ scores,
+    const uint32_t* __restrict__ max_enc, int64_t n, float* __restrict__ saved_s,
+    double* __restrict__ tile_sum, int32_t* max_count, int32_t* __restrict__ max_list) {
+  __shared__ double s_red[CS_WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t base = int64_t(blockIdx.x) * CS_TILE + int64_t(tid) * CS_ITEMS;
+  const float smax = float_order_dec(*max_enc);
   const uint64_t pol = make_evict_last_policy();
-  bool valid[CS_ITEMS];
-  float sc[CS_ITEMS], dl[CS_ITEMS], e[CS_ITEMS], c[CS_ITEMS];
+  int32_t p[CS_ITEMS];
+  load8_i32(perm, base, n, p);
+  float st[CS_ITEMS];
 #pragma unroll
-  for (int j = 0; j < CS_ITEMS; ++j) {
-    valid[j] = (base + j < n);
-    const uint32_t word = uint32_t(p[j]);
-    p[j] = int32_t(word & 0x7fffffffu);
-    dl[j] = (valid[j] && (word >> 31)) ? 1.f : 0.f;
-  }
-#pragma unroll
-  for (int j = 0; j < CS_ITEMS; ++j) {  // the random 4-byte gather (scores stay L2-resident: evict_last)
-    sc[j] = valid[j] ? ld_f32_hint(scores + p[j], pol) : 0.f;
-    if (gather_status) dl[j] = valid[j] ? __ldg(status + p[j]) : 0.f;
+  for (int j = 0; j < CS_ITEMS; ++j) {  // the random 4-byte gather (scores kept L2-resident: evict_last)
+    const bool valid = base + j < n;
+    p[j] &= 0x7fffffff;
+    st[j] = valid ? ld_f32_hint(scores + p[j], pol) : 0.f;
   }
   float run = 0.f;
 #pragma unroll
   for (int j = 0; j < CS_ITEMS; ++j) {
-    sc[j] -= smax;                                  // s~ (models.py:102)
-    e[j] = valid[j] ? expf(sc[j]) : 0.f;            // models.py:103
-    run += e[j];
-    c[j] = run;
-    if (valid[j] && sc[j] == 0.f) {                 // an argmax position (for backward)
+    const bool valid = base + j < n;
+    st[j] -= smax;                                   // s~ (models.py:102)
+    run += valid ? expf(st[j]) : 0.f;                // models.py:103
+    if (valid && st[j] == 0.f) {                     // an argmax position (for backward)
       const int pos = atomicAdd(max_count, 1);
       if (pos < COX_MAX_LIST) max_list[pos] = p[j];
     }
   }
-  // block-wide exclusive prefix of the per-thread totals, carried in fp64
+  store8_f32(saved_s, base, n, st);
+  const double t = block_sum_to_t0(double(run), s_red, lane, warp);
+  if (tid == 0) tile_sum[blockIdx.x] = t;
+}
+
+// ------------------------------------------------------------------ tile-sum scan (one block)
+// out[i] = sum_{t<i} in[t]  (reverse: sum_{t>i} in[t]); fp64; in == out allowed.
+__global__ void __launch_bounds__(1024) cox_tile_scan_kernel(const double* in, double* out, int64_t tiles,
+                                                             int reverse) {
+  __shared__ double s_w[32];
+  __shared__ double s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0.0;
+  __syncthreads();
+  for (int64_t b = 0; b < tiles; b += 1024) {
+    const int64_t i = b + tid;
+    const int64_t src = reverse ? (tiles - 1 - i) : i;
+    const double c = (i < tiles) ? in[src] : 0.0;
+    double incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    double off = s_carry;
+    for (int w = 0; w < warp; ++w) off += s_w[w];
+    __syncthreads();               // every thread has read s_carry / s_w before they change
+    if (i < tiles) out[src] = off + incl - c;
+    if (tid == 1023) s_carry = off + incl;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ forward, pass B
+__global__ void __launch_bounds__(CS_THREADS) cox_loss_kernel(
+    const int32_t* __restrict__ perm, const float* __restrict__ status,
+    const float* __restrict__ saved_s, const double* __restrict__ tile_excl, int64_t n,
+    float* __restrict__ saved_w, double* __restrict__ loss_partial, double* __restrict__ tile_wsum,
+    int32_t* nan_flag, const int32_t* __restrict__ nonbinary) {
+  __shared__ double s_warp_tot[CS_WARPS];
+  __shared__ double s_red[CS_WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t base = int64_t(blockIdx.x) * CS_TILE + int64_t(tid) * CS_ITEMS;
+  const bool gather_status = (*nonbinary != 0);
+  int32_t p[CS_ITEMS];
+  float st[CS_ITEMS], dl[CS_ITEMS], c[CS_ITEMS];
+  load8_i32(perm, base, n, p);
+  load8_f32(saved_s, base, n, st);
+  float run = 0.f;
+#pragma unroll
+  for (int j = 0; j < CS_ITEMS; ++j) {
+    const bool valid = base + j < n;
+    const uint32_t word = uint32_t(p[j]);
+    dl[j] = (valid && (word >> 31)) ? 1.f : 0.f;
+    if (gather_status) dl[j] = valid ? __ldg(status + (word & 0x7fffffffu)) : 0.f;
+    run += valid ? expf(st[j]) : 0.f;
+    c[j] = run;
+  }
+  // exclusive prefix of the per-thread totals inside the tile, carried in fp64
   const double tsum = double(run);
   double winc = tsum;
 #pragma unroll
@@ -133,65 +175,35 @@ __global__ void __launch_bounds__(CS_THREADS) cox_scan_fwd_kernel(
   }
   if (lane == 31) s_warp_tot[warp] = winc;
   __syncthreads();
-  double warp_excl = 0.0, block_total = 0.0;
+  double off = tile_excl[blockIdx.x] + (winc - tsum);
 #pragma unroll
-  for (int w = 0; w < CS_WARPS; ++w) {
-    const double t = s_warp_tot[w];
-    if (w < warp) warp_excl += t;
-    block_total += t;
-  }
-  if (warp == 0) {
-    if (lane == 0) st_volatile_u64(st.status + tile, pack_status(block_total, tile == 0 ? 2u : 1u));
-    double excl = 0.0;
-    if (tile > 0) {
-      excl = lookback_sum(st, tile, lane);
-      if (lane == 0) st_volatile_u64(st.status + tile, pack_status(excl + block_total, 2u));
-    }
-    if (lane == 0) s_block_excl = excl;
-  }
-  __syncthreads();
-  const double off = s_block_excl + warp_excl + (winc - tsum);
+  for (int w = 0; w < CS_WARPS; ++w)
+    if (w < warp) off += s_warp_tot[w];
 
-  float w[CS_ITEMS];
-  float lsum = 0.f;
+  float wv[CS_ITEMS];
+  float lsum = 0.f, wsum = 0.f;
   bool bad = false;
 #pragma unroll
   for (int j = 0; j < CS_ITEMS; ++j) {
-    const float cj = float(off + double(c[j]));      // cumsum (models.py:104)
+    const bool valid = base + j < n;
+    const float cj = float(off + double(c[j]));        // cumsum (models.py:104)
     const float den = cj + COX_EPS;
-    const float term = -(sc[j] - logf(den)) * dl[j];  // models.py:104-105
-    w[j] = dl[j] / den;
-    if (valid[j]) {
+    const float term = -(st[j] - logf(den)) * dl[j];   // models.py:104-105
+    wv[j] = valid ? dl[j] / den : 0.f;
+    if (valid) {
       lsum += term;
+      wsum += wv[j];
       bad |= (term != term);
     }
   }
-  if (base + CS_ITEMS <= n) {
-    float4* pe = reinterpret_cast<float4*>(saved_e + base);
-    float4* pw = reinterpret_cast<float4*>(saved_w + base);
-    pe[0] = make_float4(e[0], e[1], e[2], e[3]);
-    pe[1] = make_float4(e[4], e[5], e[6], e[7]);
-    pw[0] = make_float4(w[0], w[1], w[2], w[3]);
-    pw[1] = make_float4(w[4], w[5], w[6], w[7]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < CS_ITEMS; ++j)
-      if (base + j < n) {
-        saved_e[base + j] = e[j];
-        saved_w[base + j] = w[j];
-      }
-  }
-  double bl = warp_sum(double(lsum));
-  if (lane == 0) s_red[warp] = bl;
+  store8_f32(saved_w, base, n, wv);
   const unsigned any_bad = __ballot_sync(0xffffffffu, bad);
   if (lane == 0 && any_bad) atomicOr(nan_flag, 1);
+  const double tl = block_sum_to_t0(double(lsum), s_red, lane, warp);
+  if (tid == 0) loss_partial[blockIdx.x] = tl;
   __syncthreads();
-  if (tid == 0) {
-    double t = 0.0;
-#pragma unroll
-    for (int w2 = 0; w2 < CS_WARPS; ++w2) t += s_red[w2];
-    loss_partial[tile] = t;
-  }
+  const double tw = block_sum_to_t0(double(wsum), s_red, lane, warp);
+  if (tid == 0) tile_wsum[blockIdx.x] = tw;
 }
 
 __global__ void __launch_bounds__(256) cox_finalize_kernel(const double* __restrict__ partial,
@@ -214,114 +226,62 @@ __global__ void __launch_bounds__(256) cox_finalize_kernel(const double* __restr
   }
 }
 
-// ------------------------------------------------------------------ backward scan
-// Tiles walk the sorted order from the end; tile j covers
-// k in [n_pad-(j+1)*T, n_pad-j*T) so every thread's 8 positions stay 32-byte aligned.
-__global__ void __launch_bounds__(CS_THREADS) cox_scan_bwd_kernel(
+// ------------------------------------------------------------------ backward
+// W_k = sum_{i>=k} w_i  = (sum over later tiles) + suffix inside the tile;
+// g~_k = -(status_k - exp(s~_k) * W_k) * grad_loss / n, scattered to grad[perm[k]].
+__global__ void __launch_bounds__(CS_THREADS) cox_grad_kernel(
     const int32_t* __restrict__ perm, const float* __restrict__ status,
-    const float* __restrict__ saved_e, const float* __restrict__ saved_w,
-    const float* __restrict__ grad_loss, int64_t n, int64_t n_pad, float* __restrict__ grad_scores,
-    ScanState st, uint32_t* tile_counter, double* __restrict__ gsum_partial,
+    const float* __restrict__ saved_s, const float* __restrict__ saved_w,
+    const double* __restrict__ tile_suffix, const float* __restrict__ grad_loss, int64_t n,
+    float* __restrict__ grad_scores, double* __restrict__ gsum_partial,
     const int32_t* __restrict__ nonbinary) {
   __shared__ double s_warp_tot[CS_WARPS];
   __shared__ double s_red[CS_WARPS];
-  __shared__ double s_block_excl;
-  __shared__ uint32_t s_tile;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-  __syncthreads();
-  const int64_t tile = s_tile;
-  const int64_t lo = n_pad - (tile + 1) * CS_TILE;
-  const int64_t base = lo + int64_t(CS_THREADS - 1 - tid) * CS_ITEMS;  // thread 0 = highest k
+  const int64_t base = int64_t(blockIdx.x) * CS_TILE + int64_t(tid) * CS_ITEMS;
   const float scale = grad_loss[0] / float(n);
-
-  float e[CS_ITEMS], w[CS_ITEMS];
-  int32_t p[CS_ITEMS];
-  if (base + CS_ITEMS <= n) {
-    const float4 e0 = __ldg(reinterpret_cast<const float4*>(saved_e + base));
-    const float4 e1 = __ldg(reinterpret_cast<const float4*>(saved_e + base) + 1);
-    const float4 w0 = __ldg(reinterpret_cast<const float4*>(saved_w + base));
-    const float4 w1 = __ldg(reinterpret_cast<const float4*>(saved_w + base) + 1);
-    const int4 a = __ldg(reinterpret_cast<const int4*>(perm + base));
-    const int4 b = __ldg(reinterpret_cast<const int4*>(perm + base) + 1);
-    e[0] = e0.x; e[1] = e0.y; e[2] = e0.z; e[3] = e0.w; e[4] = e1.x; e[5] = e1.y; e[6] = e1.z; e[7] = e1.w;
-    w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
-    p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
-  } else {
-#pragma unroll
-    for (int j = 0; j < CS_ITEMS; ++j) {
-      const bool v = base + j < n;
-      e[j] = v ? __ldg(saved_e + base + j) : 0.f;
-      w[j] = v ? __ldg(saved_w + base + j) : 0.f;
-      p[j] = v ? __ldg(perm + base + j) : 0;
-    }
-  }
   const bool gather_status = (*nonbinary != 0);
-  bool valid[CS_ITEMS];
-  float dl[CS_ITEMS];
-#pragma unroll
-  for (int j = 0; j < CS_ITEMS; ++j) {
-    valid[j] = (base + j < n);
-    const uint32_t word = uint32_t(p[j]);
-    p[j] = int32_t(word & 0x7fffffffu);
-    dl[j] = (valid[j] && (word >> 31)) ? 1.f : 0.f;
-    if (gather_status) dl[j] = valid[j] ? __ldg(status + p[j]) : 0.f;
-  }
-
-  float suf[CS_ITEMS];  // inclusive suffix sums inside the thread (descending k)
+  int32_t p[CS_ITEMS];
+  float st[CS_ITEMS], w[CS_ITEMS], suf[CS_ITEMS];
+  load8_i32(perm, base, n, p);
+  load8_f32(saved_s, base, n, st);
+  load8_f32(saved_w, base, n, w);   // zero beyond n
   float run = 0.f;
 #pragma unroll
   for (int j = CS_ITEMS - 1; j >= 0; --j) {
     run += w[j];
-    suf[j] = run;
+    suf[j] = run;                   // inclusive suffix inside the thread
   }
   const double tsum = double(run);
-  double winc = tsum;
+  double winc = tsum;               // inclusive suffix over lanes: lane l holds sum of lanes >= l
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const double t = __shfl_up_sync(0xffffffffu, winc, o);
-    if (lane >= o) winc += t;
+    const double t = __shfl_down_sync(0xffffffffu, winc, o);
+    if (lane + o < 32) winc += t;
   }
-  if (lane == 31) s_warp_tot[warp] = winc;
+  if (lane == 0) s_warp_tot[warp] = winc;
   __syncthreads();
-  double warp_excl = 0.0, block_total = 0.0;
+  double off = tile_suffix[blockIdx.x] + (winc - tsum);
 #pragma unroll
-  for (int w2 = 0; w2 < CS_WARPS; ++w2) {
-    const double t = s_warp_tot[w2];
-    if (w2 < warp) warp_excl += t;
-    block_total += t;
-  }
-  if (warp == 0) {
-    if (lane == 0) st_volatile_u64(st.status + tile, pack_status(block_total, tile == 0 ? 2u : 1u));
-    double excl = 0.0;
-    if (tile > 0) {
-      excl = lookback_sum(st, tile, lane);
-      if (lane == 0) st_volatile_u64(st.status + tile, pack_status(excl + block_total, 2u));
-    }
-    if (lane == 0) s_block_excl = excl;
-  }
-  __syncthreads();
-  const double off = s_block_excl + warp_excl + (winc - tsum);
+  for (int w2 = 0; w2 < CS_WARPS; ++w2)
+    if (w2 > warp) off += s_warp_tot[w2];
 
   float gs = 0.f;
 #pragma unroll
   for (int j = 0; j < CS_ITEMS; ++j) {
-    if (valid[j]) {
-      const float W = float(off + double(suf[j]));      // sum_{i>=k} status_i/(C_i+eps)
-      const float g = -(dl[j] - e[j] * W) * scale;
-      grad_scores[p[j]] = g;                            // un-permute
+    if (base + j < n) {
+      const uint32_t word = uint32_t(p[j]);
+      const int32_t idx = int32_t(word & 0x7fffffffu);
+      float dl = (word >> 31) ? 1.f : 0.f;
+      if (gather_status) dl = __ldg(status + idx);
+      const float W = float(off + double(suf[j]));
+      const float g = -(dl - expf(st[j]) * W) * scale;
+      grad_scores[idx] = g;        // un-permute
       gs += g;
     }
   }
-  double bl = warp_sum(double(gs));
-  if (lane == 0) s_red[warp] = bl;
-  __syncthreads();
-  if (tid == 0) {
-    double t = 0.0;
-#pragma unroll
-    for (int w2 = 0; w2 < CS_WARPS; ++w2) t += s_red[w2];
-    gsum_partial[tile] = t;
-  }
+  const double t = block_sum_to_t0(double(gs), s_red, lane, warp);
+  if (tid == 0) gsum_partial[blockIdx.x] = t;
 }
 
 // Gradient through "- max(scores)": every argmax position receives
@@ -363,26 +323,186 @@ __global__ void __launch_bounds__(256) cox_maxfix_full_kernel(
     if (scores[i] - smax == 0.f) grad_scores[i] -= fix;
 }
 
+
+// ------------------------------------------------------------------ small risk sets (n <= 2048)
+// The training configs call the loss on 128..1024 samples per step: one block does everything
+// (bitonic sort of (key,index) words in shared memory - stable because the index breaks ties -
+// then the scans), 1 launch forward + 1 launch backward instead of 14.
+constexpr int SM_MAX = 2048;
+constexpr int SM_THREADS = 1024;
+
+// inclusive scan of one double per thread over the block (1024 threads)
+__device__ __forceinline__ double block_scan_incl(double v, double* s_w /*[32]*/, int lane, int warp) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  if (lane == 31) s_w[warp] = v;
+  __syncthreads();
+  double off = 0.0;
+  for (int w = 0; w < warp; ++w) off += s_w[w];
+  __syncthreads();
+  return v + off;
+}
+
+__global__ void __launch_bounds__(SM_THREADS) cox_small_fwd_kernel(
+    const float* __restrict__ scores, const float* __restrict__ times, const float* __restrict__ status,
+    int n, int32_t* __restrict__ perm_out, float* __restrict__ saved_s, float* __restrict__ saved_w,
+    float* __restrict__ loss_out, int32_t* __restrict__ flags_out) {
+  __shared__ unsigned long long s_kv[SM_MAX];
+  __shared__ double s_w[32];
+  __shared__ float s_maxw[32];
+  __shared__ int s_flag;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int P = 32;
+  while (P < n) P <<= 1;
+  if (tid == 0) s_flag = 0;
+  float vmax = -INFINITY;
+  bool has_nan = false;
+  for (int i = tid; i < P; i += SM_THREADS) {
+    if (i < n) {
+      s_kv[i] = (static_cast<unsigned long long>(time_key(times[i])) << 32) | unsigned(i);
+      const float sc = scores[i];
+      has_nan |= (sc != sc);
+      vmax = fmaxf(vmax, sc);
+    } else {
+      s_kv[i] = ~0ull;
+    }
+  }
+  vmax = warp_max(vmax);
+  if (lane == 0) s_maxw[warp] = vmax;
+  __syncthreads();
+  float smax = s_maxw[0];
+  for (int w = 1; w < 32; ++w) smax = fmaxf(smax, s_maxw[w]);
+  // bitonic sort, ascending
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < P; i += SM_THREADS) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = s_kv[i], b = s_kv[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { s_kv[i] = b; s_kv[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // thread t owns sorted positions 2t, 2t+1
+  const int k0 = 2 * tid;
+  float st[2] = {0.f, 0.f}, dl[2] = {0.f, 0.f}, e[2] = {0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int k = k0 + j;
+    if (k < n) {
+      const int idx = int(unsigned(s_kv[k] & 0xffffffffull));
+      st[j] = scores[idx] - smax;
+      dl[j] = status[idx];
+      e[j] = expf(st[j]);
+      perm_out[k] = int32_t(unsigned(idx) | (dl[j] != 0.f ? 0x80000000u : 0u));
+      saved_s[k] = st[j];
+    }
+  }
+  const double incl = block_scan_incl(double(e[0]) + double(e[1]), s_w, lane, warp);
+  const double excl = incl - (double(e[0]) + double(e[1]));
+  float lsum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int k = k0 + j;
+    if (k < n) {
+      const float cj = float(excl + double(e[0]) + (j ? double(e[1]) : 0.0));
+      const float den = cj + COX_EPS;
+      const float term = -(st[j] - logf(den)) * dl[j];
+      has_nan |= (term != term);
+      lsum += term;
+      saved_w[k] = dl[j] / den;
+    }
+  }
+  if (has_nan) s_flag = 1;
+  const double total = block_scan_incl(double(lsum), s_w, lane, warp);
+  if (tid == SM_THREADS - 1) {
+    const int f = s_flag;
+    loss_out[0] = f ? __int_as_float(0x7fc00000) : float(total / double(n));
+    if (flags_out) flags_out[0] = f;
+  }
+}
+
+__global__ void __launch_bounds__(SM_THREADS) cox_small_bwd_kernel(
+    const float* __restrict__ status, const int32_t* __restrict__ perm, const float* __restrict__ saved_s,
+    const float* __restrict__ saved_w, const float* __restrict__ grad_loss, int n,
+    float* __restrict__ grad_scores) {
+  __shared__ double s_w[32];
+  __shared__ double s_tot[2];
+  __shared__ int s_cnt;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_cnt = 0;
+  const float scale = grad_loss[0] / float(n);
+  const int k0 = 2 * tid;
+  float st[2] = {0.f, 0.f}, w[2] = {0.f, 0.f}, dl[2] = {0.f, 0.f};
+  int idx[2] = {0, 0};
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int k = k0 + j;
+    if (k < n) {
+      st[j] = saved_s[k];
+      w[j] = saved_w[k];
+      idx[j] = int(unsigned(perm[k]) & 0x7fffffffu);
+      dl[j] = status[idx[j]];
+    }
+  }
+  const double wsum2 = double(w[0]) + double(w[1]);
+  const double incl = block_scan_incl(wsum2, s_w, lane, warp);
+  if (tid == SM_THREADS - 1) s_tot[0] = incl;
+  __syncthreads();
+  const double T = s_tot[0];
+  // W_k = sum_{i>=k} w_i = T - sum_{i<k} w_i
+  const double before0 = incl - wsum2;
+  float g[2] = {0.f, 0.f};
+  float gs = 0.f;
+  int nmax = 0;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int k = k0 + j;
+    if (k < n) {
+      const float W = float(T - (before0 + (j ? double(w[0]) : 0.0)));
+      g[j] = -(dl[j] - expf(st[j]) * W) * scale;
+      gs += g[j];
+      nmax += (st[j] == 0.f);
+    }
+  }
+  if (nmax) atomicAdd(&s_cnt, nmax);
+  const double gincl = block_scan_incl(double(gs), s_w, lane, warp);
+  if (tid == SM_THREADS - 1) s_tot[1] = gincl;
+  __syncthreads();
+  const float fix = float(s_tot[1] / double(s_cnt));   // gradient through max(scores)
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int k = k0 + j;
+    if (k < n) grad_scores[idx[j]] = g[j] - (st[j] == 0.f ? fix : 0.f);
+  }
+}
+
 // ------------------------------------------------------------------ workspace
 struct CoxWorkspace {
   // zeroed at the start of forward (contiguous)
   uint32_t* hist;          // [4][256]
-  uint32_t* counters;      // [8]: 0-3 radix passes, 4 fwd scan, 5 bwd scan
+  uint32_t* counters;      // [8]: 0-3 radix passes
   uint32_t* max_enc;       // [1]
   int32_t* nan_flag;       // [1]
   int32_t* max_count;      // [1]
   int32_t* nonbinary;      // [1] some status value is neither 0 nor 1
   uint32_t* lookback;      // [4][rs_tiles][256]
-  unsigned long long* status_fwd;  // [cs_tiles]
   size_t zero_bytes;
-  // zeroed at the start of backward
-  unsigned long long* status_bwd;  // [cs_tiles]
   // not zeroed
   uint32_t* digit_base;    // [4][256]
   int32_t* max_list;       // [COX_MAX_LIST]
   double* gsum_total;      // [1]
-  double* loss_partial;
-  double* gsum_partial;
+  double* tile_sum;        // [cs_tiles] sums of exp(s~), scanned in place
+  double* tile_wsum;       // [cs_tiles] sums of w           (kept for backward)
+  double* tile_suffix;     // [cs_tiles] suffix scan of tile_wsum (backward)
+  double* loss_partial;    // [cs_tiles]
+  double* gsum_partial;    // [cs_tiles]
   uint32_t* keys_a; uint32_t* keys_b; uint32_t* vals_a; uint32_t* vals_b;
   size_t total_bytes;
 };
@@ -398,12 +518,13 @@ static CoxWorkspace carve_cox(void* base, int64_t n) {
   w.max_count = c.take<int32_t>(1);
   w.nonbinary = c.take<int32_t>(1);
   w.lookback = c.take<uint32_t>(size_t(4) * rt * RS_RADIX);
-  w.status_fwd = c.take<unsigned long long>(ct);
   w.zero_bytes = align_up(c.off, 256);
-  w.status_bwd = c.take<unsigned long long>(ct);
   w.digit_base = c.take<uint32_t>(4 * RS_RADIX);
   w.max_list = c.take<int32_t>(COX_MAX_LIST);
   w.gsum_total = c.take<double>(1);
+  w.tile_sum = c.take<double>(ct);
+  w.tile_wsum = c.take<double>(ct);
+  w.tile_suffix = c.take<double>(ct);
   w.loss_partial = c.take<double>(ct);
   w.gsum_partial = c.take<double>(ct);
   w.keys_a = c.take<uint32_t>(n);
@@ -453,18 +574,25 @@ extern "C" int mmbs_risk_order(const float* times, int64_t n, int32_t* perm_out,
 }
 
 extern "C" int mmbs_cox_forward(const float* scores, const float* times, const float* status,
-                                int64_t n, int32_t* perm_out, float* saved_e, float* saved_w,
+                                int64_t n, int32_t* perm_out, float* saved_s, float* saved_w,
                                 float* loss_out, int32_t* flags_out, void* workspace,
                                 size_t workspace_bytes, void* stream_) {
   if (int rc = mmbs_device_check()) return rc;
-  MMBS_REQUIRE(scores && times && status && perm_out && saved_e && saved_w && loss_out && workspace,
+  MMBS_REQUIRE(scores && times && status && perm_out && saved_s && saved_w && loss_out,
                "mmbs_cox_forward: null pointer");
   MMBS_REQUIRE(n >= 1 && n <= RS_MAX_N, "mmbs_cox_forward: n=%lld out of range [1, 2^30)",
                (long long)n);
-  MMBS_REQUIRE((reinterpret_cast<uintptr_t>(perm_out) | reinterpret_cast<uintptr_t>(saved_e) |
+  MMBS_REQUIRE((reinterpret_cast<uintptr_t>(perm_out) | reinterpret_cast<uintptr_t>(saved_s) |
                 reinterpret_cast<uintptr_t>(saved_w)) % 16 == 0,
-               "mmbs_cox_forward: perm_out/saved_e/saved_w must be 16-byte aligned");
+               "mmbs_cox_forward: perm_out/saved_s/saved_w must be 16-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n <= SM_MAX) {  // one fused block; needs no workspace
+    cox_small_fwd_kernel<<<1, SM_THREADS, 0, stream>>>(scores, times, status, int(n), perm_out, saved_s,
+                                                      saved_w, loss_out, flags_out);
+    MMBS_LAUNCH_CHECK();
+    return MMBS_OK;
+  }
+  MMBS_REQUIRE(workspace != nullptr, "mmbs_cox_forward: null workspace");
   const CoxWorkspace w = carve_cox(workspace, n);
   if (workspace_bytes < w.total_bytes) {
     set_error("mmbs_cox_forward: workspace %zu < %zu bytes", workspace_bytes, w.total_bytes);
@@ -472,10 +600,14 @@ extern "C" int mmbs_cox_forward(const float* scores, const float* times, const f
   }
   if (int rc = cox_sort_common(scores, times, status, n, perm_out, w, stream)) return rc;
   const int64_t tiles = cs_tiles(n);
-  ScanState st{w.status_fwd};
-  cox_scan_fwd_kernel<<<unsigned(tiles), CS_THREADS, 0, stream>>>(
-      perm_out, scores, status, w.max_enc, n, saved_e, saved_w, st, w.counters + 4, w.loss_partial,
-      w.nan_flag, w.max_count, w.max_list, w.nonbinary);
+  cox_gather_kernel<<<unsigned(tiles), CS_THREADS, 0, stream>>>(perm_out, scores, w.max_enc, n, saved_s,
+                                                               w.tile_sum, w.max_count, w.max_list);
+  MMBS_LAUNCH_CHECK();
+  cox_tile_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_sum, w.tile_sum, tiles, 0);
+  MMBS_LAUNCH_CHECK();
+  cox_loss_kernel<<<unsigned(tiles), CS_THREADS, 0, stream>>>(perm_out, status, saved_s, w.tile_sum, n,
+                                                             saved_w, w.loss_partial, w.tile_wsum,
+                                                             w.nan_flag, w.nonbinary);
   MMBS_LAUNCH_CHECK();
   cox_finalize_kernel<<<1, 256, 0, stream>>>(w.loss_partial, tiles, n, w.nan_flag, loss_out, flags_out);
   MMBS_LAUNCH_CHECK();
@@ -483,26 +615,35 @@ extern "C" int mmbs_cox_forward(const float* scores, const float* times, const f
 }
 
 extern "C" int mmbs_cox_backward(const float* scores, const float* status, const int32_t* perm,
-                                 const float* saved_e, const float* saved_w, const float* grad_loss,
+                                 const float* saved_s, const float* saved_w, const float* grad_loss,
                                  int64_t n, float* grad_scores, void* workspace,
                                  size_t workspace_bytes, void* stream_) {
   if (int rc = mmbs_device_check()) return rc;
-  MMBS_REQUIRE(scores && status && perm && saved_e && saved_w && grad_loss && grad_scores && workspace,
+  MMBS_REQUIRE(scores && status && perm && saved_s && saved_w && grad_loss && grad_scores,
                "mmbs_cox_backward: null pointer");
   MMBS_REQUIRE(n >= 1 && n <= RS_MAX_N, "mmbs_cox_backward: n=%lld out of range", (long long)n);
+  MMBS_REQUIRE((reinterpret_cast<uintptr_t>(perm) | reinterpret_cast<uintptr_t>(saved_s) |
+                reinterpret_cast<uintptr_t>(saved_w)) % 16 == 0,
+               "mmbs_cox_backward: perm/saved_s/saved_w must be 16-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const CoxWorkspace w = carve_cox(workspace, n);  // must be the forward's workspace (max list)
+  if (n <= SM_MAX) {
+    cox_small_bwd_kernel<<<1, SM_THREADS, 0, stream>>>(status, perm, saved_s, saved_w, grad_loss, int(n),
+                                                      grad_scores);
+    MMBS_LAUNCH_CHECK();
+    return MMBS_OK;
+  }
+  MMBS_REQUIRE(workspace != nullptr, "mmbs_cox_backward: null workspace");
+  const CoxWorkspace w = carve_cox(workspace, n);  // must be the forward's workspace (tile sums, max list)
   if (workspace_bytes < w.total_bytes) {
     set_error("mmbs_cox_backward: workspace %zu < %zu bytes", workspace_bytes, w.total_bytes);
     return MMBS_ERR_WORKSPACE;
   }
   const int64_t tiles = cs_tiles(n);
-  MMBS_CUDA_TRY(cudaMemsetAsync(w.status_bwd, 0, size_t(tiles) * sizeof(unsigned long long), stream));
-  MMBS_CUDA_TRY(cudaMemsetAsync(w.counters + 5, 0, sizeof(uint32_t), stream));
-  ScanState st{w.status_bwd};
-  cox_scan_bwd_kernel<<<unsigned(tiles), CS_THREADS, 0, stream>>>(
-      perm, status, saved_e, saved_w, grad_loss, n, tiles * CS_TILE, grad_scores, st, w.counters + 5,
-      w.gsum_partial, w.nonbinary);
+  cox_tile_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_wsum, w.tile_suffix, tiles, 1);
+  MMBS_LAUNCH_CHECK();
+  cox_grad_kernel<<<unsigned(tiles), CS_THREADS, 0, stream>>>(perm, status, saved_s, saved_w, w.tile_suffix,
+                                                             grad_loss, n, grad_scores, w.gsum_partial,
+                                                             w.nonbinary);
   MMBS_LAUNCH_CHECK();
   cox_maxfix_list_kernel<<<1, 256, 0, stream>>>(w.gsum_partial, tiles, w.max_count, w.max_list,
                                                w.gsum_total, grad_scores);

@@ -32,6 +32,9 @@ constexpr int GM_EPI_THREADS = GM_EPI_WARPS * 32;    // 256
 constexpr int GM_THREADS = 64 + GM_EPI_THREADS;      // producer warp, MMA warp, 8 epilogue warps
 constexpr int GM_MAX_TAPS = 16;
 constexpr int GM_OUT_BLK_BYTES = GM_TILE_M * 128;    // one 64-channel column block of a bf16 tile
+constexpr int GM_RES64_A_STAGE = 24 * 1024;          // halo box: up to (th + 3) * tw = 192 rows of 128 B
+constexpr int GM_RES64_BYTES = 72 * 1024;            // 64 x 576 weights (layer1 3x3) resident
+constexpr int GM_RES128_BYTES = 64 * 1024;           // 256 x 128 / 128 x 256 weights resident
 
 struct ConvParams {
   CUtensorMap a_map[4];
@@ -45,6 +48,11 @@ struct ConvParams {
   int32_t num_taps, k_chunks;
   int32_t relu, out_f32;
   int32_t total_tiles;
+  int32_t taps_per_stage;   // MMA tap groups fed by one A stage (halo mode: rows shifted by tap_row_bytes)
+  int32_t tap_row_bytes;    // tw * 128: shared-memory distance between the A views of consecutive row taps
+  int32_t a_tx_bytes;       // bytes of one A stage load
+  int32_t res_boxes;        // resident-weights mode: number of (N_TILE x 64) weight boxes loaded once
+  int32_t kb_per_tile;      // weight boxes per n-tile
   uint32_t idesc;
   int8_t tap_map[GM_MAX_TAPS];
   int8_t tap_dw[GM_MAX_TAPS];
@@ -57,20 +65,24 @@ struct ConvParams {
 
 // Shared-memory carve-up (offsets from a 1024-B aligned base):
 //   [ring: STAGES x (A 16 KB | B N_TILE*128 B)] [staging: NSTG x N_TILE/64 x 16 KB] [barriers] [tmem slot] [scale|shift]
-template <int N_TILE, int STAGES, int NSTG>
+// RES_BYTES > 0 selects the weights-resident variant: the whole weight matrix is loaded into smem once
+// per CTA and the ring holds A stages only (A_STAGE bytes each, enough for a halo box).
+template <int N_TILE, int STAGES, int NSTG, int A_STAGE, int RES_BYTES>
 struct GemmSmem {
   static constexpr int B_BYTES = N_TILE * GM_CHUNK_K * 2;
-  static constexpr int STAGE_BYTES = GM_A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = RES_BYTES > 0 ? A_STAGE : (GM_A_BYTES + B_BYTES);
   static constexpr int OUT_BLKS = (N_TILE + 63) / 64;
-  static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int RES_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int STAGING_OFFSET = RES_OFFSET + RES_BYTES;
   static constexpr int STAGING_BYTES = OUT_BLKS * GM_OUT_BLK_BYTES;    // one staging tile
   static constexpr int BAR_OFFSET = STAGING_OFFSET + NSTG * STAGING_BYTES;
-  static constexpr int NUM_BARS = 2 * STAGES + 6;   // full[S] empty[S] tfull[2] tempty[2] res[2]
+  static constexpr int NUM_BARS = 2 * STAGES + 7;   // full[S] empty[S] tfull[2] tempty[2] res[2] wres
   static constexpr int TMEM_SLOT_OFFSET = BAR_OFFSET + NUM_BARS * 8;
   static constexpr int SCALE_OFFSET = (TMEM_SLOT_OFFSET + 4 + 15) / 16 * 16;
-  static constexpr int TOTAL = SCALE_OFFSET + 2 * N_TILE * 4;
+  static constexpr int TOTAL = SCALE_OFFSET + NSTG * 2 * N_TILE * 4;   // scale|shift per epilogue group
   static constexpr int DYNAMIC = TOTAL + 1024;  // slack for the 1024-B alignment of the ring
   static constexpr int TMEM_COLS = 2 * N_TILE;  // double-buffered fp32 accumulator
+  static_assert(STAGE_BYTES % 1024 == 0 && RES_BYTES % 1024 == 0, "swizzle atoms need 1024-B alignment");
   static_assert(DYNAMIC <= 227 * 1024, "shared memory budget exceeded");
 };
 
@@ -87,10 +99,102 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int tile, i
   return c;
 }
 
-template <int N_TILE, int STAGES, int NSTG>
+// Epilogue arithmetic for columns [c_begin, c_end) of tile row r: TMEM -> scale/shift (+ residual)
+// (+ ReLU) -> bf16 into the 128B-swizzled staging tile (TMA-store path) or straight to global memory.
+template <int N_TILE>
+__device__ __forceinline__ void epilogue_columns(const ConvParams& p, uint32_t t_addr, int c_begin, int c_end,
+                                                 const float* s_scale, const float* s_shift, uint32_t stg, int r,
+                                                 bool use_tma_store, bool tma_res, bool row_ok, int64_t row_off) {
+#pragma unroll 1
+  for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+    uint32_t accr[32];
+    tc::tmem_ld_32x32(t_addr + uint32_t(c0), accr);
+    tc::tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + j);
+      const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + j);
+      v[j] = __uint_as_float(accr[j]) * sc.x + sh.x;
+      v[j + 1] = __uint_as_float(accr[j + 1]) * sc.y + sh.y;
+      v[j + 2] = __uint_as_float(accr[j + 2]) * sc.z + sh.z;
+      v[j + 3] = __uint_as_float(accr[j + 3]) * sc.w + sh.w;
+    }
+    if (use_tma_store) {
+      // staging tile: column block (c0/64), row r, 16-B chunk index XOR-swizzled by (r & 7)
+      const uint32_t blk = stg + uint32_t(c0 >> 6) * GM_OUT_BLK_BYTES + uint32_t(r) * 128u;
+      const uint32_t ch0 = uint32_t((c0 & 63) >> 3);  // first 16-B chunk of these 32 columns (0 or 4)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t addr = blk + (((ch0 + g) ^ uint32_t(r & 7)) << 4);
+        if (tma_res) {
+          uint32_t rw[4];
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]) : "r"(addr));
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[h]);
+            v[g * 8 + h * 2] += __bfloat162float(b2.x);
+            v[g * 8 + h * 2 + 1] += __bfloat162float(b2.y);
+          }
+        }
+        uint32_t w[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          float a = v[g * 8 + h * 2], b = v[g * 8 + h * 2 + 1];
+          if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+          const __nv_bfloat162 b2 = __floats2bfloat162_rn(a, b);
+          w[h] = *reinterpret_cast<const uint32_t*>(&b2);
+        }
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]),
+                     "r"(w[2]), "r"(w[3]) : "memory");
+      }
+    } else if (row_ok) {
+      // fp32 output (final block / MLP head) or narrow tiles: direct, row-predicated 128-bit stores
+      if (p.residual) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + c0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint4 rv = __ldg(rp + g);
+          const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[h]);
+            v[g * 8 + h * 2] += __bfloat162float(b2.x);
+            v[g * 8 + h * 2 + 1] += __bfloat162float(b2.y);
+          }
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+      }
+      if (p.out_f32) {
+        float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + row_off + c0);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) op[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+      } else {
+        uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row_off + c0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t w[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[g * 8 + h * 2], v[g * 8 + h * 2 + 1]);
+            w[h] = *reinterpret_cast<const uint32_t*>(&b2);
+          }
+          op[g] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+  }
+}
+
+template <int N_TILE, int STAGES, int NSTG, int A_STAGE, int RES_BYTES>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ ConvParams p) {
-  using L = GemmSmem<N_TILE, STAGES, NSTG>;
+  using L = GemmSmem<N_TILE, STAGES, NSTG, A_STAGE, RES_BYTES>;
+  constexpr bool kResident = RES_BYTES > 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = tc::smem_u32(smem_raw);
   const uint32_t base_u32 = (raw_u32 + 1023u) & ~1023u;
@@ -102,6 +206,8 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   const uint32_t tfull_bar = empty_bar + STAGES * 8;   // [2] accumulator ready   (MMA -> epilogue)
   const uint32_t tempty_bar = tfull_bar + 16;          // [2] accumulator drained (epilogue -> MMA)
   const uint32_t res_bar = tempty_bar + 16;            // [2] residual tile landed in staging[i]
+  const uint32_t wres_bar = res_bar + 16;              // resident weights landed
+  const uint32_t wres_u32 = base_u32 + L::RES_OFFSET;
   const uint32_t tmem_slot = base_u32 + L::TMEM_SLOT_OFFSET;
   const uint32_t staging_u32 = base_u32 + L::STAGING_OFFSET;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + L::TMEM_SLOT_OFFSET);
@@ -110,6 +216,9 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
 
   const int n_tiles = p.c_out / N_TILE;
   const int k_iters = p.num_taps * p.k_chunks;
+  // epilogue organisation: two independent 4-warp groups (double-staged variants without a residual),
+  // else all 8 warps on one tile (with a residual the spare staging tile prefetches the next residual)
+  const bool group_mode = (NSTG == 2) && !((N_TILE >= 64) && !p.out_f32 && p.residual != nullptr);
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tc::tma_prefetch_desc(&p.a_map[i]);
@@ -121,9 +230,10 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       tc::mbar_init(tfull_bar + 8 * a, 1);
-      tc::mbar_init(tempty_bar + 8 * a, GM_EPI_WARPS);  // one arrive per epilogue warp
+      tc::mbar_init(tempty_bar + 8 * a, group_mode ? GM_EPI_WARPS / 2 : GM_EPI_WARPS);  // arrives per accumulator
       tc::mbar_init(res_bar + 8 * a, 1);
     }
+    tc::mbar_init(wres_bar, 1);
     tc::fence_mbar_init();
   }
   if (warp == 1) {
@@ -138,6 +248,12 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer: runs ahead across tile boundaries =====
+      if (kResident) {  // the whole weight matrix, once per CTA
+        tc::mbar_expect_tx(wres_bar, uint32_t(p.res_boxes) * L::B_BYTES);
+        for (int b = 0; b < p.res_boxes; ++b)
+          tc::tma_load_2d(&p.b_map, wres_bar, wres_u32 + b * L::B_BYTES, (b % p.kb_per_tile) * GM_CHUNK_K,
+                          (b / p.kb_per_tile) * N_TILE);
+      }
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord tcd = tile_coord(p, tile, n_tiles);
@@ -148,11 +264,12 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
             const uint32_t s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             tc::mbar_wait(empty_bar + 8 * s, ph ^ 1u);
-            tc::mbar_expect_tx(full_bar + 8 * s, L::STAGE_BYTES);
+            tc::mbar_expect_tx(full_bar + 8 * s, kResident ? uint32_t(p.a_tx_bytes) : uint32_t(L::STAGE_BYTES));
             const uint32_t a_dst = base_u32 + s * L::STAGE_BYTES;
             tc::tma_load_4d(amap, full_bar + 8 * s, a_dst, c * GM_CHUNK_K, cw, ch, tcd.n0);
-            tc::tma_load_2d(&p.b_map, full_bar + 8 * s, a_dst + GM_A_BYTES,
-                            (t * p.k_chunks + c) * GM_CHUNK_K, tcd.nt * N_TILE);
+            if (!kResident)
+              tc::tma_load_2d(&p.b_map, full_bar + 8 * s, a_dst + GM_A_BYTES,
+                              (t * p.k_chunks + c) * GM_CHUNK_K, tcd.nt * N_TILE);
           }
         }
       }
@@ -161,8 +278,10 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
     if (lane == 0) {
       // ===== MMA issuer (single thread), accumulators ping-pong in TMEM =====
       uint32_t it = 0, tl = 0;
+      if (kResident) tc::mbar_wait(wres_bar, 0);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
         const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+        const uint32_t w_tile = wres_u32 + uint32_t((tile % n_tiles) * p.kb_per_tile) * L::B_BYTES;
         tc::mbar_wait(tempty_bar + 8 * acc, aph ^ 1u);  // epilogue has drained this accumulator
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * N_TILE;
@@ -172,13 +291,26 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
           tc::mbar_wait(full_bar + 8 * s, ph);
           tc::tc_fence_after();
           const uint32_t a_addr = base_u32 + s * L::STAGE_BYTES;
-          const uint64_t da = tc::make_sw128_desc(a_addr);
-          const uint64_t db = tc::make_sw128_desc(a_addr + GM_A_BYTES);
+          if (kResident) {
+            // one A stage (possibly a halo box) feeds taps_per_stage row taps: tap u reads the same
+            // box shifted by u rows of tw pixels (a multiple of the 1024-B swizzle atom)
+            for (int u = 0; u < p.taps_per_stage; ++u) {
+              const uint64_t da = tc::make_sw128_desc(a_addr + uint32_t(u * p.tap_row_bytes));
+              const uint64_t db = tc::make_sw128_desc(w_tile + uint32_t(ki * p.taps_per_stage + u) * L::B_BYTES);
 #pragma unroll
-          for (int k = 0; k < GM_CHUNK_K / 16; ++k) {
-            // +32 B per K=16 step inside the 128-B swizzle row (start-address field is >>4)
-            tc::umma_bf16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), p.idesc,
-                          (ki | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < GM_CHUNK_K / 16; ++k)
+                tc::umma_bf16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), p.idesc,
+                              (ki | u | k) != 0 ? 1u : 0u);
+            }
+          } else {
+            const uint64_t da = tc::make_sw128_desc(a_addr);
+            const uint64_t db = tc::make_sw128_desc(a_addr + GM_A_BYTES);
+#pragma unroll
+            for (int k = 0; k < GM_CHUNK_K / 16; ++k) {
+              // +32 B per K=16 step inside the 128-B swizzle row (start-address field is >>4)
+              tc::umma_bf16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), p.idesc,
+                            (ki | k) != 0 ? 1u : 0u);
+            }
           }
           tc::umma_commit(empty_bar + 8 * s);  // frees the smem stage when these MMAs retire
         }
@@ -186,17 +318,12 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
       }
     }
   } else {
-    // ===== 8 epilogue warps: TMEM lane quarter = warp % 4 (rows), column half = (warp-2)/4 =====
-    constexpr int COLS_PER_HALF = (N_TILE / 2 >= 32) ? N_TILE / 2 : 32;
-    constexpr int ACTIVE_HALVES = N_TILE / COLS_PER_HALF;  // 2, or 1 when N_TILE == 32
+    // ===== 8 epilogue warps.  TMEM lane quarter = warp % 4 (tile rows). =====
     const int q = warp & 3;
-    const int hh = (warp - 2) >> 2;
+    const int grp = (warp - 2) >> 2;
     const int r = q * 32 + lane;
-    const int et = threadIdx.x - 64;  // 0..255
     const bool use_tma_store = (N_TILE >= 64) && !p.out_f32;
     const bool tma_res = use_tma_store && (p.residual != nullptr);
-    const bool active = hh < ACTIVE_HALVES;
-    const int col_lo = hh * COLS_PER_HALF;
 
     auto issue_residual = [&](int tile, uint32_t sb) {
       const TileCoord t2 = tile_coord(p, tile, n_tiles);
@@ -205,154 +332,129 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
         tc::tma_load_4d(&p.res_map, res_bar + 8 * sb, staging_u32 + sb * L::STAGING_BYTES + b * GM_OUT_BLK_BYTES,
                         t2.nt * N_TILE + b * 64, t2.w0, t2.h0, t2.n0);
     };
-    if (NSTG == 2 && tma_res && et == 0 && int(blockIdx.x) < p.total_tiles) issue_residual(blockIdx.x, 0);
+    auto issue_store = [&](const TileCoord& tcd, uint32_t stg) {
+      for (int b = 0; b < L::OUT_BLKS; ++b) {
+        asm volatile(
+            "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                reinterpret_cast<uint64_t>(&p.out_map)),
+            "r"(stg + b * GM_OUT_BLK_BYTES), "r"(tcd.nt * N_TILE + b * 64), "r"(tcd.w0), "r"(tcd.h0), "r"(tcd.n0)
+            : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    };
+    auto load_scale_shift = [&](int nt, float* sc, float* sh, int t0, int nthreads) {
+      for (int i = t0; i < N_TILE; i += nthreads) {
+        const int n = nt * N_TILE + i;
+        sc[i] = p.scale ? __ldg(p.scale + n) : 1.0f;
+        sh[i] = p.shift ? __ldg(p.shift + n) : 0.0f;
+      }
+    };
 
-    uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
-      const TileCoord tcd = tile_coord(p, tile, n_tiles);
-      const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
-      const uint32_t sb = (NSTG == 2) ? (tl & 1u) : 0u;            // staging buffer of this tile
-      const uint32_t res_parity = (NSTG == 2) ? ((tl >> 1) & 1u) : (tl & 1u);
-      const uint32_t stg = staging_u32 + sb * L::STAGING_BYTES;
-      // staging[sb] was last read by the TMA store of tile (tl - NSTG): it must be done reading
-      if (use_tma_store && et == 0) {
-        if (NSTG == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (group_mode) {
+      // Two independent groups of 4 warps; tiles (and with them the TMEM accumulators and the
+      // staging tiles) alternate between the groups, so one group's TMEM/store/residual latencies
+      // overlap the other group's arithmetic.
+      const int gt = threadIdx.x - 64 - grp * 128;  // 0..127 inside the group
+      const uint32_t stg = staging_u32 + grp * L::STAGING_BYTES;
+      float* g_scale = s_scale + grp * 2 * N_TILE;
+      float* g_shift = g_scale + N_TILE;
+      const bool fixed_nt = (n_tiles == 1);
+      const int tstride = 2 * int(gridDim.x);
+      int tile = int(blockIdx.x) + grp * int(gridDim.x);
+      if (fixed_nt) {
+        load_scale_shift(0, g_scale, g_shift, gt, 128);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
       }
-      for (int i = et; i < N_TILE; i += GM_EPI_THREADS) {
-        const int n = tcd.nt * N_TILE + i;
-        s_scale[i] = p.scale ? __ldg(p.scale + n) : 1.0f;
-        s_shift[i] = p.shift ? __ldg(p.shift + n) : 0.0f;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (tma_res && et == 0) {
-        if (NSTG == 2) {
-          // prefetch the NEXT tile's residual into the other staging tile (its last store must be read out)
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          if (tile + int(gridDim.x) < p.total_tiles) issue_residual(tile + gridDim.x, sb ^ 1u);
-        } else {
-          issue_residual(tile, 0);
+      if (tma_res && gt == 0 && tile < p.total_tiles) issue_residual(tile, grp);
+      for (uint32_t use = 0; tile < p.total_tiles; tile += tstride, ++use) {
+        const TileCoord tcd = tile_coord(p, tile, n_tiles);
+        if (!fixed_nt) load_scale_shift(tcd.nt, g_scale, g_shift, gt, 128);
+        // staging[grp] is free: with a residual, its arrival implies the previous store was read out;
+        // otherwise the leader waited for the read-out right after committing it
+        if (!fixed_nt || (use_tma_store && !tma_res)) asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        const int pw = tcd.w0 + (r % p.tw);
+        const int phh = tcd.h0 + ((r / p.tw) % p.th);
+        const int pn = tcd.n0 + (r / (p.tw * p.th));
+        const bool row_ok = (pw < p.out_w) && (phh < p.out_h) && (pn < p.batch);
+        const int64_t row = (int64_t(pn) * p.out_h + phh) * p.out_w + pw;
+        const int64_t row_off = row * p.c_out + int64_t(tcd.nt) * N_TILE;
+        tc::mbar_wait(tfull_bar + 8 * grp, use & 1u);
+        tc::tc_fence_after();
+        if (tma_res) tc::mbar_wait(res_bar + 8 * grp, use & 1u);
+        const uint32_t t_addr = tmem_base + uint32_t(grp) * N_TILE + (uint32_t(q * 32) << 16);
+        epilogue_columns<N_TILE>(p, t_addr, 0, N_TILE, g_scale, g_shift, stg, r, use_tma_store, tma_res, row_ok,
+                                 row_off);
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tempty_bar + 8 * grp);
+        if (use_tma_store) {
+          tc::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA engine
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+          if (gt == 0) {
+            issue_store(tcd, stg);
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (tma_res && tile + tstride < p.total_tiles) issue_residual(tile + tstride, grp);
+          }
+        } else if (!fixed_nt) {
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");  // scale/shift reloaded next tile
         }
       }
-      const int pw = tcd.w0 + (r % p.tw);
-      const int phh = tcd.h0 + ((r / p.tw) % p.th);
-      const int pn = tcd.n0 + (r / (p.tw * p.th));
-      const bool row_ok = (pw < p.out_w) && (phh < p.out_h) && (pn < p.batch);
-      const int64_t row = (int64_t(pn) * p.out_h + phh) * p.out_w + pw;
-      const int64_t row_off = row * p.c_out + int64_t(tcd.nt) * N_TILE;
-
-      tc::mbar_wait(tfull_bar + 8 * acc, aph);
-      tc::tc_fence_after();
-      if (tma_res) tc::mbar_wait(res_bar + 8 * sb, res_parity);
-      const uint32_t t_addr = tmem_base + acc * N_TILE + (uint32_t(q * 32) << 16);
-      if (active) {
-#pragma unroll 1
-        for (int c0 = col_lo; c0 < col_lo + COLS_PER_HALF; c0 += 32) {
-          uint32_t accr[32];
-          tc::tmem_ld_32x32(t_addr + uint32_t(c0), accr);
-          tc::tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + j);
-            const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + j);
-            v[j] = __uint_as_float(accr[j]) * sc.x + sh.x;
-            v[j + 1] = __uint_as_float(accr[j + 1]) * sc.y + sh.y;
-            v[j + 2] = __uint_as_float(accr[j + 2]) * sc.z + sh.z;
-            v[j + 3] = __uint_as_float(accr[j + 3]) * sc.w + sh.w;
-          }
-          if (use_tma_store) {
-            // staging tile: column block (c0/64), row r, 16-B chunk index XOR-swizzled by (r & 7)
-            const uint32_t blk = stg + uint32_t(c0 >> 6) * GM_OUT_BLK_BYTES + uint32_t(r) * 128u;
-            const uint32_t ch0 = uint32_t((c0 & 63) >> 3);  // first 16-B chunk of these 32 columns (0 or 4)
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint32_t addr = blk + (((ch0 + g) ^ uint32_t(r & 7)) << 4);
-              if (tma_res) {
-                uint32_t rw[4];
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]) : "r"(addr));
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                  const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[h]);
-                  v[g * 8 + h * 2] += __bfloat162float(b2.x);
-                  v[g * 8 + h * 2 + 1] += __bfloat162float(b2.y);
-                }
-              }
-              uint32_t w[4];
-#pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                float a = v[g * 8 + h * 2], b = v[g * 8 + h * 2 + 1];
-                if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
-                const __nv_bfloat162 b2 = __floats2bfloat162_rn(a, b);
-                w[h] = *reinterpret_cast<const uint32_t*>(&b2);
-              }
-              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]),
-                           "r"(w[2]), "r"(w[3]) : "memory");
-            }
-          } else if (row_ok) {
-            // fp32 output (final block / MLP head) or narrow tiles: direct, row-predicated 128-bit stores
-            if (p.residual) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + c0);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const uint4 rv = __ldg(rp + g);
-                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                  const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[h]);
-                  v[g * 8 + h * 2] += __bfloat162float(b2.x);
-                  v[g * 8 + h * 2 + 1] += __bfloat162float(b2.y);
-                }
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-            }
-            if (p.out_f32) {
-              float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + row_off + c0);
-#pragma unroll
-              for (int g = 0; g < 8; ++g) op[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-            } else {
-              uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row_off + c0);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                uint32_t w[4];
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                  const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[g * 8 + h * 2], v[g * 8 + h * 2 + 1]);
-                  w[h] = *reinterpret_cast<const uint32_t*>(&b2);
-                }
-                op[g] = make_uint4(w[0], w[1], w[2], w[3]);
-              }
-            }
+      if (use_tma_store && gt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else {
+      // All 8 warps work on the same tile, the column range split in two halves.  With two staging
+      // tiles (NSTG == 2) the TMA store of tile i drains while tile i+1 is computed and the residual of
+      // tile i+1 is prefetched into the spare staging tile during tile i.
+      constexpr int COLS_PER_HALF = (N_TILE / 2 >= 32) ? N_TILE / 2 : 32;
+      constexpr int ACTIVE_HALVES = N_TILE / COLS_PER_HALF;  // 2, or 1 when N_TILE == 32
+      const int et = threadIdx.x - 64;  // 0..255
+      const bool active = grp < ACTIVE_HALVES;
+      const int col_lo = grp * COLS_PER_HALF;
+      if (NSTG == 2 && tma_res && et == 0 && int(blockIdx.x) < p.total_tiles) issue_residual(blockIdx.x, 0);
+      uint32_t tl = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+        const TileCoord tcd = tile_coord(p, tile, n_tiles);
+        const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+        const uint32_t sb = (NSTG == 2) ? (tl & 1u) : 0u;
+        const uint32_t res_parity = (NSTG == 2) ? ((tl >> 1) & 1u) : (tl & 1u);
+        const uint32_t stg = staging_u32 + sb * L::STAGING_BYTES;
+        // staging[sb] was last read by the TMA store of tile (tl - NSTG): it must be done reading
+        if (use_tma_store && et == 0) {
+          if (NSTG == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        load_scale_shift(tcd.nt, s_scale, s_shift, et, GM_EPI_THREADS);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tma_res && et == 0) {
+          if (NSTG == 2) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (tile + int(gridDim.x) < p.total_tiles) issue_residual(tile + gridDim.x, sb ^ 1u);
+          } else {
+            issue_residual(tile, 0);
           }
         }
-      }
-      // accumulator fully read: hand it back to the MMA warp before the stores drain
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tempty_bar + 8 * acc);
-      if (use_tma_store) {
-        tc::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA engine
+        const int pw = tcd.w0 + (r % p.tw);
+        const int phh = tcd.h0 + ((r / p.tw) % p.th);
+        const int pn = tcd.n0 + (r / (p.tw * p.th));
+        const bool row_ok = (pw < p.out_w) && (phh < p.out_h) && (pn < p.batch);
+        const int64_t row = (int64_t(pn) * p.out_h + phh) * p.out_w + pw;
+        const int64_t row_off = row * p.c_out + int64_t(tcd.nt) * N_TILE;
+        tc::mbar_wait(tfull_bar + 8 * acc, aph);
+        tc::tc_fence_after();
+        if (tma_res) tc::mbar_wait(res_bar + 8 * sb, res_parity);
+        const uint32_t t_addr = tmem_base + acc * N_TILE + (uint32_t(q * 32) << 16);
+        if (active)
+          epilogue_columns<N_TILE>(p, t_addr, col_lo, col_lo + COLS_PER_HALF, s_scale, s_shift, stg, r,
+                                   use_tma_store, tma_res, row_ok, row_off);
+        // accumulator fully read: hand it back to the MMA warp before the stores drain
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tempty_bar + 8 * acc);
+        if (use_tma_store) tc::fence_proxy_async();
         asm volatile("bar.sync 2, 256;" ::: "memory");
-        if (et == 0) {
-          for (int b = 0; b < L::OUT_BLKS; ++b) {
-            asm volatile(
-                "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                    reinterpret_cast<uint64_t>(&p.out_map)),
-                "r"(stg + b * GM_OUT_BLK_BYTES), "r"(tcd.nt * N_TILE + b * 64), "r"(tcd.w0),
-                "r"(tcd.h0), "r"(tcd.n0)
-                : "memory");
-          }
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-      } else {
-        asm volatile("bar.sync 2, 256;" ::: "memory");  // s_scale/s_shift are reloaded by the next tile
+        if (use_tma_store && et == 0) issue_store(tcd, stg);
       }
+      if (use_tma_store && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
-    if (use_tma_store && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -414,21 +516,22 @@ using namespace mmbs;
 
 struct mmbs_conv_plan {
   ConvParams p;
+  int variant;   // 0 = streamed weights, 1 = weights resident in smem
   int n_tile;
   int stages;
   unsigned grid;
 };
 
-template <int N_TILE, int STAGES, int NSTG>
+template <int N_TILE, int STAGES, int NSTG, int A_STAGE = 0, int RES_BYTES = 0>
 static int launch_conv(const mmbs_conv_plan* plan, cudaStream_t stream) {
-  using L = GemmSmem<N_TILE, STAGES, NSTG>;
+  using L = GemmSmem<N_TILE, STAGES, NSTG, A_STAGE, RES_BYTES>;
   static bool configured = false;
   if (!configured) {
-    MMBS_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE, STAGES, NSTG>,
+    MMBS_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE, STAGES, NSTG, A_STAGE, RES_BYTES>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYNAMIC));
     configured = true;
   }
-  conv_gemm_kernel<N_TILE, STAGES, NSTG><<<plan->grid, GM_THREADS, L::DYNAMIC, stream>>>(plan->p);
+  conv_gemm_kernel<N_TILE, STAGES, NSTG, A_STAGE, RES_BYTES><<<plan->grid, GM_THREADS, L::DYNAMIC, stream>>>(plan->p);
   MMBS_LAUNCH_CHECK();
   return MMBS_OK;
 }
@@ -437,6 +540,12 @@ extern "C" int mmbs_conv_run(const mmbs_conv_plan* plan, void* stream_) {
   if (int rc = mmbs_device_check()) return rc;
   MMBS_REQUIRE(plan != nullptr, "mmbs_conv_run: null plan");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (plan->variant == 1) {
+    if (plan->n_tile == 64) return launch_conv<64, 4, 2, GM_RES64_A_STAGE, GM_RES64_BYTES>(plan, stream);
+    if (plan->n_tile == 128) return launch_conv<128, 5, 2, GM_A_BYTES, GM_RES128_BYTES>(plan, stream);
+    set_error("mmbs_conv_run: no resident variant for n_tile %d", plan->n_tile);
+    return MMBS_ERR_ARG;
+  }
   switch (plan->n_tile) {
     case 256: return launch_conv<256, 3, 1>(plan, stream);
     case 128: return launch_conv<128, 4, 2>(plan, stream);
@@ -521,21 +630,60 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
   p.scale = d->scale; p.shift = d->shift;
   p.residual = static_cast<const __nv_bfloat16*>(d->residual);
   p.out = d->out;
+  // ---- variant selection
+  // resident: the whole weight matrix fits in shared memory -> loaded once per CTA, the ring holds A only
+  // halo    : (resident, 64-wide) one A box with extra rows feeds several row taps (stem: 4, 3x3: 3 per kw)
+  const int64_t w_bytes = int64_t(k_total) * d->c_out * 2;
+  bool resident = false, halo = false;
+  int forced_n_tile = 0;
+  if (!linear_mode && !d->out_f32) {
+    if (d->c_out == 64 && w_bytes <= GM_RES64_BYTES) { resident = true; forced_n_tile = 64; }
+    else if ((d->c_out == 128 || d->c_out == 256) && w_bytes <= GM_RES128_BYTES) { resident = true; forced_n_tile = 128; }
+  }
+  const bool want_halo = (d->flags & 1) != 0;
+  if (resident && forced_n_tile == 64 && (stem_mode || (want_halo && k == 3 && s == 1))) halo = true;
+  if (want_halo && !halo) {
+    set_error("conv plan: halo weight order requested for an ineligible conv (k=%d s=%d c_out=%d)", k, s, d->c_out);
+    delete plan;
+    return MMBS_ERR_ARG;
+  }
+  p.taps_per_stage = 1; p.tap_row_bytes = 0; p.a_tx_bytes = GM_A_BYTES;
+  int halo_rows = 0;
   if (linear_mode) { p.tw = 128; p.th = 1; p.tn = 1; }
-  else choose_box(out_w, out_h, d->batch, &p.tw, &p.th, &p.tn);
+  else if (halo && stem_mode) {
+    p.tw = 16; p.th = 8; p.tn = 1; halo_rows = 3;
+    p.num_taps = 1; p.taps_per_stage = 4; p.tap_dw[0] = 0; p.tap_dh[0] = 0; p.tap_map[0] = 0;
+  } else if (halo) {
+    p.tw = 8; p.th = 16; p.tn = 1; halo_rows = 2;
+    p.num_taps = 3; p.taps_per_stage = 3;   // stage t = kw; row taps kh = 0..2 inside the box
+    for (int t = 0; t < 3; ++t) { p.tap_map[t] = 0; p.tap_dw[t] = int8_t(t - 1); p.tap_dh[t] = -1; }
+  } else choose_box(out_w, out_h, d->batch, &p.tw, &p.th, &p.tn);
+  if (halo) {
+    p.tap_row_bytes = p.tw * 128;
+    p.a_tx_bytes = (p.th + halo_rows) * p.tw * 128;
+    MMBS_REQUIRE(p.a_tx_bytes <= GM_RES64_A_STAGE, "conv plan: halo box too large");
+  }
   p.tiles_w = int(ceil_div(out_w, p.tw)); p.tiles_h = int(ceil_div(out_h, p.th)); p.tiles_n = int(ceil_div(d->batch, p.tn));
   const int64_t m_tiles = int64_t(p.tiles_w) * p.tiles_h * p.tiles_n;
   plan->n_tile = pick_n_tile(d->c_out, m_tiles);
   // epilogue-bound residual layers (short K loop): 128-wide tile = double-staged epilogue with the
   // residual prefetched one tile ahead; long K loops keep the 256-wide tile (operand-feed bound)
   if (d->residual && !d->out_f32 && plan->n_tile > 128 && p.num_taps * p.k_chunks <= 4) plan->n_tile = 128;
+  plan->variant = 0;
+  if (resident) {
+    plan->variant = 1;
+    plan->n_tile = forced_n_tile;
+    p.kb_per_tile = p.num_taps * p.k_chunks * p.taps_per_stage;
+    p.res_boxes = (d->c_out / plan->n_tile) * p.kb_per_tile;
+  }
   plan->stages = 0;
   MMBS_REQUIRE(m_tiles * (d->c_out / plan->n_tile) < (int64_t(1) << 31), "conv plan: grid too large");
   p.total_tiles = int32_t(m_tiles * (d->c_out / plan->n_tile));
   plan->grid = unsigned(std::min<int64_t>(p.total_tiles, sm_count()));  // persistent: <= one CTA per SM
   p.idesc = make_idesc_bf16(GM_TILE_M, plan->n_tile);
 
-  const uint32_t box_a[4] = {64u, uint32_t(p.tw), uint32_t(p.th), uint32_t(p.tn)};
+  const uint32_t box_a[4] = {64u, uint32_t(p.tw), uint32_t(p.th + halo_rows), uint32_t(p.tn)};
+  const uint32_t box_out[4] = {64u, uint32_t(p.tw), uint32_t(p.th), uint32_t(p.tn)};
   const char* in = static_cast<const char*>(d->in);
   if (stem_mode) {
     const uint64_t dims[4] = {64, 113, 116, uint64_t(d->batch)};
@@ -568,10 +716,10 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
     const uint64_t C = uint64_t(d->c_out), W = uint64_t(out_w), H = uint64_t(out_h);
     const uint64_t dims[4] = {C, W, H, uint64_t(d->batch)};
     const uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
-    rc = encode_map(&p.out_map, d->out, 4, dims, str, box_a);
+    rc = encode_map(&p.out_map, d->out, 4, dims, str, box_out);
     if (!rc && d->residual) {
       MMBS_REQUIRE(reinterpret_cast<uintptr_t>(d->residual) % 16 == 0, "conv plan: residual must be 16-byte aligned");
-      rc = encode_map(&p.res_map, d->residual, 4, dims, str, box_a);
+      rc = encode_map(&p.res_map, d->residual, 4, dims, str, box_out);
     }
   }
   if (rc) {

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(RS_RADIX) rs_digit_base_kernel(const uint32_t*
 }
 
 // ---------------------------------------------------------------- one radix pass
-__global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(
+__global__ void __launch_bounds__(RS_THREADS, 4) rs_onesweep_kernel(
     const void* __restrict__ src, int kind, const uint32_t* __restrict__ keys_in,
     const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, int64_t n, int shift, const uint32_t* __restrict__ digit_base,
@@ -219,26 +219,26 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(
   s_digit_start[tid] = woff + incl - total;
 
   // decoupled look-back: sum this digit's counts over all earlier tiles
-  // (8 predecessors are fetched per round trip: the loads of a round are independent, so a walk
-  //  over w tiles costs ~w/8 L2 latencies instead of w)
+  // (RS_LOOKBACK predecessors are fetched per round trip: the loads of a round are independent,
+  //  so the inclusive-prefix wavefront advances up to RS_LOOKBACK tiles per L2 latency)
   uint32_t excl = 0;
   if (tile > 0) {
     int64_t p = tile - 1;
     bool done = false;
     while (!done) {
-      uint32_t v[8];
+      uint32_t v[RS_LOOKBACK];
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
+      for (int u = 0; u < RS_LOOKBACK; ++u)
         v[u] = (p - u >= 0) ? ld_volatile_u32(lookback + (p - u) * RS_RADIX + tid) : RS_FLAG_INCL;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < RS_LOOKBACK; ++u) {
         if (!done) {
           while ((v[u] & RS_FLAG_MASK) == 0) v[u] = ld_volatile_u32(lookback + (p - u) * RS_RADIX + tid);
           excl += v[u] & RS_VALUE_MASK;
           if (v[u] & RS_FLAG_INCL) done = true;
         }
       }
-      p -= 8;
+      p -= RS_LOOKBACK;
     }
     st_volatile_u32(lb + tid, RS_FLAG_INCL | (excl + total));
   }

@@ -38,7 +38,7 @@ class ConvPlan:
 
 
 def conv_plan(x, w, out, *, ksize, stride, c_in, scale=None, shift=None, residual=None, relu=False,
-              in_hw=None):
+              in_hw=None, halo_weights=False):
     """x: bf16 NHWC [B,H,W,Cin] (ksize 4 = stem: the [B,116,116,16] space-to-depth buffer);
     w: bf16 [Cout, k*k*Cin]; out: NHWC bf16 or fp32."""
     B = x.shape[0]
@@ -47,6 +47,7 @@ def conv_plan(x, w, out, *, ksize, stride, c_in, scale=None, shift=None, residua
     d.batch, d.in_h, d.in_w, d.c_in, d.c_out = B, H, W, c_in, w.shape[0]
     d.ksize, d.stride, d.relu = ksize, stride, int(relu)
     d.out_f32 = int(out.dtype == torch.float32)
+    d.flags = 1 if halo_weights else 0
     d.in_ = x.data_ptr()
     d.weight = w.data_ptr()
     d.scale = scale.data_ptr() if scale is not None else None
@@ -79,6 +80,20 @@ def pack_conv_weight(w_oihw: torch.Tensor) -> torch.Tensor:
     _lib.check(_lib.lib().mmbs_pack_conv_weight(_lib.ptr(w), _lib.ptr(out), O, I, k, _lib.stream_ptr()),
                "mmbs_pack_conv_weight")
     return out
+
+
+def halo_eligible(conv: torch.nn.Conv2d) -> bool:
+    """3x3 / stride 1 / 64 output channels with <= 72 KB of bf16 weights: the kernel keeps the
+    weights resident in shared memory and reads each input row once per kw (halo box)."""
+    return (conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.out_channels == 64
+            and conv.in_channels % 64 == 0 and 9 * conv.in_channels * 64 * 2 <= 72 * 1024)
+
+
+def pack_conv_weight_halo(w_oihw: torch.Tensor) -> torch.Tensor:
+    """OIHW fp32 -> bf16 [O][kw][I/64][kh][64] (the K order the halo variant iterates in)."""
+    O, I, kh, kw = w_oihw.shape
+    w = w_oihw.detach().float().reshape(O, I // 64, 64, kh, kw).permute(0, 4, 1, 3, 2).contiguous()
+    return w.reshape(O, kh * kw * I).to(torch.bfloat16).contiguous()
 
 
 def pack_stem_weight(w_oihw: torch.Tensor) -> torch.Tensor:
@@ -179,15 +194,16 @@ class ResNetEngine:
         steps.append(self._plan(x, w["w1"], t1, ksize=1, stride=1, c_in=Cin, scale=w["sc1"], shift=w["sh1"],
                                 relu=True).run)
         steps.append(self._plan(t1, w["w2"], t2, ksize=3, stride=s, c_in=planes, scale=w["sc2"], shift=w["sh2"],
-                                relu=True).run)
+                                relu=True, halo_weights=w["halo2"]).run)
         steps.append(self._plan(t2, w["w3"], out, ksize=1, stride=1, c_in=planes, scale=w["sc3"], shift=w["sh3"],
                                 residual=res, relu=True).run)
         return steps
 
     @staticmethod
     def _block_weights(blk):
-        w = {"w1": pack_conv_weight(blk.conv1.weight), "w2": pack_conv_weight(blk.conv2.weight),
-             "w3": pack_conv_weight(blk.conv3.weight)}
+        halo2 = halo_eligible(blk.conv2) and os.environ.get("MMBS_CONV_HALO", "1") == "1"
+        w = {"w1": pack_conv_weight(blk.conv1.weight), "w3": pack_conv_weight(blk.conv3.weight), "halo2": halo2,
+             "w2": pack_conv_weight_halo(blk.conv2.weight) if halo2 else pack_conv_weight(blk.conv2.weight)}
         w["sc1"], w["sh1"] = bn_fold(blk.bn1)
         w["sc2"], w["sh2"] = bn_fold(blk.bn2)
         w["sc3"], w["sh3"] = bn_fold(blk.bn3)

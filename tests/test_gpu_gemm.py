@@ -71,6 +71,25 @@ def test_conv_matches_torch(case):
     _assert_close(out, ref, 1e-5 if out_f32 else 6e-3, str(case))
 
 
+@pytest.mark.parametrize("B,H,W,C", [(2, 56, 56, 64), (20, 56, 56, 64), (3, 24, 40, 64)])
+def test_conv3x3_halo_variant_matches_torch(B, H, W, C):
+    """3x3/1 conv with 64 output channels: weights resident in smem, one halo box per kw."""
+    from multimodalbrainsurvival_b200 import engine
+    torch.manual_seed(B + H)
+    x = torch.randn(B, H, W, C, device=DEV)
+    w = torch.randn(64, C, 3, 3, device=DEV) / (9 * C) ** 0.5
+    scale = torch.rand(64, device=DEV) + 0.5
+    shift = torch.randn(64, device=DEV) * 0.1
+    out = torch.full((B, H, W, 64), float("nan"), device=DEV, dtype=torch.bfloat16)
+    conv = torch.nn.Conv2d(C, 64, 3, padding=1, bias=False)
+    assert engine.halo_eligible(conv)
+    engine.conv_plan(x.to(torch.bfloat16).contiguous(), engine.pack_conv_weight_halo(w), out, ksize=3, stride=1,
+                     c_in=C, scale=scale, shift=shift, relu=True, halo_weights=True).run()
+    torch.cuda.synchronize()
+    ref = _ref_conv(x, w, scale, shift, None, True, 1, 1)
+    _assert_close(out, ref, 6e-3, f"halo {B}x{H}x{W}")
+
+
 @pytest.mark.parametrize("M,N,K,relu", [(128, 4096, 12800, True), (6, 2048, 4096, False), (300, 224, 2048, True),
                                         (1000, 32, 64, False)])
 def test_linear_matches_torch(M, N, K, relu):

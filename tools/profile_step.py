@@ -35,6 +35,21 @@ elif what == "cox":
         loss.backward()
     torch.cuda.synchronize()
     print("loss", float(loss.detach()))
+    if os.environ.get("MMBS_TIME", "0") == "1":
+        ts = []
+        for _ in range(7):
+            s.grad = None
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            loss = cox.cox_loss(s, t, e)
+            m = torch.cuda.Event(enable_timing=True)
+            m.record()
+            loss.backward()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append((a.elapsed_time(b), a.elapsed_time(m)))
+        ts.sort()
+        print("cox fwd+bwd ms (median, fwd part):", ts[len(ts) // 2], "=> GB/s on 112 B/sample:", n * 112 / ts[len(ts) // 2][0] / 1e6)
 elif what == "agg":
     n, d, g = 100_000, 2048, 1000
     v = torch.randn(n, d, device=dev)
