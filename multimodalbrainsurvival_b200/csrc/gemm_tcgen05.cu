@@ -36,6 +36,26 @@ constexpr int GM_RES64_A_STAGE = 24 * 1024;          // halo box: up to (th + 3)
 constexpr int GM_RES64_BYTES = 72 * 1024;            // 64 x 576 weights (layer1 3x3) resident
 constexpr int GM_RES128_BYTES = 64 * 1024;           // 256 x 128 / 128 x 256 weights resident
 
+// Division by a runtime constant as multiply-high + shift (tile index decomposition runs per tile in
+// every epilogue thread; hardware integer division costs ~25 instructions each).
+struct FastDiv {
+  uint32_t d, mul, shr;
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t l = 0;
+  while ((1u << l) < d) ++l;
+  f.shr = l;
+  f.mul = uint32_t(((uint64_t(1) << 32) * ((uint64_t(1) << l) - d)) / d + 1);
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t x, const FastDiv& f) {
+  if (f.d == 1) return x;
+  const uint32_t t = __umulhi(x, f.mul);
+  return (t + ((x - t) >> 1)) >> (f.shr - 1);
+}
+
 struct ConvParams {
   CUtensorMap a_map[4];
   CUtensorMap b_map;
@@ -48,6 +68,8 @@ struct ConvParams {
   int32_t num_taps, k_chunks;
   int32_t relu, out_f32;
   int32_t total_tiles;
+  FastDiv fd_ntiles, fd_tw, fd_twh;   // n_tiles, tiles_w, tiles_w * tiles_h
+  int32_t tw_shift, twh_shift;        // log2(tw), log2(tw * th)  (the pixel box sides are powers of two)
   int32_t taps_per_stage;   // MMA tap groups fed by one A stage (halo mode: rows shifted by tap_row_bytes)
   int32_t tap_row_bytes;    // tw * 128: shared-memory distance between the A views of consecutive row taps
   int32_t a_tx_bytes;       // bytes of one A stage load
@@ -91,11 +113,15 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int tile, int n_tiles) {
   TileCoord c;
-  c.nt = tile % n_tiles;  // n-tile fastest: CTAs that share an A tile run back to back (L2 reuse)
-  const int mt = tile / n_tiles;
-  c.w0 = (mt % p.tiles_w) * p.tw;
-  c.h0 = ((mt / p.tiles_w) % p.tiles_h) * p.th;
-  c.n0 = (mt / (p.tiles_w * p.tiles_h)) * p.tn;
+  // n-tile fastest: CTAs that share an A tile run back to back (L2 reuse)
+  const uint32_t mt = fdiv(uint32_t(tile), p.fd_ntiles);
+  c.nt = tile - int(mt) * n_tiles;
+  const uint32_t in_ = fdiv(mt, p.fd_twh);                 // image-box index
+  const uint32_t rem = mt - in_ * p.fd_twh.d;
+  const uint32_t ih = fdiv(rem, p.fd_tw);
+  c.w0 = int(rem - ih * p.fd_tw.d) * p.tw;
+  c.h0 = int(ih) * p.th;
+  c.n0 = int(in_) * p.tn;
   return c;
 }
 
@@ -246,24 +272,27 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer: runs ahead across tile boundaries =====
-      if (kResident) {  // the whole weight matrix, once per CTA
+    // ===== TMA producer (whole warp stays converged; one elected lane issues): runs ahead across tiles =====
+    if (kResident) {  // the whole weight matrix, once per CTA
+      if (tc::elect_one()) {
         tc::mbar_expect_tx(wres_bar, uint32_t(p.res_boxes) * L::B_BYTES);
         for (int b = 0; b < p.res_boxes; ++b)
           tc::tma_load_2d(&p.b_map, wres_bar, wres_u32 + b * L::B_BYTES, (b % p.kb_per_tile) * GM_CHUNK_K,
                           (b / p.kb_per_tile) * N_TILE);
       }
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord tcd = tile_coord(p, tile, n_tiles);
-        for (int t = 0; t < p.num_taps; ++t) {
-          const CUtensorMap* amap = &p.a_map[p.tap_map[t]];
-          const int cw = tcd.w0 + p.tap_dw[t], ch = tcd.h0 + p.tap_dh[t];
-          for (int c = 0; c < p.k_chunks; ++c, ++it) {
-            const uint32_t s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1u;
-            tc::mbar_wait(empty_bar + 8 * s, ph ^ 1u);
+      __syncwarp();
+    }
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord tcd = tile_coord(p, tile, n_tiles);
+      for (int t = 0; t < p.num_taps; ++t) {
+        const CUtensorMap* amap = &p.a_map[p.tap_map[t]];
+        const int cw = tcd.w0 + p.tap_dw[t], ch = tcd.h0 + p.tap_dh[t];
+        for (int c = 0; c < p.k_chunks; ++c, ++it) {
+          const uint32_t s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          tc::mbar_wait(empty_bar + 8 * s, ph ^ 1u);
+          if (tc::elect_one()) {
             tc::mbar_expect_tx(full_bar + 8 * s, kResident ? uint32_t(p.a_tx_bytes) : uint32_t(L::STAGE_BYTES));
             const uint32_t a_dst = base_u32 + s * L::STAGE_BYTES;
             tc::tma_load_4d(amap, full_bar + 8 * s, a_dst, c * GM_CHUNK_K, cw, ch, tcd.n0);
@@ -271,26 +300,28 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
               tc::tma_load_2d(&p.b_map, full_bar + 8 * s, a_dst + GM_A_BYTES,
                               (t * p.k_chunks + c) * GM_CHUNK_K, tcd.nt * N_TILE);
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer (single thread), accumulators ping-pong in TMEM =====
-      uint32_t it = 0, tl = 0;
-      if (kResident) tc::mbar_wait(wres_bar, 0);
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
-        const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
-        const uint32_t w_tile = wres_u32 + uint32_t((tile % n_tiles) * p.kb_per_tile) * L::B_BYTES;
-        tc::mbar_wait(tempty_bar + 8 * acc, aph ^ 1u);  // epilogue has drained this accumulator
+    // ===== MMA issuer (warp converged, one elected lane issues), accumulators ping-pong in TMEM =====
+    uint32_t it = 0, tl = 0;
+    if (kResident) tc::mbar_wait(wres_bar, 0);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+      const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+      const uint32_t nt = uint32_t(tile) - fdiv(uint32_t(tile), p.fd_ntiles) * uint32_t(n_tiles);
+      const uint32_t w_tile = wres_u32 + nt * uint32_t(p.kb_per_tile) * L::B_BYTES;
+      tc::mbar_wait(tempty_bar + 8 * acc, aph ^ 1u);  // epilogue has drained this accumulator
+      tc::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * N_TILE;
+      for (int ki = 0; ki < k_iters; ++ki, ++it) {
+        const uint32_t s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1u;
+        tc::mbar_wait(full_bar + 8 * s, ph);
         tc::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * N_TILE;
-        for (int ki = 0; ki < k_iters; ++ki, ++it) {
-          const uint32_t s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
-          tc::mbar_wait(full_bar + 8 * s, ph);
-          tc::tc_fence_after();
-          const uint32_t a_addr = base_u32 + s * L::STAGE_BYTES;
+        const uint32_t a_addr = base_u32 + s * L::STAGE_BYTES;
+        if (tc::elect_one()) {
           if (kResident) {
             // one A stage (possibly a halo box) feeds taps_per_stage row taps: tap u reads the same
             // box shifted by u rows of tw pixels (a multiple of the 1024-B swizzle atom)
@@ -313,8 +344,9 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
             }
           }
           tc::umma_commit(empty_bar + 8 * s);  // frees the smem stage when these MMAs retire
+          if (ki == k_iters - 1) tc::umma_commit(tfull_bar + 8 * acc);  // accumulator complete
         }
-        tc::umma_commit(tfull_bar + 8 * acc);  // accumulator complete
+        __syncwarp();
       }
     }
   } else {
@@ -324,6 +356,10 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
     const int r = q * 32 + lane;
     const bool use_tma_store = (N_TILE >= 64) && !p.out_f32;
     const bool tma_res = use_tma_store && (p.residual != nullptr);
+    // position of tile row r inside the (tw x th x tn) pixel box (the sides are powers of two)
+    const int r_w = r & (p.tw - 1);
+    const int r_h = (r >> p.tw_shift) & (p.th - 1);
+    const int r_n = r >> p.twh_shift;
 
     auto issue_residual = [&](int tile, uint32_t sb) {
       const TileCoord t2 = tile_coord(p, tile, n_tiles);
@@ -372,12 +408,13 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
         // staging[grp] is free: with a residual, its arrival implies the previous store was read out;
         // otherwise the leader waited for the read-out right after committing it
         if (!fixed_nt || (use_tma_store && !tma_res)) asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-        const int pw = tcd.w0 + (r % p.tw);
-        const int phh = tcd.h0 + ((r / p.tw) % p.th);
-        const int pn = tcd.n0 + (r / (p.tw * p.th));
-        const bool row_ok = (pw < p.out_w) && (phh < p.out_h) && (pn < p.batch);
-        const int64_t row = (int64_t(pn) * p.out_h + phh) * p.out_w + pw;
-        const int64_t row_off = row * p.c_out + int64_t(tcd.nt) * N_TILE;
+        bool row_ok = false;
+        int64_t row_off = 0;
+        if (!use_tma_store) {   // only the direct-store path needs per-row addresses
+          const int pw = tcd.w0 + r_w, phh = tcd.h0 + r_h, pn = tcd.n0 + r_n;
+          row_ok = (pw < p.out_w) && (phh < p.out_h) && (pn < p.batch);
+          row_off = ((int64_t(pn) * p.out_h + phh) * p.out_w + pw) * p.c_out + int64_t(tcd.nt) * N_TILE;
+        }
         tc::mbar_wait(tfull_bar + 8 * grp, use & 1u);
         tc::tc_fence_after();
         if (tma_res) tc::mbar_wait(res_bar + 8 * grp, use & 1u);
@@ -432,12 +469,13 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
             issue_residual(tile, 0);
           }
         }
-        const int pw = tcd.w0 + (r % p.tw);
-        const int phh = tcd.h0 + ((r / p.tw) % p.th);
-        const int pn = tcd.n0 + (r / (p.tw * p.th));
-        const bool row_ok = (pw < p.out_w) && (phh < p.out_h) && (pn < p.batch);
-        const int64_t row = (int64_t(pn) * p.out_h + phh) * p.out_w + pw;
-        const int64_t row_off = row * p.c_out + int64_t(tcd.nt) * N_TILE;
+        bool row_ok = false;
+        int64_t row_off = 0;
+        if (!use_tma_store) {   // only the direct-store path needs per-row addresses
+          const int pw = tcd.w0 + r_w, phh = tcd.h0 + r_h, pn = tcd.n0 + r_n;
+          row_ok = (pw < p.out_w) && (phh < p.out_h) && (pn < p.batch);
+          row_off = ((int64_t(pn) * p.out_h + phh) * p.out_w + pw) * p.c_out + int64_t(tcd.nt) * N_TILE;
+        }
         tc::mbar_wait(tfull_bar + 8 * acc, aph);
         tc::tc_fence_after();
         if (tma_res) tc::mbar_wait(res_bar + 8 * sb, res_parity);
@@ -541,7 +579,7 @@ extern "C" int mmbs_conv_run(const mmbs_conv_plan* plan, void* stream_) {
   MMBS_REQUIRE(plan != nullptr, "mmbs_conv_run: null plan");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (plan->variant == 1) {
-    if (plan->n_tile == 64) return launch_conv<64, 4, 2, GM_RES64_A_STAGE, GM_RES64_BYTES>(plan, stream);
+    if (plan->n_tile == 64) return launch_conv<64, 5, 2, GM_RES64_A_STAGE, GM_RES64_BYTES>(plan, stream);
     if (plan->n_tile == 128) return launch_conv<128, 5, 2, GM_A_BYTES, GM_RES128_BYTES>(plan, stream);
     set_error("mmbs_conv_run: no resident variant for n_tile %d", plan->n_tile);
     return MMBS_ERR_ARG;
@@ -681,6 +719,12 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
   p.total_tiles = int32_t(m_tiles * (d->c_out / plan->n_tile));
   plan->grid = unsigned(std::min<int64_t>(p.total_tiles, sm_count()));  // persistent: <= one CTA per SM
   p.idesc = make_idesc_bf16(GM_TILE_M, plan->n_tile);
+  p.fd_ntiles = make_fastdiv(uint32_t(d->c_out / plan->n_tile));
+  p.fd_tw = make_fastdiv(uint32_t(p.tiles_w));
+  p.fd_twh = make_fastdiv(uint32_t(p.tiles_w) * uint32_t(p.tiles_h));
+  p.tw_shift = 0; while ((1 << p.tw_shift) < p.tw) ++p.tw_shift;
+  p.twh_shift = 0; while ((1 << p.twh_shift) < p.tw * p.th) ++p.twh_shift;
+  MMBS_REQUIRE((1 << p.tw_shift) == p.tw && (1 << p.twh_shift) == p.tw * p.th, "conv plan: pixel box sides must be powers of two");
 
   const uint32_t box_a[4] = {64u, uint32_t(p.tw), uint32_t(p.th + halo_rows), uint32_t(p.tn)};
   const uint32_t box_out[4] = {64u, uint32_t(p.tw), uint32_t(p.th), uint32_t(p.tn)};
