@@ -160,6 +160,25 @@ int mmbs_avgpool_global_f32(const float* in, float* out, int64_t batch, int64_t 
 int mmbs_cast_pad_bf16(const float* in, void* out_bf16, int64_t rows, int64_t cols,
                        int64_t cols_padded, void* stream);
 
+/* ------------------------------------------------ MLP training glue (HBM-bound)
+ * The reference's MLPs are nn.Sequential(Dropout, Linear, ReLU, ...) stacks trained with autograd
+ * (/root/reference/2_GeneExpression/1_GeneExpress_train.py:247-257, :161-164).  Forward and backward
+ * GEMMs run on mmbs_linear_plan_create plans; these kernels provide the operands:
+ *   dropout_cast      x (fp32|bf16) -> bf16, Bernoulli(1-p) mask * 1/(1-p) from Philox(seed, tag)
+ *   mlp_bwd_elementwise  dz = g * dropmask/(1-p) * relu'(act); writes dz, dz^T and db += colsum(dz)
+ *   transpose_bf16 / cast_transpose_pad_bf16   K-major operands for wgrad / dgrad
+ */
+int mmbs_dropout_cast_bf16(const void* in, int32_t in_is_bf16, int64_t in_stride, void* out_bf16, int64_t rows,
+                           int64_t cols, int64_t cols_padded, float p, uint64_t seed, uint32_t tag, void* stream);
+int mmbs_mlp_bwd_elementwise(const void* g, int32_t g_is_bf16, int64_t g_stride, const void* act_bf16,
+                             int64_t act_stride, int32_t relu, float p, uint64_t seed, uint32_t tag, int64_t m,
+                             int64_t n, int64_t n_padded, int64_t m_padded, void* dz_bf16, void* dzt_bf16, float* db,
+                             void* stream);
+int mmbs_transpose_bf16(const void* in_bf16, int64_t in_stride, int64_t rows, int64_t cols, int64_t rows_padded,
+                        void* out_bf16, void* stream);
+int mmbs_cast_transpose_pad_bf16(const float* in, int64_t n, int64_t k, int64_t k_padded, int64_t n_padded,
+                                 void* out_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

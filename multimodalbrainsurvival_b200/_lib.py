@@ -64,6 +64,13 @@ SIGNATURES = {
     "mmbs_avgpool_global": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
     "mmbs_avgpool_global_f32": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
     "mmbs_cast_pad_bf16": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
+    "mmbs_dropout_cast_bf16": (ctypes.c_int, [c_void_p, c_i32, c_i64, c_void_p, c_i64, c_i64, c_i64, c_float,
+                                              ctypes.c_uint64, ctypes.c_uint32, c_void_p]),
+    "mmbs_mlp_bwd_elementwise": (ctypes.c_int, [c_void_p, c_i32, c_i64, c_void_p, c_i64, c_i32, c_float,
+                                                ctypes.c_uint64, ctypes.c_uint32, c_i64, c_i64, c_i64, c_i64,
+                                                c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmbs_transpose_bf16": (ctypes.c_int, [c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p, c_void_p]),
+    "mmbs_cast_transpose_pad_bf16": (ctypes.c_int, [c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p, c_void_p]),
 }
 
 

@@ -261,3 +261,191 @@ extern "C" int mmbs_cast_pad_bf16(const float* in, void* out, int64_t rows, int6
   MMBS_LAUNCH_CHECK();
   return MMBS_OK;
 }
+
+// ====================================================================== MLP training glue
+// Dropout masks come from Philox-4x32-10 keyed by (seed, tag) with the element's float4 index as
+// counter, so the backward pass regenerates the forward mask instead of storing it
+// (nn.Dropout of the reference MLPs: /root/reference/2_GeneExpression/1_GeneExpress_train.py:247-257).
+namespace mmbs {
+
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
+  uint32_t c2 = 0x5851f42du, c3 = 0x14057b7eu;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+// keep-mask of the 4 elements [4*q, 4*q+4) of row `row` (q = column / 4)
+__device__ __forceinline__ uint32_t dropout_keep4(uint64_t seed, uint32_t tag, uint32_t row, uint32_t q,
+                                                  uint32_t thresh) {
+  const uint4 r = philox4x32(q, row, uint32_t(seed) ^ tag, uint32_t(seed >> 32));
+  return (r.x >= thresh ? 1u : 0u) | (r.y >= thresh ? 2u : 0u) | (r.z >= thresh ? 4u : 0u) | (r.w >= thresh ? 8u : 0u);
+}
+__device__ __forceinline__ uint32_t drop_threshold(float p) {
+  const double t = double(p) * 4294967296.0;
+  return t >= 4294967295.0 ? 0xffffffffu : uint32_t(t);
+}
+
+// in (fp32 or bf16) [rows, cols] -> bf16 [rows, cols_padded]: dropout(p) then cast, zero padding.
+__global__ void __launch_bounds__(256) dropout_cast_kernel(const void* __restrict__ in, int in_bf16,
+                                                           int64_t in_stride, uint2* __restrict__ out,
+                                                           int64_t rows, int64_t cols, int64_t cp4, float p,
+                                                           uint64_t seed, uint32_t tag) {
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= rows * cp4) return;
+  const int64_t r = i / cp4, q = i % cp4, c0 = q * 4;
+  float v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float x = 0.f;
+    if (c0 + j < cols)
+      x = in_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(in)[r * in_stride + c0 + j])
+                  : __ldg(static_cast<const float*>(in) + r * in_stride + c0 + j);
+    v[j] = x;
+  }
+  if (p > 0.f) {
+    const uint32_t keep = dropout_keep4(seed, tag, uint32_t(r), uint32_t(q), drop_threshold(p));
+    const float sc = 1.0f / (1.0f - p);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * sc : 0.f;
+  }
+  out[i] = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+}
+
+// Backward elementwise step of one layer:
+//   dz[m, n] = g[m, n] * dropmask(m, n)/(1-p) * (act[m, n] > 0 if relu)
+// g: gradient wrt the layer's (dropped) output, fp32 [M, g_stride] or bf16; act: the layer's bf16 output.
+// Writes dz bf16 [M, Np] (zero padded), its transpose dzT bf16 [Np, Mp] and accumulates the bias gradient
+// db[n] += sum_m dz[m, n] (db pre-zeroed).  One block = 32 rows x 32 columns (transposed through smem).
+__global__ void __launch_bounds__(256) mlp_bwd_elementwise_kernel(
+    const void* __restrict__ g, int g_bf16, int64_t g_stride, const __nv_bfloat16* __restrict__ act,
+    int64_t act_stride, int relu, float p, uint64_t seed, uint32_t tag, int64_t m, int64_t n, int64_t np,
+    int64_t mp, __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ dzt, float* __restrict__ db) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int64_t col = int64_t(blockIdx.x) * 32 + tx;
+  const uint32_t thresh = drop_threshold(p);
+  const float sc = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  float colsum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t row = int64_t(blockIdx.y) * 32 + ty * 4 + k;
+    float v = 0.f;
+    if (row < m && col < n) {
+      v = g_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(g)[row * g_stride + col])
+                 : static_cast<const float*>(g)[row * g_stride + col];
+      if (relu && !(__bfloat162float(act[row * act_stride + col]) > 0.f)) v = 0.f;
+      if (p > 0.f) {
+        const uint32_t keep = dropout_keep4(seed, tag, uint32_t(row), uint32_t(col >> 2), thresh);
+        v = ((keep >> (col & 3)) & 1u) ? v * sc : 0.f;
+      }
+    }
+    v = __bfloat162float(__float2bfloat16_rn(v));  // db sums exactly what the GEMMs will see
+    if (row < m && col < np) dz[row * np + col] = __float2bfloat16_rn(v);
+    tile[ty * 4 + k][tx] = v;
+    colsum += v;
+  }
+  if (db != nullptr && col < n) atomicAdd(db + col, colsum);
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t orow = int64_t(blockIdx.x) * 32 + ty * 4 + k;  // a column of dz
+    const int64_t ocol = int64_t(blockIdx.y) * 32 + tx;          // a row of dz
+    if (orow < np && ocol < mp) dzt[orow * mp + ocol] = __float2bfloat16_rn(tile[tx][ty * 4 + k]);
+  }
+}
+
+// bf16 [rows, cols] (row stride in_stride) -> bf16 [cols, rows_padded] (zero padded rows beyond `rows`)
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in,
+                                                             int64_t in_stride, int64_t rows, int64_t cols,
+                                                             int64_t rows_padded,
+                                                             __nv_bfloat16* __restrict__ out) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t r = int64_t(blockIdx.y) * 32 + ty * 4 + k, c = int64_t(blockIdx.x) * 32 + tx;
+    tile[ty * 4 + k][tx] = (r < rows && c < cols) ? in[r * in_stride + c] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t orow = int64_t(blockIdx.x) * 32 + ty * 4 + k, ocol = int64_t(blockIdx.y) * 32 + tx;
+    if (orow < cols && ocol < rows_padded) out[orow * rows_padded + ocol] = tile[tx][ty * 4 + k];
+  }
+}
+
+// fp32 W [n, k] -> bf16 W^T [k_padded, n_padded] (zero padded): the dgrad operand
+__global__ void __launch_bounds__(256) cast_transpose_kernel(const float* __restrict__ in, int64_t n, int64_t k,
+                                                             int64_t kp, int64_t np,
+                                                             __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int64_t r = int64_t(blockIdx.y) * 32 + ty * 4 + j, c = int64_t(blockIdx.x) * 32 + tx;
+    tile[ty * 4 + j][tx] = (r < n && c < k) ? __ldg(in + r * k + c) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int64_t orow = int64_t(blockIdx.x) * 32 + ty * 4 + j, ocol = int64_t(blockIdx.y) * 32 + tx;
+    if (orow < kp && ocol < np) out[orow * np + ocol] = __float2bfloat16_rn(tile[tx][ty * 4 + j]);
+  }
+}
+
+}  // namespace mmbs
+
+extern "C" int mmbs_dropout_cast_bf16(const void* in, int32_t in_is_bf16, int64_t in_stride, void* out, int64_t rows,
+                                      int64_t cols, int64_t cols_padded, float p, uint64_t seed, uint32_t tag,
+                                      void* stream) {
+  if (int rc = mmbs_device_check()) return rc;
+  MMBS_REQUIRE(in && out && rows > 0 && cols > 0 && cols_padded >= cols && cols_padded % 4 == 0 && p >= 0.f && p < 1.f,
+               "mmbs_dropout_cast_bf16: bad argument");
+  dropout_cast_kernel<<<blocks_for(rows * (cols_padded / 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, in_is_bf16, in_stride, static_cast<uint2*>(out), rows, cols, cols_padded / 4, p, seed, tag);
+  MMBS_LAUNCH_CHECK();
+  return MMBS_OK;
+}
+
+extern "C" int mmbs_mlp_bwd_elementwise(const void* g, int32_t g_is_bf16, int64_t g_stride, const void* act,
+                                        int64_t act_stride, int32_t relu, float p, uint64_t seed, uint32_t tag,
+                                        int64_t m, int64_t n, int64_t n_padded, int64_t m_padded, void* dz, void* dzt,
+                                        float* db, void* stream) {
+  if (int rc = mmbs_device_check()) return rc;
+  MMBS_REQUIRE(g && dz && dzt && m > 0 && n > 0 && n_padded >= n && m_padded >= m && (!relu || act) && p >= 0.f && p < 1.f,
+               "mmbs_mlp_bwd_elementwise: bad argument");
+  dim3 grid(unsigned(ceil_div(n_padded, 32)), unsigned(ceil_div(m_padded, 32)));
+  mlp_bwd_elementwise_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      g, g_is_bf16, g_stride, static_cast<const __nv_bfloat16*>(act), act_stride, relu, p, seed, tag, m, n, n_padded,
+      m_padded, static_cast<__nv_bfloat16*>(dz), static_cast<__nv_bfloat16*>(dzt), db);
+  MMBS_LAUNCH_CHECK();
+  return MMBS_OK;
+}
+
+extern "C" int mmbs_transpose_bf16(const void* in, int64_t in_stride, int64_t rows, int64_t cols, int64_t rows_padded,
+                                   void* out, void* stream) {
+  if (int rc = mmbs_device_check()) return rc;
+  MMBS_REQUIRE(in && out && rows > 0 && cols > 0 && rows_padded >= rows, "mmbs_transpose_bf16: bad argument");
+  dim3 grid(unsigned(ceil_div(cols, 32)), unsigned(ceil_div(rows_padded, 32)));
+  transpose_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in), in_stride, rows, cols, rows_padded, static_cast<__nv_bfloat16*>(out));
+  MMBS_LAUNCH_CHECK();
+  return MMBS_OK;
+}
+
+extern "C" int mmbs_cast_transpose_pad_bf16(const float* in, int64_t n, int64_t k, int64_t k_padded, int64_t n_padded,
+                                            void* out, void* stream) {
+  if (int rc = mmbs_device_check()) return rc;
+  MMBS_REQUIRE(in && out && n > 0 && k > 0 && k_padded >= k && n_padded >= n, "mmbs_cast_transpose_pad_bf16: bad argument");
+  dim3 grid(unsigned(ceil_div(k_padded, 32)), unsigned(ceil_div(n_padded, 32)));
+  cast_transpose_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, n, k, k_padded, n_padded,
+                                                                            static_cast<__nv_bfloat16*>(out));
+  MMBS_LAUNCH_CHECK();
+  return MMBS_OK;
+}

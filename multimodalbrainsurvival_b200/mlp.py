@@ -7,8 +7,10 @@ The reference builds its MLPs from stock ``nn.Linear`` inside the scripts
 GEMMs with the bias and ReLU fused into the epilogue, reading the ``nn.Linear`` parameters in
 place (bf16 padded copies are caches keyed on the parameters' version counters).
 
-Served by the kernels: inference (eval mode or autograd disabled) on CUDA tensors.
-Training mode (dropout masks + autograd) runs the module graph on the tensor's device.
+Served by the kernels: inference AND training on CUDA tensors.  Training goes through
+``_MLPTrainFn``: forward GEMMs with bias/ReLU epilogues, Philox dropout regenerated (not
+stored) in the backward pass, dgrad/wgrad as tcgen05 GEMMs on transposed bf16 operands with
+fp32 accumulation; the fp32 master weights stay in the ``nn.Linear`` parameters (what Adam sees).
 """
 from __future__ import annotations
 
@@ -24,21 +26,27 @@ def _pad(n, m):
     return (n + m - 1) // m * m
 
 
-def _parse(seq):
-    """-> list of (linear, relu_after) or None when the stack is not a plain MLP."""
+def _parse(seq, with_dropout=False):
+    """-> list of (linear, relu_after[, dropout_p_before]) or None when the stack is not a plain MLP."""
     if not isinstance(seq, nn.Sequential):
         return None
     layers = []
+    pending_p = 0.0
     for m in seq:
         if isinstance(m, nn.Dropout):
-            continue
-        if isinstance(m, nn.Linear):
-            layers.append([m, False])
-        elif isinstance(m, nn.ReLU) and layers and not layers[-1][1]:
+            if pending_p > 0.0 or m.p >= 1.0:
+                return None
+            pending_p = float(m.p)
+        elif isinstance(m, nn.Linear):
+            layers.append([m, False, pending_p])
+            pending_p = 0.0
+        elif isinstance(m, nn.ReLU) and layers and not layers[-1][1] and pending_p == 0.0:
             layers[-1][1] = True
         else:
             return None
-    return layers or None
+    if not layers or pending_p > 0.0:
+        return None
+    return layers if with_dropout else [l[:2] for l in layers]
 
 
 class _MLPEngine:
@@ -92,6 +100,175 @@ class _MLPEngine:
         return self.outs[-1][:, :self.layers[-1][0].out_features].clone()
 
 
+
+
+# ------------------------------------------------------------------------------- training
+def _pad64(n):
+    return _pad(n, 64)
+
+
+class _MLPTrainEngine:
+    """Buffers + GEMM plans of one MLP for a fixed batch size M (forward, dgrad, wgrad)."""
+
+    def __init__(self, layers, m_rows, device, need_dx):
+        from . import _lib
+        self.layers = layers
+        self.m, self.mp = m_rows, _pad64(m_rows)
+        self.device = device
+        self.need_dx = need_dx
+        L = len(layers)
+        self.kp = [_pad64(l[0].in_features) for l in layers]
+        self.np_ = [_pad64(l[0].out_features) for l in layers]
+        for i in range(1, L):
+            if self.kp[i] != self.np_[i - 1]:
+                raise ValueError("layer widths do not chain")
+        bf, f32 = torch.bfloat16, torch.float32
+        M, Mp = self.m, self.mp
+        with torch.cuda.device(device):
+            E = lambda *s, dtype=bf: torch.zeros(s, dtype=dtype, device=device)  # noqa: E731
+            self.hin = [E(M, self.kp[0])]                      # dropped inputs of every layer
+            self.w, self.wT, self.b, self.act = [], [], [], []
+            self.dz, self.dzT, self.hinT, self.dW, self.db, self.dh = [], [], [], [], [], []
+            for i, (lin, relu, p) in enumerate(layers):
+                last = i == L - 1
+                self.w.append(E(self.np_[i], self.kp[i]))
+                self.b.append(E(self.np_[i], dtype=f32))
+                self.act.append(E(M, self.np_[i], dtype=f32 if last else bf))
+                if not last:
+                    nxt_p = layers[i + 1][2]
+                    self.hin.append(E(M, self.np_[i]) if nxt_p > 0 else self.act[i])
+                self.wT.append(E(self.kp[i], self.np_[i]) if (i > 0 or need_dx) else None)
+                self.dz.append(E(M, self.np_[i]))
+                self.dzT.append(E(self.np_[i], Mp))
+                self.hinT.append(E(self.kp[i], Mp))
+                self.dW.append(E(self.np_[i], self.kp[i], dtype=f32))
+                self.db.append(E(self.np_[i], dtype=f32))
+                self.dh.append(E(M, self.kp[i]) if (i > 0 or need_dx) else None)
+            self.fwd = [engine.linear_plan(self.hin[i], self.w[i], self.b[i], self.act[i], relu=layers[i][1])
+                        for i in range(L)]
+            self.wgrad = [engine.linear_plan(self.dzT[i], self.hinT[i], None, self.dW[i]) for i in range(L)]
+            self.dgrad = [engine.linear_plan(self.dz[i], self.wT[i], None, self.dh[i]) if self.dh[i] is not None
+                          else None for i in range(L)]
+        self.version = None
+        self._lib = _lib
+
+    def _weights_version(self):
+        v = []
+        for lin, _, _ in self.layers:
+            v.append((lin.weight.data_ptr(), lin.weight._version))
+            if lin.bias is not None:
+                v.append((lin.bias.data_ptr(), lin.bias._version))
+        return tuple(v)
+
+    def refresh(self):
+        ver = self._weights_version()
+        if ver == self.version:
+            return
+        _lib = self._lib
+        L = _lib.lib()
+        for i, (lin, _, _) in enumerate(self.layers):
+            n, k = lin.out_features, lin.in_features
+            wsrc = lin.weight.detach().float().contiguous()
+            engine.cast_pad_bf16(wsrc, self.kp[i], out=self.w[i][:n])
+            if self.wT[i] is not None:
+                _lib.check(L.mmbs_cast_transpose_pad_bf16(_lib.ptr(wsrc), n, k, self.kp[i], self.np_[i],
+                                                          _lib.ptr(self.wT[i]), _lib.stream_ptr()),
+                           "mmbs_cast_transpose_pad_bf16")
+            if lin.bias is not None:
+                self.b[i][:n].copy_(lin.bias.detach())
+        self.version = ver
+
+    def forward(self, x, seed, training):
+        _lib = self._lib
+        L = _lib.lib()
+        self.refresh()
+        x = x.detach().float().contiguous()
+        ps = [(l[2] if training else 0.0) for l in self.layers]
+        self.ps = ps
+        _lib.check(L.mmbs_dropout_cast_bf16(_lib.ptr(x), 0, x.shape[1], _lib.ptr(self.hin[0]), self.m, x.shape[1],
+                                            self.kp[0], ps[0], seed, 0, _lib.stream_ptr()), "mmbs_dropout_cast_bf16")
+        for i in range(len(self.layers)):
+            self.fwd[i].run()
+            if i + 1 < len(self.layers) and self.hin[i + 1] is not self.act[i]:
+                _lib.check(L.mmbs_dropout_cast_bf16(_lib.ptr(self.act[i]), 1, self.np_[i], _lib.ptr(self.hin[i + 1]),
+                                                    self.m, self.np_[i], self.np_[i], ps[i + 1], seed, i + 1,
+                                                    _lib.stream_ptr()), "mmbs_dropout_cast_bf16")
+        return self.act[-1][:, :self.layers[-1][0].out_features].clone()
+
+    def backward(self, dy, seed):
+        """dy: fp32 [M, N_last].  Returns (dx or None, [dW_i views], [db_i views])."""
+        _lib = self._lib
+        L = _lib.lib()
+        g, g_bf16, g_stride = dy.detach().float().contiguous(), 0, dy.shape[1]
+        n_layers = len(self.layers)
+        for i in range(n_layers - 1, -1, -1):
+            lin, relu, _ = self.layers[i]
+            p_after = self.ps[i + 1] if i + 1 < n_layers else 0.0   # dropout applied to this layer's output
+            self.db[i].zero_()
+            _lib.check(L.mmbs_mlp_bwd_elementwise(_lib.ptr(g), g_bf16, g_stride, _lib.ptr(self.act[i]), self.np_[i],
+                                                  int(relu), p_after, seed, i + 1, self.m, lin.out_features,
+                                                  self.np_[i], self.mp, _lib.ptr(self.dz[i]), _lib.ptr(self.dzT[i]),
+                                                  _lib.ptr(self.db[i]), _lib.stream_ptr()), "mmbs_mlp_bwd_elementwise")
+            _lib.check(L.mmbs_transpose_bf16(_lib.ptr(self.hin[i]), self.kp[i], self.m, self.kp[i], self.mp,
+                                             _lib.ptr(self.hinT[i]), _lib.stream_ptr()), "mmbs_transpose_bf16")
+            self.wgrad[i].run()
+            if self.dgrad[i] is not None:
+                self.dgrad[i].run()
+                g, g_bf16, g_stride = self.dh[i], 1, self.kp[i]
+        dx = None
+        if self.need_dx:
+            k0 = self.layers[0][0].in_features
+            if self.ps[0] > 0:   # gradient through the input dropout: same Philox mask as the forward
+                _lib.check(L.mmbs_dropout_cast_bf16(_lib.ptr(self.dh[0]), 1, self.kp[0], _lib.ptr(self.dh[0]), self.m,
+                                                    self.kp[0], self.kp[0], self.ps[0], seed, 0, _lib.stream_ptr()),
+                           "mmbs_dropout_cast_bf16")
+            dx = self.dh[0][:, :k0].float()
+        dWs = [self.dW[i][:l[0].out_features, :l[0].in_features] for i, l in enumerate(self.layers)]
+        dbs = [self.db[i][:l[0].out_features] for i, l in enumerate(self.layers)]
+        return dx, dWs, dbs
+
+
+_TRAIN_ENGINES = {}
+
+
+class _MLPTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eng, training, *params):
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())   # CPU generator: torch.manual_seed reproducible
+        ctx.eng, ctx.seed = eng, seed
+        ctx.n_params = len(params)
+        ctx.has_bias = [l[0].bias is not None for l in eng.layers]
+        return eng.forward(x, seed, training)
+
+    @staticmethod
+    def backward(ctx, dy):
+        eng = ctx.eng
+        dx, dWs, dbs = eng.backward(dy, ctx.seed)
+        grads = []
+        for i, hb in enumerate(ctx.has_bias):
+            grads.append(dWs[i].clone())   # the engine's buffers are reused by the next step
+            if hb:
+                grads.append(dbs[i].clone())
+        return (dx, None, None) + tuple(grads)
+
+
+def _run_train(seq, layers, x):
+    need_dx = bool(x.requires_grad)
+    key = (id(seq), x.shape[0], x.device.index, need_dx)
+    eng = _TRAIN_ENGINES.get(key)
+    if eng is None or any(a[0] is not b[0] for a, b in zip(eng.layers, layers)):
+        eng = _MLPTrainEngine(layers, x.shape[0], x.device, need_dx)
+        if len(_TRAIN_ENGINES) > 32:
+            _TRAIN_ENGINES.clear()
+        _TRAIN_ENGINES[key] = eng
+    params = []
+    for lin, _, _ in layers:
+        params.append(lin.weight)
+        if lin.bias is not None:
+            params.append(lin.bias)
+    return _MLPTrainFn.apply(x, eng, seq.training, *params)
+
+
 _ENGINES = {}
 
 
@@ -108,11 +285,29 @@ def _fusable(seq, x):
     return layers
 
 
+def _trainable(seq, x):
+    """Plain MLP on a CUDA 2-D input with autograd active -> the fused training path."""
+    if os.environ.get("MMBS_DISABLE_KERNELS", "0") == "1" or os.environ.get("MMBS_MLP_TRAIN", "1") != "1":
+        return None
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 2 and torch.is_grad_enabled()):
+        return None
+    layers = _parse(seq, with_dropout=True)
+    if layers is None or layers[0][0].in_features != x.shape[1] or layers[-1][1]:
+        return None
+    for i in range(1, len(layers)):
+        if _pad(layers[i][0].in_features, 64) != _pad(layers[i - 1][0].out_features, 64):
+            return None
+    return layers
+
+
 def run_mlp(seq, x):
-    """Evaluate ``seq(x)``: fused kernels when the stack is a plain MLP in inference mode."""
+    """Evaluate ``seq(x)`` through the fused kernels when the stack is a plain MLP."""
     layers = _fusable(seq, x)
     if layers is None:
-        return seq(x)
+        tl = _trainable(seq, x)
+        if tl is not None:
+            return _run_train(seq, tl, x)
+        return nn.Sequential.forward(seq, x) if isinstance(seq, AcceleratedSequential) else seq(x)
     key = (id(seq), x.shape[0], x.device.index)
     eng = _ENGINES.get(key)
     if eng is None or any(a is not b[0] for a, b in zip([l[0] for l in eng.layers], layers)):
@@ -139,7 +334,4 @@ class AcceleratedSequential(nn.Sequential):
         return new
 
     def forward(self, x):
-        layers = _fusable(self, x)
-        if layers is None:
-            return nn.Sequential.forward(self, x)
         return run_mlp(self, x)
