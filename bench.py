@@ -267,9 +267,18 @@ def run_ours(args):
         # per-kernel device time of one step (events around every launch of the conv kernel)
         conv_ms = conv_kernel_time(torch, model, xs[0])
         achieved = B * GFLOP_PER_PATCH / (conv_ms * 1e-3) / 1e3 if conv_ms else None  # TFLOP/s
-        roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, 53 launches/chunk)",
+        traffic = None   # dram bytes per launch of the conv kernel, from the committed ncu capture
+        tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("conv_dram_bytes_per_launch")
+        roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, 53 launches/step)",
                     "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s",
-                    "frac": (achieved / peaks["tensor"]) if achieved else None, "traffic": None,
+                    "frac": (achieved / peaks["tensor"]) if achieved else None, "traffic": traffic,
+                    "traffic_note": "ncu dram read+write bytes per conv launch (mean of the 53 launches of one "
+                                    "512-patch step, profiles/r01_conv_traffic.json); algorithmic activation I/O "
+                                    "is 54.6 MB/patch = 527 MB per launch",
+                    "flops_per_launch": B * GFLOP_PER_PATCH * 1e9 / 53,
                     "peak_source": peaks["source"] + " (sustained bf16; burst %.1f)" % peaks["tensor_burst"],
                     "conv_ms_per_step": conv_ms}
         cpu = time_cpu(2, 1)

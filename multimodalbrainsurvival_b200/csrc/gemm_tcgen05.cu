@@ -16,6 +16,7 @@
 //   warps 2-5 = epilogue (tcgen05.ld -> scale/shift (+residual) (+ReLU) -> bf16/fp32 store).
 // * smem ring of STAGES x (A 16 KB + B N_TILE*128 B), 128-byte swizzle end to end.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -270,6 +271,11 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
+  // prefetch) overlapped the tail of the previous kernel in the stream; its results are visible after
+  // the wait.  The next kernel may start its own prologue as soon as SMs free up.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ===== TMA producer (whole warp stays converged; one elected lane issues): runs ahead across tiles =====
@@ -569,8 +575,23 @@ static int launch_conv(const mmbs_conv_plan* plan, cudaStream_t stream) {
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYNAMIC));
     configured = true;
   }
-  conv_gemm_kernel<N_TILE, STAGES, NSTG, A_STAGE, RES_BYTES><<<plan->grid, GM_THREADS, L::DYNAMIC, stream>>>(plan->p);
-  MMBS_LAUNCH_CHECK();
+  static const bool use_pdl = []() {
+    const char* e = getenv("MMBS_PDL");
+    return !(e && e[0] == '0');
+  }();
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(plan->grid);
+  cfg.blockDim = dim3(GM_THREADS);
+  cfg.dynamicSmemBytes = L::DYNAMIC;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  MMBS_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N_TILE, STAGES, NSTG, A_STAGE, RES_BYTES>, plan->p));
+  count_launch();
   return MMBS_OK;
 }
 
