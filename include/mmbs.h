@@ -140,6 +140,10 @@ int mmbs_linear_plan_create(const void* x_bf16, const void* w_bf16, const float*
  *   [B,116,116,16] (channel = (row parity, col parity, rgb), 12 used) so that the
  *   7x7/2 stem conv (resnet.py:97,152) becomes 4 K=64 taps of the GEMM kernel. */
 int mmbs_stem_pack_input(const float* x_nchw, void* out_s2d_bf16, int64_t batch, void* stream);
+/* same from raw uint8 pixels: ((x/255 - mean[c]) / std[c]) = ToTensor()+Normalize() of the reference's
+ * transforms (1_HistoPathology/4_HistoPath_extractfeatures.py:133-137); mean/std are HOST arrays of 3 */
+int mmbs_stem_pack_input_u8(const uint8_t* x_nchw, void* out_s2d_bf16, int64_t batch, const float* mean_host,
+                            const float* std_host, void* stream);
 /* stem weight: [64,3,7,7] fp32 -> bf16 [64, 4*64] in the matching (a, b, p, q, c) order */
 int mmbs_stem_pack_weight(const float* w_oihw, void* out_bf16, void* stream);
 /* conv weight OIHW fp32 -> [O][kh][kw][I] bf16 */

@@ -53,6 +53,47 @@ __global__ void __launch_bounds__(128) stem_pack_input_kernel(const float* __res
   out[pix * 2 + 1] = o1;
 }
 
+// ---- stem input from raw pixels: uint8 [B,3,224,224] -> ((x/255 - mean[c]) / std[c]) -> the same
+// space-to-depth bf16 buffer.  This is ToTensor()+Normalize() of the reference's transforms
+// (/root/reference/1_HistoPathology/4_HistoPath_extractfeatures.py:133-137) done on the device, so
+// the host ships 1 byte per value instead of 4.
+__global__ void __launch_bounds__(128) stem_pack_input_u8_kernel(const uint8_t* __restrict__ x,
+                                                                 uint4* __restrict__ out, int64_t batch,
+                                                                 float m0, float m1, float m2, float i0, float i1,
+                                                                 float i2) {
+  const int64_t pix = int64_t(blockIdx.x) * 128 + threadIdx.x;
+  const int64_t total = batch * 116 * 116;
+  if (pix >= total) return;
+  const int s = int(pix % 116), r = int((pix / 116) % 116);
+  const int64_t n = pix / (116 * 116);
+  const float mean[3] = {m0, m1, m2}, inv[3] = {i0, i1, i2};
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = 0.f;
+  const int col = 2 * (s - 2);
+  if (col >= 0 && col < 224) {
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const int row = 2 * (r - 2) + p;
+      if (row >= 0 && row < 224) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const uchar2 t = __ldg(reinterpret_cast<const uchar2*>(x + ((n * 3 + c) * 224 + row) * 224 + col));
+          v[(p * 2 + 0) * 3 + c] = (float(t.x) * (1.0f / 255.0f) - mean[c]) * inv[c];
+          v[(p * 2 + 1) * 3 + c] = (float(t.y) * (1.0f / 255.0f) - mean[c]) * inv[c];
+        }
+      }
+    }
+  }
+  uint4 o0, o1;
+  o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
+  o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
+  o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
+  o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+  out[pix * 2] = o0;
+  out[pix * 2 + 1] = o1;
+}
+
 // ---- stem weight: [64,3,7,7] fp32 -> [64][a(4)][b(4)][(p*2+q)*3+c (16)] bf16,
 // kh = 2a+p-1, kw = 2b+q-1 (the 7x7 kernel zero-extended to 8x8 at the top/left).
 __global__ void stem_pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
@@ -187,6 +228,19 @@ extern "C" int mmbs_stem_pack_input(const float* x_nchw, void* out, int64_t batc
                "mmbs_stem_pack_input: misaligned pointer");
   stem_pack_input_kernel<<<blocks_for(batch * 116 * 116, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       x_nchw, static_cast<uint4*>(out), batch);
+  MMBS_LAUNCH_CHECK();
+  return MMBS_OK;
+}
+
+extern "C" int mmbs_stem_pack_input_u8(const uint8_t* x_nchw, void* out, int64_t batch, const float* mean_host,
+                                       const float* std_host, void* stream) {
+  if (int rc = mmbs_device_check()) return rc;
+  MMBS_REQUIRE(x_nchw && out && batch > 0 && mean_host && std_host, "mmbs_stem_pack_input_u8: bad argument");
+  MMBS_REQUIRE(reinterpret_cast<uintptr_t>(x_nchw) % 2 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0,
+               "mmbs_stem_pack_input_u8: misaligned pointer");
+  stem_pack_input_u8_kernel<<<blocks_for(batch * 116 * 116, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_nchw, static_cast<uint4*>(out), batch, mean_host[0], mean_host[1], mean_host[2], 1.0f / std_host[0],
+      1.0f / std_host[1], 1.0f / std_host[2]);
   MMBS_LAUNCH_CHECK();
   return MMBS_OK;
 }

@@ -263,12 +263,20 @@ class ResNetEngine:
         self._weights_version = self.weights_version(net)
         self.n_kernels = len(self._steps) + 2
 
-    def run_chunk(self, x_nchw: torch.Tensor, out: torch.Tensor):
-        """x_nchw: fp32 [chunk,3,224,224] contiguous; out: fp32 [chunk,2048]."""
+    def run_chunk(self, x_nchw: torch.Tensor, out: torch.Tensor,
+                  norm=((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))):
+        """x_nchw: fp32 (already normalised) or uint8 (raw pixels) [chunk,3,224,224] contiguous;
+        out: fp32 [chunk,2048]."""
         L = _lib.lib()
         B = self.chunk
-        _lib.check(L.mmbs_stem_pack_input(_lib.ptr(x_nchw), _lib.ptr(self.x_s2d), B, _lib.stream_ptr()),
-                   "mmbs_stem_pack_input")
+        if x_nchw.dtype == torch.uint8:   # raw pixels: ToTensor()+Normalize() fused into the pack kernel
+            m = (ctypes.c_float * 3)(*norm[0])
+            sd = (ctypes.c_float * 3)(*norm[1])
+            _lib.check(L.mmbs_stem_pack_input_u8(_lib.ptr(x_nchw), _lib.ptr(self.x_s2d), B, m, sd, _lib.stream_ptr()),
+                       "mmbs_stem_pack_input_u8")
+        else:
+            _lib.check(L.mmbs_stem_pack_input(_lib.ptr(x_nchw), _lib.ptr(self.x_s2d), B, _lib.stream_ptr()),
+                       "mmbs_stem_pack_input")
         self._run_body()
         if self.final.dtype == torch.float32:
             _lib.check(L.mmbs_avgpool_global_f32(_lib.ptr(self.final), _lib.ptr(out), B, 49, 2048,

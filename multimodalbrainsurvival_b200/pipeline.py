@@ -3,39 +3,57 @@
 The reference moves every batch with a blocking ``.to(device)`` and reads features back with
 ``.cpu()`` (/root/reference/1_HistoPathology/4_HistoPath_extractfeatures.py:60-71).
 ``prefetch_to_device`` overlaps the H2D copy of batch i+1 with the kernels of batch i on a
-side stream (pinned staging buffers), which is what keeps the B200 busy at PCIe rates."""
+side stream, through a fixed ring of device staging buffers (no allocation, and therefore no
+implicit synchronisation, inside the loop)."""
 from __future__ import annotations
 
 import torch
 
 
 def prefetch_to_device(batches, device, depth: int = 2):
-    """Iterate over host tensors, yielding device tensors whose copy was issued one step ahead."""
+    """Iterate over host tensors, yielding device tensors whose copy was issued ``depth`` steps
+    ahead.  A yielded tensor is only valid until the next one is requested (its buffer is reused)."""
     dev = torch.device(device)
     copy_stream = torch.cuda.Stream(device=dev)
-    queue = []
+    slots = depth + 1
+    ring = [None] * slots          # device staging buffers
+    ready = [None] * slots         # copy finished (recorded on the copy stream)
+    released = [None] * slots      # consumer finished with the buffer (recorded on its stream)
     it = iter(batches)
+    head = 0                       # next slot to fill
+    pending = []
 
     def issue():
+        nonlocal head
         try:
             host = next(it)
         except StopIteration:
             return False
         if not host.is_pinned():
             host = host.pin_memory()
+        k = head
+        head = (head + 1) % slots
+        if ring[k] is None or ring[k].shape != host.shape or ring[k].dtype != host.dtype:
+            ring[k] = torch.empty(host.shape, dtype=host.dtype, device=dev)
         with torch.cuda.stream(copy_stream):
-            d = host.to(dev, non_blocking=True)
+            if released[k] is not None:
+                copy_stream.wait_event(released[k])
+            ring[k].copy_(host, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        queue.append((d, ev, host))
+        ready[k] = ev
+        pending.append((k, host))   # keep the pinned source alive until its copy is consumed
         return True
 
     for _ in range(depth):
         if not issue():
             break
-    while queue:
-        d, ev, _host = queue.pop(0)
-        torch.cuda.current_stream(dev).wait_event(ev)
-        d.record_stream(torch.cuda.current_stream(dev))
+    while pending:
+        k, _host = pending.pop(0)
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ready[k])
         issue()
-        yield d
+        yield ring[k]
+        rel = torch.cuda.Event()
+        rel.record(torch.cuda.current_stream(dev))
+        released[k] = rel

@@ -137,6 +137,17 @@ class _Trunk(nn.Module):
 
 class ResNet(_Trunk):
     _in_channels = 3
+    # uint8 inputs (raw pixels) are normalised on the device with the reference's transform constants
+    # (Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225]), 4_HistoPath_extractfeatures.py:133-137)
+    input_mean = (0.485, 0.456, 0.406)
+    input_std = (0.229, 0.224, 0.225)
+
+    def forward_extract(self, x):
+        if x.dtype == torch.uint8 and not self._can_accelerate(x):
+            mean = torch.tensor(self.input_mean, device=x.device).view(1, 3, 1, 1)
+            std = torch.tensor(self.input_std, device=x.device).view(1, 3, 1, 1)
+            x = (x.float() / 255.0 - mean) / std
+        return super().forward_extract(x)
 
     def _can_accelerate(self, x):
         if os.environ.get("MMBS_DISABLE_KERNELS", "0") == "1":
@@ -148,7 +159,7 @@ class ResNet(_Trunk):
     def _features_b200(self, x):
         from . import engine
         B = x.shape[0]
-        x = x.float().contiguous()
+        x = x.contiguous() if x.dtype == torch.uint8 else x.float().contiguous()
         out = torch.empty((B, 2048), dtype=torch.float32, device=x.device)
         done = 0
         while done < B:
@@ -159,7 +170,7 @@ class ResNet(_Trunk):
             if eng is None or eng._weights_version != ver:
                 eng = engine.ResNetEngine(self, chunk)
                 self._engines[key] = eng
-            eng.run_chunk(x[done:done + chunk], out[done:done + chunk])
+            eng.run_chunk(x[done:done + chunk], out[done:done + chunk], norm=(self.input_mean, self.input_std))
             done += chunk
         return out
 

@@ -67,3 +67,20 @@ def test_aggregation_model_extract_and_chunking(monkeypatch):
     ref = resnet_oracle.forward_extract(sd, x.reshape(-1, 3, 224, 224).cpu(), emulate_bf16=True)
     ref = ref.view(5, 2, 2048).mean(1)
     assert float((feats.cpu() - ref).norm() / ref.norm()) < 3e-3
+
+
+def test_uint8_pixels_are_normalised_on_device():
+    """uint8 patches through extract == ToTensor()+Normalize() on the host followed by the fp32 path."""
+    sd = resnet_oracle.init_state_dict(seed=13)
+    net = _model(sd)
+    g = torch.Generator().manual_seed(2)
+    xu = torch.randint(0, 256, (3, 3, 224, 224), dtype=torch.uint8, generator=g)
+    mean = torch.tensor(net.input_mean).view(1, 3, 1, 1)
+    std = torch.tensor(net.input_std).view(1, 3, 1, 1)
+    xf = (xu.float() / 255.0 - mean) / std
+    with torch.no_grad():
+        fu = net.forward_extract(xu.cuda())
+        ff = net.forward_extract(xf.cuda())
+    assert float((fu - ff).abs().max()) <= 2e-3 * float(ff.abs().max())
+    ref = resnet_oracle.forward_extract(sd, xf, emulate_bf16=True)
+    assert float((fu.cpu() - ref).norm() / ref.norm()) < 3e-3
