@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <new>
 
 #include "common.cuh"
@@ -650,7 +651,8 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
   MMBS_REQUIRE(reinterpret_cast<uintptr_t>(d->in) % 16 == 0 && reinterpret_cast<uintptr_t>(d->weight) % 16 == 0 &&
                    reinterpret_cast<uintptr_t>(d->out) % 16 == 0,
                "conv plan: pointers must be 16-byte aligned");
-  mmbs_conv_plan* plan = new (std::nothrow) mmbs_conv_plan();
+  std::unique_ptr<mmbs_conv_plan> guard(new (std::nothrow) mmbs_conv_plan());   // freed on every error return
+  mmbs_conv_plan* plan = guard.get();
   MMBS_REQUIRE(plan, "conv plan: out of host memory");
   ConvParams& p = plan->p;
   std::memset(&p, 0, sizeof(p));
@@ -703,7 +705,6 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
   if (resident && forced_n_tile == 64 && (stem_mode || (want_halo && k == 3 && s == 1))) halo = true;
   if (want_halo && !halo) {
     set_error("conv plan: halo weight order requested for an ineligible conv (k=%d s=%d c_out=%d)", k, s, d->c_out);
-    delete plan;
     return MMBS_ERR_ARG;
   }
   p.taps_per_stage = 1; p.tap_row_bytes = 0; p.a_tx_bytes = GM_A_BYTES;
@@ -787,11 +788,8 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
       rc = encode_map(&p.res_map, d->residual, 4, dims, str, box_out);
     }
   }
-  if (rc) {
-    delete plan;
-    return rc;
-  }
-  *out = plan;
+  if (rc) return rc;
+  *out = guard.release();
   return MMBS_OK;
 }
 

@@ -233,7 +233,10 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_onesweep_kernel(
 #pragma unroll
       for (int u = 0; u < RS_LOOKBACK; ++u) {
         if (!done) {
-          while ((v[u] & RS_FLAG_MASK) == 0) v[u] = ld_volatile_u32(lookback + (p - u) * RS_RADIX + tid);
+          while ((v[u] & RS_FLAG_MASK) == 0) {  // predecessor not published yet: back off instead of hammering L2
+            __nanosleep(RS_SPIN_NS);
+            v[u] = ld_volatile_u32(lookback + (p - u) * RS_RADIX + tid);
+          }
           excl += v[u] & RS_VALUE_MASK;
           if (v[u] & RS_FLAG_INCL) done = true;
         }

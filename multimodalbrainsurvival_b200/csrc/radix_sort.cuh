@@ -17,7 +17,10 @@ constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 pairs per tile
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_RADIX = 256;
-constexpr int RS_LOOKBACK = 8;  // predecessor tiles inspected per look-back round trip
+constexpr int RS_LOOKBACK = 8;
+#ifndef RS_SPIN_NS
+#define RS_SPIN_NS 200
+#endif  // predecessor tiles inspected per look-back round trip
 constexpr uint32_t RS_FLAG_AGG = 1u << 30;
 constexpr uint32_t RS_FLAG_INCL = 2u << 30;
 constexpr uint32_t RS_FLAG_MASK = 3u << 30;

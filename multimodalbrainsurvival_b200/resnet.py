@@ -168,6 +168,9 @@ class ResNet(_Trunk):
             eng = self._engines.get(key)
             ver = engine.ResNetEngine.weights_version(self)
             if eng is None or eng._weights_version != ver:
+                self._engines.pop(key, None)
+                while len(self._engines) >= 3:      # engines own GBs of activation buffers: keep a few
+                    self._engines.pop(next(iter(self._engines)))
                 eng = engine.ResNetEngine(self, chunk)
                 self._engines[key] = eng
             eng.run_chunk(x[done:done + chunk], out[done:done + chunk], norm=(self.input_mean, self.input_std))
