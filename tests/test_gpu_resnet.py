@@ -84,3 +84,27 @@ def test_uint8_pixels_are_normalised_on_device():
     assert float((fu - ff).abs().max()) <= 2e-3 * float(ff.abs().max())
     ref = resnet_oracle.forward_extract(sd, xf, emulate_bf16=True)
     assert float((fu.cpu() - ref).norm() / ref.norm()) < 3e-3
+
+
+def test_full_batch_properties_512():
+    """BASELINE batch (512 patches): size-independent properties of the kernel path - run-to-run
+    determinism (bit-exact), chunk invariance and patch-permutation equivariance."""
+    import os
+    sd = resnet_oracle.init_state_dict(seed=21)
+    net = _model(sd)
+    torch.manual_seed(4)
+    x = torch.randn(512, 3, 224, 224, device="cuda")
+    with torch.no_grad():
+        f1 = net.forward_extract(x)
+        f2 = net.forward_extract(x)
+        assert torch.equal(f1, f2)                                     # deterministic
+        perm = torch.randperm(512, device="cuda")
+        fp = net.forward_extract(x[perm])
+        assert float((fp - f1[perm]).abs().max()) <= 1e-3 * float(f1.abs().max())
+        os.environ["MMBS_RESNET_CHUNK"] = "128"
+        try:
+            f3 = net.forward_extract(x)
+        finally:
+            del os.environ["MMBS_RESNET_CHUNK"]
+    assert float((f3 - f1).abs().max()) <= 1e-3 * float(f1.abs().max())
+    assert torch.isfinite(f1).all() and float(f1.abs().max()) > 0
