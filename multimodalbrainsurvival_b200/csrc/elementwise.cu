@@ -135,18 +135,19 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
                                    *reinterpret_cast<const __nv_bfloat162*>(&b));
   return *reinterpret_cast<const uint32_t*>(&r);
 }
+// grid = (ceil(ow*c8 / 256), oh, batch): no integer divisions on the hot path
 __global__ void __launch_bounds__(256) maxpool_3x3s2_kernel(const uint4* __restrict__ in,
                                                             uint4* __restrict__ out, int64_t batch, int h,
-                                                            int w, int c8) {
+                                                            int w, int c8, int c8_shift) {
   const int oh = (h + 2 - 3) / 2 + 1, ow = (w + 2 - 3) / 2 + 1;
-  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
-  const int64_t total = batch * oh * ow * c8;
-  if (i >= total) return;
-  const int g = int(i % c8);
-  const int x = int((i / c8) % ow), y = int((i / (int64_t(c8) * ow)) % oh);
-  const int64_t n = i / (int64_t(c8) * ow * oh);
+  const int xc = blockIdx.x * 256 + threadIdx.x;      // (x, channel group) flattened, c8 = 1 << c8_shift
+  if (xc >= ow * c8) return;
+  const int g = xc & (c8 - 1), x = xc >> c8_shift;
+  const int y = blockIdx.y;
+  const int64_t n = blockIdx.z;
   const uint32_t NEG = 0xff80ff80u;  // (-inf, -inf) in bf16
   uint4 m = make_uint4(NEG, NEG, NEG, NEG);
+  const uint4* base = in + n * int64_t(h) * w * c8 + g;
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy) {
     const int iy = 2 * y - 1 + dy;
@@ -155,12 +156,12 @@ __global__ void __launch_bounds__(256) maxpool_3x3s2_kernel(const uint4* __restr
     for (int dx = 0; dx < 3; ++dx) {
       const int ix = 2 * x - 1 + dx;
       if (ix < 0 || ix >= w) continue;
-      const uint4 v = __ldg(in + ((n * h + iy) * w + ix) * c8 + g);
+      const uint4 v = __ldg(base + (int64_t(iy) * w + ix) * c8);
       m.x = max_bf16x2(m.x, v.x); m.y = max_bf16x2(m.y, v.y);
       m.z = max_bf16x2(m.z, v.z); m.w = max_bf16x2(m.w, v.w);
     }
   }
-  out[i] = m;
+  out[((n * oh + y) * int64_t(ow) + x) * c8 + g] = m;
 }
 
 // ---- AvgPool2d(7) + flatten: [B, hw, C] (bf16 or fp32) -> fp32 [B, C]
@@ -278,8 +279,13 @@ extern "C" int mmbs_maxpool_3x3s2(const void* in, void* out, int64_t batch, int6
   if (int rc = mmbs_device_check()) return rc;
   MMBS_REQUIRE(in && out && batch > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "mmbs_maxpool_3x3s2: bad argument");
   const int64_t oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;
-  maxpool_3x3s2_kernel<<<blocks_for(batch * oh * ow * (c / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(in), static_cast<uint4*>(out), batch, int(h), int(w), int(c / 8));
+  const int c8 = int(c / 8);
+  int shift = 0;
+  while ((1 << shift) < c8) ++shift;
+  MMBS_REQUIRE((1 << shift) == c8 && batch <= 65535 && oh <= 65535, "mmbs_maxpool_3x3s2: c/8 must be a power of two");
+  dim3 grid(unsigned(ceil_div(ow * c8, 256)), unsigned(oh), unsigned(batch));
+  maxpool_3x3s2_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(in), static_cast<uint4*>(out), batch, int(h), int(w), c8, shift);
   MMBS_LAUNCH_CHECK();
   return MMBS_OK;
 }
