@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(RS_RADIX) rs_digit_base_kernel(const uint32_t*
 }
 
 // ---------------------------------------------------------------- one radix pass
-__global__ void __launch_bounds__(RS_THREADS, 4) rs_onesweep_kernel(
+__global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) rs_onesweep_kernel(
     const void* __restrict__ src, int kind, const uint32_t* __restrict__ keys_in,
     const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, int64_t n, int shift, const uint32_t* __restrict__ digit_base,
@@ -125,18 +125,26 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_onesweep_kernel(
   __shared__ uint32_t s_warp_hist[RS_WARPS][RS_RADIX];
   __shared__ uint32_t s_digit_start[RS_RADIX];
   __shared__ uint32_t s_global_base[RS_RADIX];
-  __shared__ uint32_t s_keys[RS_TILE];
-  __shared__ uint32_t s_vals[RS_TILE];
-  __shared__ uint32_t s_wsum[RS_WARPS];
+  __shared__ uint32_t s_wsum[RS_RADIX / 32];
   __shared__ uint32_t s_tile;
+  extern __shared__ uint32_t s_dyn[];   // [RS_TILE] keys | [RS_TILE] payloads, in digit order
+  uint32_t* s_keys = s_dyn;
+  uint32_t* s_vals = s_dyn + RS_TILE;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // tiles are numbered in the order blocks start running: a tile only ever waits
-  // on tiles that already hold an SM, so the look-back cannot deadlock.
-  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+  const int64_t num_tiles = (n + RS_TILE - 1) / RS_TILE;
+  // Persistent blocks; tiles are handed out by an atomic ticket in the order blocks ask for them: a
+  // tile only ever waits on tiles whose ticket is already held by a running block, so the look-back
+  // cannot deadlock.  The ticket of the NEXT tile is requested one iteration ahead (latency hidden).
+  uint32_t next_ticket = 0;
+  if (tid == 0) next_ticket = atomicAdd(tile_counter, 1u);
+  while (true) {
+  if (tid == 0) s_tile = next_ticket;
   for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&s_warp_hist[0][0])[i] = 0;
   __syncthreads();
   const int64_t tile = s_tile;
+  if (tile >= num_tiles) break;
+  if (RS_PERSISTENT && tid == 0) next_ticket = atomicAdd(tile_counter, 1u);
   const int64_t tile_base = tile * RS_TILE;
   const int n_valid = int(min((long long)RS_TILE, (long long)(n - tile_base)));
 
@@ -148,21 +156,15 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_onesweep_kernel(
     const int64_t g = tile_base + it;
     if (it < n_valid) {
       key[j] = first ? rs_load_key(src, kind, g) : __ldg(keys_in + g);
-      val[j] = first ? uint32_t(g) : __ldg(vals_in + g);
-      if (first && status != nullptr) {
-        // carry the (binary) event indicator in bit 31 of the payload: the scans then never
-        // gather `status` through the permutation
-        const float st = __ldg(status + g);
-        if (st != 0.0f) val[j] |= 0x80000000u;
-        if (st != 0.0f && st != 1.0f) nonbinary = true;
-      }
+      // the payload (or, in the first pass, the status it is built from) is not needed before the
+      // shared-memory scatter: its load stays in flight during the whole ranking / look-back phase
+      val[j] = first ? ((status != nullptr) ? __float_as_uint(__ldg(status + g)) : 0u) : __ldg(vals_in + g);
     } else {
       key[j] = 0xffffffffu;  // padding sorts to the very end of the (last) tile
       val[j] = 0xffffffffu;
     }
   }
 
-  if (nonbinary) atomicOr(nonbinary_flag, 1);
   // stable rank of every key among equal digits inside its warp.  The peer mask is built
   // from 8 ballots (one per digit bit): MATCH.ANY issues ~50x slower than VOTE on sm_100.
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -194,35 +196,67 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_onesweep_kernel(
   }
   __syncthreads();
 
-  // thread `tid` owns digit `tid`: exclusive scan over warps, tile total
+  // thread `tid` < 256 owns digit `tid`: exclusive scan over warps, tile total
+  const bool digit_thread = tid < RS_RADIX;
   uint32_t total = 0;
-#pragma unroll
-  for (int w = 0; w < RS_WARPS; ++w) {
-    const uint32_t c = s_warp_hist[w][tid];
-    s_warp_hist[w][tid] = total;
-    total += c;
-  }
   uint32_t* lb = lookback + tile * RS_RADIX;
-  st_volatile_u32(lb + tid, (tile == 0 ? RS_FLAG_INCL : RS_FLAG_AGG) | total);
-
-  // tile-local exclusive scan over digits
-  uint32_t incl = total;
+  uint32_t incl = 0;
+  if (digit_thread) {
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
+    for (int w = 0; w < RS_WARPS; ++w) {
+      const uint32_t c = s_warp_hist[w][tid];
+      s_warp_hist[w][tid] = total;
+      total += c;
+    }
+    st_volatile_u32(lb + tid, (tile == 0 ? RS_FLAG_INCL : RS_FLAG_AGG) | total);
+    // tile-local exclusive scan over digits
+    incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
   }
-  if (lane == 31) s_wsum[warp] = incl;
   __syncthreads();
-  uint32_t woff = 0;
-  for (int w = 0; w < warp; ++w) woff += s_wsum[w];
-  s_digit_start[tid] = woff + incl - total;
+  if (digit_thread) {
+    uint32_t woff = 0;
+    for (int w = 0; w < warp; ++w) woff += s_wsum[w];
+    s_digit_start[tid] = woff + incl - total;
+  }
 
+  __syncthreads();   // s_digit_start complete
+  // bring the tile into digit order in shared memory, then stream it out: equal
+  // digits leave as contiguous runs (coalesced stores)
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    const uint32_t d = (key[j] >> shift) & 0xffu;
+    const uint32_t pos = s_digit_start[d] + s_warp_hist[warp][d] + rank[j];
+    uint32_t v = val[j];
+    if (first) {
+      // payload = original index; the (binary) event indicator rides in bit 31 so that the scans
+      // never gather `status` through the permutation
+      const int it = warp * (32 * RS_ITEMS) + j * 32 + lane;
+      const float st = __uint_as_float(v);
+      v = uint32_t(tile_base + it);
+      if (status != nullptr && it < n_valid) {
+        if (st != 0.0f) v |= 0x80000000u;
+        if (st != 0.0f && st != 1.0f) nonbinary = true;
+      }
+    }
+    s_keys[pos] = key[j];
+    s_vals[pos] = v;
+  }
+  if (nonbinary) atomicOr(nonbinary_flag, 1);
+  // (no barrier here: the look-back below ends with one)
+
+  // The tile aggregate was published before the scatter above, so successors are not held up; by
+  // now the predecessors have had time to publish theirs and the look-back rarely has to wait.
   // decoupled look-back: sum this digit's counts over all earlier tiles
   // (RS_LOOKBACK predecessors are fetched per round trip: the loads of a round are independent,
   //  so the inclusive-prefix wavefront advances up to RS_LOOKBACK tiles per L2 latency)
   uint32_t excl = 0;
-  if (tile > 0) {
+  if (digit_thread && tile > 0) {
     int64_t p = tile - 1;
     bool done = false;
     while (!done) {
@@ -245,26 +279,24 @@ __global__ void __launch_bounds__(RS_THREADS, 4) rs_onesweep_kernel(
     }
     st_volatile_u32(lb + tid, RS_FLAG_INCL | (excl + total));
   }
-  s_global_base[tid] = digit_base[tid] + excl;
+  if (digit_thread) s_global_base[tid] = digit_base[tid] + excl;
   __syncthreads();
 
-  // bring the tile into digit order in shared memory, then stream it out: equal
-  // digits leave as contiguous runs (coalesced stores)
-#pragma unroll
-  for (int j = 0; j < RS_ITEMS; ++j) {
-    const uint32_t d = (key[j] >> shift) & 0xffu;
-    const uint32_t pos = s_digit_start[d] + s_warp_hist[warp][d] + rank[j];
-    s_keys[pos] = key[j];
-    s_vals[pos] = val[j];
+  constexpr int kUnrollOut = RS_UNROLL_OUT;
+#pragma unroll kUnrollOut
+  for (int j = 0; j < RS_ITEMS; ++j) {   // unrolled: the shared-memory reads of a thread overlap
+    const int i = j * RS_THREADS + tid;
+    if (i < n_valid) {
+      const uint32_t k = s_keys[i];
+      const uint32_t d = (k >> shift) & 0xffu;
+      const uint32_t dst = s_global_base[d] + (uint32_t(i) - s_digit_start[d]);
+      if (!last) keys_out[dst] = k;
+      vals_out[dst] = s_vals[i];
+    }
   }
-  __syncthreads();
-  for (int i = tid; i < n_valid; i += RS_THREADS) {
-    const uint32_t k = s_keys[i];
-    const uint32_t d = (k >> shift) & 0xffu;
-    const uint32_t dst = s_global_base[d] + (uint32_t(i) - s_digit_start[d]);
-    if (!last) keys_out[dst] = k;
-    vals_out[dst] = s_vals[i];
-  }
+  if (!RS_PERSISTENT) break;
+  __syncthreads();   // shared memory is reused by the next tile
+  }  // persistent tile loop
 }
 
 int rs_histogram_enqueue(const void* src, KeyKind kind, int64_t n, int num_passes, uint32_t* hist,
@@ -286,13 +318,20 @@ int rs_sort_enqueue(const void* src, KeyKind kind, int64_t n, int num_passes,
   MMBS_REQUIRE(n >= 1 && n <= RS_MAX_N, "radix sort: n=%lld out of range [1, 2^30)", (long long)n);
   MMBS_REQUIRE(num_passes >= 1 && num_passes <= 4, "radix sort: num_passes=%d", num_passes);
   const int64_t tiles = rs_tiles(n);
+  static bool configured = false;
+  if (!configured) {
+    MMBS_CUDA_TRY(cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_DYN_SMEM));
+    configured = true;
+  }
+  const unsigned grid = RS_PERSISTENT ? unsigned(std::min<int64_t>(tiles, int64_t(sm_count()) * RS_BLOCKS_PER_SM))
+                                      : unsigned(tiles);
   const uint32_t* kin = nullptr;
   const uint32_t* vin = nullptr;
   for (int p = 0; p < num_passes; ++p) {
     const bool first = (p == 0), last = (p == num_passes - 1);
     uint32_t* kout = (p & 1) ? ws.keys_b : ws.keys_a;
     uint32_t* vout = last ? reinterpret_cast<uint32_t*>(perm_out) : ((p & 1) ? ws.vals_b : ws.vals_a);
-    rs_onesweep_kernel<<<unsigned(tiles), RS_THREADS, 0, stream>>>(
+    rs_onesweep_kernel<<<grid, RS_THREADS, RS_DYN_SMEM, stream>>>(
         src, int(kind), kin, vin, kout, vout, n, 8 * p, ws.digit_base + p * RS_RADIX,
         ws.lookback + int64_t(p) * tiles * RS_RADIX, ws.counters + p, first ? 1 : 0, last ? 1 : 0,
         first ? status : nullptr, nonbinary_flag);

@@ -12,12 +12,25 @@
 
 namespace mmbs {
 
-constexpr int RS_THREADS = 256;
+// 8192 pairs per tile: with 256 digits a tile leaves ~32 keys = one full 128-byte line per digit run
+// (4096-pair tiles wrote half lines and ran ~1.6x slower per pass)
+#ifndef RS_THREADS_DEF
+#define RS_THREADS_DEF 512
+#endif
+constexpr int RS_THREADS = RS_THREADS_DEF;
 constexpr int RS_ITEMS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 pairs per tile
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+constexpr int RS_BLOCKS_PER_SM = 1024 / RS_THREADS;   // 64 registers per thread
+constexpr int RS_DYN_SMEM = 2 * RS_TILE * 4;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_RADIX = 256;
 constexpr int RS_LOOKBACK = 8;
+#ifndef RS_PERSISTENT
+#define RS_PERSISTENT 0
+#endif
+#ifndef RS_UNROLL_OUT
+#define RS_UNROLL_OUT 4
+#endif
 #ifndef RS_SPIN_NS
 #define RS_SPIN_NS 200
 #endif  // predecessor tiles inspected per look-back round trip
