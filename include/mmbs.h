@@ -123,6 +123,8 @@ typedef struct {
   const float* shift;     /* [c_out] or NULL (=0) */
   const void* residual;   /* bf16 NHWC like out, or NULL */
   void* out;              /* NHWC [B, out_h, out_w, c_out] */
+  float* stats;           /* optional [2][c_out] fp32, pre-zeroed: += per-channel sum / sum of squares of the
+                           * (raw, bf16) output - the batch statistics of a training-mode BatchNorm2d */
 } mmbs_conv_desc;
 
 int mmbs_conv_plan_create(const mmbs_conv_desc* desc, mmbs_conv_plan** plan_out);
@@ -182,6 +184,55 @@ int mmbs_transpose_bf16(const void* in_bf16, int64_t in_stride, int64_t rows, in
                         void* out_bf16, void* stream);
 int mmbs_cast_transpose_pad_bf16(const float* in, int64_t n, int64_t k, int64_t k_padded, int64_t n_padded,
                                  void* out_bf16, void* stream);
+
+/* ------------------------------------------------ training-mode ResNet trunk (HBM-bound glue)
+ * model.train() semantics of Bottleneck.forward (/root/reference/5_JointFusion/resnet.py:70-90): every
+ * BatchNorm2d normalises with the batch mean / biased variance and updates its running statistics; autograd
+ * runs through layer4 + fc (/root/reference/1_HistoPathology/2_HistoPath_train.py:541-551).
+ * Forward:  conv (mmbs_conv_desc.stats: raw bf16 output + per-channel sum / sum of squares)
+ *           -> mmbs_bn_finalize -> mmbs_bn_apply (+ residual, ReLU)  |  mmbs_bn_relu_maxpool_3x3s2 (stem).
+ * Backward: mmbs_avgpool_global_bwd -> per BatchNorm mmbs_bn_bwd_reduce + mmbs_bn_bwd_apply ->
+ *           dgrad = conv plans on mmbs_pack_conv_weight_dgrad weights (stride 2: mmbs_scatter_stride2 first),
+ *           wgrad = linear plans on transposed operands (mmbs_im2col_t, mmbs_transpose_bf16),
+ *           mmbs_unpack_conv_wgrad -> nn.Conv2d.weight.grad layout; mmbs_add_relu_mask joins the shortcut. */
+/* stats [2][c] = per-channel sum | sum of squares over `count` values.  Writes scale = gamma*invstd,
+ * shift = beta - mean*scale, mean_out, invstd_out; running_mean/var (may be NULL) updated in place with
+ * `momentum` and the unbiased variance, like nn.BatchNorm2d. */
+int mmbs_bn_finalize(const float* stats, int64_t c, int64_t count, const float* gamma, const float* beta,
+                     float eps, float momentum, float* running_mean, float* running_var, float* scale,
+                     float* shift, float* mean_out, float* invstd_out, void* stream);
+/* out = [relu]( x*scale + shift + R ), R = 0 | residual | residual*res_scale + res_shift; bf16 [rows, c] */
+int mmbs_bn_apply(const void* x_bf16, const float* scale, const float* shift, const void* residual_bf16,
+                  const float* res_scale, const float* res_shift, int32_t relu, void* out_bf16, int64_t rows,
+                  int64_t c, void* stream);
+/* MaxPool2d(3,2,1)(relu(x*scale + shift)), NHWC bf16 (training-mode stem tail, resnet.py:152-155) */
+int mmbs_bn_relu_maxpool_3x3s2(const void* in_bf16, const float* scale, const float* shift, void* out_bf16,
+                               int64_t batch, int64_t h, int64_t w, int64_t c, void* stream);
+/* gradient of AvgPool2d(7)+flatten: dfeat fp32 [B,c] -> bf16 [B,hw,c] */
+int mmbs_avgpool_global_bwd(const float* dfeat, void* out_bf16, int64_t batch, int64_t hw, int64_t c, void* stream);
+/* sums[2][c] (pre-zeroed) += sum dz | sum dz*xhat,  dz = g * (relu_mask > 0), xhat = (raw-mean)*invstd;
+ * they are also d(beta) | d(gamma) of the BatchNorm */
+int mmbs_bn_bwd_reduce(const void* g_bf16, const void* relu_mask_bf16, const void* raw_bf16, const float* mean,
+                       const float* invstd, float* sums, int64_t rows, int64_t c, void* stream);
+/* out = scale * (dz - sums[0]/rows - xhat * sums[1]/rows): gradient wrt the conv output */
+int mmbs_bn_bwd_apply(const void* g_bf16, const void* relu_mask_bf16, const void* raw_bf16, const float* mean,
+                      const float* invstd, const float* scale, const float* sums, void* out_bf16, int64_t rows,
+                      int64_t c, void* stream);
+/* x NHWC bf16 [B,h,w,c] -> colT bf16 [ksize*ksize*c, p_padded] (pad ksize/2; zero outside and for columns
+ * >= B*oh*ow): the K-major B operand of the weight-gradient GEMM; ksize 1 / stride 1 = plain transpose */
+int mmbs_im2col_t(const void* x_bf16, void* out_bf16, int64_t batch, int64_t h, int64_t w, int64_t c, int64_t ksize,
+                  int64_t stride, int64_t p_padded, void* stream);
+/* OIHW fp32 -> bf16 [I][k][k][O] with flipped taps: the weights of the data-gradient convolution */
+int mmbs_pack_conv_weight_dgrad(const float* w_oihw, void* out_bf16, int64_t c_out, int64_t c_in, int64_t ksize,
+                                void* stream);
+/* wgrad GEMM result [O][kh][kw][I] fp32 -> OIHW fp32 */
+int mmbs_unpack_conv_wgrad(const float* g, float* out_oihw, int64_t c_out, int64_t c_in, int64_t ksize, void* stream);
+/* u[n,2y,2x,:] = g[n,y,x,:] (u [B,2h,2w,c] bf16, zero elsewhere - zeroed once by the caller) */
+int mmbs_scatter_stride2(const void* g_bf16, void* u_bf16, int64_t batch, int64_t h, int64_t w, int64_t c,
+                         void* stream);
+/* out = a + g * (mask > 0), bf16; a may be NULL */
+int mmbs_add_relu_mask(const void* a_bf16, const void* g_bf16, const void* mask_bf16, void* out_bf16, int64_t elems,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,7 @@ class ConvDesc(ctypes.Structure):
         ("batch", c_i32), ("in_h", c_i32), ("in_w", c_i32), ("c_in", c_i32), ("c_out", c_i32),
         ("ksize", c_i32), ("stride", c_i32), ("relu", c_i32), ("out_f32", c_i32), ("flags", c_i32),
         ("in_", c_void_p), ("weight", c_void_p), ("scale", c_void_p), ("shift", c_void_p),
-        ("residual", c_void_p), ("out", c_void_p),
+        ("residual", c_void_p), ("out", c_void_p), ("stats", c_void_p),
     ]
 
 
@@ -73,6 +73,22 @@ SIGNATURES = {
                                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "mmbs_transpose_bf16": (ctypes.c_int, [c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p, c_void_p]),
     "mmbs_cast_transpose_pad_bf16": (ctypes.c_int, [c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p, c_void_p]),
+    "mmbs_bn_finalize": (ctypes.c_int, [c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_float, c_float, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmbs_bn_apply": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p,
+                                     c_i64, c_i64, c_void_p]),
+    "mmbs_bn_relu_maxpool_3x3s2": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64,
+                                                  c_void_p]),
+    "mmbs_avgpool_global_bwd": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
+    "mmbs_bn_bwd_reduce": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64,
+                                          c_void_p]),
+    "mmbs_bn_bwd_apply": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_i64, c_i64, c_void_p]),
+    "mmbs_im2col_t": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_void_p]),
+    "mmbs_pack_conv_weight_dgrad": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
+    "mmbs_unpack_conv_wgrad": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
+    "mmbs_scatter_stride2": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p]),
+    "mmbs_add_relu_mask": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
 }
 
 

@@ -85,6 +85,7 @@ struct ConvParams {
   const float* shift;
   const __nv_bfloat16* residual;
   void* out;
+  float* stats;   // training-mode BatchNorm: [2][c_out] per-channel sum / sum of squares of the bf16 output
 };
 
 // Shared-memory carve-up (offsets from a 1024-B aligned base):
@@ -215,6 +216,35 @@ __device__ __forceinline__ void epilogue_columns(const ConvParams& p, uint32_t t
         }
       }
     }
+  }
+}
+
+// Training-mode BatchNorm statistics: per-channel sum and sum of squares of the bf16 values just written
+// to the staging tile (128 rows x N_TILE columns, 64-column blocks, 128-byte swizzle).  One thread owns a
+// (column, row slice); a warp reads 64 contiguous bytes of one row per step (conflict-free) and every
+// thread issues two fire-and-forget global reductions per slice.  Tile rows of images beyond the batch
+// hold conv(0) = 0 and add nothing (the plan rejects boxes that overhang the image spatially).
+template <int N_TILE>
+__device__ __forceinline__ void staging_column_stats(uint32_t stg, int t, int nthreads, float* __restrict__ stats,
+                                                     int c_out, int col_base) {
+  const int nslices = nthreads > N_TILE ? nthreads / N_TILE : 1;
+  const int rows = GM_TILE_M / nslices;
+  for (int w = t; w < N_TILE * nslices; w += nthreads) {
+    const int c = w & (N_TILE - 1), slice = w / N_TILE;
+    const uint32_t colbase = stg + uint32_t(c >> 6) * GM_OUT_BLK_BYTES + uint32_t(c & 7) * 2u;
+    const uint32_t chunk = uint32_t((c & 63) >> 3);
+    float sum = 0.f, sq = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < rows; ++i) {
+      const int r = slice * rows + i;
+      uint16_t raw;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(raw) : "r"(colbase + uint32_t(r) * 128u + ((chunk ^ uint32_t(r & 7)) << 4)));
+      const float v = __uint_as_float(uint32_t(raw) << 16);
+      sum += v;
+      sq = fmaf(v, v, sq);
+    }
+    atomicAdd(stats + col_base + c, sum);
+    atomicAdd(stats + c_out + col_base + c, sq);
   }
 }
 
@@ -434,8 +464,9 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
         if (use_tma_store) {
           tc::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA engine
           asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+          if (gt == 0) issue_store(tcd, stg);
+          if (p.stats != nullptr) staging_column_stats<N_TILE>(stg, gt, 128, p.stats, p.c_out, tcd.nt * N_TILE);
           if (gt == 0) {
-            issue_store(tcd, stg);
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             if (tma_res && tile + tstride < p.total_tiles) issue_residual(tile + tstride, grp);
           }
@@ -497,6 +528,8 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
         if (use_tma_store) tc::fence_proxy_async();
         asm volatile("bar.sync 2, 256;" ::: "memory");
         if (use_tma_store && et == 0) issue_store(tcd, stg);
+        if (use_tma_store && p.stats != nullptr)
+          staging_column_stats<N_TILE>(stg, et, GM_EPI_THREADS, p.stats, p.c_out, tcd.nt * N_TILE);
       }
       if (use_tma_store && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
@@ -618,12 +651,14 @@ extern "C" int mmbs_conv_run(const mmbs_conv_plan* plan, void* stream_) {
 extern "C" void mmbs_conv_plan_destroy(mmbs_conv_plan* plan) { delete plan; }
 
 // choose the (tw, th, tn) output-pixel box (product 128) that wastes the fewest rows
-static void choose_box(int ow, int oh, int b, int* tw, int* th, int* tn) {
+// (exact_spatial: only boxes that tile the image exactly - the batch-statistics epilogue counts every tile row)
+static void choose_box(int ow, int oh, int b, bool exact_spatial, int* tw, int* th, int* tn) {
   double best = -1.0;
   for (int w = 1; w <= 128; w *= 2)
     for (int h = 1; w * h <= 128; h *= 2) {
       const int n = 128 / (w * h);
       if (w > 256 || h > 256 || n > 256) continue;
+      if (exact_spatial && (ow % w != 0 || oh % h != 0)) continue;
       const double tiles = double(ceil_div(ow, w)) * double(ceil_div(oh, h)) * double(ceil_div(b, n));
       const double util = double(ow) * oh * b / (tiles * 128.0);
       const double score = util + 1e-6 * w + 1e-7 * h;  // ties: wider boxes (longer contiguous runs)
@@ -634,12 +669,12 @@ static void choose_box(int ow, int oh, int b, int* tw, int* th, int* tn) {
     }
 }
 
-static int pick_n_tile(int c_out, int64_t m_tiles) {
+static int pick_n_tile(int c_out, int64_t m_tiles, int min_tile) {
   // widest tile that divides c_out, narrowed while the grid cannot fill the GPU
   int nt = 256;
   while (nt > 32 && (c_out % nt) != 0) nt >>= 1;
   const int sms = sm_count();
-  while (nt > 32 && m_tiles * (c_out / nt) < sms) nt >>= 1;
+  while (nt > min_tile && m_tiles * (c_out / nt) < sms) nt >>= 1;
   return nt;
 }
 
@@ -691,6 +726,9 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
   p.scale = d->scale; p.shift = d->shift;
   p.residual = static_cast<const __nv_bfloat16*>(d->residual);
   p.out = d->out;
+  p.stats = d->stats;
+  MMBS_REQUIRE(!d->stats || (d->c_out % 64 == 0 && !d->out_f32 && !d->residual && !d->scale && !d->shift && !d->relu),
+               "conv plan: batch statistics need a raw bf16 output with c_out %% 64 == 0 (c_out=%d)", d->c_out);
   // ---- variant selection
   // resident: the whole weight matrix fits in shared memory -> loaded once per CTA, the ring holds A only
   // halo    : (resident, 64-wide) one A box with extra rows feeds several row taps (stem: 4, 3x3: 3 per kw)
@@ -717,7 +755,7 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
     p.tw = 8; p.th = 16; p.tn = 1; halo_rows = 2;
     p.num_taps = 3; p.taps_per_stage = 3;   // stage t = kw; row taps kh = 0..2 inside the box
     for (int t = 0; t < 3; ++t) { p.tap_map[t] = 0; p.tap_dw[t] = int8_t(t - 1); p.tap_dh[t] = -1; }
-  } else choose_box(out_w, out_h, d->batch, &p.tw, &p.th, &p.tn);
+  } else choose_box(out_w, out_h, d->batch, d->stats != nullptr, &p.tw, &p.th, &p.tn);
   if (halo) {
     p.tap_row_bytes = p.tw * 128;
     p.a_tx_bytes = (p.th + halo_rows) * p.tw * 128;
@@ -725,7 +763,9 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
   }
   p.tiles_w = int(ceil_div(out_w, p.tw)); p.tiles_h = int(ceil_div(out_h, p.th)); p.tiles_n = int(ceil_div(d->batch, p.tn));
   const int64_t m_tiles = int64_t(p.tiles_w) * p.tiles_h * p.tiles_n;
-  plan->n_tile = pick_n_tile(d->c_out, m_tiles);
+  plan->n_tile = pick_n_tile(d->c_out, m_tiles, d->stats ? 64 : 32);   // the statistics live on the TMA-store path
+  MMBS_REQUIRE(!d->stats || (out_w % p.tw == 0 && out_h % p.th == 0),
+               "conv plan: batch statistics need pixel boxes that tile the %dx%d output exactly", out_h, out_w);
   // epilogue-bound residual layers (short K loop): 128-wide tile = double-staged epilogue with the
   // residual prefetched one tile ahead; long K loops keep the 256-wide tile (operand-feed bound)
   if (d->residual && !d->out_f32 && plan->n_tile > 128 && p.num_taps * p.k_chunks <= 4) plan->n_tile = 128;

@@ -38,7 +38,7 @@ class ConvPlan:
 
 
 def conv_plan(x, w, out, *, ksize, stride, c_in, scale=None, shift=None, residual=None, relu=False,
-              in_hw=None, halo_weights=False):
+              in_hw=None, halo_weights=False, stats=None):
     """x: bf16 NHWC [B,H,W,Cin] (ksize 4 = stem: the [B,116,116,16] space-to-depth buffer);
     w: bf16 [Cout, k*k*Cin]; out: NHWC bf16 or fp32."""
     B = x.shape[0]
@@ -54,10 +54,11 @@ def conv_plan(x, w, out, *, ksize, stride, c_in, scale=None, shift=None, residua
     d.shift = shift.data_ptr() if shift is not None else None
     d.residual = residual.data_ptr() if residual is not None else None
     d.out = out.data_ptr()
+    d.stats = stats.data_ptr() if stats is not None else None
     h = c_void_p()
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().mmbs_conv_plan_create(ctypes.byref(d), ctypes.byref(h)), "mmbs_conv_plan_create")
-    return ConvPlan(h, (x, w, out, scale, shift, residual))
+    return ConvPlan(h, (x, w, out, scale, shift, residual, stats))
 
 
 def linear_plan(x, w, bias, out, relu=False):

@@ -12,8 +12,12 @@ ReLU and residual add fused into the epilogue (csrc/gemm_tcgen05.cu).  The
 weights stay in the stock ``nn.Conv2d`` / ``nn.BatchNorm2d`` parameters; packed bf16
 copies are caches rebuilt when a parameter's version counter moves.
 
-Training mode (batch-statistics BatchNorm + autograd through layer4) is not yet
-served by the kernels: it runs the module graph below on the tensor's own device.
+Training mode (``model.train()``: batch-statistics BatchNorm in every layer, autograd through
+``layer4``; the reference's fine-tuning configuration, 2_HistoPath_train.py:541-551) goes through
+``train_engine.ResNetTrainEngine``: the same conv kernel with a statistics epilogue, BatchNorm
+finalize/apply kernels and a layer4 backward made of dgrad/wgrad GEMMs.  Only configurations the
+kernels do not cover (gradients into stem..layer3 or into the input, other ResNet depths, CPU tensors)
+run the stock module graph below.
 """
 from __future__ import annotations
 
@@ -143,6 +147,9 @@ class ResNet(_Trunk):
     input_std = (0.229, 0.224, 0.225)
 
     def forward_extract(self, x):
+        if self._can_accelerate_train(x):
+            from . import train_engine
+            return train_engine.run_train(self, x, self._engines)
         if x.dtype == torch.uint8 and not self._can_accelerate(x):
             mean = torch.tensor(self.input_mean, device=x.device).view(1, 3, 1, 1)
             std = torch.tensor(self.input_std, device=x.device).view(1, 3, 1, 1)
@@ -156,6 +163,21 @@ class ResNet(_Trunk):
                 and x.dim() == 4 and tuple(x.shape[1:]) == (3, 224, 224)
                 and isinstance(self.layer1[0], Bottleneck) and self.fc.in_features == 2048)
 
+    def _can_accelerate_train(self, x):
+        """model.train() on CUDA, fp32 224x224 patches, ResNet-50, gradients (if any) confined to layer4."""
+        if os.environ.get("MMBS_DISABLE_KERNELS", "0") == "1" or os.environ.get("MMBS_RESNET_TRAIN", "1") != "1":
+            return False
+        if not (self.training and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+                and tuple(x.shape[1:]) == (3, 224, 224) and isinstance(self.layer1[0], Bottleneck)
+                and self.fc.in_features == 2048 and [len(l) for l in (self.layer1, self.layer2, self.layer3,
+                                                                      self.layer4)] == [3, 4, 6, 3]):
+            return False
+        if torch.is_grad_enabled():
+            from . import train_engine
+            if x.requires_grad or train_engine.trainable_outside_layer4(self):
+                return False
+        return True
+
     def _features_b200(self, x):
         from . import engine
         B = x.shape[0]
@@ -164,13 +186,13 @@ class ResNet(_Trunk):
         done = 0
         while done < B:
             chunk = engine.default_chunk(B - done)
-            key = (x.device.index, chunk)
+            key = ("eval", x.device.index, chunk)
             eng = self._engines.get(key)
             ver = engine.ResNetEngine.weights_version(self)
             if eng is None or eng._weights_version != ver:
                 self._engines.pop(key, None)
-                while len(self._engines) >= 3:      # engines own GBs of activation buffers: keep a few
-                    self._engines.pop(next(iter(self._engines)))
+                while sum(1 for k in self._engines if k[0] == "eval") >= 3:   # engines own GBs of buffers: keep a few
+                    self._engines.pop(next(k for k in self._engines if k[0] == "eval"))
                 eng = engine.ResNetEngine(self, chunk)
                 self._engines[key] = eng
             eng.run_chunk(x[done:done + chunk], out[done:done + chunk], norm=(self.input_mean, self.input_std))

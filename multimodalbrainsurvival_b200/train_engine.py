@@ -1,0 +1,406 @@
+"""Training-mode ResNet-50 trunk on libmmbs: batch-statistics BatchNorm forward for the whole
+network and the backward pass through ``layer4`` (the configuration the reference fine-tunes:
+``n_layers_to_train = 2`` -> ``fc`` + ``layer4``, /root/reference/1_HistoPathology/2_HistoPath_train.py:541-551,
+/root/reference/5_JointFusion/1_JointFusion_train.py:380-392).
+
+Reference arithmetic replaced: ``ResNet.forward_extract`` under ``model.train()``
+(/root/reference/5_JointFusion/resnet.py:151-165, ``Bottleneck.forward`` :70-90) and its autograd graph.
+
+Forward, per convolution:   tcgen05 implicit GEMM writing the raw bf16 output and the per-channel
+sum / sum of squares from its epilogue -> ``mmbs_bn_finalize`` (scale/shift, saved mean/invstd, running
+statistics updated in place like ``nn.BatchNorm2d``) -> ``mmbs_bn_apply`` (normalise + residual + ReLU).
+Backward, per layer4 conv:  BatchNorm backward (reduce + apply), data gradient = the same conv kernel
+on flipped/transposed weights, weight gradient = the same GEMM kernel on K-major (pixel-major) operands
+with fp32 accumulation and output.  PyTorch provides device memory, streams and the autograd hook only.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, engine
+from ._lib import c_void_p
+
+
+def _pad64(n):
+    return (n + 63) // 64 * 64
+
+
+def _ck(rc, what):
+    _lib.check(rc, what)
+
+
+class _BNState:
+    """Per-BatchNorm device state: epilogue sums, folded scale/shift, saved mean / invstd."""
+
+    def __init__(self, bn, arena, off):
+        c = bn.num_features
+        self.bn, self.c = bn, c
+        self.stats = arena[off:off + 2 * c]
+        self.scale = arena[off + 2 * c:off + 3 * c]
+        self.shift = arena[off + 3 * c:off + 4 * c]
+        self.mean = arena[off + 4 * c:off + 5 * c]
+        self.invstd = arena[off + 5 * c:off + 6 * c]
+
+    @staticmethod
+    def floats(bn):
+        return 6 * bn.num_features
+
+
+class _Conv:
+    """One convolution of the trunk: packed bf16 weights (repacked in place when the parameter changes),
+    the forward plan and, for layer4, the operands of its backward GEMMs."""
+
+    def __init__(self, conv, kind):
+        self.conv, self.kind = conv, kind   # kind: 'stem' | 'plain' | 'halo'
+        O, I, k, _ = conv.weight.shape
+        dev = conv.weight.device
+        cols = 256 if kind == 'stem' else k * k * I
+        self.w = torch.empty((O, cols), dtype=torch.bfloat16, device=dev)
+        self.w_dgrad = None
+        self.version = None
+
+    def refresh(self):
+        cw = self.conv.weight
+        ver = (cw.data_ptr(), cw._version)
+        if ver == self.version:
+            return
+        L = _lib.lib()
+        w = cw.detach().float().contiguous()
+        O, I, k, _ = w.shape
+        if self.kind == 'stem':
+            _ck(L.mmbs_stem_pack_weight(_lib.ptr(w), _lib.ptr(self.w), _lib.stream_ptr()), "mmbs_stem_pack_weight")
+        elif self.kind == 'halo':
+            self.w.copy_(engine.pack_conv_weight_halo(w))
+        else:
+            _ck(L.mmbs_pack_conv_weight(_lib.ptr(w), _lib.ptr(self.w), O, I, k, _lib.stream_ptr()),
+                "mmbs_pack_conv_weight")
+        if self.w_dgrad is not None:
+            _ck(L.mmbs_pack_conv_weight_dgrad(_lib.ptr(w), _lib.ptr(self.w_dgrad), O, I, k, _lib.stream_ptr()),
+                "mmbs_pack_conv_weight_dgrad")
+        self.version = ver
+
+    def want_dgrad(self):
+        O, I, k, _ = self.conv.weight.shape
+        self.w_dgrad = torch.empty((I, k * k * O), dtype=torch.bfloat16, device=self.conv.weight.device)
+        self.version = None
+
+
+class ResNetTrainEngine:
+    """Buffers + plans of one (ResNet-50 module, batch size) pair for training-mode steps."""
+
+    def __init__(self, net, batch: int):
+        p = next(net.parameters())
+        if not p.is_cuda:
+            raise RuntimeError("ResNetTrainEngine: the module must live on a CUDA device (no CPU fallback)")
+        self.net, self.B, self.device = net, int(batch), p.device
+        self._keep = []
+        self.fwd_steps = []
+        self.convs = []
+        self.bns = []
+        self.step = 0
+        self.l4 = []          # per layer4 block: dict of saved tensors / states / backward plans
+        with torch.cuda.device(self.device):
+            self._build()
+
+    # ------------------------------------------------------------------ construction helpers
+    def _buf(self, *shape, dtype=torch.bfloat16, zero=False):
+        t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+        self._keep.append(t)
+        return t
+
+    def _conv(self, conv, kind='plain'):
+        c = _Conv(conv, kind)
+        self.convs.append(c)
+        return c
+
+    def _bn(self, bn):
+        if bn.momentum is None or not bn.track_running_stats or not bn.affine:
+            raise RuntimeError("ResNetTrainEngine: BatchNorm2d needs affine=True, track_running_stats=True and a "
+                               "fixed momentum")
+        st = _BNState(bn, self.arena, self._arena_off)
+        self._arena_off += _BNState.floats(bn)
+        self.bns.append(st)
+        return st
+
+    def _add_conv_bn(self, cv, st, x, raw, *, ksize, stride, c_in, in_hw=None, halo=False):
+        plan = engine.conv_plan(x, cv.w, raw, ksize=ksize, stride=stride, c_in=c_in, in_hw=in_hw, halo_weights=halo,
+                                stats=st.stats)
+        self._keep.append(plan)
+        count = raw.shape[0] * raw.shape[1] * raw.shape[2]
+        L = _lib.lib()
+        bn = st.bn
+
+        def finalize():
+            _ck(L.mmbs_bn_finalize(_lib.ptr(st.stats), st.c, count, _lib.ptr(bn.weight), _lib.ptr(bn.bias),
+                                   float(bn.eps), float(bn.momentum), _lib.ptr(bn.running_mean),
+                                   _lib.ptr(bn.running_var), _lib.ptr(st.scale), _lib.ptr(st.shift),
+                                   _lib.ptr(st.mean), _lib.ptr(st.invstd), _lib.stream_ptr()), "mmbs_bn_finalize")
+        self.fwd_steps += [plan.run, finalize]
+
+    def _add_apply(self, raw, st, out, relu=True, res=None, res_st=None):
+        L = _lib.lib()
+        rows, c = raw.numel() // raw.shape[-1], raw.shape[-1]
+
+        def apply():
+            _ck(L.mmbs_bn_apply(_lib.ptr(raw), _lib.ptr(st.scale), _lib.ptr(st.shift), _lib.ptr(res),
+                                _lib.ptr(res_st.scale) if res_st else c_void_p(0),
+                                _lib.ptr(res_st.shift) if res_st else c_void_p(0), int(relu), _lib.ptr(out), rows, c,
+                                _lib.stream_ptr()), "mmbs_bn_apply")
+        self.fwd_steps.append(apply)
+
+    def _build(self):
+        net, B = self.net, self.B
+        L = _lib.lib()
+        all_bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+        self.arena = torch.zeros(sum(_BNState.floats(b) for b in all_bns), dtype=torch.float32, device=self.device)
+        self._arena_off = 0
+        # ---- stem
+        self.x_s2d = self._buf(B, 116, 116, 16)
+        cv0, st0 = self._conv(net.conv1, 'stem'), self._bn(net.bn1)
+        raw0 = self._buf(B, 112, 112, 64)
+        pool = self._buf(B, 56, 56, 64)
+        self._add_conv_bn(cv0, st0, self.x_s2d, raw0, ksize=4, stride=1, c_in=16, in_hw=(116, 116))
+        self.fwd_steps.append(lambda: _ck(L.mmbs_bn_relu_maxpool_3x3s2(
+            _lib.ptr(raw0), _lib.ptr(st0.scale), _lib.ptr(st0.shift), _lib.ptr(pool), B, 112, 112, 64,
+            _lib.stream_ptr()), "mmbs_bn_relu_maxpool_3x3s2"))
+        # ---- bottlenecks
+        x = pool
+        for li, layer in enumerate([net.layer1, net.layer2, net.layer3, net.layer4]):
+            for blk in layer:
+                x = self._add_block(blk, x, save=(li == 3))
+        self.final = x   # [B,7,7,2048]
+        self.g_final = self._buf(*self.final.shape)
+        self._build_backward()
+
+    def _add_block(self, blk, x, save):
+        B, H, W, Cin = x.shape
+        planes = blk.conv1.out_channels
+        s = blk.conv2.stride[0]
+        Ho, Wo = H // s, W // s
+        halo = False   # the halo variant's 8x16 pixel box overhangs a 56x56 image: its tile rows would pollute the sums
+        c1, c2, c3 = self._conv(blk.conv1), self._conv(blk.conv2, 'halo' if halo else 'plain'), self._conv(blk.conv3)
+        b1, b2, b3 = self._bn(blk.bn1), self._bn(blk.bn2), self._bn(blk.bn3)
+        raw1 = self._buf(B, H, W, planes)
+        raw2 = self._buf(B, Ho, Wo, planes)
+        raw3 = self._buf(B, Ho, Wo, planes * 4)
+        # frozen layers normalise in place; layer4 keeps raw and activated tensors for the backward pass
+        a1 = self._buf(B, H, W, planes) if save else raw1
+        a2 = self._buf(B, Ho, Wo, planes) if save else raw2
+        out = self._buf(B, Ho, Wo, planes * 4) if save else raw3
+        rec = {"blk": blk, "x": x, "raw1": raw1, "a1": a1, "raw2": raw2, "a2": a2, "raw3": raw3, "out": out,
+               "c1": c1, "c2": c2, "c3": c3, "b1": b1, "b2": b2, "b3": b3, "stride": s, "rawd": None}
+        if blk.downsample is not None:
+            cd, bd = self._conv(blk.downsample[0]), self._bn(blk.downsample[1])
+            rawd = self._buf(B, Ho, Wo, planes * 4)
+            self._add_conv_bn(cd, bd, x, rawd, ksize=1, stride=blk.downsample[0].stride[0], c_in=Cin)
+            rec.update(cd=cd, bd=bd, rawd=rawd)
+        self._add_conv_bn(c1, b1, x, raw1, ksize=1, stride=1, c_in=Cin)
+        self._add_apply(raw1, b1, a1)
+        self._add_conv_bn(c2, b2, a1, raw2, ksize=3, stride=s, c_in=planes, halo=halo)
+        self._add_apply(raw2, b2, a2)
+        self._add_conv_bn(c3, b3, a2, raw3, ksize=1, stride=1, c_in=planes)
+        if blk.downsample is not None:
+            self._add_apply(raw3, b3, out, res=rec["rawd"], res_st=rec["bd"])
+        else:
+            self._add_apply(raw3, b3, out, res=x)
+        if save:
+            self.l4.append(rec)
+        return out
+
+    # ------------------------------------------------------------------ backward construction
+    def _wgrad(self, dyT, colT, cout, kcols):
+        dw = self._buf(cout, kcols, dtype=torch.float32)
+        plan = engine.linear_plan(dyT, colT, None, dw)
+        self._keep.append(plan)
+        return dw, plan
+
+    def _build_backward(self):
+        B = self.B
+        for bi, r in enumerate(self.l4):
+            blk = r["blk"]
+            x, out = r["x"], r["out"]
+            _, Hin, Win, Cin = x.shape
+            _, Ho, Wo, Cout = out.shape
+            planes = blk.conv1.out_channels
+            s = r["stride"]
+            P, Pin = B * Ho * Wo, B * Hin * Win
+            Pp, Pinp = _pad64(P), _pad64(Pin)
+            need_dx = bi > 0
+            bf = torch.bfloat16
+            # conv3 / bn3
+            r["sums3"] = self._buf(2, Cout, dtype=torch.float32)
+            r["draw3"] = self._buf(B, Ho, Wo, Cout)
+            r["draw3T"] = self._buf(Cout, Pp)
+            r["a2T"] = self._buf(planes, Pp)
+            r["dw3"], r["wg3"] = self._wgrad(r["draw3T"], r["a2T"], Cout, planes)
+            r["c3"].want_dgrad()
+            r["da2"] = self._buf(B, Ho, Wo, planes)
+            r["dg3"] = engine.conv_plan(r["draw3"], r["c3"].w_dgrad, r["da2"], ksize=1, stride=1, c_in=Cout)
+            # conv2 / bn2
+            r["sums2"] = self._buf(2, planes, dtype=torch.float32)
+            r["draw2"] = self._buf(B, Ho, Wo, planes)
+            r["draw2T"] = self._buf(planes, Pp)
+            r["col2T"] = self._buf(9 * planes, Pp)
+            r["dw2p"], r["wg2"] = self._wgrad(r["draw2T"], r["col2T"], planes, 9 * planes)
+            r["dw2"] = self._buf(planes, planes, 3, 3, dtype=torch.float32)
+            r["c2"].want_dgrad()
+            r["u2"] = self._buf(B, Hin, Win, planes, zero=True) if s == 2 else r["draw2"]
+            r["da1"] = self._buf(B, Hin, Win, planes)
+            r["dg2"] = engine.conv_plan(r["u2"], r["c2"].w_dgrad, r["da1"], ksize=3, stride=1, c_in=planes)
+            # conv1 / bn1
+            r["sums1"] = self._buf(2, planes, dtype=torch.float32)
+            r["draw1"] = self._buf(B, Hin, Win, planes)
+            r["draw1T"] = self._buf(planes, Pinp)
+            r["xT"] = self._buf(Cin, Pinp)
+            r["dw1"], r["wg1"] = self._wgrad(r["draw1T"], r["xT"], planes, Cin)
+            if need_dx:
+                r["c1"].want_dgrad()
+                r["dx1"] = self._buf(B, Hin, Win, Cin)
+                r["dg1"] = engine.conv_plan(r["draw1"], r["c1"].w_dgrad, r["dx1"], ksize=1, stride=1, c_in=planes)
+                r["g_in"] = self._buf(B, Hin, Win, Cin)
+            if r["rawd"] is not None:
+                r["sumsd"] = self._buf(2, Cout, dtype=torch.float32)
+                r["drawd"] = self._buf(B, Ho, Wo, Cout)
+                r["drawdT"] = self._buf(Cout, Pp)
+                r["xsT"] = self._buf(Cin, Pp)
+                r["dwd"], r["wgd"] = self._wgrad(r["drawdT"], r["xsT"], Cout, Cin)
+            r["dims"] = (Hin, Win, Cin, Ho, Wo, Cout, planes, P, Pin, Pp, Pinp)
+
+    # ------------------------------------------------------------------ execution
+    def forward(self, x_nchw: torch.Tensor) -> torch.Tensor:
+        """x_nchw fp32 [B,3,224,224] -> features fp32 [B,2048]; running statistics are updated."""
+        L = _lib.lib()
+        B = self.B
+        for c in self.convs:
+            c.refresh()
+        self.step += 1
+        self.arena.zero_()   # the epilogue sums accumulate; scale/shift/mean/invstd are rewritten by the finalize steps
+        _ck(L.mmbs_stem_pack_input(_lib.ptr(x_nchw), _lib.ptr(self.x_s2d), B, _lib.stream_ptr()), "mmbs_stem_pack_input")
+        for step in self.fwd_steps:
+            step()
+        feats = torch.empty((B, 2048), dtype=torch.float32, device=self.device)
+        _ck(L.mmbs_avgpool_global(_lib.ptr(self.final), _lib.ptr(feats), B, 49, 2048, _lib.stream_ptr()),
+            "mmbs_avgpool_global")
+        torch._foreach_add_([st.bn.num_batches_tracked for st in self.bns], 1)
+        return feats
+
+    def _bn_backward(self, g, mask, raw, st, sums, out):
+        L = _lib.lib()
+        rows, c = raw.numel() // raw.shape[-1], raw.shape[-1]
+        sums.zero_()
+        _ck(L.mmbs_bn_bwd_reduce(_lib.ptr(g), _lib.ptr(mask), _lib.ptr(raw), _lib.ptr(st.mean), _lib.ptr(st.invstd),
+                                 _lib.ptr(sums), rows, c, _lib.stream_ptr()), "mmbs_bn_bwd_reduce")
+        _ck(L.mmbs_bn_bwd_apply(_lib.ptr(g), _lib.ptr(mask), _lib.ptr(raw), _lib.ptr(st.mean), _lib.ptr(st.invstd),
+                                _lib.ptr(st.scale), _lib.ptr(sums), _lib.ptr(out), rows, c, _lib.stream_ptr()),
+            "mmbs_bn_bwd_apply")
+
+    @staticmethod
+    def _transpose(src, rows, cols, rows_padded, dst):
+        _ck(_lib.lib().mmbs_transpose_bf16(_lib.ptr(src), cols, rows, cols, rows_padded, _lib.ptr(dst),
+                                           _lib.stream_ptr()), "mmbs_transpose_bf16")
+
+    @staticmethod
+    def _im2col_t(x, k, stride, p_padded, dst):
+        B, H, W, C = x.shape
+        _ck(_lib.lib().mmbs_im2col_t(_lib.ptr(x), _lib.ptr(dst), B, H, W, C, k, stride, p_padded, _lib.stream_ptr()),
+            "mmbs_im2col_t")
+
+    def backward(self, dfeat: torch.Tensor) -> dict:
+        """dfeat fp32 [B,2048] -> {parameter: gradient tensor (engine-owned, valid until the next step)}."""
+        L = _lib.lib()
+        B = self.B
+        dfeat = dfeat.detach().float().contiguous()
+        _ck(L.mmbs_avgpool_global_bwd(_lib.ptr(dfeat), _lib.ptr(self.g_final), B, 49, 2048, _lib.stream_ptr()),
+            "mmbs_avgpool_global_bwd")
+        grads = {}
+        g = self.g_final
+        for bi in range(len(self.l4) - 1, -1, -1):
+            r = self.l4[bi]
+            blk = r["blk"]
+            Hin, Win, Cin, Ho, Wo, Cout, planes, P, Pin, Pp, Pinp = r["dims"]
+            # ---- bn3 / conv3 (the block's ReLU mask comes from its output)
+            self._bn_backward(g, r["out"], r["raw3"], r["b3"], r["sums3"], r["draw3"])
+            self._transpose(r["draw3"], P, Cout, Pp, r["draw3T"])
+            self._im2col_t(r["a2"], 1, 1, Pp, r["a2T"])
+            r["wg3"].run()
+            r["dg3"].run()
+            grads[blk.conv3.weight] = r["dw3"].view(Cout, planes, 1, 1)
+            grads[blk.bn3.weight], grads[blk.bn3.bias] = r["sums3"][1], r["sums3"][0]
+            # ---- bn2 / conv2
+            self._bn_backward(r["da2"], r["a2"], r["raw2"], r["b2"], r["sums2"], r["draw2"])
+            self._transpose(r["draw2"], P, planes, Pp, r["draw2T"])
+            self._im2col_t(r["a1"], 3, r["stride"], Pp, r["col2T"])
+            r["wg2"].run()
+            _ck(L.mmbs_unpack_conv_wgrad(_lib.ptr(r["dw2p"]), _lib.ptr(r["dw2"]), planes, planes, 3, _lib.stream_ptr()),
+                "mmbs_unpack_conv_wgrad")
+            if r["stride"] == 2:
+                _ck(L.mmbs_scatter_stride2(_lib.ptr(r["draw2"]), _lib.ptr(r["u2"]), B, Ho, Wo, planes,
+                                           _lib.stream_ptr()), "mmbs_scatter_stride2")
+            r["dg2"].run()
+            grads[blk.conv2.weight] = r["dw2"]
+            grads[blk.bn2.weight], grads[blk.bn2.bias] = r["sums2"][1], r["sums2"][0]
+            # ---- bn1 / conv1
+            self._bn_backward(r["da1"], r["a1"], r["raw1"], r["b1"], r["sums1"], r["draw1"])
+            self._transpose(r["draw1"], Pin, planes, Pinp, r["draw1T"])
+            self._im2col_t(r["x"], 1, 1, Pinp, r["xT"])
+            r["wg1"].run()
+            grads[blk.conv1.weight] = r["dw1"].view(planes, Cin, 1, 1)
+            grads[blk.bn1.weight], grads[blk.bn1.bias] = r["sums1"][1], r["sums1"][0]
+            # ---- downsample branch (first block) / identity shortcut
+            if r["rawd"] is not None:
+                self._bn_backward(g, r["out"], r["rawd"], r["bd"], r["sumsd"], r["drawd"])
+                self._transpose(r["drawd"], P, Cout, Pp, r["drawdT"])
+                self._im2col_t(r["x"], 1, blk.downsample[0].stride[0], Pp, r["xsT"])
+                r["wgd"].run()
+                grads[blk.downsample[0].weight] = r["dwd"].view(Cout, Cin, 1, 1)
+                grads[blk.downsample[1].weight], grads[blk.downsample[1].bias] = r["sumsd"][1], r["sumsd"][0]
+            if bi > 0:
+                r["dg1"].run()
+                _ck(L.mmbs_add_relu_mask(_lib.ptr(r["dx1"]), _lib.ptr(g), _lib.ptr(r["out"]), _lib.ptr(r["g_in"]),
+                                         r["g_in"].numel(), _lib.stream_ptr()), "mmbs_add_relu_mask")
+                g = r["g_in"]
+        return grads
+
+
+# ---------------------------------------------------------------------------------- autograd glue
+class _TrunkTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eng, *params):
+        ctx.eng = eng
+        ctx.params = params
+        out = eng.forward(x)
+        ctx.step = eng.step
+        return out
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        if ctx.eng.step != ctx.step:
+            raise RuntimeError("ResNet training engine: backward() of a step whose saved activations were overwritten "
+                               "by a later forward of the same batch size (one outstanding forward per engine)")
+        grads = ctx.eng.backward(dfeat)
+        out = []
+        for p, need in zip(ctx.params, ctx.needs_input_grad[2:]):
+            out.append(grads[p].clone().view_as(p) if need else None)   # engine buffers are reused next step
+        return (None, None) + tuple(out)
+
+
+def trainable_outside_layer4(net) -> bool:
+    """True when a parameter the kernels do not differentiate (stem .. layer3) requires a gradient."""
+    mods = [net.conv1, net.bn1, net.layer1, net.layer2, net.layer3]
+    return any(p.requires_grad for m in mods for p in m.parameters())
+
+
+def run_train(net, x: torch.Tensor, engines: dict) -> torch.Tensor:
+    """Training-mode ``forward_extract`` of ``net`` on fp32 NCHW ``x`` (no gradient into x)."""
+    B = x.shape[0]
+    key = ("train", x.device.index, B)
+    eng = engines.get(key)
+    if eng is None:
+        for k in [k for k in engines if isinstance(k, tuple) and k and k[0] == "train"]:
+            engines.pop(k)                 # one batch size at a time: the buffers are large
+        eng = ResNetTrainEngine(net, B)
+        engines[key] = eng
+    params = [p for p in net.layer4.parameters()]
+    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        return _TrunkTrainFn.apply(x.detach().float().contiguous(), eng, *params)
+    return eng.forward(x.detach().float().contiguous())

@@ -181,6 +181,51 @@ def gen_resnet():
     print("resnet: features", tuple(f.shape), "mean", float(f.mean()), missing)
 
 
+# ---------------------------------------------------------------------- resnet, training mode
+TRAIN_SAMPLE_STRIDE = 997   # conv-weight gradients are stored as every 997th element (the full set is 60 MB)
+
+
+def gen_resnet_train():
+    """One model.train() step of the reference ResNet-50 with fc + layer4 trainable
+    (2_HistoPath_train.py:541-551 with n_layers_to_train = 2): features, layer4 gradients for a fixed
+    dLoss/dfeatures, running statistics after the step."""
+    from oracle import resnet_oracle
+    refnet = load_ref("5_JointFusion/resnet.py", "ref_resnet_train")
+    sd = resnet_oracle.init_state_dict(seed=2222, bn3_gamma_scale=0.1)   # see init_state_dict: conditioning
+    net = refnet.resnet50(pretrained=False)
+    net.load_state_dict(sd, strict=True)
+    net.train()
+    for p_ in net.parameters():
+        p_.requires_grad = False
+    for layer in [net.fc, net.layer4]:
+        for p_ in layer.parameters():
+            p_.requires_grad = True
+    x = torch.tensor(det_input((4, 3, 224, 224), a=0.7))
+    gw = torch.tensor(det_input((4, 2048), a=1.3))
+    f = net.forward_extract(x)
+    (f * gw).sum().backward()
+    out = {"features": f.detach().numpy()}
+    for name, p_ in net.layer4.named_parameters():
+        g = p_.grad.detach().flatten()
+        out["grad/layer4." + name] = (g if g.numel() <= 4096 else g[::TRAIN_SAMPLE_STRIDE]).numpy()
+        out["gnorm/layer4." + name] = np.array(float(p_.grad.double().norm()))
+    for name in ("bn1", "layer1.0.bn1", "layer2.0.downsample.1", "layer3.5.bn3", "layer4.0.bn2", "layer4.2.bn3"):
+        bn = net.get_submodule(name)
+        out["stat/" + name + ".running_mean"] = bn.running_mean.numpy()
+        out["stat/" + name + ".running_var"] = bn.running_var.numpy()
+        out["stat/" + name + ".num_batches_tracked"] = bn.num_batches_tracked.numpy()
+    # the oracle restatement must agree with the reference module to fp32 round-off
+    fo, go, so = resnet_oracle.train_step(sd, x, gw)
+    err_f = float((fo - f.detach()).norm() / f.detach().norm())
+    err_g = max(float((go[k] - p_.grad).norm() / (p_.grad.norm() + 1e-30))
+                for k, p_ in (("layer4." + n, q) for n, q in net.layer4.named_parameters()))
+    err_s = float((so["layer4.2.bn3.running_var"] - net.layer4[2].bn3.running_var).abs().max())
+    print("resnet_train: oracle vs reference  features", err_f, " max grad rel", err_g, " running_var abs", err_s)
+    assert err_f < 1e-5 and err_g < 1e-3 and err_s < 1e-5
+    np.savez_compressed(os.path.join(OUT, "resnet_train_reference.npz"), **out)
+    print("resnet_train: features", tuple(f.shape), "keys", len(out))
+
+
 # ------------------------------------------------------------------------------- mlp
 def gen_mlp():
     import torch.nn as nn
@@ -220,6 +265,6 @@ def gen_mlp():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["cox", "aggregate", "resnet", "mlp"]
+    which = sys.argv[1:] or ["cox", "aggregate", "resnet", "resnet_train", "mlp"]
     for w in which:
         globals()["gen_" + w]()
