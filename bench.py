@@ -278,6 +278,20 @@ def run_ours(args):
     value = world * B * args.steps / (ms * 1e-3)
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
 
+    # training-step secondaries (BASELINE configs 3 and 5): every rank takes part (global Cox + gradient all-reduce)
+    train_sec = {}
+    if os.environ.get("MMBS_BENCH_TRAIN", "1") == "1":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_train
+        net._engines.clear()
+        torch.cuda.empty_cache()
+        for kind in ("histo", "joint"):
+            try:
+                train_sec["train_" + kind] = bench_train.run(kind, torch, dev, world, rank, steps=max(3, min(args.steps, 10)))
+            except Exception as ex:  # secondary metrics must never kill the headline line
+                train_sec["train_" + kind] = {"error": repr(ex)}
+            torch.cuda.empty_cache()
+
     line = None
     if rank == 0:
         # per-kernel device time of one step (events around every launch of the conv kernel)
@@ -318,7 +332,7 @@ def run_ours(args):
                               "h2d_bytes_per_step": B * 3 * 224 * 224, "d2h_bytes_per_step": B * 2048 * 4,
                               "ms_per_step": ms_e2e_u8 / args.steps,
                               "input": "raw uint8 pixels, ToTensor+Normalize fused into the device pack kernel"},
-                "gpu_launches": int(launches), "clocks": clocks, "secondary": {"cox": cox_sec}}
+                "gpu_launches": int(launches), "clocks": clocks, "secondary": dict({"cox": cox_sec}, **train_sec)}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -205,7 +205,12 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
   }
 }
 
-// ---- BatchNorm backward, pass 2: draw = scale * (dz - s1/n - xhat * s2/n), scale = gamma * invstd
+// ---- BatchNorm backward, pass 2: draw = scale * (dz - s1/n - xhat * s2/n), scale = gamma * invstd, i.e.
+// draw = A*dz + Bx*raw + C with per-channel A = scale, Bx = -scale*invstd*s2/n, C = -scale*s1/n - Bx*mean.
+__device__ __forceinline__ void tr_ld8(const float* p, int g, float* v) {
+  *reinterpret_cast<float4*>(v) = __ldg(reinterpret_cast<const float4*>(p) + 2 * g);
+  *reinterpret_cast<float4*>(v + 4) = __ldg(reinterpret_cast<const float4*>(p) + 2 * g + 1);
+}
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ mask,
                                                            const uint4* __restrict__ raw,
                                                            const float* __restrict__ mean,
@@ -216,10 +221,14 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
   const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (i >= total) return;
   const int cg = int(i % c8);
-  const int64_t c = int64_t(c8) * 8;
-  float gv[8], xv[8], o[8];
+  float gv[8], xv[8], o[8], mu[8], is[8], sc[8], s1[8], s2[8];
   tr_unpack8(__ldg(g + i), gv);
   tr_unpack8(__ldg(raw + i), xv);
+  tr_ld8(mean, cg, mu);
+  tr_ld8(invstd, cg, is);
+  tr_ld8(scale, cg, sc);
+  tr_ld8(sums, cg, s1);
+  tr_ld8(sums + int64_t(c8) * 8, cg, s2);
   if (mask != nullptr) {
     float mv[8];
     tr_unpack8(__ldg(mask + i), mv);
@@ -228,43 +237,55 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int ch = cg * 8 + j;
-    const float xh = (xv[j] - __ldg(mean + ch)) * __ldg(invstd + ch);
-    o[j] = __ldg(scale + ch) * (gv[j] - __ldg(sums + ch) * inv_count - xh * __ldg(sums + c + ch) * inv_count);
+    const float xh = (xv[j] - mu[j]) * is[j];
+    o[j] = sc[j] * (gv[j] - s1[j] * inv_count - xh * s2[j] * inv_count);
   }
   out[i] = tr_pack8(o);
 }
 
 // ---- wgrad B operand: x NHWC bf16 [B,H,W,C] -> colT [k*k*C, Pp] bf16,
 // colT[(kh*k+kw)*C + c][p] = x[n, ho*s + kh - pad, wo*s + kw - pad, c] (0 outside / for p >= P), p = (n, ho, wo).
-// block (32, 8): one 32-channel x 32-pixel tile of one tap, transposed through shared memory.
+// One block = 64 channels x 64 pixels of one tap, transposed through shared memory with 16-byte global
+// accesses on both sides (8 channels of a pixel in, 8 pixels of a channel out).  C % 8 == 0, Pp % 8 == 0.
 __global__ void __launch_bounds__(256) im2col_t_kernel(const __nv_bfloat16* __restrict__ x,
                                                        __nv_bfloat16* __restrict__ out, int batch, int h, int w,
                                                        int c, int k, int stride, int pad, int oh, int ow,
                                                        int64_t p_total, int64_t p_padded) {
-  __shared__ __nv_bfloat16 tile[32][34];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  __shared__ __align__(16) uint16_t tile[64][66];   // [pixel][channel], 33-word rows: conflict-free writes, 2-way reads
   const int tap = blockIdx.z, kh = tap / k, kw = tap % k;
-  const int c0 = blockIdx.y * 32;
-  const int64_t p0 = int64_t(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 64;
+  const int64_t p0 = int64_t(blockIdx.x) * 64;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int64_t p = p0 + ty * 4 + j;
-    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
-    if (p < p_total) {
+  for (int it = 0; it < 2; ++it) {
+    const int idx = threadIdx.x + it * 256;   // 64 pixels x 8 channel groups
+    const int pl = idx >> 3, cgp = idx & 7;
+    const int64_t p = p0 + pl;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (p < p_total && c0 + cgp * 8 < c) {
       const int wo = int(p % ow), ho = int((p / ow) % oh);
       const int64_t n = p / (int64_t(ow) * oh);
       const int iy = ho * stride + kh - pad, ix = wo * stride + kw - pad;
-      if (iy >= 0 && iy < h && ix >= 0 && ix < w && c0 + tx < c) v = x[((n * h + iy) * int64_t(w) + ix) * c + c0 + tx];
+      if (iy >= 0 && iy < h && ix >= 0 && ix < w)
+        v = __ldg(reinterpret_cast<const uint4*>(x + ((n * h + iy) * int64_t(w) + ix) * c + c0 + cgp * 8));
     }
-    tile[ty * 4 + j][tx] = v;
+    uint32_t* trow = reinterpret_cast<uint32_t*>(&tile[pl][cgp * 8]);
+    trow[0] = v.x; trow[1] = v.y; trow[2] = v.z; trow[3] = v.w;
   }
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int ch = c0 + ty * 4 + j;
-    const int64_t p = p0 + tx;
-    if (ch < c && p < p_padded) out[(int64_t(tap) * c + ch) * p_padded + p] = tile[tx][ty * 4 + j];
+  for (int it = 0; it < 2; ++it) {
+    const int idx = threadIdx.x + it * 256;   // 64 channels x 8 pixel groups
+    const int cl = idx >> 3, pg = idx & 7;
+    const int ch = c0 + cl;
+    const int64_t p = p0 + pg * 8;
+    if (ch < c && p < p_padded) {
+      uint16_t e[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) e[j] = tile[pg * 8 + j][cl];
+      const uint4 v = make_uint4(uint32_t(e[0]) | (uint32_t(e[1]) << 16), uint32_t(e[2]) | (uint32_t(e[3]) << 16),
+                                 uint32_t(e[4]) | (uint32_t(e[5]) << 16), uint32_t(e[6]) | (uint32_t(e[7]) << 16));
+      *reinterpret_cast<uint4*>(out + (int64_t(tap) * c + ch) * p_padded + p) = v;
+    }
   }
 }
 
@@ -422,8 +443,9 @@ extern "C" int mmbs_im2col_t(const void* x, void* out, int64_t batch, int64_t h,
   const int pad = int(ksize / 2);
   const int64_t oh = (h + 2 * pad - ksize) / stride + 1, ow = (w + 2 * pad - ksize) / stride + 1;
   const int64_t p_total = batch * oh * ow;
-  MMBS_REQUIRE(p_padded >= p_total && ceil_div(c, 32) <= 65535, "mmbs_im2col_t: p_padded < B*oh*ow");
-  dim3 grid(unsigned(ceil_div(p_padded, 32)), unsigned(ceil_div(c, 32)), unsigned(ksize * ksize));
+  MMBS_REQUIRE(p_padded >= p_total && p_padded % 8 == 0 && c % 8 == 0 && al16(x) && al16(out),
+               "mmbs_im2col_t: need p_padded >= B*oh*ow, p_padded %% 8 == 0, c %% 8 == 0, 16-byte aligned pointers");
+  dim3 grid(unsigned(ceil_div(p_padded, 64)), unsigned(ceil_div(c, 64)), unsigned(ksize * ksize));
   im2col_t_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), int(batch), int(h), int(w), int(c),
       int(ksize), int(stride), pad, int(oh), int(ow), p_total, p_padded);

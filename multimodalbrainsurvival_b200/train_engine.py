@@ -296,8 +296,9 @@ class ResNetTrainEngine:
 
     @staticmethod
     def _transpose(src, rows, cols, rows_padded, dst):
-        _ck(_lib.lib().mmbs_transpose_bf16(_lib.ptr(src), cols, rows, cols, rows_padded, _lib.ptr(dst),
-                                           _lib.stream_ptr()), "mmbs_transpose_bf16")
+        # [rows, cols] -> [cols, rows_padded]: the 1x1 / stride-1 case of the im2col-transpose kernel
+        _ck(_lib.lib().mmbs_im2col_t(_lib.ptr(src), _lib.ptr(dst), rows, 1, 1, cols, 1, 1, rows_padded,
+                                     _lib.stream_ptr()), "mmbs_im2col_t")
 
     @staticmethod
     def _im2col_t(x, k, stride, p_padded, dst):

@@ -1,0 +1,132 @@
+#!/usr/bin/env python
+"""Training-step throughput of BASELINE configs 3 and 5:
+
+  histo : AggregationModel(resnet50, Identity) in train mode, fc + layer4 trainable, Cox loss, Adam
+          (/root/reference/1_HistoPathology/2_HistoPath_train.py:365-395, config_ffpe_train.json), B = 128 / GPU
+  joint : BagHistopathologyRNAModel(resnet50, rna MLP, Dropout(0.8)+Linear head), Cox loss, Adam
+          (/root/reference/5_JointFusion/1_JointFusion_train.py:314-325,196-230), B = 128 / GPU
+
+One step = forward (batch-statistics BatchNorm in every layer) + global Cox loss (risk set all-gathered over the
+ranks) + backward through layer4 / the MLPs + SUM all-reduce of the parameter gradients + torch.optim.Adam.
+Inputs are device resident for `value`; `e2e` feeds pinned host batches (H2D inside the timed region) and reads
+the loss back every step.  Importable (bench.py `secondary`) or  python tools/bench_train.py [histo|joint] [steps]
+(under torchrun for N > 1)."""
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+GFLOP_FWD, GFLOP_BWD_L4 = 8.174, 2.82      # per patch, SURVEY.md §8d config 3
+MLP_GFLOP_STEP = 33.3                       # RNA MLP fwd+bwd at B = 128
+
+
+def build(kind, torch, dev):
+    import torch.nn as nn
+    from multimodalbrainsurvival_b200 import models, resnet
+    from oracle import resnet_oracle   # seeded weights with the reference's key names (weights only)
+    net = resnet.resnet50()
+    net.load_state_dict(resnet_oracle.init_state_dict(seed=1111, bn3_gamma_scale=0.1))
+    for p in net.parameters():
+        p.requires_grad = False
+    for layer in (net.fc, net.layer4):       # n_layers_to_train = 2
+        for p in layer.parameters():
+            p.requires_grad = True
+    torch.manual_seed(1111)
+    if kind == "histo":
+        model = models.AggregationModel(net, models.Identity(), 2048, 2048, 1)
+    else:
+        rna = nn.Sequential(nn.Dropout(), nn.Linear(12778, 4096), nn.ReLU(), nn.Dropout(), nn.Linear(4096, 2048))
+        head = nn.Sequential(nn.Dropout(0.8), nn.Linear(4096, 1))
+        model = models.BagHistopathologyRNAModel(net, rna, head)
+    return model.to(dev).train()
+
+
+def run(kind, torch, dev, world=1, rank=0, steps=10, warmup=3, batch=128):
+    import torch.distributed as dist
+    from multimodalbrainsurvival_b200 import dist as mdist
+    from multimodalbrainsurvival_b200 import _lib
+    model = build(kind, torch, dev)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-5, weight_decay=1e-5)
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    xs = [torch.randn(batch, 1, 3, 224, 224, device=dev, generator=g) for _ in range(2)]
+    rna = torch.randn(batch, 12778, device=dev, generator=g)
+    times = torch.rand(batch, device=dev, generator=g) * 200
+    status = (torch.rand(batch, device=dev, generator=g) < 0.6).float()
+    host_x = [x.cpu().pin_memory() for x in xs]
+    host_rna = rna.cpu().pin_memory()
+
+    def step(x, r):
+        opt.zero_grad(set_to_none=True)
+        out = model(x)[0] if kind == "histo" else model(x, r)
+        loss = mdist.global_cox_loss(out.view(-1), times, status)
+        loss.backward()
+        mdist.allreduce_gradients(params)
+        opt.step()
+        return loss
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        sync()
+        l0 = _lib.launch_count()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n):
+            last = fn(i)
+        b.record()
+        sync()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / n, _lib.launch_count() - l0, last
+
+    for i in range(warmup):
+        step(xs[i % 2], rna)
+    ms, launches, loss = timed(lambda i: step(xs[i % 2], rna), steps)
+
+    def e2e_step(i):
+        x = host_x[i % 2].to(dev, non_blocking=True)
+        r = host_rna.to(dev, non_blocking=True) if kind == "joint" else None
+        return float(step(x, r).detach())      # D2H of the loss
+
+    e2e_step(0)
+    ms_e2e, _, _ = timed(e2e_step, steps)
+    gflop = batch * (GFLOP_FWD + GFLOP_BWD_L4) + (MLP_GFLOP_STEP * batch / 128 if kind == "joint" else 0.0)
+    return {"workload": f"{kind}_cox_finetune_step_b{batch}_per_gpu (fc + layer4 trainable, Adam)",
+            "steps_per_s": world * 1e3 / ms / world, "samples_per_s": world * batch * 1e3 / ms, "ms_per_step": ms,
+            "tflops_per_gpu": gflop / ms, "gflop_per_step_per_gpu": gflop, "n_gpus": world,
+            "e2e": {"ms_per_step": ms_e2e, "samples_per_s": world * batch * 1e3 / ms_e2e,
+                    "h2d_bytes_per_step": batch * 3 * 224 * 224 * 4 + (batch * 12778 * 4 if kind == "joint" else 0),
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches_per_step": launches / steps, "loss": float(loss.detach()),
+            "collectives": "all-gather of (score,time,status) triples + SUM all-reduce of gradients" if world > 1 else "none (N=1)"}
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    kind = sys.argv[1] if len(sys.argv) > 1 else "histo"
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    r = run(kind, torch, dev, world, rank, steps)
+    if rank == 0:
+        import json
+        print(json.dumps(r))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

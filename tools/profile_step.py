@@ -58,3 +58,21 @@ elif what == "agg":
         m, c, l = aggregate.segmented_mean(v, seg, g)
     torch.cuda.synchronize()
     print("mean", float(m.mean()))
+elif what == "train":
+    # one fine-tuning step of the trunk (model.train(), fc + layer4 trainable): forward + backward
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+    net = resnet.resnet50()
+    net.load_state_dict(resnet_oracle.init_state_dict(seed=1111, bn3_gamma_scale=0.1))
+    net = net.to(dev).train()
+    for p in net.parameters():
+        p.requires_grad = False
+    for p in net.layer4.parameters():
+        p.requires_grad = True
+    x = torch.randn(B, 3, 224, 224, device=dev)
+    gw = torch.randn(B, 2048, device=dev)
+    for _ in range(2):
+        net.zero_grad(set_to_none=True)
+        f = net.forward_extract(x)
+        (f * gw).sum().backward()
+    torch.cuda.synchronize()
+    print("features", tuple(f.shape), float(f.mean()))
