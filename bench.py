@@ -34,6 +34,7 @@ GFLOP_PER_PATCH = 8.174          # 2*MAC over the 53 convs at 
 BATCH = 512
 PATCHES_PER_CASE = 100
 CPU_SAMPLE = 32                  # patches per CPU-baseline pass (bounded sample)
+_OUT = sys.stdout
 METRIC = "resnet50_patch_feature_extraction_throughput"
 UNIT = "patches/s"
 
@@ -143,7 +144,7 @@ def run_reference(args):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -337,7 +338,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
 
 
 def conv_kernel_time(torch, model, x):
@@ -380,6 +381,12 @@ def conv_kernel_time(torch, model, x):
 
 
 def main():
+    # the contract is ONE JSON line on stdout: libraries that print there (NCCL prints its version banner
+    # on the first communicator) are sent to stderr; the JSON goes to the original stdout
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    global _OUT
+    _OUT = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

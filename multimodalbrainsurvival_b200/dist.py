@@ -23,10 +23,12 @@ def _world(group=None):
     return dist.get_world_size(group), dist.get_rank(group)
 
 
-def gather_risk_set(scores, times, status, group=None):
+def gather_risk_set(scores, times, status, group=None, equal_sizes=False):
     """All-gather the packed fp32 (score, time, status) triples of every rank.  Returns
     (all_scores, all_times, all_status, offset, n_local): ``all_scores[offset:offset+n_local]`` is
-    this rank's live ``scores`` tensor (autograd flows into it), the rest are constants."""
+    this rank's live ``scores`` tensor (autograd flows into it), the rest are constants.
+    ``equal_sizes=True`` (every rank holds the same number of samples, what a DistributedSampler
+    guarantees) skips the size exchange and its host synchronisation: one collective, no sync."""
     world, rank = _world(group)
     s = scores.reshape(-1)
     t = times.reshape(-1).to(s.dtype)
@@ -34,9 +36,12 @@ def gather_risk_set(scores, times, status, group=None):
     n = s.numel()
     if world == 1:
         return s, t, e, 0, n
-    sizes = [torch.zeros(1, dtype=torch.int64, device=s.device) for _ in range(world)]
-    dist.all_gather(sizes, torch.tensor([n], dtype=torch.int64, device=s.device), group=group)
-    sizes = [int(x.item()) for x in sizes]
+    if equal_sizes:
+        sizes = [n] * world
+    else:
+        sizes = [torch.zeros(1, dtype=torch.int64, device=s.device) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([n], dtype=torch.int64, device=s.device), group=group)
+        sizes = [int(x.item()) for x in sizes]
     nmax = max(sizes)
     packed = torch.zeros((nmax, 3), dtype=s.dtype, device=s.device)
     packed[:n, 0] = s.detach()
@@ -53,13 +58,13 @@ def gather_risk_set(scores, times, status, group=None):
     return (torch.cat(parts_s), torch.cat(parts_t), torch.cat(parts_e), sum(sizes[:rank]), n)
 
 
-def global_cox_loss(scores, times, status, group=None, loss_fn=None):
+def global_cox_loss(scores, times, status, group=None, loss_fn=None, equal_sizes=False):
     """Cox loss over the risk set of ALL ranks.  Every rank returns the same global loss; its
     backward yields d(global loss)/d(local scores).  Ties across ranks are ordered by
     (rank, local index) = the order of the concatenated batch."""
     if loss_fn is None:
         from .cox import cox_loss as loss_fn
-    all_s, all_t, all_e, _, _ = gather_risk_set(scores, times, status, group)
+    all_s, all_t, all_e, _, _ = gather_risk_set(scores, times, status, group, equal_sizes=equal_sizes)
     return loss_fn(all_s, all_t, all_e)
 
 

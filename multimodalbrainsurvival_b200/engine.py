@@ -165,7 +165,8 @@ class ResNetEngine:
 
     @staticmethod
     def weights_version(resnet):
-        return tuple((t.data_ptr(), t._version) for t in list(resnet.parameters()) + list(resnet.buffers()))
+        return (tuple((t.data_ptr(), t._version) for t in list(resnet.parameters()) + list(resnet.buffers()))
+                + (getattr(resnet, "_mmbs_train_steps", 0),))
 
     def _buf(self, *shape, dtype=torch.bfloat16):
         t = torch.empty(shape, dtype=dtype, device=self.device)

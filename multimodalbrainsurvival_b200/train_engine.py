@@ -15,6 +15,8 @@ with fp32 accumulation and output.  PyTorch provides device memory, streams and 
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib, engine
@@ -98,6 +100,10 @@ class ResNetTrainEngine:
         self.convs = []
         self.bns = []
         self.step = 0
+        self.use_graph = os.environ.get("MMBS_CUDA_GRAPH", "1") == "1"
+        self._graphs = {}
+        self._hot_convs = []
+        self._grads = {}
         self.l4 = []          # per layer4 block: dict of saved tensors / states / backward plans
         with torch.cuda.device(self.device):
             self._build()
@@ -169,6 +175,8 @@ class ResNetTrainEngine:
             for blk in layer:
                 x = self._add_block(blk, x, save=(li == 3))
         self.final = x   # [B,7,7,2048]
+        self.feats = self._buf(B, 2048, dtype=torch.float32)
+        self.dfeat = self._buf(B, 2048, dtype=torch.float32)
         self.g_final = self._buf(*self.final.shape)
         self._build_backward()
 
@@ -267,22 +275,63 @@ class ResNetTrainEngine:
             r["dims"] = (Hin, Win, Cin, Ho, Wo, Cout, planes, P, Pin, Pp, Pinp)
 
     # ------------------------------------------------------------------ execution
+    def _graph_key(self):
+        """Pointers the captured graphs bake in: if a parameter / buffer was re-allocated, capture again."""
+        key = []
+        for st in self.bns:
+            bn = st.bn
+            key += [bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                    bn.num_batches_tracked.data_ptr()]
+        key += [c.conv.weight.data_ptr() for c in self.convs]
+        return tuple(key)
+
+    def _run(self, which, body):
+        """Eager on the first call (kernel attributes are set lazily), captured into a CUDA graph on the second,
+        replayed afterwards (one graph launch instead of ~130 ctypes calls: the step is CPU-launch bound
+        whenever something synchronises the host, e.g. reading the loss)."""
+        st = self._graphs.setdefault(which, {"runs": 0, "graph": None, "key": None})
+        st["runs"] += 1
+        if not self.use_graph or st["runs"] == 1:
+            body()
+            return
+        key = self._graph_key()
+        if st["graph"] is None or st["key"] != key:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            st["graph"], st["key"] = g, key
+        st["graph"].replay()
+
+    def _fwd_body(self):
+        L = _lib.lib()
+        for c in self._hot_convs:    # trainable convolutions: their weights change every step
+            c.version = None
+            c.refresh()
+        self.arena.zero_()   # the epilogue sums accumulate; scale/shift/mean/invstd are rewritten by the finalize steps
+        for step in self.fwd_steps:
+            step()
+        _ck(L.mmbs_avgpool_global(_lib.ptr(self.final), _lib.ptr(self.feats), self.B, 49, 2048, _lib.stream_ptr()),
+            "mmbs_avgpool_global")
+        torch._foreach_add_([st.bn.num_batches_tracked for st in self.bns], 1)
+
     def forward(self, x_nchw: torch.Tensor) -> torch.Tensor:
         """x_nchw fp32 [B,3,224,224] -> features fp32 [B,2048]; running statistics are updated."""
         L = _lib.lib()
-        B = self.B
+        hot = [c for c in self.convs if c.conv.weight.requires_grad]
+        if [id(c) for c in hot] != [id(c) for c in self._hot_convs]:
+            self._hot_convs = hot
+            self._graphs.pop("fwd", None)
         for c in self.convs:
-            c.refresh()
+            if not c.conv.weight.requires_grad:
+                c.refresh()          # frozen weights: repacked only when their version counter moves
         self.step += 1
-        self.arena.zero_()   # the epilogue sums accumulate; scale/shift/mean/invstd are rewritten by the finalize steps
-        _ck(L.mmbs_stem_pack_input(_lib.ptr(x_nchw), _lib.ptr(self.x_s2d), B, _lib.stream_ptr()), "mmbs_stem_pack_input")
-        for step in self.fwd_steps:
-            step()
-        feats = torch.empty((B, 2048), dtype=torch.float32, device=self.device)
-        _ck(L.mmbs_avgpool_global(_lib.ptr(self.final), _lib.ptr(feats), B, 49, 2048, _lib.stream_ptr()),
-            "mmbs_avgpool_global")
-        torch._foreach_add_([st.bn.num_batches_tracked for st in self.bns], 1)
-        return feats
+        # the kernels (and graph replays) write the running statistics behind autograd's back: tell the
+        # inference engine's weight cache (engine.ResNetEngine.weights_version) that they moved
+        self.net._mmbs_train_steps = getattr(self.net, "_mmbs_train_steps", 0) + 1
+        _ck(L.mmbs_stem_pack_input(_lib.ptr(x_nchw), _lib.ptr(self.x_s2d), self.B, _lib.stream_ptr()),
+            "mmbs_stem_pack_input")
+        self._run("fwd", self._fwd_body)
+        return self.feats.clone()
 
     def _bn_backward(self, g, mask, raw, st, sums, out):
         L = _lib.lib()
@@ -308,10 +357,14 @@ class ResNetTrainEngine:
 
     def backward(self, dfeat: torch.Tensor) -> dict:
         """dfeat fp32 [B,2048] -> {parameter: gradient tensor (engine-owned, valid until the next step)}."""
+        self.dfeat.copy_(dfeat.detach())
+        self._run("bwd", self._bwd_body)
+        return self._grads
+
+    def _bwd_body(self):
         L = _lib.lib()
         B = self.B
-        dfeat = dfeat.detach().float().contiguous()
-        _ck(L.mmbs_avgpool_global_bwd(_lib.ptr(dfeat), _lib.ptr(self.g_final), B, 49, 2048, _lib.stream_ptr()),
+        _ck(L.mmbs_avgpool_global_bwd(_lib.ptr(self.dfeat), _lib.ptr(self.g_final), B, 49, 2048, _lib.stream_ptr()),
             "mmbs_avgpool_global_bwd")
         grads = {}
         g = self.g_final
@@ -360,7 +413,7 @@ class ResNetTrainEngine:
                 _ck(L.mmbs_add_relu_mask(_lib.ptr(r["dx1"]), _lib.ptr(g), _lib.ptr(r["out"]), _lib.ptr(r["g_in"]),
                                          r["g_in"].numel(), _lib.stream_ptr()), "mmbs_add_relu_mask")
                 g = r["g_in"]
-        return grads
+        self._grads = grads
 
 
 # ---------------------------------------------------------------------------------- autograd glue
