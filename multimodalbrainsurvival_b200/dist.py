@@ -75,6 +75,15 @@ def allreduce_gradients(params, group=None, bucket_bytes=256 << 20):
     grads = [p.grad for p in params if p.grad is not None]
     if world == 1 or not grads:
         return
+    if dist.get_backend(group) == "nccl" and hasattr(dist, "_coalescing_manager"):
+        # one NCCL group launch, in place on the gradient tensors: no flatten / copy-back passes
+        try:
+            with dist._coalescing_manager(group=group, device=grads[0].device, async_ops=False):
+                for g in grads:
+                    dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+            return
+        except TypeError:   # private API signature moved (raised before any collective): bucketed path
+            pass
     bucket, size = [], 0
     def flush():
         nonlocal bucket, size
