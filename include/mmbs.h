@@ -234,6 +234,16 @@ int mmbs_scatter_stride2(const void* g_bf16, void* u_bf16, int64_t batch, int64_
 int mmbs_add_relu_mask(const void* a_bf16, const void* g_bf16, const void* mask_bf16, void* out_bf16, int64_t elems,
                        void* stream);
 
+/* ------------------------------------------------ concordance index (tail of get_survival_CI)
+ * Replaces lifelines.utils.concordance_index(survival_months, -score, vital_status)
+ *   /root/reference/1_HistoPathology/3_HistoPath_savescore.py:147 (+ 7 copies).
+ * counts_out[3] (device, u64) = {admissible pairs, correct, tied}; C = (correct + tied/2) / pairs.
+ * Pair rule (restated from lifelines' _concordance_summary_statistics, PARITY UNPINNED - lifelines is not
+ * vendored/pinned by the reference): subject i vs every observed death j with t_j < t_i, plus t_j == t_i when
+ * i is censored; correct: pred_j < pred_i, tied: pred_j == pred_i.  Exact integer counts, O(n^2). */
+int mmbs_concordance_counts(const double* event_times, const double* predicted, const uint8_t* event_observed,
+                            int64_t n, unsigned long long* counts_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,7 @@ SIGNATURES = {
     "mmbs_unpack_conv_wgrad": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
     "mmbs_scatter_stride2": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p]),
     "mmbs_add_relu_mask": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
+    "mmbs_concordance_counts": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
 }
 
 

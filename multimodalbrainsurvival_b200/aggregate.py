@@ -89,13 +89,51 @@ def survival_grouping(output_list, ids_list, survival_months, vital_status):
     return ids_unique, mean[:, 0].cpu().numpy(), sm, vs
 
 
+def concordance_counts(event_times, predicted_scores, event_observed, device=None):
+    """(admissible pairs, correct, tied) of Harrell's C, counted exactly on the GPU (csrc/cindex.cu).
+    Inputs: array-likes / tensors of length n; compared in float64 like the reference's pandas columns."""
+    def f64(x):
+        if isinstance(x, torch.Tensor):
+            return x.detach().reshape(-1).to(torch.float64)
+        return torch.as_tensor(np.asarray(x, dtype=np.float64).reshape(-1))
+    t, p = f64(event_times), f64(predicted_scores)
+    e = (event_observed.detach().reshape(-1) != 0) if isinstance(event_observed, torch.Tensor) \
+        else torch.as_tensor(np.asarray(event_observed).reshape(-1) != 0)
+    n = t.numel()
+    if p.numel() != n or e.numel() != n:
+        raise ValueError(f"concordance_index: lengths differ ({n}, {p.numel()}, {e.numel()})")
+    if n == 0:
+        return 0, 0, 0
+    dev = next((x.device for x in (t, p) if x.is_cuda), None) or torch.device("cuda", torch.cuda.current_device()
+                                                                             if device is None else device)
+    t, p, e = t.to(dev).contiguous(), p.to(dev).contiguous(), e.to(dev).to(torch.uint8).contiguous()
+    out = torch.empty(3, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().mmbs_concordance_counts(_lib.ptr(t), _lib.ptr(p), _lib.ptr(e), n, _lib.ptr(out),
+                                                      _lib.stream_ptr()), "mmbs_concordance_counts")
+    pairs, correct, tied = (int(v) for v in out.cpu().tolist())
+    return pairs, correct, tied
+
+
+def concordance_index(event_times, predicted_scores, event_observed=None):
+    """Drop-in for ``lifelines.utils.concordance_index(event_times, predicted_scores, event_observed)`` as the
+    reference calls it (3_HistoPath_savescore.py:147).  Raises ZeroDivisionError without admissible pairs, like
+    lifelines."""
+    if event_observed is None:
+        event_observed = np.ones(len(event_times))
+    pairs, correct, tied = concordance_counts(event_times, predicted_scores, event_observed)
+    if pairs == 0:
+        raise ZeroDivisionError("No admissable pairs in the dataset.")
+    return (correct + tied / 2) / pairs
+
+
 def get_survival_CI(output_list, ids_list, survival_months, vital_status, concordance_index=None):
     """Same contract as the reference's ``get_survival_CI``: returns (CI, DataFrame with
-    columns id, score, survival_months, vital_status).  ``concordance_index`` defaults to
-    ``lifelines.utils.concordance_index`` (third-party, as in the reference)."""
+    columns id, score, survival_months, vital_status).  ``concordance_index`` defaults to the GPU pair count
+    above (the reference's third-party ``lifelines.utils.concordance_index`` can be passed in instead)."""
     import pandas as pd
     if concordance_index is None:
-        from lifelines.utils import concordance_index  # noqa: PLC0415 (same dependency as the reference)
+        concordance_index = globals()["concordance_index"]
     ids_unique, score_list, sm, vs = survival_grouping(output_list, ids_list, survival_months, vital_status)
     CI = concordance_index(sm, -score_list, vs)
     pandas_output = pd.DataFrame({'id': ids_unique, 'score': score_list, 'survival_months': sm,

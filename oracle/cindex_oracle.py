@@ -4,14 +4,23 @@ The reference calls ``lifelines.utils.concordance_index(survival_months,
 -score, vital_status)`` (/root/reference/1_HistoPathology/3_HistoPath_savescore.py:147
 and 7 copies).  lifelines is a third-party dependency that the
 reference neither vendors nor pins (no requirements/lock file) and it is absent
-from this image, so this is a restatement of the published definition, not a
-checked port: a pair (i, j) is admissible iff the smaller time is an observed
-event (equal times: admissible only when exactly one of the two is an event...
-lifelines drops equal-time pairs unless one is censored; we follow the plain
-Harrell rule and drop equal-time pairs); concordant when the larger predicted
-value belongs to the longer survivor; prediction ties count 1/2.
+from this image, so this is a restatement of its published algorithm
+(``lifelines.utils.concordance._concordance_summary_statistics``), not a checked
+port, and no value produced by lifelines itself pins it:
 
-Used only to compare reference-path scores with new-path scores under the SAME
+  subjects are visited in order of exit time; at each time the deaths are handled
+  (compared with the deaths that exited STRICTLY earlier, then added to the pool),
+  then the censored subjects (compared with every death in the pool, i.e. including
+  the deaths at their own exit time).  For a visited subject i and a pooled death j:
+      pairs += 1;  correct += pred_j < pred_i;  tied += pred_j == pred_i
+  C = (correct + tied / 2) / pairs.
+
+So a pair is admissible iff the earlier exit is an observed death; two deaths at the
+same time are not comparable; a death and a censoring at the same time are (the death
+counts as earlier).  ``concordance_counts`` returns the three integers, which the CUDA
+kernel (csrc/cindex.cu) must reproduce exactly.
+
+Used to compare reference-path scores with new-path scores under the SAME
 implementation (|dC| <= 0.005, BASELINE.json north_star).
 """
 from __future__ import annotations
@@ -19,18 +28,21 @@ from __future__ import annotations
 import numpy as np
 
 
-def concordance_index(event_times, predicted, event_observed) -> float:
+def concordance_counts(event_times, predicted, event_observed):
+    """(pairs, correct, tied) as Python ints.  O(n * deaths), vectorised over the deaths."""
     t = np.asarray(event_times, dtype=np.float64)
     p = np.asarray(predicted, dtype=np.float64)
     e = np.asarray(event_observed).astype(bool)
-    n = t.shape[0]
-    num = 0.0
-    den = 0.0
-    # O(n^2) blocked; n is a few thousand cases at most in tests.
-    for i in range(n):
-        if not e[i]:
-            continue
-        later = t > t[i]
-        den += later.sum()
-        num += (p[later] > p[i]).sum() + 0.5 * (p[later] == p[i]).sum()
-    return float(num / den) if den > 0 else float("nan")
+    td, pd_ = t[e], p[e]
+    pairs = correct = tied = 0
+    for i in range(t.shape[0]):
+        adm = (td < t[i]) | ((td == t[i]) if not e[i] else False)
+        pairs += int(adm.sum())
+        correct += int((pd_[adm] < p[i]).sum())
+        tied += int((pd_[adm] == p[i]).sum())
+    return pairs, correct, tied
+
+
+def concordance_index(event_times, predicted, event_observed) -> float:
+    pairs, correct, tied = concordance_counts(event_times, predicted, event_observed)
+    return (correct + 0.5 * tied) / pairs if pairs > 0 else float("nan")

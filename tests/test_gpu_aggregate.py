@@ -62,3 +62,49 @@ def test_hundred_patches_per_case_2048():
     uniq, out = aggregate.aggregate_case_features(feats, cases)
     ref = aggregate_oracle.case_mean_features(feats.cpu().numpy(), cases, uniq)
     np.testing.assert_allclose(out, ref, rtol=2e-5, atol=2e-6)
+
+
+def _ci_case(seed, n, tie_times=False, tie_pred=False, p_event=0.6):
+    rng = np.random.default_rng(seed)
+    t = rng.uniform(0, 200, n)
+    if tie_times:
+        t = np.round(t / 8) * 8          # many equal exit times (deaths with deaths, deaths with censorings)
+    p = rng.normal(size=n)
+    if tie_pred:
+        p = np.round(p, 1)
+    e = rng.random(n) < p_event
+    return t, p, e
+
+
+@pytest.mark.parametrize("n,tt,tp", [(1, False, False), (2, False, False), (37, True, True), (1000, False, False),
+                                     (1500, True, False), (1025, False, True), (3000, True, True)])
+def test_concordance_counts_bit_exact_vs_oracle(n, tt, tp):
+    from multimodalbrainsurvival_b200 import aggregate
+    from oracle import cindex_oracle
+    t, p, e = _ci_case(100 + n, n, tt, tp)
+    got = aggregate.concordance_counts(t, p, e)
+    assert got == cindex_oracle.concordance_counts(t, p, e)
+
+
+def test_concordance_index_edge_cases_and_get_survival_ci():
+    from multimodalbrainsurvival_b200 import aggregate
+    from oracle import cindex_oracle
+    t = np.array([1.0, 2.0, 3.0, 4.0])
+    assert aggregate.concordance_index(t, t, np.ones(4)) == 1.0
+    assert aggregate.concordance_index(t, -t, np.ones(4)) == 0.0
+    assert aggregate.concordance_index(t, np.zeros(4), np.ones(4)) == 0.5
+    with pytest.raises(ZeroDivisionError):
+        aggregate.concordance_index(t, t, np.zeros(4))           # all censored: no admissible pair
+    # a death and a censoring at the same time are comparable (the death is earlier), two deaths are not
+    assert aggregate.concordance_counts([5.0, 5.0], [0.0, 1.0], [1, 0]) == (1, 1, 0)
+    assert aggregate.concordance_counts([5.0, 5.0], [0.0, 1.0], [1, 1]) == (0, 0, 0)
+    # through get_survival_CI (reference call: concordance_index(survival_months, -score, vital_status))
+    rng = np.random.default_rng(5)
+    ids = [f"case{i % 40:03d}" for i in range(400)]
+    out = torch.tensor(rng.normal(size=(400, 1)).astype(np.float32)).cuda()
+    sm = np.repeat(rng.uniform(1, 100, 40), 10).reshape(10, 40).T.reshape(-1)[:400]
+    sm = np.array([sm[i % 40] for i in range(400)])
+    vs = np.array([(i % 40) % 3 != 0 for i in range(400)]).astype(np.int64)
+    ci, df = aggregate.get_survival_CI(out, ids, sm, vs)
+    ref = cindex_oracle.concordance_index(df["survival_months"], -df["score"], df["vital_status"])
+    assert ci == ref and 0.0 <= ci <= 1.0

@@ -37,6 +37,29 @@ def test_cindex_basic():
     assert cindex_oracle.concordance_index(t, np.zeros(4), np.ones(4)) == 0.5
 
 
+def test_cindex_tie_rules_and_bruteforce():
+    """The restated lifelines rule: the earlier exit must be a death; equal-time deaths are not comparable,
+    a death and a censoring at the same time are.  Checked against a literal double loop."""
+    assert cindex_oracle.concordance_counts([5.0, 5.0], [0.0, 1.0], [1, 0]) == (1, 1, 0)
+    assert cindex_oracle.concordance_counts([5.0, 5.0], [0.0, 1.0], [1, 1]) == (0, 0, 0)
+    assert cindex_oracle.concordance_counts([5.0, 5.0], [0.0, 1.0], [0, 0]) == (0, 0, 0)
+    assert cindex_oracle.concordance_counts([1.0, 2.0], [3.0, 3.0], [1, 0]) == (1, 0, 1)
+    assert cindex_oracle.concordance_counts([1.0, 2.0], [3.0, 3.0], [0, 1]) == (0, 0, 0)   # censored first: unusable
+    rng = np.random.default_rng(3)
+    for n in (1, 7, 60):
+        t = np.round(rng.uniform(0, 10, n))
+        p = np.round(rng.normal(size=n), 1)
+        e = rng.random(n) < 0.6
+        pairs = correct = tied = 0
+        for i in range(n):
+            for j in range(n):
+                if e[j] and (t[j] < t[i] or (t[j] == t[i] and not e[i])):
+                    pairs += 1
+                    correct += p[j] < p[i]
+                    tied += p[j] == p[i]
+        assert cindex_oracle.concordance_counts(t, p, e) == (pairs, int(correct), int(tied))
+
+
 def _check_rng_fingerprint(sd, g):
     for k, v in zip(g["fp_keys"], g["fp_vals"]):
         got = float(sd[str(k)].double().abs().sum())
@@ -85,3 +108,28 @@ def test_mlp_oracle_matches_reference(golden):
     y = feat @ head[0].weight.t() + head[0].bias
     np.testing.assert_allclose(feat[:, :64].detach().numpy(), g["rna_feat_head"], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(y.detach().numpy(), g["rna_out"], rtol=1e-4, atol=1e-5)
+
+
+def test_resnet_train_oracle_matches_reference_golden(golden):
+    """oracle.resnet_oracle.train_step (model.train(): batch-statistics BatchNorm, autograd through layer4) against
+    the reference module's own step (tools/make_golden.py gen_resnet_train): features, layer4 gradients, running
+    statistics, all to fp32 round-off."""
+    from conftest import det_input
+    import torch
+    g = golden("resnet_train_reference.npz")
+    sd = resnet_oracle.init_state_dict(seed=2222, bn3_gamma_scale=0.1)
+    x = torch.tensor(det_input((4, 3, 224, 224), a=0.7))
+    gw = torch.tensor(det_input((4, 2048), a=1.3))
+    f, grads, stats = resnet_oracle.train_step(sd, x, gw)
+    ref = g["features"]
+    if np.linalg.norm(f.numpy() - ref) > 1e-3 * np.linalg.norm(ref):
+        fp = float(sd["conv1.weight"].double().abs().sum())
+        pytest.skip(f"torch CPU RNG stream differs from the one that produced the golden weights (fingerprint {fp})")
+    assert np.linalg.norm(f.numpy() - ref) <= 1e-5 * np.linalg.norm(ref)
+    for key in g.files:
+        if key.startswith("grad/"):
+            gr = grads[key[5:]].flatten()
+            sample = (gr if gr.numel() <= 4096 else gr[::997]).numpy()
+            assert np.linalg.norm(sample - g[key]) <= 1e-3 * np.linalg.norm(g[key]) + 1e-12, key
+        elif key.startswith("stat/") and not key.endswith("num_batches_tracked"):
+            assert np.allclose(stats[key[5:]].numpy(), g[key], rtol=1e-5, atol=1e-6), key
