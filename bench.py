@@ -292,6 +292,12 @@ def run_ours(args):
             except Exception as ex:  # secondary metrics must never kill the headline line
                 train_sec["train_" + kind] = {"error": repr(ex)}
             torch.cuda.empty_cache()
+        for kind in ("rna", "early"):
+            try:
+                train_sec["train_" + kind] = bench_train.run_mlp(kind, torch, dev, world, rank, steps=max(3, min(args.steps, 5)))
+            except Exception as ex:
+                train_sec["train_" + kind] = {"error": repr(ex)}
+            torch.cuda.empty_cache()
 
     line = None
     if rank == 0:

@@ -377,6 +377,44 @@ __global__ void __launch_bounds__(256) dropout_cast_kernel(const void* __restric
   out[i] = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
 }
 
+// Same, 8 columns per thread with 16-byte accesses (cols, in_stride, cols_padded multiples of 8, aligned pointers).
+// The mask is the one of dropout_cast_kernel: Philox counter = (column / 4, row).
+__global__ void __launch_bounds__(256) dropout_cast_vec8_kernel(const void* __restrict__ in, int in_bf16,
+                                                                int64_t in_stride, uint4* __restrict__ out,
+                                                                int64_t rows, int64_t cols, int64_t cp8, float p,
+                                                                uint64_t seed, uint32_t tag) {
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= rows * cp8) return;
+  const int64_t r = i / cp8, g = i % cp8, c0 = g * 8;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  if (c0 < cols) {   // cols % 8 == 0: a group is entirely inside or entirely padding
+    if (in_bf16) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(in) + r * in_stride + c0));
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+    } else {
+      const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(in) + r * in_stride + c0);
+      const float4 a = __ldg(src), b = __ldg(src + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    if (p > 0.f) {
+      const uint32_t thresh = drop_threshold(p);
+      const uint32_t k0 = dropout_keep4(seed, tag, uint32_t(r), uint32_t(2 * g), thresh);
+      const uint32_t k1 = dropout_keep4(seed, tag, uint32_t(r), uint32_t(2 * g + 1), thresh);
+      const float sc = 1.0f / (1.0f - p);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j] = ((k0 >> j) & 1u) ? v[j] * sc : 0.f;
+        v[4 + j] = ((k1 >> j) & 1u) ? v[4 + j] * sc : 0.f;
+      }
+    }
+  }
+  out[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                      pack_bf16x2(v[6], v[7]));
+}
+
 // Backward elementwise step of one layer:
 //   dz[m, n] = g[m, n] * dropmask(m, n)/(1-p) * (act[m, n] > 0 if relu)
 // g: gradient wrt the layer's (dropped) output, fp32 [M, g_stride] or bf16; act: the layer's bf16 output.
@@ -417,6 +455,83 @@ __global__ void __launch_bounds__(256) mlp_bwd_elementwise_kernel(
     const int64_t orow = int64_t(blockIdx.x) * 32 + ty * 4 + k;  // a column of dz
     const int64_t ocol = int64_t(blockIdx.y) * 32 + tx;          // a row of dz
     if (orow < np && ocol < mp) dzt[orow * mp + ocol] = __float2bfloat16_rn(tile[tx][ty * 4 + k]);
+  }
+}
+
+// Same step for bf16 gradients with 16-byte accesses: one block = 64 rows x 64 columns, transposed through shared
+// memory (33-word rows: conflict-free writes, 2-way reads).  Needs g_stride, act_stride, np, mp multiples of 8.
+__global__ void __launch_bounds__(256) mlp_bwd_elementwise_vec_kernel(
+    const __nv_bfloat16* __restrict__ g, int64_t g_stride, const __nv_bfloat16* __restrict__ act, int64_t act_stride,
+    int relu, float p, uint64_t seed, uint32_t tag, int64_t m, int64_t n, int64_t np, int64_t mp,
+    __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ dzt, float* __restrict__ db) {
+  __shared__ __align__(16) uint16_t tile[64][66];
+  const int64_t r0 = int64_t(blockIdx.x) * 64, c0 = int64_t(blockIdx.y) * 64;   // rows on x: up to 2^31 blocks
+  const uint32_t thresh = drop_threshold(p);
+  const float sc = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int idx = threadIdx.x + it * 256;   // 64 rows x 8 column groups
+    const int rl = idx >> 3, cg = idx & 7;
+    const int64_t row = r0 + rl, col = c0 + cg * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (row < m && col < np) {
+      if (col < n) {   // (the last group of a row may straddle n: masked per element below)
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(g + row * g_stride + col));
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+        if (relu) {
+          const uint4 w = __ldg(reinterpret_cast<const uint4*>(act + row * act_stride + col));
+          const float2 e = unpack_bf16x2(w.x), f = unpack_bf16x2(w.y), h = unpack_bf16x2(w.z), k = unpack_bf16x2(w.w);
+          const float av[8] = {e.x, e.y, f.x, f.y, h.x, h.y, k.x, k.y};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = av[j] > 0.f ? v[j] : 0.f;
+        }
+        if (p > 0.f) {
+          const uint32_t k0 = dropout_keep4(seed, tag, uint32_t(row), uint32_t(col >> 2), thresh);
+          const uint32_t k1 = dropout_keep4(seed, tag, uint32_t(row), uint32_t((col >> 2) + 1), thresh);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[j] = ((k0 >> j) & 1u) ? v[j] * sc : 0.f;
+            v[4 + j] = ((k1 >> j) & 1u) ? v[4 + j] * sc : 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (col + j < n) ? v[j] : 0.f;
+      }
+      const uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                 pack_bf16x2(v[6], v[7]));
+      *reinterpret_cast<uint4*>(dz + row * np + col) = o;
+      uint32_t* trow = reinterpret_cast<uint32_t*>(&tile[rl][cg * 8]);
+      trow[0] = o.x; trow[1] = o.y; trow[2] = o.z; trow[3] = o.w;
+    } else {
+      uint32_t* trow = reinterpret_cast<uint32_t*>(&tile[rl][cg * 8]);
+      trow[0] = 0u; trow[1] = 0u; trow[2] = 0u; trow[3] = 0u;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int idx = threadIdx.x + it * 256;   // 64 columns x 8 row groups
+    const int cl = idx >> 3, rg = idx & 7;
+    const int64_t col = c0 + cl, row = r0 + rg * 8;
+    uint16_t e[8];
+    float colsum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      e[j] = tile[rg * 8 + j][cl];
+      colsum += __uint_as_float(uint32_t(e[j]) << 16);   // db sums exactly what the GEMMs will see
+    }
+    if (col < np && row < mp)
+      *reinterpret_cast<uint4*>(dzt + col * mp + row) =
+          make_uint4(uint32_t(e[0]) | (uint32_t(e[1]) << 16), uint32_t(e[2]) | (uint32_t(e[3]) << 16),
+                     uint32_t(e[4]) | (uint32_t(e[5]) << 16), uint32_t(e[6]) | (uint32_t(e[7]) << 16));
+    // the 8 row groups of a column sit in 8 consecutive lanes
+    colsum += __shfl_xor_sync(0xffffffffu, colsum, 1);
+    colsum += __shfl_xor_sync(0xffffffffu, colsum, 2);
+    colsum += __shfl_xor_sync(0xffffffffu, colsum, 4);
+    if (db != nullptr && rg == 0 && col < n) atomicAdd(db + col, colsum);
   }
 }
 
@@ -467,6 +582,14 @@ extern "C" int mmbs_dropout_cast_bf16(const void* in, int32_t in_is_bf16, int64_
   if (int rc = mmbs_device_check()) return rc;
   MMBS_REQUIRE(in && out && rows > 0 && cols > 0 && cols_padded >= cols && cols_padded % 4 == 0 && p >= 0.f && p < 1.f,
                "mmbs_dropout_cast_bf16: bad argument");
+  const bool vec = cols % 8 == 0 && cols_padded % 8 == 0 && in_stride % 8 == 0 &&
+                   reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0;
+  if (vec) {
+    dropout_cast_vec8_kernel<<<blocks_for(rows * (cols_padded / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        in, in_is_bf16, in_stride, static_cast<uint4*>(out), rows, cols, cols_padded / 8, p, seed, tag);
+    MMBS_LAUNCH_CHECK();
+    return MMBS_OK;
+  }
   dropout_cast_kernel<<<blocks_for(rows * (cols_padded / 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       in, in_is_bf16, in_stride, static_cast<uint2*>(out), rows, cols, cols_padded / 4, p, seed, tag);
   MMBS_LAUNCH_CHECK();
@@ -480,6 +603,19 @@ extern "C" int mmbs_mlp_bwd_elementwise(const void* g, int32_t g_is_bf16, int64_
   if (int rc = mmbs_device_check()) return rc;
   MMBS_REQUIRE(g && dz && dzt && m > 0 && n > 0 && n_padded >= n && m_padded >= m && (!relu || act) && p >= 0.f && p < 1.f,
                "mmbs_mlp_bwd_elementwise: bad argument");
+  const bool vec = g_is_bf16 && g_stride % 8 == 0 && (!relu || act_stride % 8 == 0) && n_padded % 8 == 0 &&
+                   m_padded % 8 == 0 && reinterpret_cast<uintptr_t>(g) % 16 == 0 &&
+                   (!relu || reinterpret_cast<uintptr_t>(act) % 16 == 0) && reinterpret_cast<uintptr_t>(dz) % 16 == 0 &&
+                   reinterpret_cast<uintptr_t>(dzt) % 16 == 0 && ceil_div(n_padded, 64) <= 65535;
+  if (vec) {
+    // rows beyond m up to m_padded: the transposed output is written (zeros) for every row group the grid covers
+    dim3 vgrid(unsigned(ceil_div(m_padded, 64)), unsigned(ceil_div(n_padded, 64)));
+    mlp_bwd_elementwise_vec_kernel<<<vgrid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(g), g_stride, static_cast<const __nv_bfloat16*>(act), act_stride, relu, p, seed,
+        tag, m, n, n_padded, m_padded, static_cast<__nv_bfloat16*>(dz), static_cast<__nv_bfloat16*>(dzt), db);
+    MMBS_LAUNCH_CHECK();
+    return MMBS_OK;
+  }
   dim3 grid(unsigned(ceil_div(n_padded, 32)), unsigned(ceil_div(m_padded, 32)));
   mlp_bwd_elementwise_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       g, g_is_bf16, g_stride, static_cast<const __nv_bfloat16*>(act), act_stride, relu, p, seed, tag, m, n, n_padded,
@@ -492,6 +628,12 @@ extern "C" int mmbs_transpose_bf16(const void* in, int64_t in_stride, int64_t ro
                                    void* out, void* stream) {
   if (int rc = mmbs_device_check()) return rc;
   MMBS_REQUIRE(in && out && rows > 0 && cols > 0 && rows_padded >= rows, "mmbs_transpose_bf16: bad argument");
+  if (in_stride == cols && cols % 8 == 0 && rows_padded % 8 == 0 && rows < (int64_t(1) << 31) &&
+      reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
+      ceil_div(cols, 64) <= 65535) {
+    // csrc/train.cu: 64x64 shared-memory transpose with 16-byte global accesses (1x1 "im2col" = plain transpose)
+    return mmbs_im2col_t(in, out, rows, 1, 1, cols, 1, 1, rows_padded, stream);
+  }
   dim3 grid(unsigned(ceil_div(cols, 32)), unsigned(ceil_div(rows_padded, 32)));
   transpose_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(in), in_stride, rows, cols, rows_padded, static_cast<__nv_bfloat16*>(out));

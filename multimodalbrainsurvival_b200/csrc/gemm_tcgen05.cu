@@ -77,6 +77,10 @@ struct ConvParams {
   int32_t a_tx_bytes;       // bytes of one A stage load
   int32_t res_boxes;        // resident-weights mode: number of (N_TILE x 64) weight boxes loaded once
   int32_t kb_per_tile;      // weight boxes per n-tile
+  // split-K (weight-gradient GEMMs: few output tiles, very long K): tile = ks * mn_tiles + (m, n) tile; split ks
+  // covers K chunks [ks * chunks_per_split, ...) and adds its partial sums to the pre-zeroed fp32 output
+  int32_t k_split, chunks_per_split, mn_tiles;
+  FastDiv fd_mn;
   uint32_t idesc;
   int8_t tap_map[GM_MAX_TAPS];
   int8_t tap_dw[GM_MAX_TAPS];
@@ -126,6 +130,22 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int tile, i
   c.h0 = int(ih) * p.th;
   c.n0 = int(in_) * p.tn;
   return c;
+}
+
+// split-K decomposition of a tile index: (m, n) tile and the K-chunk range [c_begin, c_end)
+struct KRange {
+  int mn, c_begin, c_end;
+};
+__device__ __forceinline__ KRange k_range(const ConvParams& p, int tile) {
+  KRange r;
+  r.mn = tile; r.c_begin = 0; r.c_end = p.k_chunks;
+  if (p.k_split > 1) {
+    const int ks = int(fdiv(uint32_t(tile), p.fd_mn));
+    r.mn = tile - ks * p.mn_tiles;
+    r.c_begin = ks * p.chunks_per_split;
+    r.c_end = min(p.k_chunks, r.c_begin + p.chunks_per_split);
+  }
+  return r;
 }
 
 // Epilogue arithmetic for columns [c_begin, c_end) of tile row r: TMEM -> scale/shift (+ residual)
@@ -198,7 +218,11 @@ __device__ __forceinline__ void epilogue_columns(const ConvParams& p, uint32_t t
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
       }
-      if (p.out_f32) {
+      if (p.out_f32 && p.k_split > 1) {
+        float* op = static_cast<float*>(p.out) + row_off + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(op + j, v[j]);   // fire-and-forget reductions (RED.ADD.F32)
+      } else if (p.out_f32) {
         float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + row_off + c0);
 #pragma unroll
         for (int g = 0; g < 8; ++g) op[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
@@ -273,7 +297,6 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   float* s_shift = s_scale + N_TILE;
 
   const int n_tiles = p.c_out / N_TILE;
-  const int k_iters = p.num_taps * p.k_chunks;
   // epilogue organisation: two independent 4-warp groups (double-staged variants without a residual),
   // else all 8 warps on one tile (with a residual the spare staging tile prefetches the next residual)
   const bool group_mode = (NSTG == 2) && !((N_TILE >= 64) && !p.out_f32 && p.residual != nullptr);
@@ -321,11 +344,12 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
     }
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord tcd = tile_coord(p, tile, n_tiles);
+      const KRange kr = k_range(p, tile);
+      const TileCoord tcd = tile_coord(p, kr.mn, n_tiles);
       for (int t = 0; t < p.num_taps; ++t) {
         const CUtensorMap* amap = &p.a_map[p.tap_map[t]];
         const int cw = tcd.w0 + p.tap_dw[t], ch = tcd.h0 + p.tap_dh[t];
-        for (int c = 0; c < p.k_chunks; ++c, ++it) {
+        for (int c = kr.c_begin; c < kr.c_end; ++c, ++it) {
           const uint32_t s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
           tc::mbar_wait(empty_bar + 8 * s, ph ^ 1u);
@@ -347,8 +371,10 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
     if (kResident) tc::mbar_wait(wres_bar, 0);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
       const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
-      const uint32_t nt = uint32_t(tile) - fdiv(uint32_t(tile), p.fd_ntiles) * uint32_t(n_tiles);
+      const KRange kr = k_range(p, tile);
+      const uint32_t nt = uint32_t(kr.mn) - fdiv(uint32_t(kr.mn), p.fd_ntiles) * uint32_t(n_tiles);
       const uint32_t w_tile = wres_u32 + nt * uint32_t(p.kb_per_tile) * L::B_BYTES;
+      const int k_iters = p.num_taps * (kr.c_end - kr.c_begin);
       tc::mbar_wait(tempty_bar + 8 * acc, aph ^ 1u);  // epilogue has drained this accumulator
       tc::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * N_TILE;
@@ -440,7 +466,7 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
       }
       if (tma_res && gt == 0 && tile < p.total_tiles) issue_residual(tile, grp);
       for (uint32_t use = 0; tile < p.total_tiles; tile += tstride, ++use) {
-        const TileCoord tcd = tile_coord(p, tile, n_tiles);
+        const TileCoord tcd = tile_coord(p, k_range(p, tile).mn, n_tiles);
         if (!fixed_nt) load_scale_shift(tcd.nt, g_scale, g_shift, gt, 128);
         // staging[grp] is free: with a residual, its arrival implies the previous store was read out;
         // otherwise the leader waited for the read-out right after committing it
@@ -487,7 +513,7 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
       if (NSTG == 2 && tma_res && et == 0 && int(blockIdx.x) < p.total_tiles) issue_residual(blockIdx.x, 0);
       uint32_t tl = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
-        const TileCoord tcd = tile_coord(p, tile, n_tiles);
+        const TileCoord tcd = tile_coord(p, k_range(p, tile).mn, n_tiles);
         const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
         const uint32_t sb = (NSTG == 2) ? (tl & 1u) : 0u;
         const uint32_t res_parity = (NSTG == 2) ? ((tl >> 1) & 1u) : (tl & 1u);
@@ -598,6 +624,7 @@ struct mmbs_conv_plan {
   int n_tile;
   int stages;
   unsigned grid;
+  size_t zero_bytes;   // split-K: the fp32 output is cleared before every run (the splits accumulate into it)
 };
 
 template <int N_TILE, int STAGES, int NSTG, int A_STAGE = 0, int RES_BYTES = 0>
@@ -623,7 +650,7 @@ static int launch_conv(const mmbs_conv_plan* plan, cudaStream_t stream) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl ? 1 : 0;
+  cfg.numAttrs = (use_pdl && plan->zero_bytes == 0) ? 1 : 0;   // a memset precedes split-K launches: plain ordering
   MMBS_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N_TILE, STAGES, NSTG, A_STAGE, RES_BYTES>, plan->p));
   count_launch();
   return MMBS_OK;
@@ -633,6 +660,7 @@ extern "C" int mmbs_conv_run(const mmbs_conv_plan* plan, void* stream_) {
   if (int rc = mmbs_device_check()) return rc;
   MMBS_REQUIRE(plan != nullptr, "mmbs_conv_run: null plan");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (plan->zero_bytes) MMBS_CUDA_TRY(cudaMemsetAsync(plan->p.out, 0, plan->zero_bytes, stream));
   if (plan->variant == 1) {
     if (plan->n_tile == 64) return launch_conv<64, 5, 2, GM_RES64_A_STAGE, GM_RES64_BYTES>(plan, stream);
     if (plan->n_tile == 128) return launch_conv<128, 5, 2, GM_A_BYTES, GM_RES128_BYTES>(plan, stream);
@@ -763,7 +791,10 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
   }
   p.tiles_w = int(ceil_div(out_w, p.tw)); p.tiles_h = int(ceil_div(out_h, p.th)); p.tiles_n = int(ceil_div(d->batch, p.tn));
   const int64_t m_tiles = int64_t(p.tiles_w) * p.tiles_h * p.tiles_n;
-  plan->n_tile = pick_n_tile(d->c_out, m_tiles, d->stats ? 64 : 32);   // the statistics live on the TMA-store path
+  // weight-gradient shaped GEMMs (fp32 output, no epilogue arithmetic): keep the widest N tile and split K
+  const bool can_split = linear_mode && d->out_f32 && !d->scale && !d->shift && !d->relu && !d->residual && !d->stats &&
+                         getenv("MMBS_NO_SPLITK") == nullptr;
+  plan->n_tile = pick_n_tile(d->c_out, m_tiles, can_split ? 256 : (d->stats ? 64 : 32));   // statistics: TMA-store path
   MMBS_REQUIRE(!d->stats || (out_w % p.tw == 0 && out_h % p.th == 0),
                "conv plan: batch statistics need pixel boxes that tile the %dx%d output exactly", out_h, out_w);
   // epilogue-bound residual layers (short K loop): 128-wide tile = double-staged epilogue with the
@@ -777,8 +808,20 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
     p.res_boxes = (d->c_out / plan->n_tile) * p.kb_per_tile;
   }
   plan->stages = 0;
-  MMBS_REQUIRE(m_tiles * (d->c_out / plan->n_tile) < (int64_t(1) << 31), "conv plan: grid too large");
-  p.total_tiles = int32_t(m_tiles * (d->c_out / plan->n_tile));
+  MMBS_REQUIRE(m_tiles * (d->c_out / plan->n_tile) < (int64_t(1) << 29), "conv plan: grid too large");
+  p.mn_tiles = int32_t(m_tiles * (d->c_out / plan->n_tile));
+  p.k_split = 1; p.chunks_per_split = p.k_chunks;
+  plan->zero_bytes = 0;
+  if (can_split && p.mn_tiles < sm_count()) {
+    int ks = std::min(sm_count() / p.mn_tiles, p.k_chunks / 4);   // fill one wave, >= 4 K chunks per split
+    if (ks >= 2) {
+      p.chunks_per_split = (p.k_chunks + ks - 1) / ks;
+      p.k_split = (p.k_chunks + p.chunks_per_split - 1) / p.chunks_per_split;   // no empty split
+      plan->zero_bytes = size_t(d->in_w) * size_t(d->c_out) * sizeof(float);
+    }
+  }
+  p.fd_mn = make_fastdiv(uint32_t(p.mn_tiles));
+  p.total_tiles = p.mn_tiles * p.k_split;
   plan->grid = unsigned(std::min<int64_t>(p.total_tiles, sm_count()));  // persistent: <= one CTA per SM
   p.idesc = make_idesc_bf16(GM_TILE_M, plan->n_tile);
   p.fd_ntiles = make_fastdiv(uint32_t(d->c_out / plan->n_tile));

@@ -182,10 +182,12 @@ class _MLPTrainEngine:
         _lib = self._lib
         L = _lib.lib()
         self.refresh()
-        x = x.detach().float().contiguous()
+        x = x.detach()
+        x = x.contiguous() if x.dtype == torch.bfloat16 else x.float().contiguous()   # bf16 cohorts are read as is
         ps = [(l[2] if training else 0.0) for l in self.layers]
         self.ps = ps
-        _lib.check(L.mmbs_dropout_cast_bf16(_lib.ptr(x), 0, x.shape[1], _lib.ptr(self.hin[0]), self.m, x.shape[1],
+        _lib.check(L.mmbs_dropout_cast_bf16(_lib.ptr(x), int(x.dtype == torch.bfloat16), x.shape[1],
+                                            _lib.ptr(self.hin[0]), self.m, x.shape[1],
                                             self.kp[0], ps[0], seed, 0, _lib.stream_ptr()), "mmbs_dropout_cast_bf16")
         for i in range(len(self.layers)):
             self.fwd[i].run()

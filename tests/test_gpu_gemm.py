@@ -131,3 +131,23 @@ def test_stem_matches_torch():
     _assert_close(out, ref.permute(0, 2, 3, 1).float(), 6e-3, "stem")
     ref_pool = F.max_pool2d(out.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).cpu()
     assert torch.equal(pooled.float().cpu(), ref_pool)
+
+
+@pytest.mark.parametrize("m,n,k", [(256, 512, 6400), (32, 256, 64 * 333), (2048, 512, 6272 + 0), (128, 4608, 64 * 7),
+                                    (512, 1024, 64 * 5)])
+def test_split_k_weight_gradient_gemm(m, n, k):
+    """fp32-output GEMMs without epilogue arithmetic (the weight-gradient shape: few output tiles, long K) take
+    the split-K path: partial sums are accumulated with fp32 reductions into the cleared output; repeated runs must
+    not accumulate across calls."""
+    from multimodalbrainsurvival_b200 import engine
+    torch.manual_seed(m + n + k)
+    a = torch.randn(m, k, device=DEV).to(torch.bfloat16)
+    b = torch.randn(n, k, device=DEV).to(torch.bfloat16)
+    out = torch.full((m, n), 7.0, dtype=torch.float32, device=DEV)     # stale contents must be discarded
+    plan = engine.linear_plan(a, b, None, out)
+    plan.run()
+    plan.run()
+    torch.cuda.synchronize()
+    ref = a.double() @ b.double().t()
+    err = float((out.double() - ref).abs().max())
+    assert err <= 2e-5 * float(ref.abs().max()) + 1e-3, f"max err {err}"

@@ -43,6 +43,72 @@ def build(kind, torch, dev):
     return model.to(dev).train()
 
 
+def run_mlp(kind, torch, dev, world=1, rank=0, steps=5, warmup=3, rows=None):
+    """kind 'rna'  : BASELINE config 1 - RNAOnlyModel (12778 -> 4096 -> 2048 -> 1), B = 128, Cox, Adam
+                     (/root/reference/2_GeneExpression/1_GeneExpress_train.py:247-257,150-170)
+       kind 'early': BASELINE config 4 - early-fusion MLP (4096 -> 2048 -> 200 -> 1) as one full-batch step over a
+                     cohort shard of `rows` samples per GPU (bf16 features generated on the device), Cox loss over the
+                     risk set all-gathered from every rank (/root/reference/3_EarlyFusion/2_EarlyFusion_train.py:242-253)."""
+    import torch.distributed as dist
+    import torch.nn as nn
+    from multimodalbrainsurvival_b200 import dist as mdist
+    from multimodalbrainsurvival_b200 import _lib, models
+    torch.manual_seed(1111)
+    if kind == "rna":
+        rows = rows or 128
+        rna = nn.Sequential(nn.Dropout(), nn.Linear(12778, 4096), nn.ReLU(), nn.Dropout(), nn.Linear(4096, 2048))
+        model = models.RNAOnlyModel(rna, nn.Sequential(nn.Linear(2048, 1))).to(dev).train()
+        width, mflop = 12778, 260.0      # SURVEY.md §8d config 1: fwd + wgrad + dgrad (no dgrad into the input)
+        dtype = torch.float32
+    else:
+        rows = rows or 1_250_000
+        model = models.accelerate(nn.Sequential(nn.Dropout(), nn.Linear(4096, 2048), nn.ReLU(), nn.Dropout(),
+                                                nn.Linear(2048, 200), nn.ReLU(), nn.Dropout(), nn.Linear(200, 1))
+                                  ).to(dev).train()
+        width, mflop = 4096, 36.0        # SURVEY.md §8d config 4
+        dtype = torch.bfloat16
+    params = list(model.parameters())
+    opt = torch.optim.Adam(params, lr=1e-5, weight_decay=1e-5)
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    x = torch.randn(rows, width, device=dev, generator=g, dtype=torch.float32 if rows <= 4096 else torch.bfloat16).to(dtype)
+    times = torch.rand(rows, device=dev, generator=g) * 200 + torch.arange(rows, device=dev) * 2.0 ** -20
+    status = (torch.rand(rows, device=dev, generator=g) < 0.6).float()
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        out = model(x)
+        loss = mdist.global_cox_loss(out.view(-1), times, status, equal_sizes=True)
+        loss.backward()
+        mdist.allreduce_gradients(params)
+        opt.step()
+        return loss
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    sync()
+    l0 = _lib.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        loss = step()
+    b.record()
+    sync()
+    ms = a.elapsed_time(b) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"workload": f"{kind}_mlp_cox_train_step ({rows} samples per GPU, risk set of {rows * world})",
+            "ms_per_step": ms, "steps_per_s": 1e3 / ms, "samples_per_s": world * rows * 1e3 / ms,
+            "tflops_per_gpu": rows * mflop * 1e6 / (ms * 1e-3) / 1e12, "n_gpus": world,
+            "gpu_launches_per_step": (_lib.launch_count() - l0) / steps, "loss": float(loss.detach())}
+
+
 def run(kind, torch, dev, world=1, rank=0, steps=10, warmup=3, batch=128):
     import torch.distributed as dist
     from multimodalbrainsurvival_b200 import dist as mdist
@@ -127,7 +193,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    r = run(kind, torch, dev, world, rank, steps)
+    r = run_mlp(kind, torch, dev, world, rank, steps) if kind in ("rna", "early") else run(kind, torch, dev, world, rank, steps)
     if rank == 0:
         import json
         print(json.dumps(r))
