@@ -208,6 +208,29 @@ int mmbs_bn_apply(const void* x_bf16, const float* scale, const float* shift, co
 /* MaxPool2d(3,2,1)(relu(x*scale + shift)), NHWC bf16 (training-mode stem tail, resnet.py:152-155) */
 int mmbs_bn_relu_maxpool_3x3s2(const void* in_bf16, const float* scale, const float* shift, void* out_bf16,
                                int64_t batch, int64_t h, int64_t w, int64_t c, void* stream);
+/* Fused finalize + apply: the kernel derives scale/shift from the epilogue sums itself (no finalize launch between the
+ * convolution and its normalisation), publishes scale/shift/mean/invstd for the backward pass and updates the running
+ * statistics (momentum, unbiased variance) exactly once.  Launched with programmatic dependent launch. */
+typedef struct {
+  const float* stats;     /* [2][c] sum | sum of squares (mmbs_conv_desc.stats) */
+  const float* gamma;     /* [c] BatchNorm2d.weight */
+  const float* beta;      /* [c] BatchNorm2d.bias */
+  float* running_mean;    /* [c] updated in place, or NULL */
+  float* running_var;
+  float* scale_out;       /* [c] each: gamma*invstd, beta - mean*scale, batch mean, 1/sqrt(var+eps) */
+  float* shift_out;
+  float* mean_out;
+  float* invstd_out;
+  float eps, momentum;
+  int64_t count;          /* values per channel = B*H*W */
+  int64_t c;
+} mmbs_bn_train_desc;
+/* out = [relu]( bn(x) + R ), R = 0 | residual | res_bn(residual); bf16 [rows, c] */
+int mmbs_bn_train_apply(const mmbs_bn_train_desc* bn, const void* x_bf16, const void* residual_bf16,
+                        const mmbs_bn_train_desc* res_bn, int32_t relu, void* out_bf16, int64_t rows, void* stream);
+/* MaxPool2d(3,2,1)(relu(bn(x))), NHWC bf16 [B,h,w,c] (training-mode stem tail) */
+int mmbs_bn_train_relu_maxpool_3x3s2(const mmbs_bn_train_desc* bn, const void* in_bf16, void* out_bf16, int64_t batch,
+                                     int64_t h, int64_t w, void* stream);
 /* gradient of AvgPool2d(7)+flatten: dfeat fp32 [B,c] -> bf16 [B,hw,c] */
 int mmbs_avgpool_global_bwd(const float* dfeat, void* out_bf16, int64_t batch, int64_t hw, int64_t c, void* stream);
 /* sums[2][c] (pre-zeroed) += sum dz | sum dz*xhat,  dz = g * (relu_mask > 0), xhat = (raw-mean)*invstd;

@@ -35,6 +35,15 @@ class ConvDesc(ctypes.Structure):
     ]
 
 
+class BnTrainDesc(ctypes.Structure):
+    """mmbs_bn_train_desc (include/mmbs.h)."""
+    _fields_ = [
+        ("stats", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("running_mean", c_void_p),
+        ("running_var", c_void_p), ("scale_out", c_void_p), ("shift_out", c_void_p), ("mean_out", c_void_p),
+        ("invstd_out", c_void_p), ("eps", c_float), ("momentum", c_float), ("count", c_i64), ("c", c_i64),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/mmbs.h declares
 SIGNATURES = {
     "mmbs_last_error": (ctypes.c_char_p, []),
@@ -89,6 +98,10 @@ SIGNATURES = {
     "mmbs_unpack_conv_wgrad": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
     "mmbs_scatter_stride2": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p]),
     "mmbs_add_relu_mask": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
+    "mmbs_bn_train_apply": (ctypes.c_int, [ctypes.POINTER(BnTrainDesc), c_void_p, c_void_p, ctypes.POINTER(BnTrainDesc),
+                                           c_i32, c_void_p, c_i64, c_void_p]),
+    "mmbs_bn_train_relu_maxpool_3x3s2": (ctypes.c_int, [ctypes.POINTER(BnTrainDesc), c_void_p, c_void_p, c_i64, c_i64,
+                                                        c_i64, c_void_p]),
     "mmbs_concordance_counts": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
 }
 

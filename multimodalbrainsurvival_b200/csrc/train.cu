@@ -8,11 +8,14 @@
 //   /root/reference/1_HistoPathology/2_HistoPath_train.py:541-551 (n_layers_to_train).
 // The per-channel sums come out of the conv kernel's epilogue (gemm_tcgen05.cu, ConvParams::stats).
 #include <algorithm>
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
 
 namespace mmbs {
+
+constexpr int BNA_ITER = 8;   // 8-channel items per thread in the BatchNorm apply kernels
 
 __device__ __forceinline__ uint32_t tr_pack2(float a, float b) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -28,6 +31,10 @@ __device__ __forceinline__ void tr_unpack8(const uint4& u, float* f) {
 }
 __device__ __forceinline__ uint4 tr_pack8(const float* f) {
   return make_uint4(tr_pack2(f[0], f[1]), tr_pack2(f[2], f[3]), tr_pack2(f[4], f[5]), tr_pack2(f[6], f[7]));
+}
+__device__ __forceinline__ void tr_ld8(const float* p, int g, float* v) {
+  *reinterpret_cast<float4*>(v) = __ldg(reinterpret_cast<const float4*>(p) + 2 * g);
+  *reinterpret_cast<float4*>(v + 4) = __ldg(reinterpret_cast<const float4*>(p) + 2 * g + 1);
 }
 
 // ---- BatchNorm (training) finalize: sums -> scale/shift for the apply pass, saved mean / invstd for the
@@ -132,6 +139,137 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const uint4* __res
   out[((n * oh + y) * int64_t(ow) + x) * c8 + g] = tr_pack8(m);
 }
 
+// ---- fused finalize + apply (training forward): the per-channel scale/shift are recomputed by every thread
+// from the epilogue sums (a handful of FMAs + one rsqrt per channel, free next to the 32-48 bytes the thread
+// moves), so no separate finalize launch sits between the convolution and its normalisation.  The first c8
+// threads of the grid also publish mean / invstd / scale / shift for the backward pass and update the running
+// statistics.  Launched with programmatic dependent launch: the prologue overlaps the tail of the convolution.
+struct BnTrain {
+  const float* stats;      // [2][c] sum | sum of squares from the conv epilogue
+  const float* gamma;
+  const float* beta;
+  float* running_mean;     // may be null
+  float* running_var;
+  float* scale_out;        // [c] each, for the backward pass
+  float* shift_out;
+  float* mean_out;
+  float* invstd_out;
+  float inv_count, unbias, eps, momentum;
+  int c;
+};
+
+__device__ __forceinline__ void bn_train_coeffs(const BnTrain& b, int g, bool publish, float* sc, float* sh) {
+  float s1[8], s2[8], ga[8], be[8];
+  tr_ld8(b.stats, g, s1);
+  tr_ld8(b.stats + b.c, g, s2);
+  tr_ld8(b.gamma, g, ga);
+  tr_ld8(b.beta, g, be);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float mean = s1[j] * b.inv_count;
+    const float var = fmaxf(fmaf(-mean, mean, s2[j] * b.inv_count), 0.f);
+    const float invstd = rsqrtf(var + b.eps);
+    sc[j] = ga[j] * invstd;
+    sh[j] = fmaf(-mean, sc[j], be[j]);
+    if (publish) {
+      const int ch = g * 8 + j;
+      b.scale_out[ch] = sc[j];
+      b.shift_out[ch] = sh[j];
+      b.mean_out[ch] = mean;
+      b.invstd_out[ch] = invstd;
+      if (b.running_mean) b.running_mean[ch] = (1.0f - b.momentum) * b.running_mean[ch] + b.momentum * mean;
+      if (b.running_var) b.running_var[ch] = (1.0f - b.momentum) * b.running_var[ch] + b.momentum * var * b.unbias;
+    }
+  }
+}
+
+// res_mode: 0 none, 1 identity residual, 2 residual normalised with its own BatchNorm (downsample branch).
+// A block covers BNA_ITER * 256 consecutive 8-channel items; c8 divides 256, so every item of a thread belongs to
+// the same channel group and the coefficients are derived once per thread (the per-item parameter loads of a naive
+// kernel move 4x more L1 bytes than the payload moves HBM bytes and bound it).
+__global__ void __launch_bounds__(256) bn_train_apply_kernel(const __grid_constant__ BnTrain bn,
+                                                             const __grid_constant__ BnTrain rbn,
+                                                             const uint4* __restrict__ x, const uint4* __restrict__ r,
+                                                             int res_mode, int relu, uint4* __restrict__ out,
+                                                             int64_t total, int c8) {
+  // (no early launch_dependents: a persistent conv CTA that became resident while this HBM-bound kernel is still
+  //  running would take 46 K registers per SM away from it)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int64_t base = int64_t(blockIdx.x) * (BNA_ITER * 256) + threadIdx.x;
+  if (base >= total) return;
+  const int g = int(base & (c8 - 1));
+  const bool publish = base < c8;
+  float sc[8], sh[8], rsc[8], rsh[8];
+  bn_train_coeffs(bn, g, publish, sc, sh);
+  if (res_mode == 2) bn_train_coeffs(rbn, g, publish, rsc, rsh);
+  uint4 xv[BNA_ITER], rv4[BNA_ITER];
+#pragma unroll
+  for (int k = 0; k < BNA_ITER; ++k) {
+    const int64_t i = base + int64_t(k) * 256;
+    if (i < total) {
+      xv[k] = x[i];
+      if (res_mode != 0) rv4[k] = __ldg(r + i);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < BNA_ITER; ++k) {
+    const int64_t i = base + int64_t(k) * 256;
+    if (i >= total) break;
+    float v[8];
+    tr_unpack8(xv[k], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+    if (res_mode != 0) {
+      float rv[8];
+      tr_unpack8(rv4[k], rv);
+      if (res_mode == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rv[j] = fmaf(rv[j], rsc[j], rsh[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += rv[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    out[i] = tr_pack8(v);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_train_relu_maxpool_kernel(const __grid_constant__ BnTrain bn,
+                                                                    const uint4* __restrict__ in,
+                                                                    uint4* __restrict__ out, int h, int w, int c8,
+                                                                    int c8_shift) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;
+  const int xc = blockIdx.x * 256 + threadIdx.x;
+  if (xc >= ow * c8) return;
+  const int g = xc & (c8 - 1), x = xc >> c8_shift;
+  const int y = blockIdx.y;
+  const int64_t n = blockIdx.z;
+  float sc[8], sh[8], m[8];
+  bn_train_coeffs(bn, g, (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && xc < c8, sc, sh);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = 0.f;   // relu(.) >= 0 and every window holds an in-range pixel
+  const uint4* base = in + n * int64_t(h) * w * c8 + g;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int iy = 2 * y - 1 + dy;
+    if (iy < 0 || iy >= h) continue;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int ix = 2 * x - 1 + dx;
+      if (ix < 0 || ix >= w) continue;
+      float v[8];
+      tr_unpack8(__ldg(base + (int64_t(iy) * w + ix) * c8), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], fmaf(v[j], sc[j], sh[j]));
+    }
+  }
+  out[((n * oh + y) * int64_t(ow) + x) * c8 + g] = tr_pack8(m);
+}
+
 // ---- grad of AvgPool2d(7)+flatten: dfeat fp32 [B, C] -> bf16 [B, hw, C] = dfeat / hw
 __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restrict__ dfeat, uint4* __restrict__ out,
                                                           int64_t total, int hw, int c8) {
@@ -207,10 +345,6 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint4* __restr
 
 // ---- BatchNorm backward, pass 2: draw = scale * (dz - s1/n - xhat * s2/n), scale = gamma * invstd, i.e.
 // draw = A*dz + Bx*raw + C with per-channel A = scale, Bx = -scale*invstd*s2/n, C = -scale*s1/n - Bx*mean.
-__device__ __forceinline__ void tr_ld8(const float* p, int g, float* v) {
-  *reinterpret_cast<float4*>(v) = __ldg(reinterpret_cast<const float4*>(p) + 2 * g);
-  *reinterpret_cast<float4*>(v + 4) = __ldg(reinterpret_cast<const float4*>(p) + 2 * g + 1);
-}
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ mask,
                                                            const uint4* __restrict__ raw,
                                                            const float* __restrict__ mean,
@@ -218,29 +352,52 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
                                                            const float* __restrict__ scale,
                                                            const float* __restrict__ sums, float inv_count,
                                                            uint4* __restrict__ out, int64_t total, int c8) {
-  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
-  if (i >= total) return;
-  const int cg = int(i % c8);
-  float gv[8], xv[8], o[8], mu[8], is[8], sc[8], s1[8], s2[8];
-  tr_unpack8(__ldg(g + i), gv);
-  tr_unpack8(__ldg(raw + i), xv);
-  tr_ld8(mean, cg, mu);
-  tr_ld8(invstd, cg, is);
-  tr_ld8(scale, cg, sc);
-  tr_ld8(sums, cg, s1);
-  tr_ld8(sums + int64_t(c8) * 8, cg, s2);
-  if (mask != nullptr) {
-    float mv[8];
-    tr_unpack8(__ldg(mask + i), mv);
+  // c8 divides 256: all items of a thread share one channel group, the coefficients are derived once
+  const int64_t base = int64_t(blockIdx.x) * (BNA_ITER * 256) + threadIdx.x;
+  if (base >= total) return;
+  const int cg = int(base & (c8 - 1));
+  float a[8], bx[8], c0[8];
+  {
+    float mu[8], is[8], sc[8], s1[8], s2[8];
+    tr_ld8(mean, cg, mu);
+    tr_ld8(invstd, cg, is);
+    tr_ld8(scale, cg, sc);
+    tr_ld8(sums, cg, s1);
+    tr_ld8(sums + int64_t(c8) * 8, cg, s2);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) gv[j] = mv[j] > 0.f ? gv[j] : 0.f;
+    for (int j = 0; j < 8; ++j) {
+      a[j] = sc[j];
+      bx[j] = -sc[j] * is[j] * s2[j] * inv_count;
+      c0[j] = -sc[j] * s1[j] * inv_count - bx[j] * mu[j];
+    }
+  }
+  uint4 gv4[BNA_ITER], xv4[BNA_ITER], mv4[BNA_ITER];
+#pragma unroll
+  for (int k = 0; k < BNA_ITER; ++k) {
+    const int64_t i = base + int64_t(k) * 256;
+    if (i < total) {
+      gv4[k] = __ldg(g + i);
+      xv4[k] = __ldg(raw + i);
+      if (mask != nullptr) mv4[k] = __ldg(mask + i);
+    }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float xh = (xv[j] - mu[j]) * is[j];
-    o[j] = sc[j] * (gv[j] - s1[j] * inv_count - xh * s2[j] * inv_count);
+  for (int k = 0; k < BNA_ITER; ++k) {
+    const int64_t i = base + int64_t(k) * 256;
+    if (i >= total) break;
+    float gv[8], xv[8], o[8];
+    tr_unpack8(gv4[k], gv);
+    tr_unpack8(xv4[k], xv);
+    if (mask != nullptr) {
+      float mv[8];
+      tr_unpack8(mv4[k], mv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gv[j] = mv[j] > 0.f ? gv[j] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(a[j], gv[j], fmaf(bx[j], xv[j], c0[j]));
+    out[i] = tr_pack8(o);
   }
-  out[i] = tr_pack8(o);
 }
 
 // ---- wgrad B operand: x NHWC bf16 [B,H,W,C] -> colT [k*k*C, Pp] bf16,
@@ -427,7 +584,8 @@ extern "C" int mmbs_bn_bwd_apply(const void* g, const void* relu_mask, const voi
                    al16(raw) && al16(relu_mask) && al16(out),
                "mmbs_bn_bwd_apply: bad argument");
   const int64_t total = rows * (c / 8);
-  bn_bwd_apply_kernel<<<tr_blocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  MMBS_REQUIRE(c / 8 <= 256 && ((c / 8) & (c / 8 - 1)) == 0, "mmbs_bn_bwd_apply: c/8 must be a power of two <= 256");
+  bn_bwd_apply_kernel<<<tr_blocks(total, 256 * BNA_ITER), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(g), static_cast<const uint4*>(relu_mask), static_cast<const uint4*>(raw), mean, invstd,
       scale, sums, 1.0f / float(rows), static_cast<uint4*>(out), total, int(c / 8));
   MMBS_LAUNCH_CHECK();
@@ -495,4 +653,81 @@ extern "C" int mmbs_add_relu_mask(const void* a, const void* g, const void* mask
       static_cast<uint4*>(out), elems / 8);
   MMBS_LAUNCH_CHECK();
   return MMBS_OK;
+}
+
+// ------------------------------------------------------------------ fused finalize + apply (training forward)
+static int make_bn_train(const mmbs_bn_train_desc* d, BnTrain* b, const char* what) {
+  MMBS_REQUIRE(d && d->stats && d->gamma && d->beta && d->scale_out && d->shift_out && d->mean_out && d->invstd_out &&
+                   d->c > 0 && d->c % 8 == 0 && d->count > 0 && al16(d->stats) && al16(d->gamma) && al16(d->beta),
+               "%s: bad BatchNorm descriptor", what);
+  b->stats = d->stats; b->gamma = d->gamma; b->beta = d->beta;
+  b->running_mean = d->running_mean; b->running_var = d->running_var;
+  b->scale_out = d->scale_out; b->shift_out = d->shift_out; b->mean_out = d->mean_out; b->invstd_out = d->invstd_out;
+  b->inv_count = float(1.0 / double(d->count));
+  b->unbias = d->count > 1 ? float(double(d->count) / double(d->count - 1)) : 1.0f;
+  b->eps = d->eps; b->momentum = d->momentum; b->c = int(d->c);
+  return MMBS_OK;
+}
+
+template <typename... KArgs, typename... Args>
+static int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  // Programmatic dependent launch is opt-in here (MMBS_TRAIN_PDL=1): measured on B200 it makes the step SLOWER
+  // (forward 3.79 -> 4.08 ms at B = 128) - blocks of these wide grids become resident behind the running
+  // persistent convolution and take issue slots / registers from it.
+  static const bool use_pdl = []() {
+    const char* e = getenv("MMBS_TRAIN_PDL");
+    return e && e[0] == '1';
+  }();
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  MMBS_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, args...));
+  count_launch();
+  return MMBS_OK;
+}
+
+extern "C" int mmbs_bn_train_apply(const mmbs_bn_train_desc* bn, const void* x, const void* residual,
+                                   const mmbs_bn_train_desc* res_bn, int32_t relu, void* out, int64_t rows,
+                                   void* stream) {
+  if (int rc = mmbs_device_check()) return rc;
+  BnTrain b, rb;
+  if (int rc = make_bn_train(bn, &b, "mmbs_bn_train_apply")) return rc;
+  rb = b;
+  if (res_bn) {
+    if (int rc = make_bn_train(res_bn, &rb, "mmbs_bn_train_apply (residual)")) return rc;
+    MMBS_REQUIRE(res_bn->c == bn->c && residual, "mmbs_bn_train_apply: residual BatchNorm width mismatch");
+  }
+  MMBS_REQUIRE(x && out && rows > 0 && al16(x) && al16(out) && al16(residual), "mmbs_bn_train_apply: bad argument");
+  const int c8 = int(bn->c / 8);
+  MMBS_REQUIRE(c8 <= 256 && (c8 & (c8 - 1)) == 0, "mmbs_bn_train_apply: c/8 must be a power of two <= 256 (c=%lld)",
+               (long long)bn->c);
+  const int64_t total = rows * c8;
+  const int res_mode = residual ? (res_bn ? 2 : 1) : 0;
+  return launch_pdl(bn_train_apply_kernel, dim3(tr_blocks(total, 256 * BNA_ITER)), dim3(256), static_cast<cudaStream_t>(stream), b,
+                    rb, static_cast<const uint4*>(x), static_cast<const uint4*>(residual), res_mode, int(relu),
+                    static_cast<uint4*>(out), total, c8);
+}
+
+extern "C" int mmbs_bn_train_relu_maxpool_3x3s2(const mmbs_bn_train_desc* bn, const void* in, void* out, int64_t batch,
+                                                int64_t h, int64_t w, void* stream) {
+  if (int rc = mmbs_device_check()) return rc;
+  BnTrain b;
+  if (int rc = make_bn_train(bn, &b, "mmbs_bn_train_relu_maxpool_3x3s2")) return rc;
+  MMBS_REQUIRE(in && out && batch > 0 && h > 0 && w > 0, "mmbs_bn_train_relu_maxpool_3x3s2: bad argument");
+  const int64_t oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;
+  const int c8 = int(bn->c / 8);
+  int shift_bits = 0;
+  while ((1 << shift_bits) < c8) ++shift_bits;
+  MMBS_REQUIRE((1 << shift_bits) == c8 && batch <= 65535 && oh <= 65535,
+               "mmbs_bn_train_relu_maxpool_3x3s2: c/8 must be a power of two");
+  dim3 grid(unsigned(ceil_div(ow * c8, 256)), unsigned(oh), unsigned(batch));
+  return launch_pdl(bn_train_relu_maxpool_kernel, grid, dim3(256), static_cast<cudaStream_t>(stream), b,
+                    static_cast<const uint4*>(in), static_cast<uint4*>(out), int(h), int(w), c8, shift_bits);
 }

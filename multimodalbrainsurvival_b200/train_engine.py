@@ -7,20 +7,22 @@ Reference arithmetic replaced: ``ResNet.forward_extract`` under ``model.train()`
 (/root/reference/5_JointFusion/resnet.py:151-165, ``Bottleneck.forward`` :70-90) and its autograd graph.
 
 Forward, per convolution:   tcgen05 implicit GEMM writing the raw bf16 output and the per-channel
-sum / sum of squares from its epilogue -> ``mmbs_bn_finalize`` (scale/shift, saved mean/invstd, running
-statistics updated in place like ``nn.BatchNorm2d``) -> ``mmbs_bn_apply`` (normalise + residual + ReLU).
+sum / sum of squares from its epilogue -> ``mmbs_bn_train_apply`` (finalize fused into the normalise + residual +
+ReLU pass: scale/shift derived in-kernel, saved mean/invstd, running statistics updated in place like
+``nn.BatchNorm2d``).
 Backward, per layer4 conv:  BatchNorm backward (reduce + apply), data gradient = the same conv kernel
 on flipped/transposed weights, weight gradient = the same GEMM kernel on K-major (pixel-major) operands
 with fp32 accumulation and output.  PyTorch provides device memory, streams and the autograd hook only.
 """
 from __future__ import annotations
 
+import ctypes
 import os
 
 import torch
 
 from . import _lib, engine
-from ._lib import c_void_p
+from ._lib import BnTrainDesc
 
 
 def _pad64(n):
@@ -129,29 +131,36 @@ class ResNetTrainEngine:
         return st
 
     def _add_conv_bn(self, cv, st, x, raw, *, ksize, stride, c_in, in_hw=None, halo=False):
+        """The convolution writing its raw bf16 output and the per-channel sums of its BatchNorm."""
         plan = engine.conv_plan(x, cv.w, raw, ksize=ksize, stride=stride, c_in=c_in, in_hw=in_hw, halo_weights=halo,
                                 stats=st.stats)
         self._keep.append(plan)
-        count = raw.shape[0] * raw.shape[1] * raw.shape[2]
-        L = _lib.lib()
-        bn = st.bn
+        st.count = raw.shape[0] * raw.shape[1] * raw.shape[2]
+        self.fwd_steps.append(plan.run)
 
-        def finalize():
-            _ck(L.mmbs_bn_finalize(_lib.ptr(st.stats), st.c, count, _lib.ptr(bn.weight), _lib.ptr(bn.bias),
-                                   float(bn.eps), float(bn.momentum), _lib.ptr(bn.running_mean),
-                                   _lib.ptr(bn.running_var), _lib.ptr(st.scale), _lib.ptr(st.shift),
-                                   _lib.ptr(st.mean), _lib.ptr(st.invstd), _lib.stream_ptr()), "mmbs_bn_finalize")
-        self.fwd_steps += [plan.run, finalize]
+    @staticmethod
+    def _bn_desc(st):
+        """mmbs_bn_train_desc of one BatchNorm (built per call: parameters may have been re-allocated)."""
+        bn = st.bn
+        d = BnTrainDesc()
+        d.stats, d.gamma, d.beta = st.stats.data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr()
+        d.running_mean, d.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+        d.scale_out, d.shift_out = st.scale.data_ptr(), st.shift.data_ptr()
+        d.mean_out, d.invstd_out = st.mean.data_ptr(), st.invstd.data_ptr()
+        d.eps, d.momentum, d.count, d.c = float(bn.eps), float(bn.momentum), st.count, st.c
+        return d
 
     def _add_apply(self, raw, st, out, relu=True, res=None, res_st=None):
+        """Fused BatchNorm finalize + normalise (+ residual) (+ ReLU): mmbs_bn_train_apply."""
         L = _lib.lib()
-        rows, c = raw.numel() // raw.shape[-1], raw.shape[-1]
+        rows = raw.numel() // raw.shape[-1]
 
         def apply():
-            _ck(L.mmbs_bn_apply(_lib.ptr(raw), _lib.ptr(st.scale), _lib.ptr(st.shift), _lib.ptr(res),
-                                _lib.ptr(res_st.scale) if res_st else c_void_p(0),
-                                _lib.ptr(res_st.shift) if res_st else c_void_p(0), int(relu), _lib.ptr(out), rows, c,
-                                _lib.stream_ptr()), "mmbs_bn_apply")
+            d = self._bn_desc(st)
+            rd = self._bn_desc(res_st) if res_st is not None else None
+            _ck(L.mmbs_bn_train_apply(ctypes.byref(d), _lib.ptr(raw), _lib.ptr(res),
+                                      ctypes.byref(rd) if rd is not None else None, int(relu), _lib.ptr(out), rows,
+                                      _lib.stream_ptr()), "mmbs_bn_train_apply")
         self.fwd_steps.append(apply)
 
     def _build(self):
@@ -166,9 +175,9 @@ class ResNetTrainEngine:
         raw0 = self._buf(B, 112, 112, 64)
         pool = self._buf(B, 56, 56, 64)
         self._add_conv_bn(cv0, st0, self.x_s2d, raw0, ksize=4, stride=1, c_in=16, in_hw=(116, 116))
-        self.fwd_steps.append(lambda: _ck(L.mmbs_bn_relu_maxpool_3x3s2(
-            _lib.ptr(raw0), _lib.ptr(st0.scale), _lib.ptr(st0.shift), _lib.ptr(pool), B, 112, 112, 64,
-            _lib.stream_ptr()), "mmbs_bn_relu_maxpool_3x3s2"))
+        self.fwd_steps.append(lambda: _ck(L.mmbs_bn_train_relu_maxpool_3x3s2(
+            ctypes.byref(self._bn_desc(st0)), _lib.ptr(raw0), _lib.ptr(pool), B, 112, 112, _lib.stream_ptr()),
+            "mmbs_bn_train_relu_maxpool_3x3s2"))
         # ---- bottlenecks
         x = pool
         for li, layer in enumerate([net.layer1, net.layer2, net.layer3, net.layer4]):
