@@ -119,6 +119,26 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat
   out[i] = __float2bfloat16_rn(w[((o * c_in + ci) * k + kh) * k + kw]);
 }
 
+// k = 1: a plain cast, 4 elements per thread
+__global__ void __launch_bounds__(256) cast_bf16_vec4_kernel(const float4* __restrict__ in, uint2* __restrict__ out,
+                                                             int64_t n4) {
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = __ldg(in + i);
+  out[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+// k = 3: one thread per (o, ci) moves the 9 taps (contiguous 36-byte read, 9 writes coalesced over ci)
+__global__ void __launch_bounds__(256) pack_conv_weight3_kernel(const float* __restrict__ w,
+                                                                __nv_bfloat16* __restrict__ out, int64_t c_out,
+                                                                int64_t c_in) {
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= c_out * c_in) return;
+  const int64_t ci = i % c_in, o = i / c_in;
+  const float* src = w + i * 9;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) out[(o * 9 + t) * c_in + ci] = __float2bfloat16_rn(__ldg(src + t));
+}
+
 __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ mean, const float* __restrict__ var, float eps,
                                int64_t c, float* __restrict__ scale, float* __restrict__ shift) {
@@ -258,8 +278,16 @@ extern "C" int mmbs_pack_conv_weight(const float* w, void* out, int64_t c_out, i
                                      void* stream) {
   if (int rc = mmbs_device_check()) return rc;
   MMBS_REQUIRE(w && out && c_out > 0 && c_in > 0 && k > 0, "mmbs_pack_conv_weight: bad argument");
-  pack_conv_weight_kernel<<<blocks_for(c_out * c_in * k * k, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, static_cast<__nv_bfloat16*>(out), c_out, c_in, k);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t total = c_out * c_in * k * k;
+  if (k == 1 && total % 4 == 0 && reinterpret_cast<uintptr_t>(w) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 8 == 0)
+    cast_bf16_vec4_kernel<<<blocks_for(total / 4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(w),
+                                                                     static_cast<uint2*>(out), total / 4);
+  else if (k == 3)
+    pack_conv_weight3_kernel<<<blocks_for(c_out * c_in, 256), 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(out), c_out,
+                                                                           c_in);
+  else
+    pack_conv_weight_kernel<<<blocks_for(total, 256), 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(out), c_out, c_in, k);
   MMBS_LAUNCH_CHECK();
   return MMBS_OK;
 }

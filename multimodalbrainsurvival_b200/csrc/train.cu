@@ -457,6 +457,18 @@ __global__ void pack_conv_weight_dgrad_kernel(const float* __restrict__ w, __nv_
   out[i] = __float2bfloat16_rn(w[((o * c_in + ci) * k + (k - 1 - kh)) * k + (k - 1 - kw)]);
 }
 
+// k = 3 variant: one thread per (ci, o), o fastest: 9 writes coalesced over o, one 36-byte read
+__global__ void __launch_bounds__(256) pack_conv_weight_dgrad3_kernel(const float* __restrict__ w,
+                                                                      __nv_bfloat16* __restrict__ out, int64_t c_out,
+                                                                      int64_t c_in) {
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= c_out * c_in) return;
+  const int64_t o = i % c_out, ci = i / c_out;
+  const float* src = w + (o * c_in + ci) * 9;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) out[(ci * 9 + t) * c_out + o] = __float2bfloat16_rn(__ldg(src + 8 - t));
+}
+
 // ---- wgrad result [O][kh][kw][I] fp32 -> OIHW fp32 (the layout of nn.Conv2d.weight.grad)
 __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ g, float* __restrict__ out, int64_t c_out,
                                          int64_t c_in, int64_t k) {
@@ -615,8 +627,14 @@ extern "C" int mmbs_pack_conv_weight_dgrad(const float* w, void* out, int64_t c_
                                            void* stream) {
   if (int rc = mmbs_device_check()) return rc;
   MMBS_REQUIRE(w && out && c_out > 0 && c_in > 0 && k > 0, "mmbs_pack_conv_weight_dgrad: bad argument");
-  pack_conv_weight_dgrad_kernel<<<tr_blocks(c_out * c_in * k * k, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, static_cast<__nv_bfloat16*>(out), c_out, c_in, k);
+  if (k == 1)   // the transposed matrix: 32x32 tiled cast-transpose (csrc/elementwise.cu)
+    return mmbs_cast_transpose_pad_bf16(w, c_out, c_in, c_in, c_out, out, stream);
+  if (k == 3)
+    pack_conv_weight_dgrad3_kernel<<<tr_blocks(c_out * c_in, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w, static_cast<__nv_bfloat16*>(out), c_out, c_in);
+  else
+    pack_conv_weight_dgrad_kernel<<<tr_blocks(c_out * c_in * k * k, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w, static_cast<__nv_bfloat16*>(out), c_out, c_in, k);
   MMBS_LAUNCH_CHECK();
   return MMBS_OK;
 }
