@@ -148,17 +148,13 @@ __device__ __forceinline__ KRange k_range(const ConvParams& p, int tile) {
   return r;
 }
 
-// Epilogue arithmetic for columns [c_begin, c_end) of tile row r: TMEM -> scale/shift (+ residual)
+// Epilogue arithmetic for 32 columns starting at c0 of tile row r: accumulators -> scale/shift (+ residual)
 // (+ ReLU) -> bf16 into the 128B-swizzled staging tile (TMA-store path) or straight to global memory.
 template <int N_TILE>
-__device__ __forceinline__ void epilogue_columns(const ConvParams& p, uint32_t t_addr, int c_begin, int c_end,
-                                                 const float* s_scale, const float* s_shift, uint32_t stg, int r,
-                                                 bool use_tma_store, bool tma_res, bool row_ok, int64_t row_off) {
-#pragma unroll 1
-  for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-    uint32_t accr[32];
-    tc::tmem_ld_32x32(t_addr + uint32_t(c0), accr);
-    tc::tmem_ld_wait();
+__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32_t (&accr)[32], int c0,
+                                               const float* s_scale, const float* s_shift, uint32_t stg, int r,
+                                               bool use_tma_store, bool tma_res, bool row_ok, int64_t row_off) {
+  {
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -239,6 +235,29 @@ __device__ __forceinline__ void epilogue_columns(const ConvParams& p, uint32_t t
           op[g] = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
+    }
+  }
+}
+
+// The 32-column chunks of [c_begin, c_end): the TMEM load of chunk i+1 is issued before chunk i is processed
+// (two register buffers), so its latency hides behind the arithmetic / shared-memory traffic of chunk i - with
+// two epilogue warps per scheduler nothing else would cover it.
+template <int N_TILE>
+__device__ __forceinline__ void epilogue_columns(const ConvParams& p, uint32_t t_addr, int c_begin, int c_end,
+                                                 const float* s_scale, const float* s_shift, uint32_t stg, int r,
+                                                 bool use_tma_store, bool tma_res, bool row_ok, int64_t row_off) {
+  uint32_t acc_a[32], acc_b[32];
+  tc::tmem_ld_32x32(t_addr + uint32_t(c_begin), acc_a);
+#pragma unroll 1
+  for (int c0 = c_begin; c0 < c_end; c0 += 64) {
+    tc::tmem_ld_wait();
+    const bool more1 = c0 + 32 < c_end;
+    if (more1) tc::tmem_ld_32x32(t_addr + uint32_t(c0 + 32), acc_b);
+    epilogue_chunk<N_TILE>(p, acc_a, c0, s_scale, s_shift, stg, r, use_tma_store, tma_res, row_ok, row_off);
+    if (more1) {
+      tc::tmem_ld_wait();
+      if (c0 + 64 < c_end) tc::tmem_ld_32x32(t_addr + uint32_t(c0 + 64), acc_a);
+      epilogue_chunk<N_TILE>(p, acc_b, c0 + 32, s_scale, s_shift, stg, r, use_tma_store, tma_res, row_ok, row_off);
     }
   }
 }
@@ -835,7 +854,11 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
                "conv plan: batch statistics need pixel boxes that tile the %dx%d output exactly", out_h, out_w);
   // epilogue-bound residual layers (short K loop): 128-wide tile = double-staged epilogue with the
   // residual prefetched one tile ahead; long K loops keep the 256-wide tile (operand-feed bound)
-  if (d->residual && !d->out_f32 && plan->n_tile > 128 && p.num_taps * p.k_chunks <= 4) plan->n_tile = 128;
+  if (d->residual && !d->out_f32 && plan->n_tile > 128 && p.num_taps * p.k_chunks <= 8) plan->n_tile = 128;
+  if (const char* e = getenv("MMBS_FORCE_NTILE")) {   // experiments only
+    const int f = atoi(e);
+    if ((f == 64 || f == 128 || f == 256) && d->c_out % f == 0 && !can_split) plan->n_tile = f;
+  }
   plan->variant = 0;
   if (resident) {
     plan->variant = 1;
