@@ -560,6 +560,11 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
       const int et = threadIdx.x - 64;  // 0..255
       const bool active = grp < ACTIVE_HALVES;
       const int col_lo = grp * COLS_PER_HALF;
+      // 256-wide tiles without residual / statistics: every 4-warp half stores its two 64-column blocks itself,
+      // each block as soon as it is complete, so only the read-out of the LAST 16 KB block (not of the whole
+      // 64 KB tile) is exposed before the next tile may overwrite the staging tile
+      const bool split_store = (N_TILE == 256) && use_tma_store && !tma_res && p.stats == nullptr;
+      const bool store_leader = split_store ? ((et & 127) == 0) : (et == 0);
       if (NSTG == 2 && tma_res && et == 0 && int(blockIdx.x) < p.total_tiles) issue_residual(blockIdx.x, 0);
       uint32_t tl = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
@@ -569,7 +574,7 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
         const uint32_t res_parity = (NSTG == 2) ? ((tl >> 1) & 1u) : (tl & 1u);
         const uint32_t stg = staging_u32 + sb * L::STAGING_BYTES;
         // staging[sb] was last read by the TMA store of tile (tl - NSTG): it must be done reading
-        if (use_tma_store && et == 0) {
+        if (use_tma_store && store_leader) {
           if (NSTG == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
@@ -594,6 +599,31 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
         tc::tc_fence_after();
         if (tma_res) tc::mbar_wait(res_bar + 8 * sb, res_parity);
         const uint32_t t_addr = tmem_base + acc * N_TILE + (uint32_t(q * 32) << 16);
+        if (split_store) {
+#pragma unroll 1
+          for (int b = 0; b < 2; ++b) {
+            epilogue_columns<N_TILE>(p, t_addr, col_lo + 64 * b, col_lo + 64 * b + 64, s_scale, s_shift, stg, r, true,
+                                     false, false, 0);
+            if (b == 1) {   // accumulator fully read: hand it back to the MMA warp
+              tc::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) tc::mbar_arrive(tempty_bar + 8 * acc);
+            }
+            tc::fence_proxy_async();
+            asm volatile("bar.sync %0, 128;" ::"r"(3 + grp) : "memory");
+            if (store_leader) {
+              const int blk = grp * 2 + b;
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                      reinterpret_cast<uint64_t>(&p.out_map)),
+                  "r"(stg + blk * GM_OUT_BLK_BYTES), "r"(tcd.nt * N_TILE + blk * 64), "r"(tcd.w0), "r"(tcd.h0),
+                  "r"(tcd.n0)
+                  : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+          continue;
+        }
         if (active)
           epilogue_columns<N_TILE>(p, t_addr, col_lo, col_lo + COLS_PER_HALF, s_scale, s_shift, stg, r,
                                    use_tma_store, tma_res, row_ok, row_off);
@@ -609,7 +639,7 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
             staging_column_stats<N_TILE>(st_acc, stg, et, GM_EPI_THREADS, p.stats, p.c_out, tcd.nt);
         }
       }
-      if (use_tma_store && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      if (use_tma_store && store_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       if constexpr (N_TILE >= 64) {
         if (p.stats != nullptr) stats_flush<N_TILE>(st_acc, et, GM_EPI_THREADS, p.stats, p.c_out);
       }
