@@ -459,10 +459,14 @@ def run_train(net, x: torch.Tensor, engines: dict) -> torch.Tensor:
     key = ("train", x.device.index, B)
     eng = engines.get(key)
     if eng is None:
-        for k in [k for k in engines if isinstance(k, tuple) and k and k[0] == "train"]:
-            engines.pop(k)                 # one batch size at a time: the buffers are large
+        # keep two batch sizes (the regular one and the tail batch of an epoch): the buffers are large
+        old = [k for k in engines if isinstance(k, tuple) and k and k[0] == "train"]
+        for k in old[:-1]:
+            engines.pop(k)
         eng = ResNetTrainEngine(net, B)
-        engines[key] = eng
+    else:
+        engines.pop(key)                   # re-insert: most recently used last
+    engines[key] = eng
     params = [p for p in net.layer4.parameters()]
     if torch.is_grad_enabled() and any(p.requires_grad for p in params):
         return _TrunkTrainFn.apply(x.detach().float().contiguous(), eng, *params)
