@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import torch
 from multimodalbrainsurvival_b200 import engine
 
-def bench(B, H, W, Cin, Cout, k, s, res, relu=True, f32=False, stats=False, reps=20):
+def bench(B, H, W, Cin, Cout, k, s, res, relu=True, f32=False, stats=False, reps=20, warm=3):
     dev = "cuda"
     x = torch.randn(B, H, W, Cin, device=dev).to(torch.bfloat16)
     w = (torch.randn(Cout, k * k * Cin, device=dev) / (k * k * Cin) ** 0.5).to(torch.bfloat16)
@@ -18,7 +18,7 @@ def bench(B, H, W, Cin, Cout, k, s, res, relu=True, f32=False, stats=False, reps
     plan = engine.conv_plan(x, w, out, ksize=k, stride=s, c_in=Cin, scale=sc, shift=sh, residual=r,
                             relu=relu and not stats, stats=st)
     big = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for _ in range(3):
+    for _ in range(warm):
         plan.run()
     ts = []
     for _ in range(reps):
