@@ -172,6 +172,9 @@ class ResNet(_Trunk):
                 and self.fc.in_features == 2048 and [len(l) for l in (self.layer1, self.layer2, self.layer3,
                                                                       self.layer4)] == [3, 4, 6, 3]):
             return False
+        # a BatchNorm put back into eval mode by hand (frozen-statistics fine-tuning) must use its running statistics
+        if not all(m.training for m in self.modules() if isinstance(m, nn.BatchNorm2d)):
+            return False
         if torch.is_grad_enabled():
             from . import train_engine
             if x.requires_grad or train_engine.trainable_outside_layer4(self):
