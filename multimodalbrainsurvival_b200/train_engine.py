@@ -298,7 +298,7 @@ class ResNetTrainEngine:
         """Eager on the first call (kernel attributes are set lazily), captured into a CUDA graph on the second,
         replayed afterwards (one graph launch instead of ~130 ctypes calls: the step is CPU-launch bound
         whenever something synchronises the host, e.g. reading the loss)."""
-        st = self._graphs.setdefault(which, {"runs": 0, "graph": None, "key": None})
+        st = self._graphs.setdefault(which, {"runs": 0, "graph": None, "key": None, "kernels": 0})
         st["runs"] += 1
         if not self.use_graph or st["runs"] == 1:
             body()
@@ -306,10 +306,12 @@ class ResNetTrainEngine:
         key = self._graph_key()
         if st["graph"] is None or st["key"] != key:
             g = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count()
             with torch.cuda.graph(g):
                 body()
-            st["graph"], st["key"] = g, key
+            st["graph"], st["key"], st["kernels"] = g, key, _lib.launch_count() - l0
         st["graph"].replay()
+        engine.GRAPH_LAUNCHES += st["kernels"]   # libmmbs kernels inside the replayed graph (bench.py's gpu_launches)
 
     def _fwd_body(self):
         L = _lib.lib()
