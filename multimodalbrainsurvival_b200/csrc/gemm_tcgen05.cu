@@ -31,7 +31,8 @@ constexpr int GM_CHUNK_K = 64;                       // bf16 elements = 128 B = 
 constexpr int GM_A_BYTES = GM_TILE_M * GM_CHUNK_K * 2;  // 16 KB
 constexpr int GM_EPI_WARPS = 8;
 constexpr int GM_EPI_THREADS = GM_EPI_WARPS * 32;    // 256
-constexpr int GM_THREADS = 64 + GM_EPI_THREADS;      // producer warp, MMA warp, 8 epilogue warps
+constexpr int GM_DMA_WARP = 2 + GM_EPI_WARPS;        // warp 10: output stores / residual loads of the 256-wide path
+constexpr int GM_THREADS = 64 + GM_EPI_THREADS + 32;  // producer warp, MMA warp, 8 epilogue warps, output-DMA warp
 constexpr int GM_MAX_TAPS = 16;
 constexpr int GM_OUT_BLK_BYTES = GM_TILE_M * 128;    // one 64-channel column block of a bf16 tile
 constexpr int GM_RES64_A_STAGE = 24 * 1024;          // halo box: up to (th + 3) * tw = 192 rows of 128 B
@@ -105,7 +106,7 @@ struct GemmSmem {
   static constexpr int STAGING_OFFSET = RES_OFFSET + RES_BYTES;
   static constexpr int STAGING_BYTES = OUT_BLKS * GM_OUT_BLK_BYTES;    // one staging tile
   static constexpr int BAR_OFFSET = STAGING_OFFSET + NSTG * STAGING_BYTES;
-  static constexpr int NUM_BARS = 2 * STAGES + 7;   // full[S] empty[S] tfull[2] tempty[2] res[2] wres
+  static constexpr int NUM_BARS = 2 * STAGES + 15;  // full[S] empty[S] tfull[2] tempty[2] res[2] wres blk_in[4] blk_out[4]
   static constexpr int TMEM_SLOT_OFFSET = BAR_OFFSET + NUM_BARS * 8;
   static constexpr int SCALE_OFFSET = (TMEM_SLOT_OFFSET + 4 + 15) / 16 * 16;
   static constexpr int TOTAL = SCALE_OFFSET + NSTG * 2 * N_TILE * 4;   // scale|shift per epilogue group
@@ -333,6 +334,8 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   const uint32_t tempty_bar = tfull_bar + 16;          // [2] accumulator drained (epilogue -> MMA)
   const uint32_t res_bar = tempty_bar + 16;            // [2] residual tile landed in staging[i]
   const uint32_t wres_bar = res_bar + 16;              // resident weights landed
+  const uint32_t blk_in_bar = wres_bar + 8;            // [4] staging block b usable by the epilogue (residual landed / free)
+  const uint32_t blk_out_bar = blk_in_bar + 32;        // [4] staging block b written by the epilogue: store it
   const uint32_t wres_u32 = base_u32 + L::RES_OFFSET;
   const uint32_t tmem_slot = base_u32 + L::TMEM_SLOT_OFFSET;
   const uint32_t staging_u32 = base_u32 + L::STAGING_OFFSET;
@@ -345,10 +348,17 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   // else all 8 warps on one tile (with a residual the spare staging tile prefetches the next residual)
   const bool group_mode = (NSTG == 2) && !((N_TILE >= 64) && !p.out_f32 && p.residual != nullptr);
 
+  // 256-wide bf16 tiles (no statistics): the epilogue hands every finished 64-column staging block to the output-DMA
+  // warp, which stores it and, once the store has read the block out, re-arms it for the next tile - with that
+  // tile's residual block loaded into it (in-place add) or simply as free.  No epilogue thread ever waits for a
+  // store, and only 16 KB (not the 64 KB tile) sit between a block's last write and its reuse.
+  const bool dma_mode = (N_TILE == 256) && !p.out_f32 && p.stats == nullptr;
+
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tc::tma_prefetch_desc(&p.a_map[i]);
     tc::tma_prefetch_desc(&p.b_map);
     if (N_TILE >= 64 && !p.out_f32) tc::tma_prefetch_desc(&p.out_map);
+    if (N_TILE >= 64 && !p.out_f32 && p.residual != nullptr) tc::tma_prefetch_desc(&p.res_map);
     for (int s = 0; s < STAGES; ++s) {
       tc::mbar_init(full_bar + 8 * s, 1);
       tc::mbar_init(empty_bar + 8 * s, 1);
@@ -359,6 +369,10 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
       tc::mbar_init(res_bar + 8 * a, 1);
     }
     tc::mbar_init(wres_bar, 1);
+    for (int b = 0; b < 4; ++b) {
+      tc::mbar_init(blk_in_bar + 8 * b, 1);
+      tc::mbar_init(blk_out_bar + 8 * b, 1);
+    }
     tc::fence_mbar_init();
   }
   if (warp == 1) {
@@ -456,6 +470,50 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
         __syncwarp();
       }
     }
+  } else if (warp == GM_DMA_WARP) {
+    // ===== output-DMA warp (256-wide path): TMA stores per 64-column block + residual loads / block recycling =====
+    if (dma_mode && tc::elect_one()) {
+      const bool has_res = p.residual != nullptr;
+      auto provide = [&](int tile, int b) {   // make staging block b usable for `tile`
+        if (has_res) {
+          const TileCoord t2 = tile_coord(p, k_range(p, tile).mn, n_tiles);
+          tc::mbar_expect_tx(blk_in_bar + 8 * b, GM_OUT_BLK_BYTES);
+          tc::tma_load_4d(&p.res_map, blk_in_bar + 8 * b, staging_u32 + b * GM_OUT_BLK_BYTES, t2.nt * N_TILE + b * 64,
+                          t2.w0, t2.h0, t2.n0);
+        } else {
+          tc::mbar_arrive(blk_in_bar + 8 * b);
+        }
+      };
+      if (int(blockIdx.x) < p.total_tiles)
+        for (int b = 0; b < 4; ++b) provide(blockIdx.x, b);
+      uint32_t tl = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+        const TileCoord tcd = tile_coord(p, k_range(p, tile).mn, n_tiles);
+        const int next = tile + int(gridDim.x);
+        // the halves finish blocks (0, 2) first, then (1, 3)
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+          const int b = ((i & 1) << 1) | (i >> 1);
+          tc::mbar_wait(blk_out_bar + 8 * b, tl & 1u);
+          asm volatile(
+              "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                  reinterpret_cast<uint64_t>(&p.out_map)),
+              "r"(staging_u32 + b * GM_OUT_BLK_BYTES), "r"(tcd.nt * N_TILE + b * 64), "r"(tcd.w0), "r"(tcd.h0),
+              "r"(tcd.n0)
+              : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (i >= 1) {   // the previous block's store has been read out: recycle that block
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            const int pb = (((i - 1) & 1) << 1) | ((i - 1) >> 1);
+            if (next < p.total_tiles) provide(next, pb);
+          }
+        }
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (next < p.total_tiles) provide(next, 3);
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
   } else {
     // ===== 8 epilogue warps.  TMEM lane quarter = warp % 4 (tile rows). =====
     const int q = warp & 3;
@@ -560,12 +618,8 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
       const int et = threadIdx.x - 64;  // 0..255
       const bool active = grp < ACTIVE_HALVES;
       const int col_lo = grp * COLS_PER_HALF;
-      // 256-wide tiles without residual / statistics: every 4-warp half stores its two 64-column blocks itself,
-      // each block as soon as it is complete, so only the read-out of the LAST 16 KB block (not of the whole
-      // 64 KB tile) is exposed before the next tile may overwrite the staging tile
-      const bool split_store = (N_TILE == 256) && use_tma_store && !tma_res && p.stats == nullptr;
-      const bool store_leader = split_store ? ((et & 127) == 0) : (et == 0);
-      if (NSTG == 2 && tma_res && et == 0 && int(blockIdx.x) < p.total_tiles) issue_residual(blockIdx.x, 0);
+      const bool tma_res_old = tma_res && !dma_mode;   // residual through res_bar / issue_residual (non-DMA variants)
+      if (NSTG == 2 && tma_res_old && et == 0 && int(blockIdx.x) < p.total_tiles) issue_residual(blockIdx.x, 0);
       uint32_t tl = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
         const TileCoord tcd = tile_coord(p, k_range(p, tile).mn, n_tiles);
@@ -574,13 +628,13 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
         const uint32_t res_parity = (NSTG == 2) ? ((tl >> 1) & 1u) : (tl & 1u);
         const uint32_t stg = staging_u32 + sb * L::STAGING_BYTES;
         // staging[sb] was last read by the TMA store of tile (tl - NSTG): it must be done reading
-        if (use_tma_store && store_leader) {
+        if (use_tma_store && !dma_mode && et == 0) {
           if (NSTG == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
         load_scale_shift(tcd.nt, s_scale, s_shift, et, GM_EPI_THREADS);
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (tma_res && et == 0) {
+        if (tma_res_old && et == 0) {
           if (NSTG == 2) {
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             if (tile + int(gridDim.x) < p.total_tiles) issue_residual(tile + gridDim.x, sb ^ 1u);
@@ -597,30 +651,23 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
         }
         tc::mbar_wait(tfull_bar + 8 * acc, aph);
         tc::tc_fence_after();
-        if (tma_res) tc::mbar_wait(res_bar + 8 * sb, res_parity);
+        if (tma_res_old) tc::mbar_wait(res_bar + 8 * sb, res_parity);
         const uint32_t t_addr = tmem_base + acc * N_TILE + (uint32_t(q * 32) << 16);
-        if (split_store) {
+        if (dma_mode) {
 #pragma unroll 1
           for (int b = 0; b < 2; ++b) {
-            epilogue_columns<N_TILE>(p, t_addr, col_lo + 64 * b, col_lo + 64 * b + 64, s_scale, s_shift, stg, r, true,
-                                     false, false, 0);
+            const int blk = grp * 2 + b;
+            tc::mbar_wait(blk_in_bar + 8 * blk, tl & 1u);   // previous store read out (+ this tile's residual landed)
+            epilogue_columns<N_TILE>(p, t_addr, blk * 64, blk * 64 + 64, s_scale, s_shift, stg, r, true, tma_res, false,
+                                     0);
             if (b == 1) {   // accumulator fully read: hand it back to the MMA warp
               tc::tc_fence_before();
               __syncwarp();
               if (lane == 0) tc::mbar_arrive(tempty_bar + 8 * acc);
             }
-            tc::fence_proxy_async();
+            tc::fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA engine
             asm volatile("bar.sync %0, 128;" ::"r"(3 + grp) : "memory");
-            if (store_leader) {
-              const int blk = grp * 2 + b;
-              asm volatile(
-                  "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
-                      reinterpret_cast<uint64_t>(&p.out_map)),
-                  "r"(stg + blk * GM_OUT_BLK_BYTES), "r"(tcd.nt * N_TILE + blk * 64), "r"(tcd.w0), "r"(tcd.h0),
-                  "r"(tcd.n0)
-                  : "memory");
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
+            if ((et & 127) == 0) tc::mbar_arrive(blk_out_bar + 8 * blk);
           }
           continue;
         }
@@ -639,7 +686,7 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
             staging_column_stats<N_TILE>(st_acc, stg, et, GM_EPI_THREADS, p.stats, p.c_out, tcd.nt);
         }
       }
-      if (use_tma_store && store_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      if (use_tma_store && !dma_mode && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       if constexpr (N_TILE >= 64) {
         if (p.stats != nullptr) stats_flush<N_TILE>(st_acc, et, GM_EPI_THREADS, p.stats, p.c_out);
       }
@@ -884,7 +931,10 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
                "conv plan: batch statistics need pixel boxes that tile the %dx%d output exactly", out_h, out_w);
   // epilogue-bound residual layers (short K loop): 128-wide tile = double-staged epilogue with the
   // residual prefetched one tile ahead; long K loops keep the 256-wide tile (operand-feed bound)
-  if (d->residual && !d->out_f32 && plan->n_tile > 128 && p.num_taps * p.k_chunks <= 8) plan->n_tile = 128;
+  // (the 256-wide path recycles its staging blocks through the output-DMA warp, residual included; the 128-wide
+  //  double-staged variant is kept selectable for comparison: MMBS_RES_NTILE=128)
+  if (const char* e = getenv("MMBS_RES_NTILE"))
+    if (atoi(e) == 128 && d->residual && !d->out_f32 && plan->n_tile > 128 && p.num_taps * p.k_chunks <= 8) plan->n_tile = 128;
   if (const char* e = getenv("MMBS_FORCE_NTILE")) {   // experiments only
     const int f = atoi(e);
     if ((f == 64 || f == 128 || f == 256) && d->c_out % f == 0 && !can_split) plan->n_tile = f;
