@@ -897,7 +897,9 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
   int forced_n_tile = 0;
   if (!linear_mode && !d->out_f32) {
     if (d->c_out == 64 && w_bytes <= GM_RES64_BYTES) { resident = true; forced_n_tile = 64; }
-    else if ((d->c_out == 128 || d->c_out == 256) && w_bytes <= GM_RES128_BYTES) { resident = true; forced_n_tile = 128; }
+    // (256-output convs with tiny K - layer1 conv3 / downsample - are faster on the streamed 256-wide path with the
+    //  output-DMA warp: 310 vs 332 us with the residual, 190 vs 215 us without; MMBS_RES256=1 restores the old choice)
+    else if ((d->c_out == 128 || (d->c_out == 256 && getenv("MMBS_RES256") != nullptr)) && w_bytes <= GM_RES128_BYTES) { resident = true; forced_n_tile = 128; }
   }
   const bool want_halo = (d->flags & 1) != 0;
   if (resident && forced_n_tile == 64 && (stem_mode || (want_halo && k == 3 && s == 1))) halo = true;
