@@ -155,7 +155,11 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
                                    *reinterpret_cast<const __nv_bfloat162*>(&b));
   return *reinterpret_cast<const uint32_t*>(&r);
 }
-// grid = (ceil(ow*c8 / 256), oh, batch): no integer divisions on the hot path
+// grid = (ceil(ow*c8 / 256), ceil(oh / MP_ROWS), batch): no integer divisions on the hot path.  A thread produces
+// MP_ROWS vertically adjacent outputs of one (x, 8-channel group): the 2*MP_ROWS+1 input rows they cover are each
+// reduced over their 3 columns once (6.75 loads per output instead of 9; an input row is fetched by 1.125 blocks
+// instead of 1.5).
+constexpr int MP_ROWS = 4;
 __global__ void __launch_bounds__(256) maxpool_3x3s2_kernel(const uint4* __restrict__ in,
                                                             uint4* __restrict__ out, int64_t batch, int h,
                                                             int w, int c8, int c8_shift) {
@@ -163,25 +167,39 @@ __global__ void __launch_bounds__(256) maxpool_3x3s2_kernel(const uint4* __restr
   const int xc = blockIdx.x * 256 + threadIdx.x;      // (x, channel group) flattened, c8 = 1 << c8_shift
   if (xc >= ow * c8) return;
   const int g = xc & (c8 - 1), x = xc >> c8_shift;
-  const int y = blockIdx.y;
+  const int y0 = blockIdx.y * MP_ROWS;
   const int64_t n = blockIdx.z;
   const uint32_t NEG = 0xff80ff80u;  // (-inf, -inf) in bf16
-  uint4 m = make_uint4(NEG, NEG, NEG, NEG);
   const uint4* base = in + n * int64_t(h) * w * c8 + g;
+  uint4 m[MP_ROWS];
 #pragma unroll
-  for (int dy = 0; dy < 3; ++dy) {
-    const int iy = 2 * y - 1 + dy;
-    if (iy < 0 || iy >= h) continue;
+  for (int k = 0; k < MP_ROWS; ++k) m[k] = make_uint4(NEG, NEG, NEG, NEG);
 #pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      const int ix = 2 * x - 1 + dx;
-      if (ix < 0 || ix >= w) continue;
-      const uint4 v = __ldg(base + (int64_t(iy) * w + ix) * c8);
-      m.x = max_bf16x2(m.x, v.x); m.y = max_bf16x2(m.y, v.y);
-      m.z = max_bf16x2(m.z, v.z); m.w = max_bf16x2(m.w, v.w);
+  for (int r = 0; r < 2 * MP_ROWS + 1; ++r) {
+    const int iy = 2 * y0 - 1 + r;
+    uint4 rm = make_uint4(NEG, NEG, NEG, NEG);
+    if (iy >= 0 && iy < h) {
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int ix = 2 * x - 1 + dx;
+        if (ix < 0 || ix >= w) continue;
+        const uint4 v = __ldg(base + (int64_t(iy) * w + ix) * c8);
+        rm.x = max_bf16x2(rm.x, v.x); rm.y = max_bf16x2(rm.y, v.y);
+        rm.z = max_bf16x2(rm.z, v.z); rm.w = max_bf16x2(rm.w, v.w);
+      }
+    }
+    // input row r belongs to outputs k with 2k <= r <= 2k + 2
+#pragma unroll
+    for (int k = 0; k < MP_ROWS; ++k) {
+      if (r >= 2 * k && r <= 2 * k + 2) {
+        m[k].x = max_bf16x2(m[k].x, rm.x); m[k].y = max_bf16x2(m[k].y, rm.y);
+        m[k].z = max_bf16x2(m[k].z, rm.z); m[k].w = max_bf16x2(m[k].w, rm.w);
+      }
     }
   }
-  out[((n * oh + y) * int64_t(ow) + x) * c8 + g] = m;
+#pragma unroll
+  for (int k = 0; k < MP_ROWS; ++k)
+    if (y0 + k < oh) out[((n * oh + y0 + k) * int64_t(ow) + x) * c8 + g] = m[k];
 }
 
 // ---- AvgPool2d(7) + flatten: [B, hw, C] (bf16 or fp32) -> fp32 [B, C]
@@ -311,7 +329,7 @@ extern "C" int mmbs_maxpool_3x3s2(const void* in, void* out, int64_t batch, int6
   int shift = 0;
   while ((1 << shift) < c8) ++shift;
   MMBS_REQUIRE((1 << shift) == c8 && batch <= 65535 && oh <= 65535, "mmbs_maxpool_3x3s2: c/8 must be a power of two");
-  dim3 grid(unsigned(ceil_div(ow * c8, 256)), unsigned(oh), unsigned(batch));
+  dim3 grid(unsigned(ceil_div(ow * c8, 256)), unsigned(ceil_div(oh, MP_ROWS)), unsigned(batch));
   maxpool_3x3s2_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(in), static_cast<uint4*>(out), batch, int(h), int(w), c8, shift);
   MMBS_LAUNCH_CHECK();

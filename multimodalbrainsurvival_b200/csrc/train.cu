@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(256) bn_train_apply_kernel(const __grid_consta
   }
 }
 
+constexpr int TMP_ROWS = 4;   // vertically adjacent outputs per thread (each input row is normalised and reduced once)
 __global__ void __launch_bounds__(256) bn_train_relu_maxpool_kernel(const __grid_constant__ BnTrain bn,
                                                                     const uint4* __restrict__ in,
                                                                     uint4* __restrict__ out, int h, int w, int c8,
@@ -246,28 +247,44 @@ __global__ void __launch_bounds__(256) bn_train_relu_maxpool_kernel(const __grid
   const int xc = blockIdx.x * 256 + threadIdx.x;
   if (xc >= ow * c8) return;
   const int g = xc & (c8 - 1), x = xc >> c8_shift;
-  const int y = blockIdx.y;
+  const int y0 = blockIdx.y * TMP_ROWS;
   const int64_t n = blockIdx.z;
-  float sc[8], sh[8], m[8];
+  float sc[8], sh[8];
   bn_train_coeffs(bn, g, (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && xc < c8, sc, sh);
+  float m[TMP_ROWS][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) m[j] = 0.f;   // relu(.) >= 0 and every window holds an in-range pixel
+  for (int k = 0; k < TMP_ROWS; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[k][j] = 0.f;   // relu(.) >= 0 and every window holds an in-range pixel
   const uint4* base = in + n * int64_t(h) * w * c8 + g;
 #pragma unroll
-  for (int dy = 0; dy < 3; ++dy) {
-    const int iy = 2 * y - 1 + dy;
-    if (iy < 0 || iy >= h) continue;
+  for (int r = 0; r < 2 * TMP_ROWS + 1; ++r) {
+    const int iy = 2 * y0 - 1 + r;
+    float rm[8];
 #pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      const int ix = 2 * x - 1 + dx;
-      if (ix < 0 || ix >= w) continue;
-      float v[8];
-      tr_unpack8(__ldg(base + (int64_t(iy) * w + ix) * c8), v);
+    for (int j = 0; j < 8; ++j) rm[j] = 0.f;
+    if (iy >= 0 && iy < h) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], fmaf(v[j], sc[j], sh[j]));
+      for (int dx = 0; dx < 3; ++dx) {
+        const int ix = 2 * x - 1 + dx;
+        if (ix < 0 || ix >= w) continue;
+        float v[8];
+        tr_unpack8(__ldg(base + (int64_t(iy) * w + ix) * c8), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rm[j] = fmaxf(rm[j], fmaf(v[j], sc[j], sh[j]));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < TMP_ROWS; ++k) {
+      if (r >= 2 * k && r <= 2 * k + 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[k][j] = fmaxf(m[k][j], rm[j]);
+      }
     }
   }
-  out[((n * oh + y) * int64_t(ow) + x) * c8 + g] = tr_pack8(m);
+#pragma unroll
+  for (int k = 0; k < TMP_ROWS; ++k)
+    if (y0 + k < oh) out[((n * oh + y0 + k) * int64_t(ow) + x) * c8 + g] = tr_pack8(m[k]);
 }
 
 // ---- grad of AvgPool2d(7)+flatten: dfeat fp32 [B, C] -> bf16 [B, hw, C] = dfeat / hw
@@ -745,7 +762,7 @@ extern "C" int mmbs_bn_train_relu_maxpool_3x3s2(const mmbs_bn_train_desc* bn, co
   while ((1 << shift_bits) < c8) ++shift_bits;
   MMBS_REQUIRE((1 << shift_bits) == c8 && batch <= 65535 && oh <= 65535,
                "mmbs_bn_train_relu_maxpool_3x3s2: c/8 must be a power of two");
-  dim3 grid(unsigned(ceil_div(ow * c8, 256)), unsigned(oh), unsigned(batch));
+  dim3 grid(unsigned(ceil_div(ow * c8, 256)), unsigned(ceil_div(oh, TMP_ROWS)), unsigned(batch));
   return launch_pdl(bn_train_relu_maxpool_kernel, grid, dim3(256), static_cast<cudaStream_t>(stream), b,
                     static_cast<const uint4*>(in), static_cast<uint4*>(out), int(h), int(w), c8, shift_bits);
 }
