@@ -57,3 +57,25 @@ def prefetch_to_device(batches, device, depth: int = 2):
         rel = torch.cuda.Event()
         rel.record(torch.cuda.current_stream(dev))
         released[k] = rel
+
+
+class HostWriter:
+    """Device -> pinned-host copies on a side stream: the D2H read-back of step i overlaps the kernels of step i+1
+    instead of sitting in the compute stream (a 4 MB feature block at PCIe speed stalls it for ~0.15 ms).
+    ``write`` orders the copy after everything enqueued so far on the current stream; ``wait`` makes the host
+    wait for all pending copies (call it before reading the host buffers)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+
+    def write(self, src: torch.Tensor, dst_host: torch.Tensor) -> None:
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        self.stream.wait_event(ready)
+        with torch.cuda.stream(self.stream):
+            dst_host.copy_(src, non_blocking=True)
+        src.record_stream(self.stream)     # the caching allocator must not recycle src before the copy ran
+
+    def wait(self) -> None:
+        self.stream.synchronize()

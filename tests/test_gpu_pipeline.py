@@ -17,3 +17,16 @@ def test_prefetch_to_device_preserves_order_and_contents():
     u8 = [torch.randint(0, 256, (5, 3, 8, 8), dtype=torch.uint8) for _ in range(3)]     # pageable, uint8
     got = [d.clone().cpu() for d in pipeline.prefetch_to_device(iter(u8), "cuda:0", depth=1)]
     assert all(torch.equal(a, b) for a, b in zip(got, u8))
+
+
+def test_host_writer_copies_on_a_side_stream():
+    from multimodalbrainsurvival_b200 import pipeline
+    w = pipeline.HostWriter("cuda:0")
+    outs = [torch.empty(256, 512).pin_memory() for _ in range(4)]
+    for i, o in enumerate(outs):
+        x = torch.full((256, 512), float(i), device="cuda:0") * 3 + 1     # produced on the current stream
+        w.write(x, o)
+        del x                                                              # the writer keeps the storage alive
+    w.wait()
+    assert [float(o[0, 0]) for o in outs] == [1.0, 4.0, 7.0, 10.0]
+    assert all(bool((o == o[0, 0]).all()) for o in outs)
