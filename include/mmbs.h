@@ -242,9 +242,11 @@ int mmbs_bn_bwd_apply(const void* g_bf16, const void* relu_mask_bf16, const void
                       const float* invstd, const float* scale, const float* sums, void* out_bf16, int64_t rows,
                       int64_t c, void* stream);
 /* x NHWC bf16 [B,h,w,c] -> colT bf16 [ksize*ksize*c, p_padded] (pad ksize/2; zero outside and for columns
- * >= B*oh*ow): the K-major B operand of the weight-gradient GEMM; ksize 1 / stride 1 = plain transpose */
+ * >= B*oh*ow): the K-major B operand of the weight-gradient GEMM; ksize 1 / stride 1 = plain transpose.
+ * Row order (tap, channel) when oihw_rows = 0, (channel, tap) when 1: with the latter the GEMM result
+ * [c_out, c*ksize*ksize] IS nn.Conv2d.weight.grad (OIHW). */
 int mmbs_im2col_t(const void* x_bf16, void* out_bf16, int64_t batch, int64_t h, int64_t w, int64_t c, int64_t ksize,
-                  int64_t stride, int64_t p_padded, void* stream);
+                  int64_t stride, int64_t p_padded, int32_t oihw_rows, void* stream);
 /* OIHW fp32 -> bf16 [I][k][k][O] with flipped taps: the weights of the data-gradient convolution */
 int mmbs_pack_conv_weight_dgrad(const float* w_oihw, void* out_bf16, int64_t c_out, int64_t c_in, int64_t ksize,
                                 void* stream);

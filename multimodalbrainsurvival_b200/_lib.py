@@ -93,7 +93,8 @@ SIGNATURES = {
                                           c_void_p]),
     "mmbs_bn_bwd_apply": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_i64, c_i64, c_void_p]),
-    "mmbs_im2col_t": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_void_p]),
+    "mmbs_im2col_t": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i32,
+                                     c_void_p]),
     "mmbs_pack_conv_weight_dgrad": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
     "mmbs_unpack_conv_wgrad": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
     "mmbs_scatter_stride2": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p]),

@@ -678,7 +678,7 @@ extern "C" int mmbs_transpose_bf16(const void* in, int64_t in_stride, int64_t ro
       reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
       ceil_div(cols, 64) <= 65535) {
     // csrc/train.cu: 64x64 shared-memory transpose with 16-byte global accesses (1x1 "im2col" = plain transpose)
-    return mmbs_im2col_t(in, out, rows, 1, 1, cols, 1, 1, rows_padded, stream);
+    return mmbs_im2col_t(in, out, rows, 1, 1, cols, 1, 1, rows_padded, 0, stream);
   }
   dim3 grid(unsigned(ceil_div(cols, 32)), unsigned(ceil_div(rows_padded, 32)));
   transpose_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(

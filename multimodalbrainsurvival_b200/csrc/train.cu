@@ -421,10 +421,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restri
 // colT[(kh*k+kw)*C + c][p] = x[n, ho*s + kh - pad, wo*s + kw - pad, c] (0 outside / for p >= P), p = (n, ho, wo).
 // One block = 64 channels x 64 pixels of one tap, transposed through shared memory with 16-byte global
 // accesses on both sides (8 channels of a pixel in, 8 pixels of a channel out).  C % 8 == 0, Pp % 8 == 0.
+// row order: (tap, channel) [oihw_rows = 0: matches the packed weight layout] or (channel, tap) [oihw_rows = 1: the
+// weight-gradient GEMM then produces nn.Conv2d.weight.grad's OIHW layout directly].
 __global__ void __launch_bounds__(256) im2col_t_kernel(const __nv_bfloat16* __restrict__ x,
                                                        __nv_bfloat16* __restrict__ out, int batch, int h, int w,
                                                        int c, int k, int stride, int pad, int oh, int ow,
-                                                       int64_t p_total, int64_t p_padded) {
+                                                       int64_t p_total, int64_t p_padded, int oihw_rows) {
   __shared__ __align__(16) uint16_t tile[64][66];   // [pixel][channel], 33-word rows: conflict-free writes, 2-way reads
   const int tap = blockIdx.z, kh = tap / k, kw = tap % k;
   const int c0 = blockIdx.y * 64;
@@ -458,7 +460,8 @@ __global__ void __launch_bounds__(256) im2col_t_kernel(const __nv_bfloat16* __re
       for (int j = 0; j < 8; ++j) e[j] = tile[pg * 8 + j][cl];
       const uint4 v = make_uint4(uint32_t(e[0]) | (uint32_t(e[1]) << 16), uint32_t(e[2]) | (uint32_t(e[3]) << 16),
                                  uint32_t(e[4]) | (uint32_t(e[5]) << 16), uint32_t(e[6]) | (uint32_t(e[7]) << 16));
-      *reinterpret_cast<uint4*>(out + (int64_t(tap) * c + ch) * p_padded + p) = v;
+      const int64_t orow = oihw_rows ? (int64_t(ch) * (k * k) + tap) : (int64_t(tap) * c + ch);
+      *reinterpret_cast<uint4*>(out + orow * p_padded + p) = v;
     }
   }
 }
@@ -622,7 +625,7 @@ extern "C" int mmbs_bn_bwd_apply(const void* g, const void* relu_mask, const voi
 }
 
 extern "C" int mmbs_im2col_t(const void* x, void* out, int64_t batch, int64_t h, int64_t w, int64_t c, int64_t ksize,
-                             int64_t stride, int64_t p_padded, void* stream) {
+                             int64_t stride, int64_t p_padded, int32_t oihw_rows, void* stream) {
   if (int rc = mmbs_device_check()) return rc;
   MMBS_REQUIRE(x && out && batch > 0 && h > 0 && w > 0 && c > 0 && (ksize == 1 || ksize == 3) &&
                    (stride == 1 || stride == 2),
@@ -635,7 +638,7 @@ extern "C" int mmbs_im2col_t(const void* x, void* out, int64_t batch, int64_t h,
   dim3 grid(unsigned(ceil_div(p_padded, 64)), unsigned(ceil_div(c, 64)), unsigned(ksize * ksize));
   im2col_t_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), int(batch), int(h), int(w), int(c),
-      int(ksize), int(stride), pad, int(oh), int(ow), p_total, p_padded);
+      int(ksize), int(stride), pad, int(oh), int(ow), p_total, p_padded, int(oihw_rows));
   MMBS_LAUNCH_CHECK();
   return MMBS_OK;
 }

@@ -258,8 +258,7 @@ class ResNetTrainEngine:
             r["draw2"] = self._buf(B, Ho, Wo, planes)
             r["draw2T"] = self._buf(planes, Pp)
             r["col2T"] = self._buf(9 * planes, Pp)
-            r["dw2p"], r["wg2"] = self._wgrad(r["draw2T"], r["col2T"], planes, 9 * planes)
-            r["dw2"] = self._buf(planes, planes, 3, 3, dtype=torch.float32)
+            r["dw2"], r["wg2"] = self._wgrad(r["draw2T"], r["col2T"], planes, 9 * planes)   # [co, (ci, kh, kw)] = OIHW
             r["c2"].want_dgrad()
             r["u2"] = self._buf(B, Hin, Win, planes, zero=True) if s == 2 else r["draw2"]
             r["da1"] = self._buf(B, Hin, Win, planes)
@@ -357,14 +356,15 @@ class ResNetTrainEngine:
     @staticmethod
     def _transpose(src, rows, cols, rows_padded, dst):
         # [rows, cols] -> [cols, rows_padded]: the 1x1 / stride-1 case of the im2col-transpose kernel
-        _ck(_lib.lib().mmbs_im2col_t(_lib.ptr(src), _lib.ptr(dst), rows, 1, 1, cols, 1, 1, rows_padded,
+        _ck(_lib.lib().mmbs_im2col_t(_lib.ptr(src), _lib.ptr(dst), rows, 1, 1, cols, 1, 1, rows_padded, 0,
                                      _lib.stream_ptr()), "mmbs_im2col_t")
 
     @staticmethod
     def _im2col_t(x, k, stride, p_padded, dst):
+        """Rows in (channel, tap) order: the weight-gradient GEMM then writes the OIHW gradient directly."""
         B, H, W, C = x.shape
-        _ck(_lib.lib().mmbs_im2col_t(_lib.ptr(x), _lib.ptr(dst), B, H, W, C, k, stride, p_padded, _lib.stream_ptr()),
-            "mmbs_im2col_t")
+        _ck(_lib.lib().mmbs_im2col_t(_lib.ptr(x), _lib.ptr(dst), B, H, W, C, k, stride, p_padded, 1,
+                                     _lib.stream_ptr()), "mmbs_im2col_t")
 
     def backward(self, dfeat: torch.Tensor) -> dict:
         """dfeat fp32 [B,2048] -> {parameter: gradient tensor (engine-owned, valid until the next step)}."""
@@ -396,13 +396,11 @@ class ResNetTrainEngine:
             self._transpose(r["draw2"], P, planes, Pp, r["draw2T"])
             self._im2col_t(r["a1"], 3, r["stride"], Pp, r["col2T"])
             r["wg2"].run()
-            _ck(L.mmbs_unpack_conv_wgrad(_lib.ptr(r["dw2p"]), _lib.ptr(r["dw2"]), planes, planes, 3, _lib.stream_ptr()),
-                "mmbs_unpack_conv_wgrad")
             if r["stride"] == 2:
                 _ck(L.mmbs_scatter_stride2(_lib.ptr(r["draw2"]), _lib.ptr(r["u2"]), B, Ho, Wo, planes,
                                            _lib.stream_ptr()), "mmbs_scatter_stride2")
             r["dg2"].run()
-            grads[blk.conv2.weight] = r["dw2"]
+            grads[blk.conv2.weight] = r["dw2"].view(planes, planes, 3, 3)
             grads[blk.bn2.weight], grads[blk.bn2.bias] = r["sums2"][1], r["sums2"][0]
             # ---- bn1 / conv1
             self._bn_backward(r["da1"], r["a1"], r["raw1"], r["b1"], r["sums1"], r["draw1"])
