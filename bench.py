@@ -105,7 +105,8 @@ class ClockSampler:
 
 
 def make_state_dict():
-    from oracle import resnet_oracle  # weights only: a seeded init with the reference's key names
+    """CPU arm only: the oracle's seeded state_dict (reference key names) for the oracle's functional forward."""
+    from oracle import resnet_oracle
     return resnet_oracle.init_state_dict(seed=1111)
 
 
@@ -190,8 +191,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
 
-    net = resnet.resnet50()
-    net.load_state_dict(make_state_dict())
+    torch.manual_seed(1111)
+    net = resnet.randomize_batchnorm_(resnet.resnet50(), seed=1111)   # random-init weights of the named architecture
     model = models.AggregationModel(net, models.Identity(), 2048, 2048, 1).to(dev).eval()
 
     B = BATCH

@@ -253,6 +253,23 @@ def _build(name, pretrained, cls=ResNet, **kwargs):
     return model
 
 
+def randomize_batchnorm_(model, seed=1111, bn3_gamma_scale=1.0):
+    """Synthetic stand-in for trained BatchNorm state (benchmarks / smoke runs have no checkpoint to load): seeded
+    gamma in [0.5, 1.5], small beta, running_mean ~ N(0, 0.1), running_var in [0.5, 1.5], so that the folded
+    scale/shift of the eval path is exercised; ``bn3_gamma_scale`` shrinks every block's last gamma (trained
+    ResNets look like that; the training-mode cases use 0.1).  In place; returns the model."""
+    g = torch.Generator().manual_seed(seed)
+    for name, m in model.named_modules():
+        if isinstance(m, nn.BatchNorm2d):
+            c = m.num_features
+            with torch.no_grad():
+                m.weight.copy_((0.5 + torch.rand(c, generator=g)) * (bn3_gamma_scale if name.endswith("bn3") else 1.0))
+                m.bias.copy_(0.1 * torch.randn(c, generator=g))
+                m.running_mean.copy_(0.1 * torch.randn(c, generator=g))
+                m.running_var.copy_(0.5 + torch.rand(c, generator=g))
+    return model
+
+
 def resnet18(pretrained=False, **kwargs):
     return _build('resnet18', pretrained, **kwargs)
 

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import weakref
 
 import torch
 
@@ -96,7 +97,8 @@ class ResNetTrainEngine:
         p = next(net.parameters())
         if not p.is_cuda:
             raise RuntimeError("ResNetTrainEngine: the module must live on a CUDA device (no CPU fallback)")
-        self.net, self.B, self.device = net, int(batch), p.device
+        self._net_ref = weakref.ref(net)   # the module owns the engine (net._engines): no strong cycle
+        self.B, self.device = int(batch), p.device
         self._keep = []
         self.fwd_steps = []
         self.convs = []
@@ -164,7 +166,7 @@ class ResNetTrainEngine:
         self.fwd_steps.append(apply)
 
     def _build(self):
-        net, B = self.net, self.B
+        net, B = self._net_ref(), self.B
         L = _lib.lib()
         all_bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)]
         self.arena = torch.zeros(sum(_BNState.floats(b) for b in all_bns), dtype=torch.float32, device=self.device)
@@ -337,7 +339,9 @@ class ResNetTrainEngine:
         self.step += 1
         # the kernels (and graph replays) write the running statistics behind autograd's back: tell the
         # inference engine's weight cache (engine.ResNetEngine.weights_version) that they moved
-        self.net._mmbs_train_steps = getattr(self.net, "_mmbs_train_steps", 0) + 1
+        net = self._net_ref()
+        if net is not None:
+            net._mmbs_train_steps = getattr(net, "_mmbs_train_steps", 0) + 1
         _ck(L.mmbs_stem_pack_input(_lib.ptr(x_nchw), _lib.ptr(self.x_s2d), self.B, _lib.stream_ptr()),
             "mmbs_stem_pack_input")
         self._run("fwd", self._fwd_body)

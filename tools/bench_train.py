@@ -25,9 +25,8 @@ MLP_GFLOP_STEP = 33.3                       # RNA MLP fwd+bwd at B = 128 (SURVEY
 def build(kind, torch, dev):
     import torch.nn as nn
     from multimodalbrainsurvival_b200 import models, resnet
-    from oracle import resnet_oracle   # seeded weights with the reference's key names (weights only)
-    net = resnet.resnet50()
-    net.load_state_dict(resnet_oracle.init_state_dict(seed=1111, bn3_gamma_scale=0.1))
+    torch.manual_seed(1111)
+    net = resnet.randomize_batchnorm_(resnet.resnet50(), seed=1111, bn3_gamma_scale=0.1)
     for p in net.parameters():
         p.requires_grad = False
     for layer in (net.fc, net.layer4):       # n_layers_to_train = 2
