@@ -137,6 +137,13 @@ int mmbs_linear_plan_create(const void* x_bf16, const void* w_bf16, const float*
                             void* y, int64_t m, int64_t n, int64_t k, int32_t relu,
                             int32_t out_f32, mmbs_conv_plan** plan_out);
 
+/* TN GEMM: y[M,N] (fp32, row stride N) = a[K,M]^T b[K,N]; a / b bf16 ROW-major with K outermost (MN-major tcgen05
+ * operands).  The weight gradient dW[co,ci] = sum_p dY[p,co] X[p,ci] of a 1x1 convolution / a linear layer straight
+ * from the NHWC / [batch, features] tensors - no transposed copies.  m % 8 == 0, n % 64 == 0, any k (rows beyond k
+ * are zero-filled).  Few output tiles + long K: split-K with fp32 reductions into the cleared output. */
+int mmbs_linear_tn_plan_create(const void* a_km_bf16, const void* b_kn_bf16, float* y, int64_t m, int64_t n, int64_t k,
+                               mmbs_conv_plan** plan_out);
+
 /* ------------------------------------------------ ResNet glue kernels (HBM-bound)
  * stem input: NCHW fp32 [B,3,224,224] -> space-to-depth, zero-padded NHWC bf16
  *   [B,116,116,16] (channel = (row parity, col parity, rgb), 12 used) so that the

@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(256) mlp_bwd_elementwise_kernel(
   for (int k = 0; k < 4; ++k) {
     const int64_t orow = int64_t(blockIdx.x) * 32 + ty * 4 + k;  // a column of dz
     const int64_t ocol = int64_t(blockIdx.y) * 32 + tx;          // a row of dz
-    if (orow < np && ocol < mp) dzt[orow * mp + ocol] = __float2bfloat16_rn(tile[tx][ty * 4 + k]);
+    if (dzt != nullptr && orow < np && ocol < mp) dzt[orow * mp + ocol] = __float2bfloat16_rn(tile[tx][ty * 4 + k]);
   }
 }
 
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(256) mlp_bwd_elementwise_vec_kernel(
       e[j] = tile[rg * 8 + j][cl];
       colsum += __uint_as_float(uint32_t(e[j]) << 16);   // db sums exactly what the GEMMs will see
     }
-    if (col < np && row < mp)
+    if (dzt != nullptr && col < np && row < mp)
       *reinterpret_cast<uint4*>(dzt + col * mp + row) =
           make_uint4(uint32_t(e[0]) | (uint32_t(e[1]) << 16), uint32_t(e[2]) | (uint32_t(e[3]) << 16),
                      uint32_t(e[4]) | (uint32_t(e[5]) << 16), uint32_t(e[6]) | (uint32_t(e[7]) << 16));
@@ -647,8 +647,8 @@ extern "C" int mmbs_mlp_bwd_elementwise(const void* g, int32_t g_is_bf16, int64_
                                         int64_t m, int64_t n, int64_t n_padded, int64_t m_padded, void* dz, void* dzt,
                                         float* db, void* stream) {
   if (int rc = mmbs_device_check()) return rc;
-  MMBS_REQUIRE(g && dz && dzt && m > 0 && n > 0 && n_padded >= n && m_padded >= m && (!relu || act) && p >= 0.f && p < 1.f,
-               "mmbs_mlp_bwd_elementwise: bad argument");
+  MMBS_REQUIRE(g && dz && m > 0 && n > 0 && n_padded >= n && m_padded >= m && (!relu || act) && p >= 0.f && p < 1.f,
+               "mmbs_mlp_bwd_elementwise: bad argument");   // dzt may be NULL (TN weight-gradient GEMMs read dz itself)
   const bool vec = g_is_bf16 && g_stride % 8 == 0 && (!relu || act_stride % 8 == 0) && n_padded % 8 == 0 &&
                    m_padded % 8 == 0 && reinterpret_cast<uintptr_t>(g) % 16 == 0 &&
                    (!relu || reinterpret_cast<uintptr_t>(act) % 16 == 0) && reinterpret_cast<uintptr_t>(dz) % 16 == 0 &&

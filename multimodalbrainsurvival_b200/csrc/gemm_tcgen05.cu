@@ -81,6 +81,7 @@ struct ConvParams {
   // split-K (weight-gradient GEMMs: few output tiles, very long K): tile = ks * mn_tiles + (m, n) tile; split ks
   // covers K chunks [ks * chunks_per_split, ...) and adds its partial sums to the pre-zeroed fp32 output
   int32_t k_split, chunks_per_split, mn_tiles;
+  int32_t mn_major;   // TN GEMM: A is row-major [K, M], B row-major [K, N] (weight gradients straight from NHWC tensors)
   FastDiv fd_mn;
   uint32_t idesc;
   int8_t tap_map[GM_MAX_TAPS];
@@ -414,10 +415,19 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
           if (tc::elect_one()) {
             tc::mbar_expect_tx(full_bar + 8 * s, kResident ? uint32_t(p.a_tx_bytes) : uint32_t(L::STAGE_BYTES));
             const uint32_t a_dst = base_u32 + s * L::STAGE_BYTES;
-            tc::tma_load_4d(amap, full_bar + 8 * s, a_dst, c * GM_CHUNK_K, cw, ch, tcd.n0);
-            if (!kResident)
-              tc::tma_load_2d(&p.b_map, full_bar + 8 * s, a_dst + GM_A_BYTES,
-                              (t * p.k_chunks + c) * GM_CHUNK_K, tcd.nt * N_TILE);
+            if (!kResident && p.mn_major) {
+              // boxes of 64 (M|N) x 64 (K rows) out of the row-major [K, M] / [K, N] matrices
+              for (int j = 0; j < 2; ++j)
+                tc::tma_load_2d(amap, full_bar + 8 * s, a_dst + j * 8192, tcd.w0 + 64 * j, c * GM_CHUNK_K);
+              for (int j = 0; j < N_TILE / 64; ++j)
+                tc::tma_load_2d(&p.b_map, full_bar + 8 * s, a_dst + GM_A_BYTES + j * 8192, tcd.nt * N_TILE + 64 * j,
+                                c * GM_CHUNK_K);
+            } else {
+              tc::tma_load_4d(amap, full_bar + 8 * s, a_dst, c * GM_CHUNK_K, cw, ch, tcd.n0);
+              if (!kResident)
+                tc::tma_load_2d(&p.b_map, full_bar + 8 * s, a_dst + GM_A_BYTES,
+                                (t * p.k_chunks + c) * GM_CHUNK_K, tcd.nt * N_TILE);
+            }
           }
           __syncwarp();
         }
@@ -453,6 +463,13 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
               for (int k = 0; k < GM_CHUNK_K / 16; ++k)
                 tc::umma_bf16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), p.idesc,
                               (ki | u | k) != 0 ? 1u : 0u);
+            }
+          } else if (p.mn_major) {
+#pragma unroll
+            for (int k = 0; k < GM_CHUNK_K / 16; ++k) {   // 16 K rows = 2048 bytes further down every box
+              tc::umma_bf16(d_tmem, tc::make_sw128_mn_desc(a_addr + uint32_t(k) * 2048u),
+                            tc::make_sw128_mn_desc(a_addr + GM_A_BYTES + uint32_t(k) * 2048u), p.idesc,
+                            (ki | k) != 0 ? 1u : 0u);
             }
           } else {
             const uint64_t da = tc::make_sw128_desc(a_addr);
@@ -860,13 +877,14 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
     p.num_taps = 4; p.k_chunks = 1; k_total = 256;
     for (int a = 0; a < 4; ++a) { p.tap_map[a] = 0; p.tap_dw[a] = 0; p.tap_dh[a] = int8_t(a); }
   } else {
-    MMBS_REQUIRE(d->c_in > 0 && d->c_in % 64 == 0, "conv plan: c_in=%d must be a multiple of 64", d->c_in);
+    MMBS_REQUIRE(d->c_in > 0 && (linear_mode == 2 || d->c_in % 64 == 0), "conv plan: c_in=%d must be a multiple of 64",
+                 d->c_in);
     MMBS_REQUIRE((k == 1 || k == 3) && (s == 1 || s == 2), "conv plan: ksize=%d stride=%d unsupported", k, s);
     MMBS_REQUIRE(s == 1 || (d->in_h % 2 == 0 && d->in_w % 2 == 0), "conv plan: stride 2 needs even H, W");
     const int pad = k / 2;
     out_h = (d->in_h + 2 * pad - k) / s + 1;
     out_w = (d->in_w + 2 * pad - k) / s + 1;
-    p.num_taps = k * k; p.k_chunks = d->c_in / 64; k_total = k * k * d->c_in;
+    p.num_taps = k * k; p.k_chunks = (d->c_in + 63) / 64; k_total = k * k * d->c_in;   // (TN GEMM: K rows, OOB zero)
     for (int kh = 0; kh < k; ++kh)
       for (int kw = 0; kw < k; ++kw) {
         const int t = kh * k + kw;
@@ -964,7 +982,8 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
   p.fd_mn = make_fastdiv(uint32_t(p.mn_tiles));
   p.total_tiles = p.mn_tiles * p.k_split;
   plan->grid = unsigned(std::min<int64_t>(p.total_tiles, sm_count()));  // persistent: <= one CTA per SM
-  p.idesc = make_idesc_bf16(GM_TILE_M, plan->n_tile);
+  p.mn_major = (linear_mode == 2) ? 1 : 0;
+  p.idesc = make_idesc_bf16(GM_TILE_M, plan->n_tile, linear_mode == 2);
   p.fd_ntiles = make_fastdiv(uint32_t(d->c_out / plan->n_tile));
   p.fd_tw = make_fastdiv(uint32_t(p.tiles_w));
   p.fd_twh = make_fastdiv(uint32_t(p.tiles_w) * uint32_t(p.tiles_h));
@@ -975,6 +994,24 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
   const uint32_t box_a[4] = {64u, uint32_t(p.tw), uint32_t(p.th + halo_rows), uint32_t(p.tn)};
   const uint32_t box_out[4] = {64u, uint32_t(p.tw), uint32_t(p.th), uint32_t(p.tn)};
   const char* in = static_cast<const char*>(d->in);
+  if (linear_mode == 2) {
+    // TN GEMM out[M, N] = A[K, M]^T B[K, N]: both operands row-major with K outermost, 64 x 64 boxes
+    MMBS_REQUIRE(plan->n_tile >= 64 && d->in_w % 8 == 0 && d->c_out % 64 == 0,
+                 "TN linear plan: need M %% 8 == 0 and N %% 64 == 0 (M=%d N=%d)", d->in_w, d->c_out);
+    const uint32_t box[2] = {64u, 64u};
+    const uint64_t adims[2] = {uint64_t(d->in_w), uint64_t(d->c_in)};
+    const uint64_t astr[1] = {uint64_t(d->in_w) * 2};
+    rc = encode_map(&p.a_map[0], in, 2, adims, astr, box);
+    for (int i = 1; i < 4 && !rc; ++i) p.a_map[i] = p.a_map[0];
+    if (!rc) {
+      const uint64_t bdims[2] = {uint64_t(d->c_out), uint64_t(d->c_in)};
+      const uint64_t bstr[1] = {uint64_t(d->c_out) * 2};
+      rc = encode_map(&p.b_map, d->weight, 2, bdims, bstr, box);
+    }
+    if (rc) return rc;
+    *out = guard.release();
+    return MMBS_OK;
+  }
   if (stem_mode) {
     const uint64_t dims[4] = {64, 113, 116, uint64_t(d->batch)};
     const uint64_t str[3] = {32, 116ull * 32, 116ull * 116 * 32};
@@ -1036,4 +1073,20 @@ extern "C" int mmbs_linear_plan_create(const void* x_bf16, const void* w_bf16, c
   d.ksize = 1; d.stride = 1; d.relu = relu; d.out_f32 = out_f32;
   d.in = x_bf16; d.weight = w_bf16; d.scale = nullptr; d.shift = bias; d.residual = nullptr; d.out = y;
   return build_plan(&d, 0, 1, plan_out);
+}
+
+/* TN GEMM: y[M, N] (fp32) = a[K, M]^T b[K, N], a / b bf16 row-major with K outermost - the weight gradient
+ * dW[co, ci] = sum_p dY[p, co] X[p, ci] straight from the NHWC tensors (no transposed copies). */
+extern "C" int mmbs_linear_tn_plan_create(const void* a_km_bf16, const void* b_kn_bf16, float* y, int64_t m, int64_t n,
+                                          int64_t k, mmbs_conv_plan** plan_out) {
+  if (int rc = mmbs_device_check()) return rc;
+  MMBS_REQUIRE(m > 0 && n > 0 && k > 0 && m < (int64_t(1) << 31) && k < (int64_t(1) << 31) && m % 8 == 0 && n % 64 == 0,
+               "mmbs_linear_tn_plan_create: need m %% 8 == 0 and n %% 64 == 0 (m=%lld n=%lld k=%lld)", (long long)m,
+               (long long)n, (long long)k);
+  mmbs_conv_desc d;
+  std::memset(&d, 0, sizeof(d));
+  d.batch = 1; d.in_h = 1; d.in_w = int32_t(m); d.c_in = int32_t(k); d.c_out = int32_t(n);
+  d.ksize = 1; d.stride = 1; d.relu = 0; d.out_f32 = 1;
+  d.in = a_km_bf16; d.weight = b_kn_bf16; d.out = y;
+  return build_plan(&d, 0, 2, plan_out);
 }

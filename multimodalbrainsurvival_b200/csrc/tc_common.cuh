@@ -151,13 +151,27 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// Same for an MN-major operand (the M / N index is the contiguous one: a row-major [K, M] matrix).  A tile is a
+// stack of TMA boxes of 64 (M|N, 128 bytes) x 64 (K rows): inside a box consecutive K rows are 128 bytes apart
+// (8-row groups: stride byte offset 1024), the next 64-wide M|N block is the next box (leading byte offset 8192).
+// Canonical form ((8,8,m),(8,k)):((1,8,LBO),(64,SBO)) of cute's UMMA Major-MN SWIZZLE_128B descriptors.
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr & 0x3ffffu) >> 4);
+  d |= uint64_t(8192 >> 4) << 16;
+  d |= uint64_t(1024 >> 4) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
+
 }  // namespace tc
 
 // Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, both operands K-major.
 //   [4,6) D format (1 = F32)  [7,10) A format (1 = BF16)  [10,13) B format (1 = BF16)
 //   [15] A major (0 = K)  [16] B major (0 = K)  [17,23) N >> 3  [24,29) M >> 4
-static inline uint32_t make_idesc_bf16(int m, int n) {
-  uint32_t d = 0;
+static inline uint32_t make_idesc_bf16(int m, int n, bool mn_major = false) {
+  uint32_t d = mn_major ? ((1u << 15) | (1u << 16)) : 0u;   // both operands MN-major (row-major [K, M] / [K, N])
   d |= 1u << 4;
   d |= 1u << 7;
   d |= 1u << 10;

@@ -73,6 +73,18 @@ def linear_plan(x, w, bias, out, relu=False):
     return ConvPlan(h, (x, w, bias, out))
 
 
+def linear_tn_plan(a_km, b_kn, out):
+    """out fp32 [M, N] = a_km[K, M]^T @ b_kn[K, N]; a / b bf16 row-major (K outermost), M % 8 == 0, N % 64 == 0."""
+    K, M = a_km.shape
+    N = b_kn.shape[1]
+    assert b_kn.shape[0] == K and tuple(out.shape) == (M, N) and out.dtype == torch.float32
+    h = c_void_p()
+    with torch.cuda.device(a_km.device):
+        _lib.check(_lib.lib().mmbs_linear_tn_plan_create(_lib.ptr(a_km), _lib.ptr(b_kn), _lib.ptr(out), M, N, K,
+                                                         ctypes.byref(h)), "mmbs_linear_tn_plan_create")
+    return ConvPlan(h, (a_km, b_kn, out))
+
+
 # ------------------------------------------------------------------ small wrappers
 def pack_conv_weight(w_oihw: torch.Tensor) -> torch.Tensor:
     O, I, k, _ = w_oihw.shape

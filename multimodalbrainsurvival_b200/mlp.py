@@ -128,7 +128,7 @@ class _MLPTrainEngine:
             E = lambda *s, dtype=bf: torch.zeros(s, dtype=dtype, device=device)  # noqa: E731
             self.hin = [E(M, self.kp[0])]                      # dropped inputs of every layer
             self.w, self.wT, self.b, self.act = [], [], [], []
-            self.dz, self.dzT, self.hinT, self.dW, self.db, self.dh = [], [], [], [], [], []
+            self.dz, self.dW, self.db, self.dh = [], [], [], []
             for i, (lin, relu, p) in enumerate(layers):
                 last = i == L - 1
                 self.w.append(E(self.np_[i], self.kp[i]))
@@ -139,14 +139,13 @@ class _MLPTrainEngine:
                     self.hin.append(E(M, self.np_[i]) if nxt_p > 0 else self.act[i])
                 self.wT.append(E(self.kp[i], self.np_[i]) if (i > 0 or need_dx) else None)
                 self.dz.append(E(M, self.np_[i]))
-                self.dzT.append(E(self.np_[i], Mp))
-                self.hinT.append(E(self.kp[i], Mp))
                 self.dW.append(E(self.np_[i], self.kp[i], dtype=f32))
                 self.db.append(E(self.np_[i], dtype=f32))
                 self.dh.append(E(M, self.kp[i]) if (i > 0 or need_dx) else None)
             self.fwd = [engine.linear_plan(self.hin[i], self.w[i], self.b[i], self.act[i], relu=layers[i][1])
                         for i in range(L)]
-            self.wgrad = [engine.linear_plan(self.dzT[i], self.hinT[i], None, self.dW[i]) for i in range(L)]
+            # dW[n, k] = sum_m dz[m, n] hin[m, k]: a TN GEMM on the row-major tensors themselves (MN-major operands)
+            self.wgrad = [engine.linear_tn_plan(self.dz[i], self.hin[i], self.dW[i]) for i in range(L)]
             self.dgrad = [engine.linear_plan(self.dz[i], self.wT[i], None, self.dh[i]) if self.dh[i] is not None
                           else None for i in range(L)]
         self.version = None
@@ -209,10 +208,8 @@ class _MLPTrainEngine:
             self.db[i].zero_()
             _lib.check(L.mmbs_mlp_bwd_elementwise(_lib.ptr(g), g_bf16, g_stride, _lib.ptr(self.act[i]), self.np_[i],
                                                   int(relu), p_after, seed, i + 1, self.m, lin.out_features,
-                                                  self.np_[i], self.mp, _lib.ptr(self.dz[i]), _lib.ptr(self.dzT[i]),
+                                                  self.np_[i], self.mp, _lib.ptr(self.dz[i]), None,
                                                   _lib.ptr(self.db[i]), _lib.stream_ptr()), "mmbs_mlp_bwd_elementwise")
-            _lib.check(L.mmbs_transpose_bf16(_lib.ptr(self.hin[i]), self.kp[i], self.m, self.kp[i], self.mp,
-                                             _lib.ptr(self.hinT[i]), _lib.stream_ptr()), "mmbs_transpose_bf16")
             self.wgrad[i].run()
             if self.dgrad[i] is not None:
                 self.dgrad[i].run()

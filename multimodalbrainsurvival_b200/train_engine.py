@@ -227,6 +227,14 @@ class ResNetTrainEngine:
         return out
 
     # ------------------------------------------------------------------ backward construction
+    def _wgrad_tn(self, dy2d, x2d):
+        """dW[co, ci] = sum_p dY[p, co] X[p, ci] of a 1x1 convolution: a TN GEMM on the NHWC tensors themselves
+        (MN-major tcgen05 operands, no transposed copies), split-K, fp32 output."""
+        dw = self._buf(dy2d.shape[1], x2d.shape[1], dtype=torch.float32)
+        plan = engine.linear_tn_plan(dy2d, x2d, dw)
+        self._keep.append(plan)
+        return dw, plan
+
     def _wgrad(self, dyT, colT, cout, kcols):
         dw = self._buf(cout, kcols, dtype=torch.float32)
         plan = engine.linear_plan(dyT, colT, None, dw)
@@ -249,9 +257,7 @@ class ResNetTrainEngine:
             # conv3 / bn3
             r["sums3"] = self._buf(2, Cout, dtype=torch.float32)
             r["draw3"] = self._buf(B, Ho, Wo, Cout)
-            r["draw3T"] = self._buf(Cout, Pp)
-            r["a2T"] = self._buf(planes, Pp)
-            r["dw3"], r["wg3"] = self._wgrad(r["draw3T"], r["a2T"], Cout, planes)
+            r["dw3"], r["wg3"] = self._wgrad_tn(r["draw3"].view(P, Cout), r["a2"].view(P, planes))
             r["c3"].want_dgrad()
             r["da2"] = self._buf(B, Ho, Wo, planes)
             r["dg3"] = engine.conv_plan(r["draw3"], r["c3"].w_dgrad, r["da2"], ksize=1, stride=1, c_in=Cout)
@@ -268,9 +274,7 @@ class ResNetTrainEngine:
             # conv1 / bn1
             r["sums1"] = self._buf(2, planes, dtype=torch.float32)
             r["draw1"] = self._buf(B, Hin, Win, planes)
-            r["draw1T"] = self._buf(planes, Pinp)
-            r["xT"] = self._buf(Cin, Pinp)
-            r["dw1"], r["wg1"] = self._wgrad(r["draw1T"], r["xT"], planes, Cin)
+            r["dw1"], r["wg1"] = self._wgrad_tn(r["draw1"].view(Pin, planes), x.view(Pin, Cin))
             if need_dx:
                 r["c1"].want_dgrad()
                 r["dx1"] = self._buf(B, Hin, Win, Cin)
@@ -389,8 +393,6 @@ class ResNetTrainEngine:
             Hin, Win, Cin, Ho, Wo, Cout, planes, P, Pin, Pp, Pinp = r["dims"]
             # ---- bn3 / conv3 (the block's ReLU mask comes from its output)
             self._bn_backward(g, r["out"], r["raw3"], r["b3"], r["sums3"], r["draw3"])
-            self._transpose(r["draw3"], P, Cout, Pp, r["draw3T"])
-            self._im2col_t(r["a2"], 1, 1, Pp, r["a2T"])
             r["wg3"].run()
             r["dg3"].run()
             grads[blk.conv3.weight] = r["dw3"].view(Cout, planes, 1, 1)
@@ -408,8 +410,6 @@ class ResNetTrainEngine:
             grads[blk.bn2.weight], grads[blk.bn2.bias] = r["sums2"][1], r["sums2"][0]
             # ---- bn1 / conv1
             self._bn_backward(r["da1"], r["a1"], r["raw1"], r["b1"], r["sums1"], r["draw1"])
-            self._transpose(r["draw1"], Pin, planes, Pinp, r["draw1T"])
-            self._im2col_t(r["x"], 1, 1, Pinp, r["xT"])
             r["wg1"].run()
             grads[blk.conv1.weight] = r["dw1"].view(planes, Cin, 1, 1)
             grads[blk.bn1.weight], grads[blk.bn1.bias] = r["sums1"][1], r["sums1"][0]

@@ -151,3 +151,22 @@ def test_split_k_weight_gradient_gemm(m, n, k):
     ref = a.double() @ b.double().t()
     err = float((out.double() - ref).abs().max())
     assert err <= 2e-5 * float(ref.abs().max()) + 1e-3, f"max err {err}"
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 64, 64), (512, 256, 6272), (2048, 512, 6272), (512, 1024, 25088), (64, 64, 100),
+                                    (4096, 12800, 128), (256, 2048, 333)])
+def test_tn_gemm_mn_major_operands(m, n, k):
+    """y[M, N] = a[K, M]^T b[K, N] with both operands row-major (MN-major tcgen05 descriptors): the weight-gradient
+    GEMM straight from [pixels, channels] tensors.  K need not be a multiple of 64 (TMA zero-fills the tail)."""
+    from multimodalbrainsurvival_b200 import engine
+    torch.manual_seed(m + n + k)
+    a = torch.randn(k, m, device=DEV).to(torch.bfloat16)
+    b = torch.randn(k, n, device=DEV).to(torch.bfloat16)
+    out = torch.full((m, n), -3.0, dtype=torch.float32, device=DEV)
+    plan = engine.linear_tn_plan(a, b, out)
+    plan.run()
+    plan.run()
+    torch.cuda.synchronize()
+    ref = a.double().t() @ b.double()
+    err = float((out.double() - ref).abs().max())
+    assert err <= 2e-5 * float(ref.abs().max()) + 1e-3, f"max err {err}"
