@@ -386,15 +386,29 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t k
   }
   return make_uint4(c0, c1, c2, c3);
 }
-// keep-mask of the 4 elements [4*q, 4*q+4) of row `row` (q = column / 4)
+// keep-mask of the 8 elements [8*q8, 8*q8+8) of row `row`: one Philox call yields eight 16-bit uniforms, element j is
+// kept when its uniform is >= thresh16 = round(p * 65536).  Every kernel (forward / backward, scalar / vector)
+// derives its mask from this function, so the backward pass regenerates exactly the forward mask.
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t tag, uint32_t row, uint32_t q8,
+                                                  uint32_t thresh16) {
+  const uint4 r = philox4x32(q8, row, uint32_t(seed) ^ tag, uint32_t(seed >> 32));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t keep = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    keep |= ((w[i] & 0xffffu) >= thresh16 ? 1u : 0u) << (2 * i);
+    keep |= ((w[i] >> 16) >= thresh16 ? 1u : 0u) << (2 * i + 1);
+  }
+  return keep;
+}
+// keep-mask of the 4 elements [4*q, 4*q+4) of row `row` (q = column / 4): one nibble of the 8-element group
 __device__ __forceinline__ uint32_t dropout_keep4(uint64_t seed, uint32_t tag, uint32_t row, uint32_t q,
-                                                  uint32_t thresh) {
-  const uint4 r = philox4x32(q, row, uint32_t(seed) ^ tag, uint32_t(seed >> 32));
-  return (r.x >= thresh ? 1u : 0u) | (r.y >= thresh ? 2u : 0u) | (r.z >= thresh ? 4u : 0u) | (r.w >= thresh ? 8u : 0u);
+                                                  uint32_t thresh16) {
+  return (dropout_keep8(seed, tag, row, q >> 1, thresh16) >> (4 * (q & 1u))) & 0xfu;
 }
 __device__ __forceinline__ uint32_t drop_threshold(float p) {
-  const double t = double(p) * 4294967296.0;
-  return t >= 4294967295.0 ? 0xffffffffu : uint32_t(t);
+  const float t = p * 65536.0f + 0.5f;
+  return t >= 65535.0f ? 65535u : uint32_t(t);
 }
 
 // in (fp32 or bf16) [rows, cols] -> bf16 [rows, cols_padded]: dropout(p) then cast, zero padding.
@@ -447,14 +461,10 @@ __global__ void __launch_bounds__(256) dropout_cast_vec8_kernel(const void* __re
     }
     if (p > 0.f) {
       const uint32_t thresh = drop_threshold(p);
-      const uint32_t k0 = dropout_keep4(seed, tag, uint32_t(r), uint32_t(2 * g), thresh);
-      const uint32_t k1 = dropout_keep4(seed, tag, uint32_t(r), uint32_t(2 * g + 1), thresh);
+      const uint32_t k8 = dropout_keep8(seed, tag, uint32_t(r), uint32_t(g), thresh);
       const float sc = 1.0f / (1.0f - p);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[j] = ((k0 >> j) & 1u) ? v[j] * sc : 0.f;
-        v[4 + j] = ((k1 >> j) & 1u) ? v[4 + j] * sc : 0.f;
-      }
+      for (int j = 0; j < 8; ++j) v[j] = ((k8 >> j) & 1u) ? v[j] * sc : 0.f;
     }
   }
   out[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
@@ -506,78 +516,84 @@ __global__ void __launch_bounds__(256) mlp_bwd_elementwise_kernel(
 
 // Same step for bf16 gradients with 16-byte accesses: one block = 64 rows x 64 columns, transposed through shared
 // memory (33-word rows: conflict-free writes, 2-way reads).  Needs g_stride, act_stride, np, mp multiples of 8.
+constexpr int MBV_RT = 16;   // 64-row tiles per block: the bias-gradient atomics are issued once per block, not per tile
 __global__ void __launch_bounds__(256) mlp_bwd_elementwise_vec_kernel(
     const __nv_bfloat16* __restrict__ g, int64_t g_stride, const __nv_bfloat16* __restrict__ act, int64_t act_stride,
     int relu, float p, uint64_t seed, uint32_t tag, int64_t m, int64_t n, int64_t np, int64_t mp,
     __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ dzt, float* __restrict__ db) {
   __shared__ __align__(16) uint16_t tile[64][66];
-  const int64_t r0 = int64_t(blockIdx.x) * 64, c0 = int64_t(blockIdx.y) * 64;   // rows on x: up to 2^31 blocks
+  const int64_t c0 = int64_t(blockIdx.y) * 64;   // rows on x: up to 2^31 blocks
   const uint32_t thresh = drop_threshold(p);
   const float sc = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  float colsum[2] = {0.f, 0.f};   // this thread's (column, row group) partial of db, over all row tiles of the block
+  for (int rt = 0; rt < MBV_RT; ++rt) {
+    const int64_t r0 = (int64_t(blockIdx.x) * MBV_RT + rt) * 64;
+    if (r0 >= mp) break;
 #pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const int idx = threadIdx.x + it * 256;   // 64 rows x 8 column groups
-    const int rl = idx >> 3, cg = idx & 7;
-    const int64_t row = r0 + rl, col = c0 + cg * 8;
-    float v[8];
+    for (int it = 0; it < 2; ++it) {
+      const int idx = threadIdx.x + it * 256;   // 64 rows x 8 column groups
+      const int rl = idx >> 3, cg = idx & 7;
+      const int64_t row = r0 + rl, col = c0 + cg * 8;
+      float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    if (row < m && col < np) {
-      if (col < n) {   // (the last group of a row may straddle n: masked per element below)
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(g + row * g_stride + col));
-        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
-        if (relu) {
-          const uint4 w = __ldg(reinterpret_cast<const uint4*>(act + row * act_stride + col));
-          const float2 e = unpack_bf16x2(w.x), f = unpack_bf16x2(w.y), h = unpack_bf16x2(w.z), k = unpack_bf16x2(w.w);
-          const float av[8] = {e.x, e.y, f.x, f.y, h.x, h.y, k.x, k.y};
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (row < m && col < np) {
+        if (col < n) {   // (the last group of a row may straddle n: masked per element below)
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(g + row * g_stride + col));
+          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+          v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+          if (relu) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(act + row * act_stride + col));
+            const float2 e = unpack_bf16x2(w.x), f = unpack_bf16x2(w.y), h = unpack_bf16x2(w.z), k = unpack_bf16x2(w.w);
+            const float av[8] = {e.x, e.y, f.x, f.y, h.x, h.y, k.x, k.y};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = av[j] > 0.f ? v[j] : 0.f;
-        }
-        if (p > 0.f) {
-          const uint32_t k0 = dropout_keep4(seed, tag, uint32_t(row), uint32_t(col >> 2), thresh);
-          const uint32_t k1 = dropout_keep4(seed, tag, uint32_t(row), uint32_t((col >> 2) + 1), thresh);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            v[j] = ((k0 >> j) & 1u) ? v[j] * sc : 0.f;
-            v[4 + j] = ((k1 >> j) & 1u) ? v[4 + j] * sc : 0.f;
+            for (int j = 0; j < 8; ++j) v[j] = av[j] > 0.f ? v[j] : 0.f;
           }
-        }
+          if (p > 0.f) {
+            const uint32_t k8 = dropout_keep8(seed, tag, uint32_t(row), uint32_t(col >> 3), thresh);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (col + j < n) ? v[j] : 0.f;
+            for (int j = 0; j < 8; ++j) v[j] = ((k8 >> j) & 1u) ? v[j] * sc : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = (col + j < n) ? v[j] : 0.f;
+        }
+        o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                       pack_bf16x2(v[6], v[7]));
+        *reinterpret_cast<uint4*>(dz + row * np + col) = o;
       }
-      const uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                 pack_bf16x2(v[6], v[7]));
-      *reinterpret_cast<uint4*>(dz + row * np + col) = o;
       uint32_t* trow = reinterpret_cast<uint32_t*>(&tile[rl][cg * 8]);
       trow[0] = o.x; trow[1] = o.y; trow[2] = o.z; trow[3] = o.w;
-    } else {
-      uint32_t* trow = reinterpret_cast<uint32_t*>(&tile[rl][cg * 8]);
-      trow[0] = 0u; trow[1] = 0u; trow[2] = 0u; trow[3] = 0u;
     }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int idx = threadIdx.x + it * 256;   // 64 columns x 8 row groups
+      const int cl = idx >> 3, rg = idx & 7;
+      const int64_t col = c0 + cl, row = r0 + rg * 8;
+      uint16_t e[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        e[j] = tile[rg * 8 + j][cl];
+        colsum[it] += __uint_as_float(uint32_t(e[j]) << 16);   // db sums exactly what the GEMMs will see
+      }
+      if (dzt != nullptr && col < np && row < mp)
+        *reinterpret_cast<uint4*>(dzt + col * mp + row) =
+            make_uint4(uint32_t(e[0]) | (uint32_t(e[1]) << 16), uint32_t(e[2]) | (uint32_t(e[3]) << 16),
+                       uint32_t(e[4]) | (uint32_t(e[5]) << 16), uint32_t(e[6]) | (uint32_t(e[7]) << 16));
+    }
+    __syncthreads();   // the tile is rewritten by the next row tile
   }
-  __syncthreads();
 #pragma unroll
   for (int it = 0; it < 2; ++it) {
-    const int idx = threadIdx.x + it * 256;   // 64 columns x 8 row groups
+    const int idx = threadIdx.x + it * 256;
     const int cl = idx >> 3, rg = idx & 7;
-    const int64_t col = c0 + cl, row = r0 + rg * 8;
-    uint16_t e[8];
-    float colsum = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      e[j] = tile[rg * 8 + j][cl];
-      colsum += __uint_as_float(uint32_t(e[j]) << 16);   // db sums exactly what the GEMMs will see
-    }
-    if (dzt != nullptr && col < np && row < mp)
-      *reinterpret_cast<uint4*>(dzt + col * mp + row) =
-          make_uint4(uint32_t(e[0]) | (uint32_t(e[1]) << 16), uint32_t(e[2]) | (uint32_t(e[3]) << 16),
-                     uint32_t(e[4]) | (uint32_t(e[5]) << 16), uint32_t(e[6]) | (uint32_t(e[7]) << 16));
-    // the 8 row groups of a column sit in 8 consecutive lanes
-    colsum += __shfl_xor_sync(0xffffffffu, colsum, 1);
-    colsum += __shfl_xor_sync(0xffffffffu, colsum, 2);
-    colsum += __shfl_xor_sync(0xffffffffu, colsum, 4);
-    if (db != nullptr && rg == 0 && col < n) atomicAdd(db + col, colsum);
+    const int64_t col = c0 + cl;
+    float cs = colsum[it];   // the 8 row groups of a column sit in 8 consecutive lanes
+    cs += __shfl_xor_sync(0xffffffffu, cs, 1);
+    cs += __shfl_xor_sync(0xffffffffu, cs, 2);
+    cs += __shfl_xor_sync(0xffffffffu, cs, 4);
+    if (db != nullptr && rg == 0 && col < n) atomicAdd(db + col, cs);
   }
 }
 
@@ -655,7 +671,7 @@ extern "C" int mmbs_mlp_bwd_elementwise(const void* g, int32_t g_is_bf16, int64_
                    reinterpret_cast<uintptr_t>(dzt) % 16 == 0 && ceil_div(n_padded, 64) <= 65535;
   if (vec) {
     // rows beyond m up to m_padded: the transposed output is written (zeros) for every row group the grid covers
-    dim3 vgrid(unsigned(ceil_div(m_padded, 64)), unsigned(ceil_div(n_padded, 64)));
+    dim3 vgrid(unsigned(ceil_div(ceil_div(m_padded, 64), MBV_RT)), unsigned(ceil_div(n_padded, 64)));
     mlp_bwd_elementwise_vec_kernel<<<vgrid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(g), g_stride, static_cast<const __nv_bfloat16*>(act), act_stride, relu, p, seed,
         tag, m, n, n_padded, m_padded, static_cast<__nv_bfloat16*>(dz), static_cast<__nv_bfloat16*>(dzt), db);
