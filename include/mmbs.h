@@ -116,7 +116,10 @@ typedef struct {
   int32_t stride;         /* 1 or 2 */
   int32_t relu;           /* apply ReLU in the epilogue */
   int32_t out_f32;        /* 1: out is float32 (row stride c_out), else bf16 */
-  int32_t flags;          /* bit0: 3x3 weights are [c_out][kw][c_in/64][kh][64] (halo variant) */
+  int32_t flags;          /* bit0: 3x3 weights are [c_out][kw][c_in/64][kh][64] (halo variant)
+                           * bit1: data-gradient convolution reading the FORWARD conv's packed weights: `weight` is
+                           *       [c_in][ksize][ksize][c_out] (the forward [Cout][kh][kw][Cin] matrix), taps are flipped
+                           *       by the kernel, the B operand is fed MN-major - no transposed weight copy (stride 1) */
   const void* in;         /* bf16 NHWC [B, in_h, in_w, c_in] */
   const void* weight;     /* bf16 [c_out, ksize*ksize*c_in] */
   const float* scale;     /* [c_out] or NULL (=1) */

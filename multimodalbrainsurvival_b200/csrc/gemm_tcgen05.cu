@@ -81,7 +81,9 @@ struct ConvParams {
   // split-K (weight-gradient GEMMs: few output tiles, very long K): tile = ks * mn_tiles + (m, n) tile; split ks
   // covers K chunks [ks * chunks_per_split, ...) and adds its partial sums to the pre-zeroed fp32 output
   int32_t k_split, chunks_per_split, mn_tiles;
-  int32_t mn_major;   // TN GEMM: A is row-major [K, M], B row-major [K, N] (weight gradients straight from NHWC tensors)
+  int32_t mn_major;   // bit0: A is MN-major (row-major [K, M]); bit1: B is MN-major (row-major [K, N]).  3 = TN GEMM (weight
+                      // gradients from NHWC tensors); 2 = data gradient reading the FORWARD conv's packed weights
+  int32_t b_tap_stride;   // mode 2: columns per tap of the forward weight matrix (= forward c_in = this conv's c_out)
   FastDiv fd_mn;
   uint32_t idesc;
   int8_t tap_map[GM_MAX_TAPS];
@@ -416,11 +418,17 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
             tc::mbar_expect_tx(full_bar + 8 * s, kResident ? uint32_t(p.a_tx_bytes) : uint32_t(L::STAGE_BYTES));
             const uint32_t a_dst = base_u32 + s * L::STAGE_BYTES;
             if (!kResident && p.mn_major) {
-              // boxes of 64 (M|N) x 64 (K rows) out of the row-major [K, M] / [K, N] matrices
-              for (int j = 0; j < 2; ++j)
-                tc::tma_load_2d(amap, full_bar + 8 * s, a_dst + j * 8192, tcd.w0 + 64 * j, c * GM_CHUNK_K);
+              // MN-major operands: boxes of 64 (M|N) x 64 (K rows) out of a row-major [K, M] / [K, N] matrix
+              if (p.mn_major & 1) {
+                for (int j = 0; j < 2; ++j)
+                  tc::tma_load_2d(amap, full_bar + 8 * s, a_dst + j * 8192, tcd.w0 + 64 * j, c * GM_CHUNK_K);
+              } else {
+                tc::tma_load_4d(amap, full_bar + 8 * s, a_dst, c * GM_CHUNK_K, cw, ch, tcd.n0);
+              }
+              // mode 2 (data gradient): K rows = forward output channels, columns = (flipped tap, forward input channel)
+              const int b_col0 = ((p.mn_major & 1) ? 0 : (p.num_taps - 1 - t) * p.b_tap_stride) + tcd.nt * N_TILE;
               for (int j = 0; j < N_TILE / 64; ++j)
-                tc::tma_load_2d(&p.b_map, full_bar + 8 * s, a_dst + GM_A_BYTES + j * 8192, tcd.nt * N_TILE + 64 * j,
+                tc::tma_load_2d(&p.b_map, full_bar + 8 * s, a_dst + GM_A_BYTES + j * 8192, b_col0 + 64 * j,
                                 c * GM_CHUNK_K);
             } else {
               tc::tma_load_4d(amap, full_bar + 8 * s, a_dst, c * GM_CHUNK_K, cw, ch, tcd.n0);
@@ -465,10 +473,12 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
                               (ki | u | k) != 0 ? 1u : 0u);
             }
           } else if (p.mn_major) {
+            const uint64_t da_k = tc::make_sw128_desc(a_addr);
 #pragma unroll
-            for (int k = 0; k < GM_CHUNK_K / 16; ++k) {   // 16 K rows = 2048 bytes further down every box
-              tc::umma_bf16(d_tmem, tc::make_sw128_mn_desc(a_addr + uint32_t(k) * 2048u),
-                            tc::make_sw128_mn_desc(a_addr + GM_A_BYTES + uint32_t(k) * 2048u), p.idesc,
+            for (int k = 0; k < GM_CHUNK_K / 16; ++k) {   // MN-major: 16 K rows = 2048 bytes further down every box
+              const uint64_t da = (p.mn_major & 1) ? tc::make_sw128_mn_desc(a_addr + uint32_t(k) * 2048u)
+                                                   : da_k + uint64_t(2 * k);
+              tc::umma_bf16(d_tmem, da, tc::make_sw128_mn_desc(a_addr + GM_A_BYTES + uint32_t(k) * 2048u), p.idesc,
                             (ki | k) != 0 ? 1u : 0u);
             }
           } else {
@@ -913,7 +923,7 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
   const int64_t w_bytes = int64_t(k_total) * d->c_out * 2;
   bool resident = false, halo = false;
   int forced_n_tile = 0;
-  if (!linear_mode && !d->out_f32) {
+  if (!linear_mode && !d->out_f32 && !(d->flags & 2)) {
     if (d->c_out == 64 && w_bytes <= GM_RES64_BYTES) { resident = true; forced_n_tile = 64; }
     // (256-output convs with tiny K - layer1 conv3 / downsample - are faster on the streamed 256-wide path with the
     //  output-DMA warp: 310 vs 332 us with the residual, 190 vs 215 us without; MMBS_RES256=1 restores the old choice)
@@ -946,7 +956,7 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
   // weight-gradient shaped GEMMs (fp32 output, no epilogue arithmetic): keep the widest N tile and split K
   const bool can_split = linear_mode && d->out_f32 && !d->scale && !d->shift && !d->relu && !d->residual && !d->stats &&
                          getenv("MMBS_NO_SPLITK") == nullptr;
-  plan->n_tile = pick_n_tile(d->c_out, m_tiles, can_split ? 256 : (d->stats ? 64 : 32));   // statistics: TMA-store path
+  plan->n_tile = pick_n_tile(d->c_out, m_tiles, can_split ? 256 : ((d->stats || (d->flags & 2)) ? 64 : 32));   // statistics: TMA-store path
   MMBS_REQUIRE(!d->stats || (out_w % p.tw == 0 && out_h % p.th == 0),
                "conv plan: batch statistics need pixel boxes that tile the %dx%d output exactly", out_h, out_w);
   // epilogue-bound residual layers (short K loop): 128-wide tile = double-staged epilogue with the
@@ -982,8 +992,12 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
   p.fd_mn = make_fastdiv(uint32_t(p.mn_tiles));
   p.total_tiles = p.mn_tiles * p.k_split;
   plan->grid = unsigned(std::min<int64_t>(p.total_tiles, sm_count()));  // persistent: <= one CTA per SM
-  p.mn_major = (linear_mode == 2) ? 1 : 0;
-  p.idesc = make_idesc_bf16(GM_TILE_M, plan->n_tile, linear_mode == 2);
+  const bool fwd_weights = !linear_mode && !stem_mode && (d->flags & 2) != 0;   // dgrad on the forward conv's weights
+  p.mn_major = (linear_mode == 2) ? 3 : (fwd_weights ? 2 : 0);
+  p.b_tap_stride = d->c_out;
+  MMBS_REQUIRE(!fwd_weights || (!resident && plan->n_tile >= 64 && s == 1),
+               "conv plan: forward-weight data gradients need stride 1, c_out %% 64 == 0 and streamed weights");
+  p.idesc = make_idesc_bf16(GM_TILE_M, plan->n_tile, linear_mode == 2, linear_mode == 2 || fwd_weights);
   p.fd_ntiles = make_fastdiv(uint32_t(d->c_out / plan->n_tile));
   p.fd_tw = make_fastdiv(uint32_t(p.tiles_w));
   p.fd_twh = make_fastdiv(uint32_t(p.tiles_w) * uint32_t(p.tiles_h));
@@ -1032,7 +1046,14 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
         rc = encode_map(&p.a_map[ph * 2 + pw], in + (uint64_t(ph) * W + pw) * C * 2, 4, dims, str, box_a);
       }
   }
-  if (!rc) {
+  if (!rc && fwd_weights) {
+    // the forward conv's matrix [c_in (its c_out) rows][taps * c_out (its c_in) columns], 64 x 64 boxes (MN-major B)
+    const uint64_t cols = uint64_t(k) * k * d->c_out;
+    const uint64_t dims[2] = {cols, uint64_t(d->c_in)};
+    const uint64_t str[1] = {cols * 2};
+    const uint32_t box_b[2] = {64u, 64u};
+    rc = encode_map(&p.b_map, d->weight, 2, dims, str, box_b);
+  } else if (!rc) {
     const uint64_t dims[2] = {uint64_t(k_total), uint64_t(d->c_out)};
     const uint64_t str[1] = {uint64_t(k_total) * 2};
     const uint32_t box_b[2] = {64u, uint32_t(plan->n_tile)};

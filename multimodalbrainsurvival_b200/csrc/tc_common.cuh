@@ -170,8 +170,8 @@ __device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr) {
 // Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, both operands K-major.
 //   [4,6) D format (1 = F32)  [7,10) A format (1 = BF16)  [10,13) B format (1 = BF16)
 //   [15] A major (0 = K)  [16] B major (0 = K)  [17,23) N >> 3  [24,29) M >> 4
-static inline uint32_t make_idesc_bf16(int m, int n, bool mn_major = false) {
-  uint32_t d = mn_major ? ((1u << 15) | (1u << 16)) : 0u;   // both operands MN-major (row-major [K, M] / [K, N])
+static inline uint32_t make_idesc_bf16(int m, int n, bool a_mn_major = false, bool b_mn_major = false) {
+  uint32_t d = (a_mn_major ? (1u << 15) : 0u) | (b_mn_major ? (1u << 16) : 0u);   // MN-major = row-major [K, M|N]
   d |= 1u << 4;
   d |= 1u << 7;
   d |= 1u << 10;

@@ -38,16 +38,19 @@ class ConvPlan:
 
 
 def conv_plan(x, w, out, *, ksize, stride, c_in, scale=None, shift=None, residual=None, relu=False,
-              in_hw=None, halo_weights=False, stats=None):
+              in_hw=None, halo_weights=False, stats=None, fwd_weights=False):
     """x: bf16 NHWC [B,H,W,Cin] (ksize 4 = stem: the [B,116,116,16] space-to-depth buffer);
-    w: bf16 [Cout, k*k*Cin]; out: NHWC bf16 or fp32."""
+    w: bf16 [Cout, k*k*Cin]; out: NHWC bf16 or fp32.
+    fwd_weights=True: a data-gradient convolution on the FORWARD conv's packed weights (w is the forward
+    [Cin_of_this_conv, k*k*Cout_of_this_conv] matrix; taps flipped in the kernel, MN-major B operand)."""
     B = x.shape[0]
     H, W = (x.shape[1], x.shape[2]) if in_hw is None else in_hw
     d = ConvDesc()
-    d.batch, d.in_h, d.in_w, d.c_in, d.c_out = B, H, W, c_in, w.shape[0]
+    c_out = w.shape[1] // (ksize * ksize) if fwd_weights else w.shape[0]
+    d.batch, d.in_h, d.in_w, d.c_in, d.c_out = B, H, W, c_in, c_out
     d.ksize, d.stride, d.relu = ksize, stride, int(relu)
     d.out_f32 = int(out.dtype == torch.float32)
-    d.flags = 1 if halo_weights else 0
+    d.flags = (1 if halo_weights else 0) | (2 if fwd_weights else 0)
     d.in_ = x.data_ptr()
     d.weight = w.data_ptr()
     d.scale = scale.data_ptr() if scale is not None else None

@@ -52,8 +52,9 @@ class _BNState:
 
 
 class _Conv:
-    """One convolution of the trunk: packed bf16 weights (repacked in place when the parameter changes),
-    the forward plan and, for layer4, the operands of its backward GEMMs."""
+    """One convolution of the trunk: packed bf16 weights [Cout][kh][kw][Cin], repacked in place when the parameter
+    changes.  The layer4 data-gradient convolutions read the same matrix (MN-major B operand, taps flipped in the
+    kernel), so no transposed copy exists."""
 
     def __init__(self, conv, kind):
         self.conv, self.kind = conv, kind   # kind: 'stem' | 'plain' | 'halo'
@@ -61,7 +62,6 @@ class _Conv:
         dev = conv.weight.device
         cols = 256 if kind == 'stem' else k * k * I
         self.w = torch.empty((O, cols), dtype=torch.bfloat16, device=dev)
-        self.w_dgrad = None
         self.version = None
 
     def refresh(self):
@@ -79,15 +79,7 @@ class _Conv:
         else:
             _ck(L.mmbs_pack_conv_weight(_lib.ptr(w), _lib.ptr(self.w), O, I, k, _lib.stream_ptr()),
                 "mmbs_pack_conv_weight")
-        if self.w_dgrad is not None:
-            _ck(L.mmbs_pack_conv_weight_dgrad(_lib.ptr(w), _lib.ptr(self.w_dgrad), O, I, k, _lib.stream_ptr()),
-                "mmbs_pack_conv_weight_dgrad")
         self.version = ver
-
-    def want_dgrad(self):
-        O, I, k, _ = self.conv.weight.shape
-        self.w_dgrad = torch.empty((I, k * k * O), dtype=torch.bfloat16, device=self.conv.weight.device)
-        self.version = None
 
 
 class ResNetTrainEngine:
@@ -258,27 +250,26 @@ class ResNetTrainEngine:
             r["sums3"] = self._buf(2, Cout, dtype=torch.float32)
             r["draw3"] = self._buf(B, Ho, Wo, Cout)
             r["dw3"], r["wg3"] = self._wgrad_tn(r["draw3"].view(P, Cout), r["a2"].view(P, planes))
-            r["c3"].want_dgrad()
             r["da2"] = self._buf(B, Ho, Wo, planes)
-            r["dg3"] = engine.conv_plan(r["draw3"], r["c3"].w_dgrad, r["da2"], ksize=1, stride=1, c_in=Cout)
+            # data gradients read the forward conv's packed weights (MN-major B operand, taps flipped in the kernel)
+            r["dg3"] = engine.conv_plan(r["draw3"], r["c3"].w, r["da2"], ksize=1, stride=1, c_in=Cout, fwd_weights=True)
             # conv2 / bn2
             r["sums2"] = self._buf(2, planes, dtype=torch.float32)
             r["draw2"] = self._buf(B, Ho, Wo, planes)
             r["draw2T"] = self._buf(planes, Pp)
             r["col2T"] = self._buf(9 * planes, Pp)
             r["dw2"], r["wg2"] = self._wgrad(r["draw2T"], r["col2T"], planes, 9 * planes)   # [co, (ci, kh, kw)] = OIHW
-            r["c2"].want_dgrad()
             r["u2"] = self._buf(B, Hin, Win, planes, zero=True) if s == 2 else r["draw2"]
             r["da1"] = self._buf(B, Hin, Win, planes)
-            r["dg2"] = engine.conv_plan(r["u2"], r["c2"].w_dgrad, r["da1"], ksize=3, stride=1, c_in=planes)
+            r["dg2"] = engine.conv_plan(r["u2"], r["c2"].w, r["da1"], ksize=3, stride=1, c_in=planes, fwd_weights=True)
             # conv1 / bn1
             r["sums1"] = self._buf(2, planes, dtype=torch.float32)
             r["draw1"] = self._buf(B, Hin, Win, planes)
             r["dw1"], r["wg1"] = self._wgrad_tn(r["draw1"].view(Pin, planes), x.view(Pin, Cin))
             if need_dx:
-                r["c1"].want_dgrad()
                 r["dx1"] = self._buf(B, Hin, Win, Cin)
-                r["dg1"] = engine.conv_plan(r["draw1"], r["c1"].w_dgrad, r["dx1"], ksize=1, stride=1, c_in=planes)
+                r["dg1"] = engine.conv_plan(r["draw1"], r["c1"].w, r["dx1"], ksize=1, stride=1, c_in=planes,
+                                            fwd_weights=True)
                 r["g_in"] = self._buf(B, Hin, Win, Cin)
             if r["rawd"] is not None:
                 r["sumsd"] = self._buf(2, Cout, dtype=torch.float32)
