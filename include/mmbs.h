@@ -147,6 +147,11 @@ int mmbs_linear_plan_create(const void* x_bf16, const void* w_bf16, const float*
 int mmbs_linear_tn_plan_create(const void* a_km_bf16, const void* b_kn_bf16, float* y, int64_t m, int64_t n, int64_t k,
                                mmbs_conv_plan** plan_out);
 
+/* NN GEMM: y[M,N] = act(x[M,K] w[K,N] + bias[N]); w bf16 row-major with K outermost (MN-major B operand): the data
+ * gradient dh = dz W of a linear layer straight from the forward weights W[N_out, K_in]. k % 64 == 0, n % 64 == 0. */
+int mmbs_linear_nn_plan_create(const void* x_bf16, const void* w_kn_bf16, const float* bias, void* y, int64_t m,
+                               int64_t n, int64_t k, int32_t relu, int32_t out_f32, mmbs_conv_plan** plan_out);
+
 /* ------------------------------------------------ ResNet glue kernels (HBM-bound)
  * stem input: NCHW fp32 [B,3,224,224] -> space-to-depth, zero-padded NHWC bf16
  *   [B,116,116,16] (channel = (row parity, col parity, rgb), 12 used) so that the

@@ -1003,7 +1003,7 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
   p.fd_mn = make_fastdiv(uint32_t(p.mn_tiles));
   p.total_tiles = p.mn_tiles * p.k_split;
   plan->grid = unsigned(std::min<int64_t>(p.total_tiles, sm_count()));  // persistent: <= one CTA per SM
-  const bool fwd_weights = !linear_mode && !stem_mode && (d->flags & 2) != 0;   // dgrad on the forward conv's weights
+  const bool fwd_weights = linear_mode != 2 && !stem_mode && (d->flags & 2) != 0;   // dgrad on the forward weights
   p.mn_major = (linear_mode == 2) ? 3 : (fwd_weights ? 2 : 0);
   p.b_tap_stride = d->c_out;
   MMBS_REQUIRE(!fwd_weights || (!resident && plan->n_tile >= 64 && s == 1),
@@ -1121,4 +1121,21 @@ extern "C" int mmbs_linear_tn_plan_create(const void* a_km_bf16, const void* b_k
   d.ksize = 1; d.stride = 1; d.relu = 0; d.out_f32 = 1;
   d.in = a_km_bf16; d.weight = b_kn_bf16; d.out = y;
   return build_plan(&d, 0, 2, plan_out);
+}
+
+/* NN GEMM: y[M, N] = x[M, K] w[K, N] (+ bias, ReLU): w is row-major with K outermost - the data gradient
+ * dh = dz W of a linear layer straight from the forward weight matrix W[N_out, K_in] (MN-major B operand). */
+extern "C" int mmbs_linear_nn_plan_create(const void* x_bf16, const void* w_kn_bf16, const float* bias, void* y,
+                                          int64_t m, int64_t n, int64_t k, int32_t relu, int32_t out_f32,
+                                          mmbs_conv_plan** plan_out) {
+  if (int rc = mmbs_device_check()) return rc;
+  MMBS_REQUIRE(m > 0 && n > 0 && k > 0 && m < (int64_t(1) << 31) && k % 64 == 0 && n % 64 == 0,
+               "mmbs_linear_nn_plan_create: need k %% 64 == 0 and n %% 64 == 0 (m=%lld n=%lld k=%lld)", (long long)m,
+               (long long)n, (long long)k);
+  mmbs_conv_desc d;
+  std::memset(&d, 0, sizeof(d));
+  d.batch = 1; d.in_h = 1; d.in_w = int32_t(m); d.c_in = int32_t(k); d.c_out = int32_t(n);
+  d.ksize = 1; d.stride = 1; d.relu = relu; d.out_f32 = out_f32; d.flags = 2;
+  d.in = x_bf16; d.weight = w_kn_bf16; d.scale = nullptr; d.shift = bias; d.residual = nullptr; d.out = y;
+  return build_plan(&d, 0, 1, plan_out);
 }

@@ -76,6 +76,19 @@ def linear_plan(x, w, bias, out, relu=False):
     return ConvPlan(h, (x, w, bias, out))
 
 
+def linear_nn_plan(x, w_kn, bias, out, relu=False):
+    """out [M, N] = x[M, K] @ w_kn[K, N] (+ bias, ReLU); w_kn bf16 row-major (K outermost), K % 64 == 0, N % 64 == 0."""
+    M, K = x.shape
+    N = w_kn.shape[1]
+    assert w_kn.shape[0] == K and tuple(out.shape) == (M, N)
+    h = c_void_p()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().mmbs_linear_nn_plan_create(
+            _lib.ptr(x), _lib.ptr(w_kn), _lib.ptr(bias), _lib.ptr(out), M, N, K, int(relu),
+            int(out.dtype == torch.float32), ctypes.byref(h)), "mmbs_linear_nn_plan_create")
+    return ConvPlan(h, (x, w_kn, bias, out))
+
+
 def linear_tn_plan(a_km, b_kn, out):
     """out fp32 [M, N] = a_km[K, M]^T @ b_kn[K, N]; a / b bf16 row-major (K outermost), M % 8 == 0, N % 64 == 0."""
     K, M = a_km.shape

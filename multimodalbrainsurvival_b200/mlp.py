@@ -127,7 +127,7 @@ class _MLPTrainEngine:
         with torch.cuda.device(device):
             E = lambda *s, dtype=bf: torch.zeros(s, dtype=dtype, device=device)  # noqa: E731
             self.hin = [E(M, self.kp[0])]                      # dropped inputs of every layer
-            self.w, self.wT, self.b, self.act = [], [], [], []
+            self.w, self.b, self.act = [], [], []
             self.dz, self.dW, self.db, self.dh = [], [], [], []
             for i, (lin, relu, p) in enumerate(layers):
                 last = i == L - 1
@@ -137,7 +137,6 @@ class _MLPTrainEngine:
                 if not last:
                     nxt_p = layers[i + 1][2]
                     self.hin.append(E(M, self.np_[i]) if nxt_p > 0 else self.act[i])
-                self.wT.append(E(self.kp[i], self.np_[i]) if (i > 0 or need_dx) else None)
                 self.dz.append(E(M, self.np_[i]))
                 self.dW.append(E(self.np_[i], self.kp[i], dtype=f32))
                 self.db.append(E(self.np_[i], dtype=f32))
@@ -146,7 +145,8 @@ class _MLPTrainEngine:
                         for i in range(L)]
             # dW[n, k] = sum_m dz[m, n] hin[m, k]: a TN GEMM on the row-major tensors themselves (MN-major operands)
             self.wgrad = [engine.linear_tn_plan(self.dz[i], self.hin[i], self.dW[i]) for i in range(L)]
-            self.dgrad = [engine.linear_plan(self.dz[i], self.wT[i], None, self.dh[i]) if self.dh[i] is not None
+            # dh[m, k] = sum_n dz[m, n] W[n, k]: an NN GEMM on the forward weight matrix itself (MN-major B operand)
+            self.dgrad = [engine.linear_nn_plan(self.dz[i], self.w[i], None, self.dh[i]) if self.dh[i] is not None
                           else None for i in range(L)]
         self.version = None
         self._lib = _lib
@@ -169,10 +169,6 @@ class _MLPTrainEngine:
             n, k = lin.out_features, lin.in_features
             wsrc = lin.weight.detach().float().contiguous()
             engine.cast_pad_bf16(wsrc, self.kp[i], out=self.w[i][:n])
-            if self.wT[i] is not None:
-                _lib.check(L.mmbs_cast_transpose_pad_bf16(_lib.ptr(wsrc), n, k, self.kp[i], self.np_[i],
-                                                          _lib.ptr(self.wT[i]), _lib.stream_ptr()),
-                           "mmbs_cast_transpose_pad_bf16")
             if lin.bias is not None:
                 self.b[i][:n].copy_(lin.bias.detach())
         self.version = ver

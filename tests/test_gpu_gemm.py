@@ -170,3 +170,23 @@ def test_tn_gemm_mn_major_operands(m, n, k):
     ref = a.double().t() @ b.double()
     err = float((out.double() - ref).abs().max())
     assert err <= 2e-5 * float(ref.abs().max()) + 1e-3, f"max err {err}"
+
+
+@pytest.mark.parametrize("m,n,k,relu,f32", [(128, 4096, 2048, False, False), (300, 64, 256, True, True),
+                                            (1024, 2048, 256, False, False)])
+def test_nn_gemm_mn_major_weights(m, n, k, relu, f32):
+    """y = act(x[M, K] @ w[K, N] + bias): the B operand is a row-major [K, N] matrix fed MN-major (the data
+    gradient of a linear layer on its forward weights)."""
+    from multimodalbrainsurvival_b200 import engine
+    torch.manual_seed(m + n + k)
+    x = torch.randn(m, k, device=DEV).to(torch.bfloat16)
+    w = (torch.randn(k, n, device=DEV) / k ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(n, device=DEV)
+    out = torch.empty(m, n, device=DEV, dtype=torch.float32 if f32 else torch.bfloat16)
+    engine.linear_nn_plan(x, w, bias, out, relu=relu).run()
+    torch.cuda.synchronize()
+    ref = x.double() @ w.double() + bias.double()
+    if relu:
+        ref = torch.relu(ref)
+    err = float((out.double() - ref).abs().max())
+    assert err <= (1e-5 if f32 else 1e-2) * float(ref.abs().max()) + 1e-4, f"max err {err}"
