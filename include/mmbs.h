@@ -152,6 +152,14 @@ int mmbs_linear_tn_plan_create(const void* a_km_bf16, const void* b_kn_bf16, flo
 int mmbs_linear_nn_plan_create(const void* x_bf16, const void* w_kn_bf16, const float* bias, void* y, int64_t m,
                                int64_t n, int64_t k, int32_t relu, int32_t out_f32, mmbs_conv_plan** plan_out);
 
+/* Implicit weight-gradient GEMM of a convolution (ksize 1|3, stride 1|2, pad ksize/2):
+ *   dw[co,ci,kh,kw] (fp32, OIHW = nn.Conv2d.weight.grad) = sum_{n,ho,wo} dy[n,ho,wo,co] * x[n, ho*s+kh-pad, wo*s+kw-pad, ci]
+ * dy [B,oh,ow,c_out] and x [B,in_h,in_w,c_in] are the bf16 NHWC tensors themselves (MN-major operands, K chunk = 64
+ * images at one output pixel, TMA zero fill = padding): no im2col buffer, no transposed copies.  Split-K. */
+int mmbs_conv_wgrad_plan_create(const void* dy_bf16, const void* x_bf16, float* dw_oihw, int64_t batch, int64_t in_h,
+                                int64_t in_w, int64_t c_in, int64_t c_out, int64_t ksize, int64_t stride,
+                                mmbs_conv_plan** plan_out);
+
 /* ------------------------------------------------ ResNet glue kernels (HBM-bound)
  * stem input: NCHW fp32 [B,3,224,224] -> space-to-depth, zero-padded NHWC bf16
  *   [B,116,116,16] (channel = (row parity, col parity, rgb), 12 used) so that the

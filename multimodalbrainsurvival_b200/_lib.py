@@ -68,6 +68,8 @@ SIGNATURES = {
                                                   ctypes.POINTER(c_void_p)]),
     "mmbs_linear_nn_plan_create": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64,
                                                   c_i32, c_i32, ctypes.POINTER(c_void_p)]),
+    "mmbs_conv_wgrad_plan_create": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
+                                                   c_i64, ctypes.POINTER(c_void_p)]),
     "mmbs_stem_pack_input": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
     "mmbs_stem_pack_input_u8": (ctypes.c_int, [c_void_p, c_void_p, c_i64, ctypes.POINTER(c_float),
                                                ctypes.POINTER(c_float), c_void_p]),

@@ -83,6 +83,9 @@ struct ConvParams {
   int32_t k_split, chunks_per_split, mn_tiles;
   int32_t mn_major;   // bit0: A is MN-major (row-major [K, M]); bit1: B is MN-major (row-major [K, N]).  3 = TN GEMM (weight
                       // gradients from NHWC tensors); 2 = data gradient reading the FORWARD conv's packed weights
+  // implicit weight-gradient GEMM of a convolution (mn_major == 3, wg_conv): K chunk = 64 images at one output pixel
+  int32_t wg_conv, wg_nb, wg_ow, wg_stride, wg_ksize, wg_cin, wg_cin_tiles;
+  int32_t out_col_stride;   // fp32 direct-store epilogue: distance between consecutive output columns (OIHW: k*k)
   int32_t b_tap_stride;   // mode 2: columns per tap of the forward weight matrix (= forward c_in = this conv's c_out)
   FastDiv fd_mn;
   uint32_t idesc;
@@ -218,7 +221,16 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
       }
-      if (p.out_f32 && p.k_split > 1) {
+      if (p.out_f32 && p.out_col_stride != 1) {   // strided columns (OIHW weight gradient): scalar stores / reductions
+        float* op = static_cast<float*>(p.out) + row_off + int64_t(c0) * p.out_col_stride;
+        if (p.k_split > 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(op + j * p.out_col_stride, v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) op[j * p.out_col_stride] = v[j];
+        }
+      } else if (p.out_f32 && p.k_split > 1) {
         float* op = static_cast<float*>(p.out) + row_off + c0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) atomicAdd(op + j, v[j]);   // fire-and-forget reductions (RED.ADD.F32)
@@ -419,7 +431,20 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
             const uint32_t a_dst = base_u32 + s * L::STAGE_BYTES;
             if (!kResident && p.mn_major) {
               // MN-major operands: boxes of 64 (M|N) x 64 (K rows) out of a row-major [K, M] / [K, N] matrix
-              if (p.mn_major & 1) {
+              if (p.wg_conv) {
+                // dW[co, ci, kh, kw] = sum over (pixel, image) of dY[n, ho, wo, co] * X[n, ho*s+kh-pad, wo*s+kw-pad, ci]:
+                // K chunk c = 64 images at output pixel (ho, wo); the N tile fixes the tap and a block of ci
+                const int pos = c / p.wg_nb, nb = c - pos * p.wg_nb;
+                const int ho = pos / p.wg_ow, wo = pos - ho * p.wg_ow;
+                const int tap = tcd.nt / p.wg_cin_tiles, ci0 = (tcd.nt - tap * p.wg_cin_tiles) * N_TILE;
+                const int pad = p.wg_ksize >> 1;
+                const int iy = ho * p.wg_stride + tap / p.wg_ksize - pad, ix = wo * p.wg_stride + tap % p.wg_ksize - pad;
+                for (int j = 0; j < 2; ++j)
+                  tc::tma_load_4d(amap, full_bar + 8 * s, a_dst + j * 8192, tcd.w0 + 64 * j, wo, ho, nb * 64);
+                for (int j = 0; j < N_TILE / 64; ++j)
+                  tc::tma_load_4d(&p.b_map, full_bar + 8 * s, a_dst + GM_A_BYTES + j * 8192, ci0 + 64 * j, ix, iy,
+                                  nb * 64);
+              } else if (p.mn_major & 1) {
                 for (int j = 0; j < 2; ++j)
                   tc::tma_load_2d(amap, full_bar + 8 * s, a_dst + j * 8192, tcd.w0 + 64 * j, c * GM_CHUNK_K);
               } else {
@@ -427,9 +452,10 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
               }
               // mode 2 (data gradient): K rows = forward output channels, columns = (flipped tap, forward input channel)
               const int b_col0 = ((p.mn_major & 1) ? 0 : (p.num_taps - 1 - t) * p.b_tap_stride) + tcd.nt * N_TILE;
-              for (int j = 0; j < N_TILE / 64; ++j)
-                tc::tma_load_2d(&p.b_map, full_bar + 8 * s, a_dst + GM_A_BYTES + j * 8192, b_col0 + 64 * j,
-                                c * GM_CHUNK_K);
+              if (!p.wg_conv)
+                for (int j = 0; j < N_TILE / 64; ++j)
+                  tc::tma_load_2d(&p.b_map, full_bar + 8 * s, a_dst + GM_A_BYTES + j * 8192, b_col0 + 64 * j,
+                                  c * GM_CHUNK_K);
             } else {
               tc::tma_load_4d(amap, full_bar + 8 * s, a_dst, c * GM_CHUNK_K, cw, ch, tcd.n0);
               if (!kResident)
@@ -607,6 +633,10 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
           const int pw = tcd.w0 + r_w, phh = tcd.h0 + r_h, pn = tcd.n0 + r_n;
           row_ok = (pw < p.out_w) && (phh < p.out_h) && (pn < p.batch);
           row_off = ((int64_t(pn) * p.out_h + phh) * p.out_w + pw) * p.c_out + int64_t(tcd.nt) * N_TILE;
+          if (p.wg_conv) {   // OIHW: ((co * Cin + ci) * k*k + tap), co = pw
+            const int tap = tcd.nt / p.wg_cin_tiles, ci0 = (tcd.nt - tap * p.wg_cin_tiles) * N_TILE;
+            row_off = (int64_t(pw) * p.wg_cin + ci0) * p.out_col_stride + tap;
+          }
         }
         tc::mbar_wait(tfull_bar + 8 * grp, use & 1u);
         tc::tc_fence_after();
@@ -675,6 +705,10 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
           const int pw = tcd.w0 + r_w, phh = tcd.h0 + r_h, pn = tcd.n0 + r_n;
           row_ok = (pw < p.out_w) && (phh < p.out_h) && (pn < p.batch);
           row_off = ((int64_t(pn) * p.out_h + phh) * p.out_w + pw) * p.c_out + int64_t(tcd.nt) * N_TILE;
+          if (p.wg_conv) {   // OIHW: ((co * Cin + ci) * k*k + tap), co = pw
+            const int tap = tcd.nt / p.wg_cin_tiles, ci0 = (tcd.nt - tap * p.wg_cin_tiles) * N_TILE;
+            row_off = (int64_t(pw) * p.wg_cin + ci0) * p.out_col_stride + tap;
+          }
         }
         tc::mbar_wait(tfull_bar + 8 * acc, aph);
         tc::tc_fence_after();
@@ -1005,6 +1039,7 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
   plan->grid = unsigned(std::min<int64_t>(p.total_tiles, sm_count()));  // persistent: <= one CTA per SM
   const bool fwd_weights = linear_mode != 2 && !stem_mode && (d->flags & 2) != 0;   // dgrad on the forward weights
   p.mn_major = (linear_mode == 2) ? 3 : (fwd_weights ? 2 : 0);
+  p.out_col_stride = 1;
   p.b_tap_stride = d->c_out;
   MMBS_REQUIRE(!fwd_weights || (!resident && plan->n_tile >= 64 && s == 1),
                "conv plan: forward-weight data gradients need stride 1, c_out %% 64 == 0 and streamed weights");
@@ -1138,4 +1173,50 @@ extern "C" int mmbs_linear_nn_plan_create(const void* x_bf16, const void* w_kn_b
   d.ksize = 1; d.stride = 1; d.relu = relu; d.out_f32 = out_f32; d.flags = 2;
   d.in = x_bf16; d.weight = w_kn_bf16; d.scale = nullptr; d.shift = bias; d.residual = nullptr; d.out = y;
   return build_plan(&d, 0, 1, plan_out);
+}
+
+/* Implicit weight-gradient GEMM of a convolution: dw[co, ci, kh, kw] (fp32, OIHW) = sum_{n, ho, wo}
+ * dy[n, ho, wo, co] * x[n, ho*stride + kh - pad, wo*stride + kw - pad, ci]; dy / x bf16 NHWC.  Both operands are
+ * fed MN-major straight from the NHWC tensors (K chunk = 64 images at one output pixel, zero fill = padding);
+ * split-K with fp32 reductions into the cleared output.  c_in % 64 == 0 (256 | c_in when c_in > 128), c_out % 8 == 0. */
+extern "C" int mmbs_conv_wgrad_plan_create(const void* dy_bf16, const void* x_bf16, float* dw_oihw, int64_t batch,
+                                           int64_t in_h, int64_t in_w, int64_t c_in, int64_t c_out, int64_t ksize,
+                                           int64_t stride, mmbs_conv_plan** plan_out) {
+  if (int rc = mmbs_device_check()) return rc;
+  MMBS_REQUIRE(dy_bf16 && x_bf16 && dw_oihw && plan_out && batch > 0 && in_h > 0 && in_w > 0 && c_in > 0 && c_out > 0 &&
+                   (ksize == 1 || ksize == 3) && (stride == 1 || stride == 2) && c_in % 64 == 0 && c_out % 8 == 0,
+               "mmbs_conv_wgrad_plan_create: bad argument");
+  const int pad = int(ksize / 2);
+  const int64_t oh = (in_h + 2 * pad - ksize) / stride + 1, ow = (in_w + 2 * pad - ksize) / stride + 1;
+  const int64_t kk = ksize * ksize, nb = (batch + 63) / 64;
+  mmbs_conv_desc d;
+  std::memset(&d, 0, sizeof(d));
+  d.batch = 1; d.in_h = 1; d.in_w = int32_t(c_out);                 // M = c_out rows
+  d.c_in = int32_t(oh * ow * nb * 64);                               // K = 64-image chunks over every output pixel
+  d.c_out = int32_t(kk * c_in);                                      // N = (tap, ci)
+  d.ksize = 1; d.stride = 1; d.out_f32 = 1;
+  d.in = dy_bf16; d.weight = x_bf16; d.out = dw_oihw;
+  mmbs_conv_plan* plan = nullptr;
+  if (int rc = build_plan(&d, 0, 2, &plan)) return rc;
+  std::unique_ptr<mmbs_conv_plan> guard(plan);
+  ConvParams& p = plan->p;
+  MMBS_REQUIRE(c_in % plan->n_tile == 0, "mmbs_conv_wgrad_plan_create: c_in=%lld must be a multiple of the %d-wide N tile",
+               (long long)c_in, plan->n_tile);
+  p.wg_conv = 1; p.wg_nb = int32_t(nb); p.wg_ow = int32_t(ow); p.wg_stride = int32_t(stride);
+  p.wg_ksize = int32_t(ksize); p.wg_cin = int32_t(c_in); p.wg_cin_tiles = int32_t(c_in / plan->n_tile);
+  p.out_col_stride = int32_t(kk);
+  const uint32_t box[4] = {64u, 1u, 1u, 64u};
+  {
+    const uint64_t dims[4] = {uint64_t(c_out), uint64_t(ow), uint64_t(oh), uint64_t(batch)};
+    const uint64_t str[3] = {uint64_t(c_out) * 2, uint64_t(ow) * c_out * 2, uint64_t(oh) * ow * c_out * 2};
+    if (int rc = encode_map(&p.a_map[0], dy_bf16, 4, dims, str, box)) return rc;
+    for (int i = 1; i < 4; ++i) p.a_map[i] = p.a_map[0];
+  }
+  {
+    const uint64_t dims[4] = {uint64_t(c_in), uint64_t(in_w), uint64_t(in_h), uint64_t(batch)};
+    const uint64_t str[3] = {uint64_t(c_in) * 2, uint64_t(in_w) * c_in * 2, uint64_t(in_h) * in_w * c_in * 2};
+    if (int rc = encode_map(&p.b_map, x_bf16, 4, dims, str, box)) return rc;
+  }
+  *plan_out = guard.release();
+  return MMBS_OK;
 }

@@ -89,6 +89,18 @@ def linear_nn_plan(x, w_kn, bias, out, relu=False):
     return ConvPlan(h, (x, w_kn, bias, out))
 
 
+def conv_wgrad_plan(dy, x, dw, *, ksize, stride):
+    """dw fp32 OIHW [Cout, Cin, k, k] = weight gradient of conv(x, w, stride, pad=k//2) given dy; dy / x bf16 NHWC."""
+    B, H, W, Cin = x.shape
+    Cout = dy.shape[3]
+    assert tuple(dw.shape) == (Cout, Cin, ksize, ksize) and dw.dtype == torch.float32 and dw.is_contiguous()
+    h = c_void_p()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().mmbs_conv_wgrad_plan_create(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(dw), B, H, W, Cin, Cout,
+                                                          ksize, stride, ctypes.byref(h)), "mmbs_conv_wgrad_plan_create")
+    return ConvPlan(h, (dy, x, dw))
+
+
 def linear_tn_plan(a_km, b_kn, out):
     """out fp32 [M, N] = a_km[K, M]^T @ b_kn[K, N]; a / b bf16 row-major (K outermost), M % 8 == 0, N % 64 == 0."""
     K, M = a_km.shape

@@ -227,9 +227,11 @@ class ResNetTrainEngine:
         self._keep.append(plan)
         return dw, plan
 
-    def _wgrad(self, dyT, colT, cout, kcols):
-        dw = self._buf(cout, kcols, dtype=torch.float32)
-        plan = engine.linear_plan(dyT, colT, None, dw)
+    def _wgrad_conv(self, dy, x, ksize, stride):
+        """Weight gradient of a 3x3 / strided convolution as an implicit TN GEMM on the NHWC tensors (K chunk = 64
+        images at one output pixel, padding = TMA zero fill): no im2col buffer, OIHW fp32 output."""
+        dw = self._buf(dy.shape[3], x.shape[3], ksize, ksize, dtype=torch.float32)
+        plan = engine.conv_wgrad_plan(dy, x, dw, ksize=ksize, stride=stride)
         self._keep.append(plan)
         return dw, plan
 
@@ -256,9 +258,7 @@ class ResNetTrainEngine:
             # conv2 / bn2
             r["sums2"] = self._buf(2, planes, dtype=torch.float32)
             r["draw2"] = self._buf(B, Ho, Wo, planes)
-            r["draw2T"] = self._buf(planes, Pp)
-            r["col2T"] = self._buf(9 * planes, Pp)
-            r["dw2"], r["wg2"] = self._wgrad(r["draw2T"], r["col2T"], planes, 9 * planes)   # [co, (ci, kh, kw)] = OIHW
+            r["dw2"], r["wg2"] = self._wgrad_conv(r["draw2"], r["a1"], 3, s)
             r["u2"] = self._buf(B, Hin, Win, planes, zero=True) if s == 2 else r["draw2"]
             r["da1"] = self._buf(B, Hin, Win, planes)
             r["dg2"] = engine.conv_plan(r["u2"], r["c2"].w, r["da1"], ksize=3, stride=1, c_in=planes, fwd_weights=True)
@@ -274,9 +274,7 @@ class ResNetTrainEngine:
             if r["rawd"] is not None:
                 r["sumsd"] = self._buf(2, Cout, dtype=torch.float32)
                 r["drawd"] = self._buf(B, Ho, Wo, Cout)
-                r["drawdT"] = self._buf(Cout, Pp)
-                r["xsT"] = self._buf(Cin, Pp)
-                r["dwd"], r["wgd"] = self._wgrad(r["drawdT"], r["xsT"], Cout, Cin)
+                r["dwd"], r["wgd"] = self._wgrad_conv(r["drawd"], x, 1, blk.downsample[0].stride[0])
             r["dims"] = (Hin, Win, Cin, Ho, Wo, Cout, planes, P, Pin, Pp, Pinp)
 
     # ------------------------------------------------------------------ execution
@@ -352,19 +350,6 @@ class ResNetTrainEngine:
                                 _lib.ptr(st.scale), _lib.ptr(sums), _lib.ptr(out), rows, c, _lib.stream_ptr()),
             "mmbs_bn_bwd_apply")
 
-    @staticmethod
-    def _transpose(src, rows, cols, rows_padded, dst):
-        # [rows, cols] -> [cols, rows_padded]: the 1x1 / stride-1 case of the im2col-transpose kernel
-        _ck(_lib.lib().mmbs_im2col_t(_lib.ptr(src), _lib.ptr(dst), rows, 1, 1, cols, 1, 1, rows_padded, 0,
-                                     _lib.stream_ptr()), "mmbs_im2col_t")
-
-    @staticmethod
-    def _im2col_t(x, k, stride, p_padded, dst):
-        """Rows in (channel, tap) order: the weight-gradient GEMM then writes the OIHW gradient directly."""
-        B, H, W, C = x.shape
-        _ck(_lib.lib().mmbs_im2col_t(_lib.ptr(x), _lib.ptr(dst), B, H, W, C, k, stride, p_padded, 1,
-                                     _lib.stream_ptr()), "mmbs_im2col_t")
-
     def backward(self, dfeat: torch.Tensor) -> dict:
         """dfeat fp32 [B,2048] -> {parameter: gradient tensor (engine-owned, valid until the next step)}."""
         self.dfeat.copy_(dfeat.detach())
@@ -390,14 +375,12 @@ class ResNetTrainEngine:
             grads[blk.bn3.weight], grads[blk.bn3.bias] = r["sums3"][1], r["sums3"][0]
             # ---- bn2 / conv2
             self._bn_backward(r["da2"], r["a2"], r["raw2"], r["b2"], r["sums2"], r["draw2"])
-            self._transpose(r["draw2"], P, planes, Pp, r["draw2T"])
-            self._im2col_t(r["a1"], 3, r["stride"], Pp, r["col2T"])
             r["wg2"].run()
             if r["stride"] == 2:
                 _ck(L.mmbs_scatter_stride2(_lib.ptr(r["draw2"]), _lib.ptr(r["u2"]), B, Ho, Wo, planes,
                                            _lib.stream_ptr()), "mmbs_scatter_stride2")
             r["dg2"].run()
-            grads[blk.conv2.weight] = r["dw2"].view(planes, planes, 3, 3)
+            grads[blk.conv2.weight] = r["dw2"]
             grads[blk.bn2.weight], grads[blk.bn2.bias] = r["sums2"][1], r["sums2"][0]
             # ---- bn1 / conv1
             self._bn_backward(r["da1"], r["a1"], r["raw1"], r["b1"], r["sums1"], r["draw1"])
@@ -407,10 +390,8 @@ class ResNetTrainEngine:
             # ---- downsample branch (first block) / identity shortcut
             if r["rawd"] is not None:
                 self._bn_backward(g, r["out"], r["rawd"], r["bd"], r["sumsd"], r["drawd"])
-                self._transpose(r["drawd"], P, Cout, Pp, r["drawdT"])
-                self._im2col_t(r["x"], 1, blk.downsample[0].stride[0], Pp, r["xsT"])
                 r["wgd"].run()
-                grads[blk.downsample[0].weight] = r["dwd"].view(Cout, Cin, 1, 1)
+                grads[blk.downsample[0].weight] = r["dwd"]
                 grads[blk.downsample[1].weight], grads[blk.downsample[1].bias] = r["sumsd"][1], r["sumsd"][0]
             if bi > 0:
                 r["dg1"].run()

@@ -190,3 +190,25 @@ def test_nn_gemm_mn_major_weights(m, n, k, relu, f32):
         ref = torch.relu(ref)
     err = float((out.double() - ref).abs().max())
     assert err <= (1e-5 if f32 else 1e-2) * float(ref.abs().max()) + 1e-4, f"max err {err}"
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,s", [(5, 7, 7, 512, 512, 3, 1), (70, 14, 14, 512, 512, 3, 2),
+                                                (128, 7, 7, 256, 128, 3, 1), (9, 14, 14, 1024, 2048, 1, 2),
+                                                (3, 8, 8, 64, 64, 3, 1)])
+def test_conv_weight_gradient_implicit_gemm(B, H, W, Cin, Cout, k, s):
+    """mmbs_conv_wgrad_plan_create vs torch autograd (fp64 on the bf16-rounded operands): OIHW layout, padding
+    through TMA zero fill, stride 2, image counts that are not multiples of the 64-image K chunk."""
+    from multimodalbrainsurvival_b200 import engine
+    torch.manual_seed(B + H + Cin + Cout + k + s)
+    Ho, Wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
+    x = torch.randn(B, H, W, Cin, device=DEV).to(torch.bfloat16)
+    dy = torch.randn(B, Ho, Wo, Cout, device=DEV).to(torch.bfloat16)
+    dw = torch.full((Cout, Cin, k, k), 5.0, device=DEV)
+    plan = engine.conv_wgrad_plan(dy, x, dw, ksize=k, stride=s)
+    plan.run()
+    plan.run()
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_weight(x.permute(0, 3, 1, 2).double(), (Cout, Cin, k, k), dy.permute(0, 3, 1, 2).double(),
+                                      stride=s, padding=k // 2)
+    err = float((dw.double() - ref).abs().max())
+    assert err <= 2e-5 * float(ref.abs().max()) + 1e-3, f"max err {err} (scale {float(ref.abs().max())})"
