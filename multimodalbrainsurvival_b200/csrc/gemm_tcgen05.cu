@@ -1,8 +1,9 @@
 // Implicit-GEMM convolution / linear layer on the 5th-gen tensor cores (sm_100a).
 //
 // One warp-specialised kernel serves every conv of ResNet.forward_extract
-// (/root/reference/5_JointFusion/resnet.py:151-165, Bottleneck.forward :70-90) and every
-// nn.Linear of the RNA / fusion MLPs (2_GeneExpression/1_GeneExpress_train.py:247-257 ...):
+// (/root/reference/5_JointFusion/resnet.py:151-165, Bottleneck.forward :70-90) in eval and training mode, its
+// layer4 backward, and every nn.Linear of the RNA / fusion MLPs
+// (2_GeneExpression/1_GeneExpress_train.py:247-257 ...), forward and backward:
 //
 //   out[m, n] = act( scale[n] * sum_k A[m, k] * W[n, k] + shift[n] (+ residual[m, n]) )
 //
@@ -11,10 +12,18 @@
 //   NHWC input shifted by the tap offset (out-of-range rows/cols zero-filled by TMA =
 //   the conv padding).  Stride-2 convs read one of four "parity" views of the input
 //   (base pointer offset + doubled strides), so they are shifted boxes as well.
-// * W is [Cout][kh][kw][Cin] bf16: K-major, one 2-D TMA box per (tap, 64-channel chunk).
-// * warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (accumulator in TMEM),
-//   warps 2-5 = epilogue (tcgen05.ld -> scale/shift (+residual) (+ReLU) -> bf16/fp32 store).
+// * W is [Cout][kh][kw][Cin] bf16: K-major, one 2-D TMA box per (tap, 64-channel chunk); small weight matrices
+//   stay resident in shared memory (RES_BYTES > 0), the stem and 64-channel 3x3 convs use halo boxes.
+// * warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (accumulators ping-pong in TMEM), warps 2-9 = epilogue
+//   (tcgen05.ld -> scale/shift (+residual) (+ReLU) -> bf16 staging -> TMA store, or fp32 direct stores),
+//   warp 10 = output-DMA warp of the 256-wide path (per-block TMA stores, residual loads, staging recycling).
 // * smem ring of STAGES x (A 16 KB + B N_TILE*128 B), 128-byte swizzle end to end.
+// * Operand majors (ConvParams::mn_major): K-major A and B (forward convs / linear layers); MN-major B = the data
+//   gradient reading the FORWARD weights (flags bit 1, mmbs_linear_nn_plan_create); MN-major A and B = weight
+//   gradients straight from the row-major activations / gradients (mmbs_linear_tn_plan_create), with 4-D boxes of
+//   64 images at one output pixel as the K chunk for 3x3 / strided convs (mmbs_conv_wgrad_plan_create).
+// * Training-mode BatchNorm: the epilogue also accumulates per-channel sum / sum of squares (ConvParams::stats).
+// * Split-K (fp32 reductions into a cleared output) for weight-gradient shaped problems.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
