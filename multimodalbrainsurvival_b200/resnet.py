@@ -173,7 +173,9 @@ class ResNet(_Trunk):
                                                                       self.layer4)] == [3, 4, 6, 3]):
             return False
         # a BatchNorm put back into eval mode by hand (frozen-statistics fine-tuning) must use its running statistics
-        if not all(m.training for m in self.modules() if isinstance(m, nn.BatchNorm2d)):
+        # (and exotic BatchNorm configurations - cumulative momentum, no affine / running statistics - stay on it too)
+        if not all(m.training and m.momentum is not None and m.affine and m.track_running_stats
+                   for m in self.modules() if isinstance(m, nn.BatchNorm2d)):
             return False
         if torch.is_grad_enabled():
             from . import train_engine
