@@ -86,6 +86,8 @@ int mmbs_risk_order(const float* times, int64_t n, int32_t* perm_out, void* work
  * values [n,d] float, seg_ids [n] int32 in [0,n_seg): out[g,:] = mean of rows with
  * seg_ids==g (fp32 accumulation in ascending row order), counts[g] = number of rows;
  * last_row[g] = largest row index of segment g ("last row seen", savescore.py:137-138), -1 if empty.
+ * A seg_id outside [0,n_seg) poisons the whole result (no host synchronisation): every mean is NaN,
+ * every count is -1, every last_row is -1.
  */
 size_t mmbs_segmented_mean_workspace_bytes(int64_t n, int64_t n_seg);
 int mmbs_segmented_mean(const float* values, const int32_t* seg_ids, int64_t n, int64_t d,

@@ -21,7 +21,9 @@ from . import _lib
 
 def segmented_mean(values: torch.Tensor, seg_ids: torch.Tensor, n_seg: int):
     """values [n, ...] fp32 CUDA, seg_ids [n] int32 CUDA in [0, n_seg) ->
-    (mean [n_seg, ...] fp32, counts [n_seg] int32, last_row [n_seg] int32)."""
+    (mean [n_seg, ...] fp32, counts [n_seg] int32, last_row [n_seg] int32).
+    An id outside [0, n_seg) does not raise (that would cost a host synchronisation per call): the kernel poisons
+    the whole result instead - NaN means, counts == -1, last_row == -1."""
     if not values.is_cuda or not seg_ids.is_cuda:
         raise RuntimeError("segmented_mean: CUDA tensors required (no CPU fallback in this build)")
     n = values.shape[0]

@@ -46,6 +46,20 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int sm_count();
 
+// cudaFuncSetAttribute is per DEVICE: a function-local "configured once" flag would leave the kernel unconfigured on
+// the second GPU of a process.  One flag per (call site, device); returns true the first time it is asked for the
+// current device.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;   // unknown device: always configure
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 // Bump allocator over the caller's workspace.
 struct Carver {
   char* base;

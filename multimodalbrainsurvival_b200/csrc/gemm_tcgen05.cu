@@ -832,12 +832,10 @@ struct mmbs_conv_plan {
 template <int N_TILE, int STAGES, int NSTG, int A_STAGE = 0, int RES_BYTES = 0>
 static int launch_conv(const mmbs_conv_plan* plan, cudaStream_t stream) {
   using L = GemmSmem<N_TILE, STAGES, NSTG, A_STAGE, RES_BYTES>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first())
     MMBS_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE, STAGES, NSTG, A_STAGE, RES_BYTES>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYNAMIC));
-    configured = true;
-  }
   static const bool use_pdl = []() {
     const char* e = getenv("MMBS_PDL");
     return !(e && e[0] == '0');

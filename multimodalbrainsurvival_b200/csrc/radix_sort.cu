@@ -318,11 +318,9 @@ int rs_sort_enqueue(const void* src, KeyKind kind, int64_t n, int num_passes,
   MMBS_REQUIRE(n >= 1 && n <= RS_MAX_N, "radix sort: n=%lld out of range [1, 2^30)", (long long)n);
   MMBS_REQUIRE(num_passes >= 1 && num_passes <= 4, "radix sort: num_passes=%d", num_passes);
   const int64_t tiles = rs_tiles(n);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first())
     MMBS_CUDA_TRY(cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_DYN_SMEM));
-    configured = true;
-  }
   const unsigned grid = RS_PERSISTENT ? unsigned(std::min<int64_t>(tiles, int64_t(sm_count()) * RS_BLOCKS_PER_SM))
                                       : unsigned(tiles);
   const uint32_t* kin = nullptr;

@@ -30,17 +30,22 @@ __global__ void __launch_bounds__(256) seg_count_kernel(const int32_t* __restric
   }
 }
 
-// single-block exclusive scan counts -> offsets[n_seg+1]
-__global__ void __launch_bounds__(1024) seg_offsets_kernel(const int32_t* __restrict__ counts,
-                                                           int64_t n_seg, int32_t* __restrict__ offsets) {
+// single-block exclusive scan counts -> offsets[n_seg+1].
+// A segment id outside [0, n_seg) (flag `bad`) poisons the whole result instead of shifting every later
+// segment's row list silently: all segments become empty (mean = 0/0 = NaN, last_row = -1) and counts = -1.
+__global__ void __launch_bounds__(1024) seg_offsets_kernel(int32_t* __restrict__ counts,
+                                                           int64_t n_seg, int32_t* __restrict__ offsets,
+                                                           const int32_t* __restrict__ bad) {
   __shared__ int32_t s_w[32];
   __shared__ int32_t s_carry;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_carry = 0;
+  const bool poisoned = (*bad != 0);
   __syncthreads();
   for (int64_t b = 0; b < n_seg; b += 1024) {
     const int64_t i = b + tid;
-    const int32_t c = (i < n_seg) ? counts[i] : 0;
+    if (poisoned && i < n_seg) counts[i] = -1;
+    const int32_t c = (i < n_seg && !poisoned) ? counts[i] : 0;
     int32_t incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -165,7 +170,7 @@ extern "C" int mmbs_segmented_mean(const float* values, const int32_t* seg_ids, 
   const int grid = int(std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256 * 4), int64_t(sm_count()) * 8)));
   seg_count_kernel<<<grid, 256, 0, stream>>>(seg_ids, n, n_seg, counts, w.bad);
   MMBS_LAUNCH_CHECK();
-  seg_offsets_kernel<<<1, 1024, 0, stream>>>(counts, n_seg, w.offsets);
+  seg_offsets_kernel<<<1, 1024, 0, stream>>>(counts, n_seg, w.offsets, w.bad);
   MMBS_LAUNCH_CHECK();
   int passes = 1;
   while (passes < 4 && (uint64_t(n_seg - 1) >> (8 * passes)) != 0) ++passes;

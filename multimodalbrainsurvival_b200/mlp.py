@@ -15,6 +15,7 @@ fp32 accumulation; the fp32 master weights stay in the ``nn.Linear`` parameters 
 from __future__ import annotations
 
 import os
+import weakref
 
 import torch
 import torch.nn as nn
@@ -150,6 +151,18 @@ class _MLPTrainEngine:
                           else None for i in range(L)]
         self.version = None
         self._lib = _lib
+        # The activations / dropout probabilities / gradient buffers of ONE forward live in this engine.  `step`
+        # counts forwards; the autograd node that owns the current contents is tracked by weak reference, so that a
+        # second forward while the first one still awaits its backward (two micro-batches summed before backward, a
+        # siamese call) gets ANOTHER engine instead of overwriting the saved state (see _run_train).
+        self.step = 0
+        self._owner = None
+        self._backward_done = True
+
+    def busy(self):
+        """True while a forward's autograd node is alive and has not run its backward yet."""
+        owner = self._owner() if self._owner is not None else None
+        return owner is not None and not self._backward_done
 
     def _weights_version(self):
         v = []
@@ -223,7 +236,8 @@ class _MLPTrainEngine:
         return dx, dWs, dbs
 
 
-_TRAIN_ENGINES = {}
+_TRAIN_ENGINES = {}      # key -> [engines]; more than one only while several forwards await their backward
+_MAX_ENGINES_PER_KEY = 8
 
 
 class _MLPTrainFn(torch.autograd.Function):
@@ -233,11 +247,19 @@ class _MLPTrainFn(torch.autograd.Function):
         ctx.eng, ctx.seed = eng, seed
         ctx.n_params = len(params)
         ctx.has_bias = [l[0].bias is not None for l in eng.layers]
+        eng.step += 1
+        ctx.step = eng.step
+        eng._owner, eng._backward_done = weakref.ref(ctx), False
         return eng.forward(x, seed, training)
 
     @staticmethod
     def backward(ctx, dy):
         eng = ctx.eng
+        if eng.step != ctx.step:
+            raise RuntimeError("fused MLP backward: the activations saved by this forward were overwritten by a later "
+                               "forward of the same module (a second backward through a retained graph after the "
+                               "engine was reused); call backward once per forward, or set MMBS_MLP_TRAIN=0")
+        eng._backward_done = True
         dx, dWs, dbs = eng.backward(dy, ctx.seed)
         grads = []
         for i, hb in enumerate(ctx.has_bias):
@@ -250,12 +272,18 @@ class _MLPTrainFn(torch.autograd.Function):
 def _run_train(seq, layers, x):
     need_dx = bool(x.requires_grad)
     key = (id(seq), x.shape[0], x.device.index, need_dx)
-    eng = _TRAIN_ENGINES.get(key)
-    if eng is None or any(a[0] is not b[0] for a, b in zip(eng.layers, layers)):
-        eng = _MLPTrainEngine(layers, x.shape[0], x.device, need_dx)
+    pool = _TRAIN_ENGINES.get(key)
+    if pool is None or any(a[0] is not b[0] for a, b in zip(pool[0].layers, layers)):
         if len(_TRAIN_ENGINES) > 32:
             _TRAIN_ENGINES.clear()
-        _TRAIN_ENGINES[key] = eng
+        pool = _TRAIN_ENGINES[key] = []
+    eng = next((e for e in pool if not e.busy()), None)
+    if eng is None:   # every engine of this module still holds the saved state of a forward awaiting its backward
+        if len(pool) >= _MAX_ENGINES_PER_KEY:
+            raise RuntimeError(f"fused MLP: {len(pool)} forwards of the same module are waiting for their backward; "
+                               "run backward (or drop the outputs) before calling it again, or set MMBS_MLP_TRAIN=0")
+        eng = _MLPTrainEngine(layers, x.shape[0], x.device, need_dx)
+        pool.append(eng)
     params = []
     for lin, _, _ in layers:
         params.append(lin.weight)

@@ -149,7 +149,13 @@ class ResNet(_Trunk):
     def forward_extract(self, x):
         if self._can_accelerate_train(x):
             from . import train_engine
-            return train_engine.run_train(self, x, self._engines)
+            with torch.cuda.device(x.device):   # the kernels launch on the CURRENT device's stream
+                return train_engine.run_train(self, x, self._engines)
+        if not x.is_cuda and os.environ.get("MMBS_DISABLE_KERNELS", "0") != "1" and isinstance(self.layer1[0], Bottleneck):
+            # north_star: no CPU fallback.  (MMBS_DISABLE_KERNELS=1 keeps the stock module graph reachable for
+            # host-side tooling: checkpoint round-trips, oracle pinning.)
+            raise RuntimeError("ResNet.forward_extract: input must be a CUDA tensor (this build has no CPU path; "
+                               "move the model and the batch to the GPU)")
         if x.dtype == torch.uint8 and not self._can_accelerate(x):
             mean = torch.tensor(self.input_mean, device=x.device).view(1, 3, 1, 1)
             std = torch.tensor(self.input_std, device=x.device).view(1, 3, 1, 1)
@@ -177,6 +183,10 @@ class ResNet(_Trunk):
         if not all(m.training and m.momentum is not None and m.affine and m.track_running_stats
                    for m in self.modules() if isinstance(m, nn.BatchNorm2d)):
             return False
+        # the BatchNorm / weight-pack kernels read parameters and buffers through raw float* pointers
+        for t in list(self.parameters()) + [b for b in self.buffers() if b.dtype.is_floating_point]:
+            if t.dtype != torch.float32 or t.device != x.device:
+                return False
         if torch.is_grad_enabled():
             from . import train_engine
             if x.requires_grad or train_engine.trainable_outside_layer4(self):
@@ -184,6 +194,10 @@ class ResNet(_Trunk):
         return True
 
     def _features_b200(self, x):
+        with torch.cuda.device(x.device):       # the kernels launch on the CURRENT device's stream
+            return self._features_b200_impl(x)
+
+    def _features_b200_impl(self, x):
         from . import engine
         B = x.shape[0]
         x = x.contiguous() if x.dtype == torch.uint8 else x.float().contiguous()

@@ -134,7 +134,8 @@ def train_step(sd, x, grad_features, momentum: float = 0.1, prefix: str = "", em
     (nn.BatchNorm2d defaults used by resnet.py:60-66,99); autograd through layer4 only (the reference's
     fine-tuning set, /root/reference/1_HistoPathology/2_HistoPath_train.py:541-551, n_layers_to_train = 2).
 
-    x (B,3,224,224) fp32, grad_features (B,2048) = dLoss/dfeatures.
+    x (B,3,224,224) fp32, grad_features (B,2048) = dLoss/dfeatures, or a callable ``f(features) -> dLoss/dfeatures``
+    evaluated on the detached features of this very forward pass (a head + loss on top of the trunk).
     ``emulate_bf16`` rounds the input, the weights, every raw convolution output (the statistics are taken
     from the rounded values) and every activation to bf16, where the CUDA path stores bf16.
     Returns (features, {layer4 parameter name: gradient}, {bn buffer name: updated value})."""
@@ -169,5 +170,7 @@ def train_step(sd, x, grad_features, momentum: float = 0.1, prefix: str = "", em
             t = _r(F.relu(out + res), e)
     feats = F.avg_pool2d(t, 7, 1).flatten(1)
     names = sorted(leaves)
+    if callable(grad_features):
+        grad_features = grad_features(feats.detach())
     grads = torch.autograd.grad(feats, [leaves[k] for k in names], grad_outputs=grad_features.float())
     return feats.detach(), dict(zip(names, grads)), new_stats

@@ -52,6 +52,22 @@ def test_segmented_mean_random(n, d, g):
     assert np.isnan(m[~nz]).all()
 
 
+def test_out_of_range_segment_id_poisons_the_result():
+    """A segment id outside [0, n_seg) must not shift the other segments silently: NaN means, counts -1."""
+    from multimodalbrainsurvival_b200 import aggregate
+    v = torch.randn(300, 8, device="cuda")
+    seg = (torch.arange(300, device="cuda") % 7).to(torch.int32)
+    seg[123] = 7
+    mean, counts, last = aggregate.segmented_mean(v, seg, 7)
+    assert torch.isnan(mean).all() and (counts == -1).all() and (last == -1).all()
+    seg[123] = -2
+    mean, counts, last = aggregate.segmented_mean(v, seg, 7)
+    assert torch.isnan(mean).all() and (counts == -1).all()
+    seg[123] = 3
+    mean, counts, _ = aggregate.segmented_mean(v, seg, 7)
+    assert torch.isfinite(mean).all() and int(counts.sum()) == 300
+
+
 def test_hundred_patches_per_case_2048():
     """BASELINE config 2 tail: 100 patches per case, 2048-d features."""
     from multimodalbrainsurvival_b200 import aggregate

@@ -1,0 +1,145 @@
+"""GPU parity of the DOWNSTREAM metric: the concordance index computed from kernel-path scores must agree with the
+one computed from reference-path (fp32, CPU oracle) scores within 0.005 (BASELINE.json north_star) - in eval mode,
+after K fine-tuning steps, and after K data-parallel fine-tuning steps with per-rank BatchNorm statistics (the
+documented deviation of DESIGN.md 4.6 / SURVEY.md 8e(3): the reference semantics is the single-process global batch).
+
+Both sides use the SAME c-index implementation (oracle/cindex_oracle.py, parity unpinned: lifelines is absent) and
+the reference's per-case mean aggregation (3_HistoPath_savescore.py:134-145).  Reference path restated in
+tests/_cohort.py on top of oracle/resnet_oracle.py + oracle/cox_oracle.py.
+"""
+import copy
+import functools
+
+import numpy as np
+import pytest
+import torch
+
+import _cohort as C
+from oracle import resnet_oracle
+
+pytestmark = pytest.mark.gpu
+
+CINDEX_TOL = 0.005          # north_star tolerance
+LR, WD, K, B = 5e-4, 1e-5, 3, 16   # the reference's Adam settings (config_ffpe_train.json), 3 steps of 16 patches
+N_CASES_FT = 96
+
+
+def _head(seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(1, 2048, generator=g) * 2 - 1) / np.sqrt(2048), torch.zeros(1)
+
+
+def _kernel_model(sd, fc_w, fc_b, train):
+    from multimodalbrainsurvival_b200 import models, resnet
+    net = resnet.resnet50(pretrained=False)
+    net.load_state_dict(sd, strict=True)
+    model = models.AggregationModel(net, models.Identity(), 2048, 2048, 1)
+    with torch.no_grad():
+        model.fc.weight.copy_(fc_w)
+        model.fc.bias.copy_(fc_b)
+    model = model.cuda()
+    if train:   # 2_HistoPath_train.py:541-556: freeze everything, unfreeze fc + layer4 (n_layers_to_train = 2) + head
+        for p in model.parameters():
+            p.requires_grad = False
+        for layer in (model.resnet.fc, model.resnet.layer4, model.fc):
+            for p in layer.parameters():
+                p.requires_grad = True
+    return model
+
+
+def _kernel_scores(model, x, chunk=128):
+    model.eval()
+    outs = []
+    with torch.no_grad():
+        for i in range(0, x.shape[0], chunk):
+            xb = x[i:i + chunk].cuda().unsqueeze(1)        # (B, bag = 1, 3, 224, 224)
+            out, _ = model(xb)
+            outs.append(out.view(-1).float().cpu())
+    assert any(k[0] == "eval" for k in model.resnet._engines), "the CUDA eval engine did not run"
+    return torch.cat(outs).numpy()
+
+
+def test_eval_scores_give_the_same_cindex():
+    """200 cases x 2 patches, eval mode: fp32 oracle scores vs bf16 kernel scores."""
+    sd = resnet_oracle.init_state_dict(seed=51)
+    fc_w, fc_b = _head(5)
+    x, case = C.make_cohort(200, 2, seed=6)
+    ref = C.case_mean(C.oracle_scores(sd, fc_w, fc_b, x), case)
+    t, e = C.survival_from_scores(ref, seed=9)
+    got = C.case_mean(_kernel_scores(_kernel_model(sd, fc_w, fc_b, train=False), x), case)
+    c_ref, c_got = C.cindex(ref, t, e), C.cindex(got, t, e)
+    print(f"eval c-index: reference {c_ref:.5f} kernels {c_got:.5f}")
+    assert 0.6 < c_ref < 0.95                      # a non-degenerate cohort
+    assert abs(c_ref - c_got) <= CINDEX_TOL
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-2
+
+
+@functools.lru_cache(maxsize=1)
+def _finetune_case():
+    """Cohort, batches and the reference-path result (fp32 CPU oracle, single-process global batch)."""
+    sd = resnet_oracle.init_state_dict(seed=61, bn3_gamma_scale=0.1)   # conditioning: see oracle.init_state_dict
+    fc_w, fc_b = _head(7)
+    x, case = C.make_cohort(N_CASES_FT, 1, seed=8)
+    s0 = C.case_mean(C.oracle_scores(sd, fc_w, fc_b, x), case)
+    t, e = C.survival_from_scores(s0, seed=9)
+    g = torch.Generator().manual_seed(10)
+    batches = []
+    for _ in range(K):
+        idx = torch.randperm(N_CASES_FT, generator=g)[:B]
+        batches.append((x[idx], t[idx.numpy()], e[idx.numpy()]))
+    sd2, w2, b2, losses = C.oracle_finetune(sd, fc_w, fc_b, batches, LR, WD)
+    ref = C.case_mean(C.oracle_scores(sd2, w2, b2, x), case)
+    return dict(sd=sd, fc=(fc_w, fc_b), x=x, case=case, t=t, e=e, batches=batches, s0=s0, ref=ref, ref_losses=losses)
+
+
+def _kernel_finetune(case, ranks):
+    from multimodalbrainsurvival_b200 import models
+    fc_w, fc_b = case["fc"]
+    replicas = [_kernel_model(case["sd"], fc_w, fc_b, train=True) for _ in range(ranks)]
+    opts = [torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=LR, weight_decay=WD) for m in replicas]
+    losses = []
+    for x, t, e in case["batches"]:
+        per = x.shape[0] // ranks
+        outs = []
+        for r, m in enumerate(replicas):
+            m.train()
+            opts[r].zero_grad(set_to_none=True)
+            out, _ = m(x[r * per:(r + 1) * per].cuda().unsqueeze(1))
+            outs.append(out.view(-1))
+            assert any(k[0] == "train" for k in m.resnet._engines), "the CUDA training engine did not run"
+        # the risk set is the global batch (dist.global_cox_loss); every replica back-propagates its slice
+        loss = models.cox_loss(torch.cat(outs), torch.tensor(t).cuda(), torch.tensor(e).cuda())
+        loss.backward()
+        losses.append(float(loss.detach()))
+        if ranks > 1:   # dist.allreduce_gradients: SUM over ranks
+            for ps in zip(*[list(m.parameters()) for m in replicas]):
+                if ps[0].grad is None:
+                    continue
+                total = torch.stack([p.grad for p in ps]).sum(0)
+                for p in ps:
+                    p.grad.copy_(total)
+        for o in opts:
+            o.step()
+    return replicas[0], losses
+
+
+@pytest.mark.parametrize("ranks", [1, 2])
+def test_finetuned_scores_give_the_same_cindex(ranks):
+    """K Adam steps on fc + layer4 (batch-statistics BatchNorm everywhere), then eval-mode scoring of the cohort:
+    reference path (fp32, one process, global-batch BatchNorm) vs kernel path on 1 rank and on 2 emulated ranks with
+    per-rank BatchNorm statistics, a global Cox risk set and SUM-reduced gradients."""
+    case = _finetune_case()
+    model, losses = _kernel_finetune(case, ranks)
+    got = C.case_mean(_kernel_scores(model, case["x"]), case["case"])
+    t, e = case["t"], case["e"]
+    c0, c_ref, c_got = C.cindex(case["s0"], t, e), C.cindex(case["ref"], t, e), C.cindex(got, t, e)
+    moved = np.linalg.norm(case["ref"] - case["s0"]) / np.linalg.norm(case["s0"])
+    rel = np.linalg.norm(got - case["ref"]) / np.linalg.norm(case["ref"])
+    print(f"ranks={ranks}: c-index before {c0:.5f}, reference {c_ref:.5f}, kernels {c_got:.5f}; losses "
+          f"{[round(l, 4) for l in losses]} vs {[round(l, 4) for l in case['ref_losses']]}; scores moved {moved:.3f}, "
+          f"kernel-vs-reference {rel:.4f}")
+    assert moved > 0.2, "fine-tuning did not move the scores: the comparison would be vacuous"
+    assert abs(losses[0] - case["ref_losses"][0]) <= 1e-2 * abs(case["ref_losses"][0])
+    assert abs(c_ref - c_got) <= CINDEX_TOL
+    if ranks == 1:
+        assert rel < 2e-2   # same batch statistics: the scores themselves agree

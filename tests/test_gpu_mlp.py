@@ -60,6 +60,57 @@ def test_early_fusion_inference_matches_reference_golden(golden):
     _close(ye, torch.tensor(g["early_out"]), 2e-2, "early fusion output")
 
 
+class _FakeResnet(nn.Module):
+    """Stand-in trunk of the golden generator (tools/make_golden.py gen_mlp): features = the first 2048 pixels."""
+
+    def forward_extract(self, p):
+        return p.flatten(1)[:, :2048]
+
+
+def test_joint_model_inference_matches_reference_golden(golden):
+    """BagHistopathologyRNAModel.forward (5_JointFusion/models.py:94-104) - bag mean of the trunk
+    features, RNA MLP, concat, Dropout(0.8)-Linear(4096,1) head - against the output of the REFERENCE class."""
+    from multimodalbrainsurvival_b200 import mlp, models
+    g = golden("mlp_reference.npz")
+    rna, _ = _rna(1111)
+    torch.manual_seed(3333)
+    jhead = nn.Sequential(nn.Dropout(0.8), nn.Linear(4096, 1))
+    jm = models.BagHistopathologyRNAModel(_FakeResnet(), rna, jhead).to(DEV).eval()
+    bag = torch.tensor(det_input((6, 2, 1, 32, 64), a=0.05), device=DEV)
+    x = torch.tensor(det_input((6, 12778), a=0.11), device=DEV)
+    mlp._ENGINES.clear()
+    with torch.no_grad():
+        yj = jm(bag, x)
+    assert len(mlp._ENGINES) == 2, "rna_mlp and final_mlp must both run on the fused engine"
+    assert yj.shape == (6, 1)
+    _close(yj, torch.tensor(g["joint_out"]), 2e-2, "joint output")
+
+
+def test_joint_model_with_the_real_trunk_matches_the_oracle():
+    """a5 end to end: ResNet-50 kernels + RNA MLP + head vs the fp32 oracle composition (eval mode)."""
+    from multimodalbrainsurvival_b200 import models, resnet
+    from oracle import resnet_oracle
+    sd = resnet_oracle.init_state_dict(seed=17)
+    net = resnet.resnet50(pretrained=False)
+    net.load_state_dict(sd, strict=True)
+    rna, _ = _rna(4)
+    torch.manual_seed(5)
+    jhead = nn.Sequential(nn.Dropout(0.8), nn.Linear(4096, 1))
+    jm = models.BagHistopathologyRNAModel(net, rna, jhead).to(DEV).eval()
+    torch.manual_seed(6)
+    bag = torch.randn(3, 2, 3, 224, 224)
+    x = torch.randn(3, 12778)
+    with torch.no_grad():
+        yj = jm(bag.to(DEV), x.to(DEV))
+    assert net._engines, "the CUDA trunk engine did not run"
+    img = resnet_oracle.forward_extract(sd, bag.reshape(-1, 3, 224, 224)).view(3, 2, 2048).mean(1)
+    cpu = lambda m: {k: v.detach().cpu() for k, v in m.state_dict().items()}  # noqa: E731
+    rsd, hsd = cpu(rna), cpu(jhead)
+    feats = mlp_oracle.mlp_forward(x, mlp_oracle.rna_layers(rsd, prefix=""))[-1]
+    ref = torch.cat([img, feats], 1) @ hsd["1.weight"].t() + hsd["1.bias"]
+    _close(yj, ref, 2e-2, "joint output, real trunk")
+
+
 @pytest.mark.parametrize("dims,M", [((300, 256, 128, 1), 37), ((12778, 4096, 2048), 128)])
 def test_training_without_dropout_matches_torch_autograd(dims, M):
     from multimodalbrainsurvival_b200 import mlp
@@ -106,8 +157,7 @@ def test_training_with_dropout_is_consistent_with_its_own_masks():
     R = torch.randn(M, 64, device=DEV)
     out = mlp.run_mlp(seq, x)
     (out * R).sum().backward()
-    eng = next(iter(mlp._TRAIN_ENGINES.values())) if len(mlp._TRAIN_ENGINES) == 1 else \
-        [e for e in mlp._TRAIN_ENGINES.values() if e.m == M and e.need_dx][-1]
+    eng = [e for pool in mlp._TRAIN_ENGINES.values() for e in pool if e.m == M and e.need_dx][-1]
     mask0 = (eng.hin[0][:, :512].float() != 0).float()
     assert abs(mask0.mean().item() - 0.2) < 0.02
     got = {n: p.grad.clone() for n, p in seq.named_parameters()}
@@ -131,6 +181,42 @@ def test_training_with_dropout_is_consistent_with_its_own_masks():
     _close(got["1.bias"], lin1.bias.grad, 3e-2, "db1")
     _close(got_dx, xr.grad, 3e-2, "dx")
     assert float((got_dx[mask0 == 0]).abs().max()) == 0.0
+
+
+def test_two_forwards_before_backward_keep_their_own_saved_state():
+    """Two micro-batches through the same Sequential, summed, ONE backward (gradient accumulation / siamese use):
+    every forward must keep its own activations - gradients equal the sum of the two separate passes."""
+    from multimodalbrainsurvival_b200 import mlp
+    torch.manual_seed(11)
+    seq = nn.Sequential(nn.Dropout(0.0), nn.Linear(256, 128), nn.ReLU(), nn.Dropout(0.0), nn.Linear(128, 64)).to(DEV).train()
+    xa, xb = torch.randn(64, 256, device=DEV), torch.randn(64, 256, device=DEV)
+    ra, rb = torch.randn(64, 64, device=DEV), torch.randn(64, 64, device=DEV)
+    sep = {}
+    for x, r in ((xa, ra), (xb, rb)):
+        seq.zero_grad()
+        (mlp.run_mlp(seq, x) * r).sum().backward()
+        for n, p in seq.named_parameters():
+            sep[n] = sep.get(n, 0) + p.grad.clone()
+    seq.zero_grad()
+    ya = mlp.run_mlp(seq, xa)
+    yb = mlp.run_mlp(seq, xb)           # same module, same batch size, first forward still awaits its backward
+    ((ya * ra).sum() + (yb * rb).sum()).backward()
+    for n, p in seq.named_parameters():
+        _close(p.grad, sep[n], 1e-5, f"accumulated grad {n}")
+    pool = [pl for pl in mlp._TRAIN_ENGINES.values() if pl[0].m == 64 and pl[0].layers[0][0] is seq[1]][0]
+    assert len(pool) == 2 and not any(e.busy() for e in pool)
+    # forward-only calls (validation under autograd) must not leak engines: the graph dies with the output
+    for _ in range(5):
+        mlp.run_mlp(seq, xa)
+    assert len(pool) == 2
+    # a second backward through a retained graph after the engine was reused is an error, not a silent wrong result
+    y1 = mlp.run_mlp(seq, xa)
+    (y1 * ra).sum().backward(retain_graph=True)
+    y2 = mlp.run_mlp(seq, xb)
+    eng1 = y1.grad_fn.eng if hasattr(y1.grad_fn, "eng") else None
+    if eng1 is not None and y2.grad_fn.eng is eng1:
+        with pytest.raises(RuntimeError, match="overwritten"):
+            (y1 * ra).sum().backward()
 
 
 def test_rna_model_train_step_reduces_cox_loss():

@@ -90,12 +90,14 @@ def test_state_dict_contract_and_torch_path_matches_oracle():
     net.load_state_dict(osd, strict=True)                    # reference key names load both ways
     net.eval()
     x = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(0))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):   # no CPU path behind the public entry point
+        net.forward_extract(x)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        model.eval()(x.view(1, 1, 3, 224, 224))
     with torch.no_grad():
-        f = net.forward_extract(x)                           # CPU tensor -> module-graph path
+        f = net._features_torch(x)     # the stock module graph itself: the tree is wired like the reference's
     ref = resnet_oracle.forward_extract(osd, x)
     assert float((f - ref).abs().max()) <= 1e-3 * float(ref.abs().max())
-    out, att = model.eval()(x.view(1, 1, 3, 224, 224))
-    assert out.shape == (1, 1) and att.shape == (1, 1)
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
