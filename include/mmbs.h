@@ -294,6 +294,32 @@ int mmbs_add_relu_mask(const void* a_bf16, const void* g_bf16, const void* mask_
 int mmbs_concordance_counts(const double* event_times, const double* predicted, const uint8_t* event_observed,
                             int64_t n, unsigned long long* counts_out, void* stream);
 
+/* ------------------------------------------------ fused multi-tensor Adam
+ * Replaces the arithmetic of torch.optim.Adam.step() as the reference's scripts build it
+ *   /root/reference/2_GeneExpression/1_GeneExpress_train.py:303-305 (two parameter groups),
+ *   /root/reference/1_HistoPathology/2_HistoPath_train.py:558, /root/reference/5_JointFusion/1_JointFusion_train.py:413-416:
+ *   g += weight_decay * p (L2 form, not AdamW);  m += (1-beta1) (g - m);  v = beta2 v + (1-beta2) g^2;
+ *   p -= step_size * m / (sqrt(v) / bias_correction2_sqrt + eps),  step_size = lr / (1 - beta1^t),
+ *   bias_correction2_sqrt = sqrt(1 - beta2^t)  (computed by the caller from its step counter, like torch does).
+ * One pass over (p, g, m, v), all fp32 device tensors; the descriptor tables are HOST arrays (copied into the
+ * kernel's parameter space: nothing to keep alive after the call returns). */
+#define MMBS_ADAM_MAX_TENSORS 64   /* per launch; longer lists are split over several launches */
+#define MMBS_ADAM_MAX_GROUPS 8
+typedef struct {
+  float step_size, beta1, beta2, eps, weight_decay, bias_correction2_sqrt;
+} mmbs_adam_group;
+typedef struct {
+  void* p;          /* parameter, updated in place */
+  const void* g;    /* gradient */
+  void* m;          /* exp_avg, updated in place */
+  void* v;          /* exp_avg_sq, updated in place */
+  int64_t n;        /* elements */
+  int32_t group;    /* index into the group table */
+  int32_t reserved;
+} mmbs_adam_tensor;
+int mmbs_adam_step(const mmbs_adam_tensor* tensors_host, int32_t n_tensors, const mmbs_adam_group* groups_host,
+                   int32_t n_groups, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,18 @@ class BnTrainDesc(ctypes.Structure):
     ]
 
 
+class AdamGroup(ctypes.Structure):
+    """mmbs_adam_group (include/mmbs.h)."""
+    _fields_ = [("step_size", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
+                ("weight_decay", c_float), ("bias_correction2_sqrt", c_float)]
+
+
+class AdamTensor(ctypes.Structure):
+    """mmbs_adam_tensor (include/mmbs.h)."""
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("n", c_i64),
+                ("group", c_i32), ("reserved", c_i32)]
+
+
 # name -> (restype, argtypes); every symbol include/mmbs.h declares
 SIGNATURES = {
     "mmbs_last_error": (ctypes.c_char_p, []),
@@ -110,6 +122,7 @@ SIGNATURES = {
     "mmbs_bn_train_relu_maxpool_3x3s2": (ctypes.c_int, [ctypes.POINTER(BnTrainDesc), c_void_p, c_void_p, c_i64, c_i64,
                                                         c_i64, c_void_p]),
     "mmbs_concordance_counts": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
+    "mmbs_adam_step": (ctypes.c_int, [ctypes.POINTER(AdamTensor), c_i32, ctypes.POINTER(AdamGroup), c_i32, c_void_p]),
 }
 
 

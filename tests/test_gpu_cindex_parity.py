@@ -89,7 +89,11 @@ def _finetune_case():
         batches.append((x[idx], t[idx.numpy()], e[idx.numpy()]))
     sd2, w2, b2, losses = C.oracle_finetune(sd, fc_w, fc_b, batches, LR, WD)
     ref = C.case_mean(C.oracle_scores(sd2, w2, b2, x), case)
-    return dict(sd=sd, fc=(fc_w, fc_b), x=x, case=case, t=t, e=e, batches=batches, s0=s0, ref=ref, ref_losses=losses)
+    # the same restatement with the batch normalised in two per-rank halves: what the 2-rank kernel path computes
+    sd3, w3, b3, losses2 = C.oracle_finetune(sd, fc_w, fc_b, batches, LR, WD, ranks=2)
+    ref2 = C.case_mean(C.oracle_scores(sd3, w3, b3, x), case)
+    return dict(sd=sd, fc=(fc_w, fc_b), x=x, case=case, t=t, e=e, batches=batches, s0=s0, ref=ref, ref_losses=losses,
+                ref_per_rank={1: (ref, losses), 2: (ref2, losses2)})
 
 
 def _kernel_finetune(case, ranks):
@@ -139,7 +143,12 @@ def test_finetuned_scores_give_the_same_cindex(ranks):
           f"{[round(l, 4) for l in losses]} vs {[round(l, 4) for l in case['ref_losses']]}; scores moved {moved:.3f}, "
           f"kernel-vs-reference {rel:.4f}")
     assert moved > 0.05, "fine-tuning did not move the scores: the comparison would be vacuous"
-    assert abs(losses[0] - case["ref_losses"][0]) <= 1e-2 * abs(case["ref_losses"][0])
+    # acceptance criterion of the north_star (and of the per-rank BatchNorm deviation): the c-index of the
+    # single-process, global-batch reference
     assert abs(c_ref - c_got) <= CINDEX_TOL
-    if ranks == 1:
-        assert rel < 2e-2   # same batch statistics: the scores themselves agree
+    # tight check against the restatement with the SAME BatchNorm partition (ranks = 2: per-rank statistics are a
+    # semantic difference, not rounding - the oracle reproduces it): losses of every step and the final scores
+    same_scores, same_losses = case["ref_per_rank"][ranks]
+    for got_l, ref_l in zip(losses, same_losses):
+        assert abs(got_l - ref_l) <= 5e-3 * abs(ref_l), (losses, same_losses)
+    assert np.linalg.norm(got - same_scores) / np.linalg.norm(same_scores) < 2e-2

@@ -145,3 +145,26 @@ def test_nll_loss_matches_manual():
     s = torch.cumprod(1 - hz, 1)
     manual = (-(torch.log(s[0, 0]) + torch.log(hz[0, 1])) - torch.log(s[1, 2])) / 2
     torch.testing.assert_close(loss, manual)
+
+
+def test_accelerate_optimizer_keeps_the_torch_object_and_state_layout():
+    """Host logic of optim.accelerate_optimizer: same object, same param groups, CPU parameters step through torch's
+    own Adam (the fused kernel needs CUDA tensors), state_dict layout identical to a stock optimizer's."""
+    from multimodalbrainsurvival_b200 import optim
+    torch.manual_seed(0)
+    m1, m2 = nn.Linear(5, 3), nn.Linear(5, 3)
+    m2.load_state_dict(m1.state_dict())
+    groups = lambda m: [{"params": [m.weight], "lr": 1e-3}, {"params": [m.bias], "lr": 1e-2}]  # noqa: E731
+    o1 = torch.optim.Adam(groups(m1), weight_decay=1e-5)
+    o2 = torch.optim.Adam(groups(m2), weight_decay=1e-5)
+    assert optim.accelerate_optimizer(o1) is o1 and optim.accelerate_optimizer(o1) is o1
+    x = torch.randn(4, 5)
+    for _ in range(3):
+        for m, o in ((m1, o1), (m2, o2)):
+            o.zero_grad()
+            m(x).pow(2).sum().backward()
+            o.step()
+    assert torch.equal(m1.weight, m2.weight) and torch.equal(m1.bias, m2.bias)
+    s1, s2 = o1.state_dict(), o2.state_dict()
+    assert s1["param_groups"] == s2["param_groups"]
+    assert {k: sorted(v) for k, v in s1["state"].items()} == {k: sorted(v) for k, v in s2["state"].items()}

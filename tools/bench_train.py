@@ -7,7 +7,8 @@
           (/root/reference/5_JointFusion/1_JointFusion_train.py:314-325,196-230), B = 128 / GPU
 
 One step = forward (batch-statistics BatchNorm in every layer) + global Cox loss (risk set all-gathered over the
-ranks) + backward through layer4 / the MLPs + SUM all-reduce of the parameter gradients + torch.optim.Adam.
+ranks) + backward through layer4 / the MLPs + SUM all-reduce of the parameter gradients + the scripts' torch.optim.Adam
+stepping through the fused multi-tensor kernel (optim.accelerate_optimizer).
 Inputs are device resident for `value`; `e2e` feeds pinned host batches (H2D inside the timed region) and reads
 the loss back every step.  Importable (bench.py `secondary`) or  python tools/bench_train.py [histo|joint] [steps]
 (under torchrun for N > 1)."""
@@ -42,6 +43,14 @@ def build(kind, torch, dev):
     return model.to(dev).train()
 
 
+def _adam(torch, params):
+    """The scripts' torch.optim.Adam (lr / weight_decay of the example configs), stepping through the fused
+    multi-tensor kernel (optim.accelerate_optimizer; MMBS_BENCH_STOCK_ADAM=1 times torch's own foreach step)."""
+    from multimodalbrainsurvival_b200 import optim
+    opt = torch.optim.Adam(params, lr=1e-5, weight_decay=1e-5)
+    return opt if os.environ.get("MMBS_BENCH_STOCK_ADAM", "0") == "1" else optim.accelerate_optimizer(opt)
+
+
 def run_mlp(kind, torch, dev, world=1, rank=0, steps=5, warmup=3, rows=None):
     """kind 'rna'  : BASELINE config 1 - RNAOnlyModel (12778 -> 4096 -> 2048 -> 1), B = 128, Cox, Adam
                      (/root/reference/2_GeneExpression/1_GeneExpress_train.py:247-257,150-170)
@@ -67,7 +76,7 @@ def run_mlp(kind, torch, dev, world=1, rank=0, steps=5, warmup=3, rows=None):
         width, mflop = 4096, 36.0
         dtype = torch.bfloat16
     params = list(model.parameters())
-    opt = torch.optim.Adam(params, lr=1e-5, weight_decay=1e-5)
+    opt = _adam(torch, params)
     g = torch.Generator(device=dev).manual_seed(99 + rank)
     x = torch.randn(rows, width, device=dev, generator=g, dtype=torch.float32 if rows <= 4096 else torch.bfloat16).to(dtype)
     times = torch.rand(rows, device=dev, generator=g) * 200 + torch.arange(rows, device=dev) * 2.0 ** -20
@@ -114,7 +123,7 @@ def run(kind, torch, dev, world=1, rank=0, steps=10, warmup=3, batch=128):
     from multimodalbrainsurvival_b200 import _lib, engine
     model = build(kind, torch, dev)
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.Adam(params, lr=1e-5, weight_decay=1e-5)
+    opt = _adam(torch, params)
     g = torch.Generator(device=dev).manual_seed(77 + rank)
     xs = [torch.randn(batch, 1, 3, 224, 224, device=dev, generator=g) for _ in range(2)]
     rna = torch.randn(batch, 12778, device=dev, generator=g)
