@@ -4,9 +4,12 @@
 // and its three textual copies):
 //   sort(-times) -> gather -> subtract max -> exp -> cumsum -> log(.+1e-5) -> mask -> mean.
 //
-// Forward  = histogram(+max of scores) -> 4 Onesweep radix passes (payload = index | event bit)
-//            -> reduce-then-scan over the sorted order:
-//               cox_gather_kernel  : s~ = scores[perm]-max, tile sums of exp(s~)      (1 gather)
+// Forward  = risk-set sort -> reduce-then-scan over the sorted order.
+//            Sort, 2048 < n <= FS_MAX_N: the two-pass sort of cox_sort.cu (MSD partition + block-local sort, which
+//            also writes s~ = scores[perm]-max: the gather is fused); larger n, or inputs that sort gave up on
+//            (device flag, no host sync): histogram -> 4 Onesweep radix passes (payload = index | event bit) ->
+//            cox_gather_kernel (s~ through the permutation).
+//               cox_tilesum_kernel : tile sums of exp(s~)
 //               cox_tile_scan_kernel: exclusive scan of the 2048-element tile sums (fp64)
 //               cox_loss_kernel    : C = cumsum, log, mask, loss partials; saves w = status/(C+eps)
 //                                    and the tile sums of w for the backward pass
@@ -16,8 +19,9 @@
 // chained-scan version with decoupled look-back spent >40 % of its time waiting on predecessor
 // tiles: profiles/r01_ncu_stalls_cox_scan_fwd.txt); fp32 inside a tile, fp64 across tiles.
 #include <algorithm>
+#include <cstdlib>
 
-#include "radix_sort.cuh"
+#include "cox_sort.cuh"
 
 namespace mmbs {
 
@@ -79,9 +83,9 @@ __device__ __forceinline__ double block_sum_to_t0(double v, double* s_red, int l
 __global__ void __launch_bounds__(CS_THREADS) cox_gather_kernel(
     const int32_t* __restrict__ perm, const float* __restrict__ scores,
     const uint32_t* __restrict__ max_enc, int64_t n, float* __restrict__ saved_s,
-    double* __restrict__ tile_sum, int32_t* max_count, int32_t* __restrict__ max_list) {
-  __shared__ double s_red[CS_WARPS];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int32_t* max_count, int32_t* __restrict__ max_list, const int32_t* __restrict__ enable) {
+  if (enable != nullptr && *enable == 0) return;   // the two-pass sort already wrote s~ (cox_sort.cu)
+  const int tid = threadIdx.x;
   const int64_t base = int64_t(blockIdx.x) * CS_TILE + int64_t(tid) * CS_ITEMS;
   const float smax = float_order_dec(*max_enc);
   const uint64_t pol = make_evict_last_policy();
@@ -94,18 +98,29 @@ __global__ void __launch_bounds__(CS_THREADS) cox_gather_kernel(
     p[j] &= 0x7fffffff;
     st[j] = valid ? ld_f32_hint(scores + p[j], pol) : 0.f;
   }
-  float run = 0.f;
 #pragma unroll
   for (int j = 0; j < CS_ITEMS; ++j) {
     const bool valid = base + j < n;
     st[j] -= smax;                                   // s~ (models.py:102)
-    run += valid ? expf(st[j]) : 0.f;                // models.py:103
     if (valid && st[j] == 0.f) {                     // an argmax position (for backward)
       const int pos = atomicAdd(max_count, 1);
       if (pos < COX_MAX_LIST) max_list[pos] = p[j];
     }
   }
   store8_f32(saved_s, base, n, st);
+}
+
+// tile sums of exp(s~) over the sorted order (models.py:103), one streaming read of s~
+__global__ void __launch_bounds__(CS_THREADS) cox_tilesum_kernel(const float* __restrict__ saved_s, int64_t n,
+                                                                 double* __restrict__ tile_sum) {
+  __shared__ double s_red[CS_WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t base = int64_t(blockIdx.x) * CS_TILE + int64_t(tid) * CS_ITEMS;
+  float st[CS_ITEMS];
+  load8_f32(saved_s, base, n, st);
+  float run = 0.f;
+#pragma unroll
+  for (int j = 0; j < CS_ITEMS; ++j) run += (base + j < n) ? expf(st[j]) : 0.f;
   const double t = block_sum_to_t0(double(run), s_red, lane, warp);
   if (tid == 0) tile_sum[blockIdx.x] = t;
 }
@@ -287,9 +302,13 @@ __global__ void __launch_bounds__(CS_THREADS) cox_grad_kernel(
 // Gradient through "- max(scores)": every argmax position receives
 // -(sum_k g~_k)/count  (torch's full-reduction max backward splits evenly).
 __global__ void __launch_bounds__(256) cox_maxfix_list_kernel(
-    const double* __restrict__ gsum_partial, int64_t tiles, const int32_t* __restrict__ max_count,
-    const int32_t* __restrict__ max_list, double* __restrict__ gsum_total,
+    const double* __restrict__ gsum_partial, int64_t tiles, const int32_t* __restrict__ max_count_pair,
+    const int32_t* __restrict__ max_list_pair, const int32_t* __restrict__ fallback, double* __restrict__ gsum_total,
     float* __restrict__ grad_scores) {
+  // [0]: written by the two-pass sort's gather, [1]: by cox_gather_kernel (LSD path)
+  const int which = (*fallback != 0) ? 1 : 0;
+  const int32_t* max_count = max_count_pair + which;
+  const int32_t* max_list = max_list_pair + which * COX_MAX_LIST;
   __shared__ double s_red[8];
   __shared__ double s_total;
   double t = 0.0;
@@ -313,9 +332,9 @@ __global__ void __launch_bounds__(256) cox_maxfix_list_kernel(
 
 __global__ void __launch_bounds__(256) cox_maxfix_full_kernel(
     const float* __restrict__ scores, const uint32_t* __restrict__ max_enc,
-    const int32_t* __restrict__ max_count, const double* __restrict__ gsum_total, int64_t n,
-    float* __restrict__ grad_scores) {
-  const int cnt = *max_count;
+    const int32_t* __restrict__ max_count_pair, const int32_t* __restrict__ fallback,
+    const double* __restrict__ gsum_total, int64_t n, float* __restrict__ grad_scores) {
+  const int cnt = max_count_pair[(*fallback != 0) ? 1 : 0];
   if (cnt <= COX_MAX_LIST) return;  // handled by the list kernel
   const float smax = float_order_dec(*max_enc);
   const float fix = float(gsum_total[0] / double(cnt));
@@ -490,13 +509,22 @@ struct CoxWorkspace {
   uint32_t* counters;      // [8]: 0-3 radix passes
   uint32_t* max_enc;       // [1]
   int32_t* nan_flag;       // [1]
-  int32_t* max_count;      // [1]
+  int32_t* max_count;      // [2] argmax positions found by {two-pass sort's gather, cox_gather_kernel}
   int32_t* nonbinary;      // [1] some status value is neither 0 nor 1
+  int32_t* fallback;       // [1] 1: the LSD sort (re)did the sort (always 1 when n > FS_MAX_N)
   uint32_t* lookback;      // [4][rs_tiles][256]
+  uint32_t* fs_hist12;     // two-pass sort (cox_sort.cuh FastSortWs): [FS_BINS]
+  uint32_t* fs_bucket_count;   // [FS_MAX_BUCKETS]
+  uint32_t* fs_counters;   // [4]
+  uint32_t* fs_lookback;   // [fs_tiles][FS_MAX_BUCKETS]
   size_t zero_bytes;
   // not zeroed
   uint32_t* digit_base;    // [4][256]
-  int32_t* max_list;       // [COX_MAX_LIST]
+  uint2* fs_lut;           // [FS_BINS]
+  uint32_t* fs_bucket_base;    // [FS_MAX_BUCKETS + 1]
+  uint4* fs_work;          // [FS_MAX_WORK]
+  uint32_t* fs_params;     // [4]
+  int32_t* max_list;       // [2][COX_MAX_LIST]
   double* gsum_total;      // [1]
   double* tile_sum;        // [cs_tiles] sums of exp(s~), scanned in place
   double* tile_wsum;       // [cs_tiles] sums of w           (kept for backward)
@@ -515,12 +543,21 @@ static CoxWorkspace carve_cox(void* base, int64_t n) {
   w.counters = c.take<uint32_t>(8);
   w.max_enc = c.take<uint32_t>(1);
   w.nan_flag = c.take<int32_t>(1);
-  w.max_count = c.take<int32_t>(1);
+  w.max_count = c.take<int32_t>(2);
   w.nonbinary = c.take<int32_t>(1);
+  w.fallback = c.take<int32_t>(1);
   w.lookback = c.take<uint32_t>(size_t(4) * rt * RS_RADIX);
+  w.fs_hist12 = c.take<uint32_t>(FS_BINS);
+  w.fs_bucket_count = c.take<uint32_t>(FS_MAX_BUCKETS);
+  w.fs_counters = c.take<uint32_t>(4);
+  w.fs_lookback = c.take<uint32_t>(n <= FS_MAX_N ? size_t(fs_tiles(n)) * FS_MAX_BUCKETS : 1);
   w.zero_bytes = align_up(c.off, 256);
   w.digit_base = c.take<uint32_t>(4 * RS_RADIX);
-  w.max_list = c.take<int32_t>(COX_MAX_LIST);
+  w.fs_lut = c.take<uint2>(FS_BINS);
+  w.fs_bucket_base = c.take<uint32_t>(FS_MAX_BUCKETS + 1);
+  w.fs_work = c.take<uint4>(FS_MAX_WORK);
+  w.fs_params = c.take<uint32_t>(4);
+  w.max_list = c.take<int32_t>(2 * COX_MAX_LIST);
   w.gsum_total = c.take<double>(1);
   w.tile_sum = c.take<double>(ct);
   w.tile_wsum = c.take<double>(ct);
@@ -551,13 +588,36 @@ extern "C" size_t mmbs_cox_workspace_bytes(int64_t n) {
   return carve_cox(nullptr, n).total_bytes;
 }
 
+static bool use_two_pass_sort(int64_t n) {
+  static const bool disabled = []() {
+    const char* e = getenv("MMBS_COX_LSD");   // experiments / tests: force the 4-pass LSD sort
+    return e && e[0] == '1';
+  }();
+  return !disabled && n <= FS_MAX_N;
+}
+
+// Risk-set sort (+ s~ = scores[perm] - max and the argmax list when `scores` is given).
 static int cox_sort_common(const float* scores, const float* times, const float* status, int64_t n,
-                           int32_t* perm_out, const CoxWorkspace& w, cudaStream_t stream) {
+                           int32_t* perm_out, float* saved_s, const CoxWorkspace& w, cudaStream_t stream) {
   MMBS_CUDA_TRY(cudaMemsetAsync(w.hist, 0, w.zero_bytes, stream));
-  int rc = rs_histogram_enqueue(times, KEY_NEG_TIME_F32, n, 4, w.hist, w.digit_base, scores,
-                                w.max_enc, w.nan_flag, stream);
+  const int32_t* enable = nullptr;
+  if (use_two_pass_sort(n)) {
+    FastSortWs f;
+    f.hist12 = w.fs_hist12; f.bucket_count = w.fs_bucket_count; f.counters = w.fs_counters; f.fallback = w.fallback;
+    f.lookback = w.fs_lookback; f.lut = w.fs_lut; f.bucket_base = w.fs_bucket_base; f.work = w.fs_work;
+    f.params = w.fs_params; f.keys = w.keys_a; f.vals = w.vals_a;
+    if (int rc = fs_sort_enqueue(times, status, scores, n, f, w.max_enc, w.nan_flag, w.nonbinary, perm_out, saved_s,
+                                 w.max_count, w.max_list, COX_MAX_LIST, stream))
+      return rc;
+    enable = w.fallback;   // the kernels below return at once unless the two-pass sort gave up
+    scores = nullptr;      // max(scores) and the NaN flag are already known
+  } else {
+    MMBS_CUDA_TRY(cudaMemsetAsync(w.fallback, 0xff, sizeof(int32_t), stream));   // != 0: the LSD path is the sort
+  }
+  int rc = rs_histogram_enqueue(times, KEY_NEG_TIME_F32, n, 4, w.hist, w.digit_base, scores, w.max_enc, w.nan_flag,
+                                stream, enable);
   if (rc) return rc;
-  return rs_sort_enqueue(times, KEY_NEG_TIME_F32, n, 4, sort_ws(w), perm_out, stream, status, w.nonbinary);
+  return rs_sort_enqueue(times, KEY_NEG_TIME_F32, n, 4, sort_ws(w), perm_out, stream, status, w.nonbinary, enable);
 }
 
 extern "C" int mmbs_risk_order(const float* times, int64_t n, int32_t* perm_out, void* workspace,
@@ -570,7 +630,7 @@ extern "C" int mmbs_risk_order(const float* times, int64_t n, int32_t* perm_out,
     set_error("mmbs_risk_order: workspace %zu < %zu bytes", workspace_bytes, w.total_bytes);
     return MMBS_ERR_WORKSPACE;
   }
-  return cox_sort_common(nullptr, times, nullptr, n, perm_out, w, static_cast<cudaStream_t>(stream));
+  return cox_sort_common(nullptr, times, nullptr, n, perm_out, nullptr, w, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mmbs_cox_forward(const float* scores, const float* times, const float* status,
@@ -598,10 +658,14 @@ extern "C" int mmbs_cox_forward(const float* scores, const float* times, const f
     set_error("mmbs_cox_forward: workspace %zu < %zu bytes", workspace_bytes, w.total_bytes);
     return MMBS_ERR_WORKSPACE;
   }
-  if (int rc = cox_sort_common(scores, times, status, n, perm_out, w, stream)) return rc;
+  if (int rc = cox_sort_common(scores, times, status, n, perm_out, saved_s, w, stream)) return rc;
   const int64_t tiles = cs_tiles(n);
+  // LSD path only (returns at once when the two-pass sort wrote s~): the gather through the permutation
   cox_gather_kernel<<<unsigned(tiles), CS_THREADS, 0, stream>>>(perm_out, scores, w.max_enc, n, saved_s,
-                                                               w.tile_sum, w.max_count, w.max_list);
+                                                               w.max_count + 1, w.max_list + COX_MAX_LIST,
+                                                               use_two_pass_sort(n) ? w.fallback : nullptr);
+  MMBS_LAUNCH_CHECK();
+  cox_tilesum_kernel<<<unsigned(tiles), CS_THREADS, 0, stream>>>(saved_s, n, w.tile_sum);
   MMBS_LAUNCH_CHECK();
   cox_tile_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_sum, w.tile_sum, tiles, 0);
   MMBS_LAUNCH_CHECK();
@@ -645,11 +709,11 @@ extern "C" int mmbs_cox_backward(const float* scores, const float* status, const
                                                              grad_loss, n, grad_scores, w.gsum_partial,
                                                              w.nonbinary);
   MMBS_LAUNCH_CHECK();
-  cox_maxfix_list_kernel<<<1, 256, 0, stream>>>(w.gsum_partial, tiles, w.max_count, w.max_list,
+  cox_maxfix_list_kernel<<<1, 256, 0, stream>>>(w.gsum_partial, tiles, w.max_count, w.max_list, w.fallback,
                                                w.gsum_total, grad_scores);
   MMBS_LAUNCH_CHECK();
   const int grid = int(std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256 * 8), int64_t(sm_count()) * 4)));
-  cox_maxfix_full_kernel<<<grid, 256, 0, stream>>>(scores, w.max_enc, w.max_count, w.gsum_total, n,
+  cox_maxfix_full_kernel<<<grid, 256, 0, stream>>>(scores, w.max_enc, w.max_count, w.fallback, w.gsum_total, n,
                                                   grad_scores);
   MMBS_LAUNCH_CHECK();
   return MMBS_OK;

@@ -15,9 +15,11 @@ namespace mmbs {
 // `scores` again after the sort has streamed through L2) and a NaN flag.
 __global__ void __launch_bounds__(256) rs_histogram_kernel(
     const void* __restrict__ src, int kind, int64_t n, int num_passes, uint32_t* __restrict__ hist,
-    const float* __restrict__ scores, uint32_t* __restrict__ max_enc, int32_t* __restrict__ nan_flag) {
+    const float* __restrict__ scores, uint32_t* __restrict__ max_enc, int32_t* __restrict__ nan_flag,
+    const int32_t* __restrict__ enable) {
   __shared__ uint32_t s_hist[4][RS_RADIX];
   __shared__ uint32_t s_max[8];
+  if (enable != nullptr && *enable == 0) return;   // fallback sort not needed (see cox_sort.cu)
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   for (int i = tid; i < 4 * RS_RADIX; i += 256) (&s_hist[0][0])[i] = 0;
@@ -98,8 +100,10 @@ __global__ void __launch_bounds__(256) rs_histogram_kernel(
 
 // Exclusive scan of each pass's 256 counters -> first global slot of every digit.
 __global__ void __launch_bounds__(RS_RADIX) rs_digit_base_kernel(const uint32_t* __restrict__ hist,
-                                                                 uint32_t* __restrict__ digit_base) {
+                                                                 uint32_t* __restrict__ digit_base,
+                                                                 const int32_t* __restrict__ enable) {
   __shared__ uint32_t s_w[8];
+  if (enable != nullptr && *enable == 0) return;
   const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t c = hist[p * RS_RADIX + tid];
   uint32_t incl = c;
@@ -121,7 +125,8 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) rs_onesweep_kern
     const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, int64_t n, int shift, const uint32_t* __restrict__ digit_base,
     uint32_t* lookback, uint32_t* tile_counter, int first, int last,
-    const float* __restrict__ status, int32_t* __restrict__ nonbinary_flag) {
+    const float* __restrict__ status, int32_t* __restrict__ nonbinary_flag, const int32_t* __restrict__ enable) {
+  if (enable != nullptr && *enable == 0) return;   // fallback sort not needed (see cox_sort.cu)
   __shared__ uint32_t s_warp_hist[RS_WARPS][RS_RADIX];
   __shared__ uint32_t s_digit_start[RS_RADIX];
   __shared__ uint32_t s_global_base[RS_RADIX];
@@ -301,20 +306,20 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) rs_onesweep_kern
 
 int rs_histogram_enqueue(const void* src, KeyKind kind, int64_t n, int num_passes, uint32_t* hist,
                          uint32_t* digit_base, const float* scores, uint32_t* max_enc,
-                         int32_t* nan_flag, cudaStream_t stream) {
+                         int32_t* nan_flag, cudaStream_t stream, const int32_t* enable) {
   const int64_t want = ceil_div(n, 256 * 8);
   const int grid = int(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(sm_count()) * 8)));
   rs_histogram_kernel<<<grid, 256, 0, stream>>>(src, int(kind), n, num_passes, hist, scores, max_enc,
-                                                nan_flag);
+                                                nan_flag, enable);
   MMBS_LAUNCH_CHECK();
-  rs_digit_base_kernel<<<num_passes, RS_RADIX, 0, stream>>>(hist, digit_base);
+  rs_digit_base_kernel<<<num_passes, RS_RADIX, 0, stream>>>(hist, digit_base, enable);
   MMBS_LAUNCH_CHECK();
   return MMBS_OK;
 }
 
 int rs_sort_enqueue(const void* src, KeyKind kind, int64_t n, int num_passes,
                     const SortWorkspace& ws, int32_t* perm_out, cudaStream_t stream,
-                    const float* status, int32_t* nonbinary_flag) {
+                    const float* status, int32_t* nonbinary_flag, const int32_t* enable) {
   MMBS_REQUIRE(n >= 1 && n <= RS_MAX_N, "radix sort: n=%lld out of range [1, 2^30)", (long long)n);
   MMBS_REQUIRE(num_passes >= 1 && num_passes <= 4, "radix sort: num_passes=%d", num_passes);
   const int64_t tiles = rs_tiles(n);
@@ -332,7 +337,7 @@ int rs_sort_enqueue(const void* src, KeyKind kind, int64_t n, int num_passes,
     rs_onesweep_kernel<<<grid, RS_THREADS, RS_DYN_SMEM, stream>>>(
         src, int(kind), kin, vin, kout, vout, n, 8 * p, ws.digit_base + p * RS_RADIX,
         ws.lookback + int64_t(p) * tiles * RS_RADIX, ws.counters + p, first ? 1 : 0, last ? 1 : 0,
-        first ? status : nullptr, nonbinary_flag);
+        first ? status : nullptr, nonbinary_flag, enable);
     MMBS_LAUNCH_CHECK();
     kin = kout;
     vin = vout;

@@ -61,14 +61,17 @@ static inline int64_t rs_tiles(int64_t n) { return n > 0 ? (n + RS_TILE - 1) / R
 // to perm_out.  num_passes in [1,4]: number of low bytes that can differ.
 // When `status` is given, bit 31 of every output word carries (status[idx] != 0) and
 // *nonbinary_flag is set if some status value is neither 0 nor 1.
+// `enable` (device flag, optional): every kernel returns at once when *enable == 0 - the sort is then enqueued
+// unconditionally behind the two-pass sort of cox_sort.cu and only runs when that one gave up (no host sync).
 int rs_sort_enqueue(const void* src, KeyKind kind, int64_t n, int num_passes,
                     const SortWorkspace& ws, int32_t* perm_out, cudaStream_t stream,
-                    const float* status = nullptr, int32_t* nonbinary_flag = nullptr);
+                    const float* status = nullptr, int32_t* nonbinary_flag = nullptr,
+                    const int32_t* enable = nullptr);
 
 // Plain histogram (+ optional fused max / NaN flag over `scores`).
 int rs_histogram_enqueue(const void* src, KeyKind kind, int64_t n, int num_passes, uint32_t* hist,
                          uint32_t* digit_base, const float* scores, uint32_t* max_enc,
-                         int32_t* nan_flag, cudaStream_t stream);
+                         int32_t* nan_flag, cudaStream_t stream, const int32_t* enable = nullptr);
 
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t rs_load_key(const void* src, int kind, int64_t i) {

@@ -65,6 +65,67 @@ def test_heavy_ties_are_stable(n, distinct):
     _check(s, t, e, f"ties n={n}")
 
 
+@pytest.mark.parametrize("n", [8192, 8193, 16384, 16385, 40000, 1_000_003])
+def test_two_pass_sort_bucket_boundaries(n):
+    """Sizes around the partition tile (8192), the bucket target and the local-sort capacity (16384)."""
+    rng = np.random.default_rng(n)
+    s = rng.standard_normal(n).astype(np.float32)
+    t = rng.exponential(30.0, n).astype(np.float32)          # skewed survival times
+    e = (rng.uniform(size=n) < 0.6).astype(np.float32)
+    _check(s, t, e, f"exp n={n}")
+
+
+@pytest.mark.parametrize("kind", ["clustered", "two_heavy_values", "one_heavy_plus_noise", "tiny_range", "negatives"])
+def test_two_pass_sort_unbalanced_inputs(kind):
+    """Inputs the equalised-CDF bucket map cannot balance: oversized single-key buckets are copied through,
+    anything else raises the device-side flag and the LSD sort redoes the work - same results either way."""
+    rng = np.random.default_rng(len(kind))
+    n = 150_000
+    if kind == "clustered":          # every key inside one narrow range of one 12-bit bin
+        t = (100.0 + rng.uniform(0, 1e-3, n)).astype(np.float32)
+    elif kind == "two_heavy_values":  # two adjacent floats, 75 k copies each
+        t = np.where(rng.uniform(size=n) < 0.5, np.float32(7.0), np.nextafter(np.float32(7.0), np.float32(8.0))).astype(np.float32)
+    elif kind == "one_heavy_plus_noise":
+        t = np.where(rng.uniform(size=n) < 0.7, np.float32(12.0), rng.uniform(0, 200, n).astype(np.float32)).astype(np.float32)
+    elif kind == "tiny_range":
+        t = (rng.integers(0, 3, n) * np.float32(1e-30)).astype(np.float32)
+    else:
+        t = rng.normal(0, 50, n).astype(np.float32)   # negative times are legal keys
+    s = rng.standard_normal(n).astype(np.float32)
+    e = (rng.uniform(size=n) < 0.6).astype(np.float32)
+    _check(s, t, e, kind)
+
+
+def test_integer_month_ties_at_300k():
+    """Integer months (what real cohorts look like): ~1500 copies per value, many values per bucket."""
+    rng = np.random.default_rng(12)
+    n = 300_000
+    s = rng.standard_normal(n).astype(np.float32)
+    t = np.round(rng.uniform(0, 200, n)).astype(np.float32)   # integer months: ~1500 copies per value
+    e = (rng.uniform(size=n) < 0.6).astype(np.float32)
+    _check(s, t, e, "integer months")
+
+
+def test_lsd_path_above_fast_sort_limit():
+    """n > FS_MAX_N (12 M) takes the 4-pass LSD sort: order checked against torch.sort(stable)."""
+    from multimodalbrainsurvival_b200 import cox
+    n = 12_500_000
+    dev = "cuda:0"
+    g = torch.Generator(device=dev).manual_seed(3)
+    t = torch.rand(n, device=dev, generator=g) * 200
+    s = torch.randn(n, device=dev, generator=g).requires_grad_(True)
+    e = (torch.rand(n, device=dev, generator=g) < 0.6).float()
+    perm = cox.risk_order(t).long()
+    _, idx = torch.sort(-t, stable=True)
+    assert bool((idx == perm).all())
+    loss = cox.cox_loss(s, t, e)
+    loss.backward()
+    cs = s.detach()[idx] - s.detach().max()
+    ref = (-(cs - torch.log(torch.cumsum(torch.exp(cs).double(), 0).float() + 1e-5)) * e[idx]).double().mean()
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert abs(float(s.grad.double().sum())) < 1e-6
+
+
 def test_upstream_gradient_scaling_and_all_censored():
     rng = np.random.default_rng(5)
     n = 3000
