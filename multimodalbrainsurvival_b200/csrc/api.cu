@@ -1,4 +1,5 @@
 // Library-wide state of libmmbs: last-error string, launch counter, device check.
+#include <cstdlib>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -19,6 +20,13 @@ void set_error(const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool debug_sync() {
+  static const bool on = []() {
+    const char* e = getenv("MMBS_DEBUG_SYNC");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
 
 int sm_count() {
   static int cached[64] = {0};

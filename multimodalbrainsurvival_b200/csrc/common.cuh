@@ -11,6 +11,7 @@ namespace mmbs {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+bool debug_sync();   // MMBS_DEBUG_SYNC=1: synchronise after every launch so that a device fault names its kernel
 
 #define MMBS_CUDA_TRY(expr)                                                        \
   do {                                                                             \
@@ -25,7 +26,7 @@ void count_launch(int n = 1);
 #define MMBS_LAUNCH_CHECK()                                                        \
   do {                                                                             \
     ::mmbs::count_launch();                                                        \
-    cudaError_t _e = cudaPeekAtLastError();                                        \
+    cudaError_t _e = ::mmbs::debug_sync() ? cudaDeviceSynchronize() : cudaPeekAtLastError(); \
     if (_e != cudaSuccess) {                                                       \
       ::mmbs::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__,          \
                         cudaGetErrorString(_e));                                   \

@@ -4,10 +4,11 @@
 // and its three textual copies):
 //   sort(-times) -> gather -> subtract max -> exp -> cumsum -> log(.+1e-5) -> mask -> mean.
 //
+// n <= 2048 (every training config): one fused block forward, one backward (cox_small_*).
+// 2048 < n <= FS_MAX_N: the bucketed pipeline of cox_sort.cu (3 kernels forward, 1 backward).
+// Larger n, or inputs the bucketed pipeline gave up on (device flag `fallback`, no host sync) - the kernels below:
 // Forward  = risk-set sort -> reduce-then-scan over the sorted order.
-//            Sort, 2048 < n <= FS_MAX_N: the two-pass sort of cox_sort.cu (MSD partition + block-local sort, which
-//            also writes s~ = scores[perm]-max: the gather is fused); larger n, or inputs that sort gave up on
-//            (device flag, no host sync): histogram -> 4 Onesweep radix passes (payload = index | event bit) ->
+//            histogram -> 4 Onesweep radix passes (payload = index | event bit) ->
 //            cox_gather_kernel (s~ through the permutation).
 //               cox_tilesum_kernel : tile sums of exp(s~)
 //               cox_tile_scan_kernel: exclusive scan of the 2048-element tile sums (fp64)
@@ -112,8 +113,10 @@ __global__ void __launch_bounds__(CS_THREADS) cox_gather_kernel(
 
 // tile sums of exp(s~) over the sorted order (models.py:103), one streaming read of s~
 __global__ void __launch_bounds__(CS_THREADS) cox_tilesum_kernel(const float* __restrict__ saved_s, int64_t n,
-                                                                 double* __restrict__ tile_sum) {
+                                                                 double* __restrict__ tile_sum,
+                                                                 const int32_t* __restrict__ enable) {
   __shared__ double s_red[CS_WARPS];
+  if (enable != nullptr && *enable == 0) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t base = int64_t(blockIdx.x) * CS_TILE + int64_t(tid) * CS_ITEMS;
   float st[CS_ITEMS];
@@ -128,9 +131,10 @@ __global__ void __launch_bounds__(CS_THREADS) cox_tilesum_kernel(const float* __
 // ------------------------------------------------------------------ tile-sum scan (one block)
 // out[i] = sum_{t<i} in[t]  (reverse: sum_{t>i} in[t]); fp64; in == out allowed.
 __global__ void __launch_bounds__(1024) cox_tile_scan_kernel(const double* in, double* out, int64_t tiles,
-                                                             int reverse) {
+                                                             int reverse, const int32_t* __restrict__ enable) {
   __shared__ double s_w[32];
   __shared__ double s_carry;
+  if (enable != nullptr && *enable == 0) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_carry = 0.0;
   __syncthreads();
@@ -160,9 +164,10 @@ __global__ void __launch_bounds__(CS_THREADS) cox_loss_kernel(
     const int32_t* __restrict__ perm, const float* __restrict__ status,
     const float* __restrict__ saved_s, const double* __restrict__ tile_excl, int64_t n,
     float* __restrict__ saved_w, double* __restrict__ loss_partial, double* __restrict__ tile_wsum,
-    int32_t* nan_flag, const int32_t* __restrict__ nonbinary) {
+    int32_t* nan_flag, const int32_t* __restrict__ nonbinary, const int32_t* __restrict__ enable) {
   __shared__ double s_warp_tot[CS_WARPS];
   __shared__ double s_red[CS_WARPS];
+  if (enable != nullptr && *enable == 0) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t base = int64_t(blockIdx.x) * CS_TILE + int64_t(tid) * CS_ITEMS;
   const bool gather_status = (*nonbinary != 0);
@@ -225,8 +230,10 @@ __global__ void __launch_bounds__(256) cox_finalize_kernel(const double* __restr
                                                            int64_t tiles, int64_t n,
                                                            const int32_t* __restrict__ nan_flag,
                                                            float* __restrict__ loss_out,
-                                                           int32_t* __restrict__ flags_out) {
+                                                           int32_t* __restrict__ flags_out,
+                                                           const int32_t* __restrict__ enable) {
   __shared__ double s_red[8];
+  if (enable != nullptr && *enable == 0) return;
   double t = 0.0;
   for (int64_t i = threadIdx.x; i < tiles; i += 256) t += partial[i];
   t = warp_sum(t);
@@ -249,12 +256,13 @@ __global__ void __launch_bounds__(CS_THREADS) cox_grad_kernel(
     const float* __restrict__ saved_s, const float* __restrict__ saved_w,
     const double* __restrict__ tile_suffix, const float* __restrict__ grad_loss, int64_t n,
     float* __restrict__ grad_scores, double* __restrict__ gsum_partial,
-    const int32_t* __restrict__ nonbinary) {
+    const int32_t* __restrict__ nonbinary, const int32_t* __restrict__ enable) {
   __shared__ double s_warp_tot[CS_WARPS];
   __shared__ double s_red[CS_WARPS];
+  if (enable != nullptr && *enable == 0) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t base = int64_t(blockIdx.x) * CS_TILE + int64_t(tid) * CS_ITEMS;
-  const float scale = grad_loss[0] / float(n);
+  const double scale = double(grad_loss[0]) / double(n);
   const bool gather_status = (*nonbinary != 0);
   int32_t p[CS_ITEMS];
   float st[CS_ITEMS], w[CS_ITEMS], suf[CS_ITEMS];
@@ -281,7 +289,7 @@ __global__ void __launch_bounds__(CS_THREADS) cox_grad_kernel(
   for (int w2 = 0; w2 < CS_WARPS; ++w2)
     if (w2 > warp) off += s_warp_tot[w2];
 
-  float gs = 0.f;
+  double gs = 0.0;   // summed in fp64: the argmax position receives -sum(g~), a sum of n rounded terms otherwise
 #pragma unroll
   for (int j = 0; j < CS_ITEMS; ++j) {
     if (base + j < n) {
@@ -289,13 +297,13 @@ __global__ void __launch_bounds__(CS_THREADS) cox_grad_kernel(
       const int32_t idx = int32_t(word & 0x7fffffffu);
       float dl = (word >> 31) ? 1.f : 0.f;
       if (gather_status) dl = __ldg(status + idx);
-      const float W = float(off + double(suf[j]));
-      const float g = -(dl - expf(st[j]) * W) * scale;
-      grad_scores[idx] = g;        // un-permute
+      const double W = off + double(suf[j]);
+      const double g = -(double(dl) - double(expf(st[j])) * W) * scale;
+      grad_scores[idx] = float(g);        // un-permute
       gs += g;
     }
   }
-  const double t = block_sum_to_t0(double(gs), s_red, lane, warp);
+  const double t = block_sum_to_t0(gs, s_red, lane, warp);
   if (tid == 0) gsum_partial[blockIdx.x] = t;
 }
 
@@ -305,10 +313,10 @@ __global__ void __launch_bounds__(256) cox_maxfix_list_kernel(
     const double* __restrict__ gsum_partial, int64_t tiles, const int32_t* __restrict__ max_count_pair,
     const int32_t* __restrict__ max_list_pair, const int32_t* __restrict__ fallback, double* __restrict__ gsum_total,
     float* __restrict__ grad_scores) {
-  // [0]: written by the two-pass sort's gather, [1]: by cox_gather_kernel (LSD path)
-  const int which = (*fallback != 0) ? 1 : 0;
-  const int32_t* max_count = max_count_pair + which;
-  const int32_t* max_list = max_list_pair + which * COX_MAX_LIST;
+  // [0]: written by the bucketed pipeline (which also applies it, cox_sort.cu), [1]: by cox_gather_kernel (LSD path)
+  if (*fallback == 0) return;
+  const int32_t* max_count = max_count_pair + 1;
+  const int32_t* max_list = max_list_pair + COX_MAX_LIST;
   __shared__ double s_red[8];
   __shared__ double s_total;
   double t = 0.0;
@@ -504,26 +512,33 @@ __global__ void __launch_bounds__(SM_THREADS) cox_small_bwd_kernel(
 
 // ------------------------------------------------------------------ workspace
 struct CoxWorkspace {
-  // zeroed at the start of forward (contiguous)
+  // zeroed at the start of forward (contiguous, ~50 KB)
   uint32_t* hist;          // [4][256]
   uint32_t* counters;      // [8]: 0-3 radix passes
   uint32_t* max_enc;       // [1]
   int32_t* nan_flag;       // [1]
-  int32_t* max_count;      // [2] argmax positions found by {two-pass sort's gather, cox_gather_kernel}
+  int32_t* max_count;      // [2] argmax positions found by {bucketed pipeline, cox_gather_kernel}
   int32_t* nonbinary;      // [1] some status value is neither 0 nor 1
-  int32_t* fallback;       // [1] 1: the LSD sort (re)did the sort (always 1 when n > FS_MAX_N)
-  uint32_t* lookback;      // [4][rs_tiles][256]
-  uint32_t* fs_hist12;     // two-pass sort (cox_sort.cuh FastSortWs): [FS_BINS]
-  uint32_t* fs_bucket_count;   // [FS_MAX_BUCKETS]
-  uint32_t* fs_counters;   // [4]
-  uint32_t* fs_lookback;   // [fs_tiles][FS_MAX_BUCKETS]
+  int32_t* fallback;       // [1] != 0: the LSD pipeline (re)does the work (always when n > FS_MAX_N)
+  uint32_t* fs_hist12;     // bucketed pipeline (cox_sort.cuh FastSortWs): [FS_BINS]
+  uint32_t* fs_kext;       // [2]
+  uint32_t* fs_counters;   // [8]
+  uint32_t* fs_cursor;     // [FS_MAX_BUCKETS]
+  double* fs_agg_val;      // [FS_MAX_BUCKETS]
   size_t zero_bytes;
+  // zeroed by the LSD pipeline itself, only when it runs
+  uint32_t* lookback;      // [4][rs_tiles][256]
+  size_t lookback_words;
   // not zeroed
   uint32_t* digit_base;    // [4][256]
   uint2* fs_lut;           // [FS_BINS]
-  uint32_t* fs_bucket_base;    // [FS_MAX_BUCKETS + 1]
-  uint4* fs_work;          // [FS_MAX_WORK]
-  uint32_t* fs_params;     // [4]
+  FsEdge* fs_edge;         // [1]
+  double* fs_exp_prefix;   // [FS_MAX_BUCKETS] each
+  double* fs_wsum;
+  double* fs_loss_part;
+  double* fs_gsum_part;
+  uint32_t* fs_bucket_base;
+  uint32_t* fs_bucket_cnt;
   int32_t* max_list;       // [2][COX_MAX_LIST]
   double* gsum_total;      // [1]
   double* tile_sum;        // [cs_tiles] sums of exp(s~), scanned in place
@@ -531,12 +546,15 @@ struct CoxWorkspace {
   double* tile_suffix;     // [cs_tiles] suffix scan of tile_wsum (backward)
   double* loss_partial;    // [cs_tiles]
   double* gsum_partial;    // [cs_tiles]
+  // the two pipelines never hold sort buffers at the same time: the bucket regions alias the LSD ping-pong arrays
   uint32_t* keys_a; uint32_t* keys_b; uint32_t* vals_a; uint32_t* vals_b;
+  uint2* fs_pairs;         // [nb * FS_CAP]
   size_t total_bytes;
 };
 
 static CoxWorkspace carve_cox(void* base, int64_t n) {
   const int64_t rt = rs_tiles(n), ct = cs_tiles(n);
+  const bool fast = n <= FS_MAX_N;
   Carver c(base);
   CoxWorkspace w;
   w.hist = c.take<uint32_t>(4 * RS_RADIX);
@@ -546,17 +564,23 @@ static CoxWorkspace carve_cox(void* base, int64_t n) {
   w.max_count = c.take<int32_t>(2);
   w.nonbinary = c.take<int32_t>(1);
   w.fallback = c.take<int32_t>(1);
-  w.lookback = c.take<uint32_t>(size_t(4) * rt * RS_RADIX);
   w.fs_hist12 = c.take<uint32_t>(FS_BINS);
-  w.fs_bucket_count = c.take<uint32_t>(FS_MAX_BUCKETS);
-  w.fs_counters = c.take<uint32_t>(4);
-  w.fs_lookback = c.take<uint32_t>(n <= FS_MAX_N ? size_t(fs_tiles(n)) * FS_MAX_BUCKETS : 1);
+  w.fs_kext = c.take<uint32_t>(2);
+  w.fs_counters = c.take<uint32_t>(8);
+  w.fs_cursor = c.take<uint32_t>(FS_MAX_BUCKETS);
+  w.fs_agg_val = c.take<double>(FS_MAX_BUCKETS);
   w.zero_bytes = align_up(c.off, 256);
+  w.lookback_words = size_t(4) * rt * RS_RADIX;
+  w.lookback = c.take<uint32_t>(w.lookback_words);
   w.digit_base = c.take<uint32_t>(4 * RS_RADIX);
   w.fs_lut = c.take<uint2>(FS_BINS);
-  w.fs_bucket_base = c.take<uint32_t>(FS_MAX_BUCKETS + 1);
-  w.fs_work = c.take<uint4>(FS_MAX_WORK);
-  w.fs_params = c.take<uint32_t>(4);
+  w.fs_edge = c.take<FsEdge>(1);
+  w.fs_exp_prefix = c.take<double>(FS_MAX_BUCKETS);
+  w.fs_wsum = c.take<double>(FS_MAX_BUCKETS);
+  w.fs_loss_part = c.take<double>(FS_MAX_BUCKETS);
+  w.fs_gsum_part = c.take<double>(FS_MAX_BUCKETS);
+  w.fs_bucket_base = c.take<uint32_t>(FS_MAX_BUCKETS);
+  w.fs_bucket_cnt = c.take<uint32_t>(FS_MAX_BUCKETS);
   w.max_list = c.take<int32_t>(2 * COX_MAX_LIST);
   w.gsum_total = c.take<double>(1);
   w.tile_sum = c.take<double>(ct);
@@ -564,10 +588,14 @@ static CoxWorkspace carve_cox(void* base, int64_t n) {
   w.tile_suffix = c.take<double>(ct);
   w.loss_partial = c.take<double>(ct);
   w.gsum_partial = c.take<double>(ct);
-  w.keys_a = c.take<uint32_t>(n);
-  w.keys_b = c.take<uint32_t>(n);
-  w.vals_a = c.take<uint32_t>(n);
-  w.vals_b = c.take<uint32_t>(n);
+  const size_t lsd_words = size_t(4) * size_t(n);
+  const size_t fs_words = fast ? size_t(fs_plan(n).nb) * FS_CAP * 2 : 0;
+  uint32_t* sortbuf = c.take<uint32_t>(std::max(lsd_words, fs_words));
+  w.keys_a = sortbuf;
+  w.keys_b = sortbuf + n;
+  w.vals_a = sortbuf + 2 * n;
+  w.vals_b = sortbuf + 3 * n;
+  w.fs_pairs = reinterpret_cast<uint2*>(sortbuf);
   w.total_bytes = align_up(c.off, 256);
   return w;
 }
@@ -579,6 +607,26 @@ static SortWorkspace sort_ws(const CoxWorkspace& w) {
   return s;
 }
 
+static FastSortWs fast_ws(const CoxWorkspace& w) {
+  FastSortWs f;
+  f.hist12 = w.fs_hist12; f.kext = w.fs_kext; f.counters = w.fs_counters; f.cursor = w.fs_cursor;
+  f.agg_val = w.fs_agg_val; f.fallback = w.fallback; f.lut = w.fs_lut; f.edge = w.fs_edge;
+  f.exp_prefix = w.fs_exp_prefix; f.wsum = w.fs_wsum; f.loss_part = w.fs_loss_part; f.gsum_part = w.fs_gsum_part;
+  f.bucket_base = w.fs_bucket_base; f.bucket_cnt = w.fs_bucket_cnt; f.pairs = w.fs_pairs;
+  return f;
+}
+
+// the decoupled look-back words of the LSD sort are cleared by the pipeline that uses them (a no-op otherwise)
+__global__ void __launch_bounds__(256) cox_zero_words_kernel(uint32_t* __restrict__ p, size_t words,
+                                                             const int32_t* __restrict__ enable) {
+  if (*enable == 0) return;
+  uint4* q = reinterpret_cast<uint4*>(p);   // Carver hands out 256-byte aligned arrays
+  const size_t quads = words / 4;
+  for (size_t i = size_t(blockIdx.x) * 256 + threadIdx.x; i < quads; i += size_t(gridDim.x) * 256)
+    q[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (blockIdx.x == 0 && threadIdx.x < words % 4) p[quads * 4 + threadIdx.x] = 0u;
+}
+
 }  // namespace mmbs
 
 using namespace mmbs;
@@ -588,40 +636,28 @@ extern "C" size_t mmbs_cox_workspace_bytes(int64_t n) {
   return carve_cox(nullptr, n).total_bytes;
 }
 
-static bool use_two_pass_sort(int64_t n) {
+static bool use_bucketed(int64_t n) {
   static const bool disabled = []() {
-    const char* e = getenv("MMBS_COX_LSD");   // experiments / tests: force the 4-pass LSD sort
+    const char* e = getenv("MMBS_COX_LSD");   // experiments / tests: force the LSD-sort pipeline
     return e && e[0] == '1';
   }();
   return !disabled && n <= FS_MAX_N;
 }
 
-// Risk-set sort (+ s~ = scores[perm] - max and the argmax list when `scores` is given).
-static int cox_sort_common(const float* scores, const float* times, const float* status, int64_t n,
-                           int32_t* perm_out, float* saved_s, const CoxWorkspace& w, cudaStream_t stream) {
-  MMBS_CUDA_TRY(cudaMemsetAsync(w.hist, 0, w.zero_bytes, stream));
-  const int32_t* enable = nullptr;
-  if (use_two_pass_sort(n)) {
-    FastSortWs f;
-    f.hist12 = w.fs_hist12; f.bucket_count = w.fs_bucket_count; f.counters = w.fs_counters; f.fallback = w.fallback;
-    f.lookback = w.fs_lookback; f.lut = w.fs_lut; f.bucket_base = w.fs_bucket_base; f.work = w.fs_work;
-    f.params = w.fs_params; f.keys = w.keys_a; f.vals = w.vals_a;
-    if (int rc = fs_sort_enqueue(times, status, scores, n, f, w.max_enc, w.nan_flag, w.nonbinary, perm_out, saved_s,
-                                 w.max_count, w.max_list, COX_MAX_LIST, stream))
-      return rc;
-    enable = w.fallback;   // the kernels below return at once unless the two-pass sort gave up
-    scores = nullptr;      // max(scores) and the NaN flag are already known
-  } else {
-    MMBS_CUDA_TRY(cudaMemsetAsync(w.fallback, 0xff, sizeof(int32_t), stream));   // != 0: the LSD path is the sort
-  }
+// LSD pipeline up to the permutation (+ max(scores) / NaN flag when `scores` is given).  Runs when *w.fallback != 0.
+static int cox_lsd_sort(const float* scores, const float* times, const float* status, int64_t n, int32_t* perm_out,
+                        const CoxWorkspace& w, cudaStream_t stream) {
+  const int zgrid = int(std::max<size_t>(1, std::min<size_t>(w.lookback_words / 4 / 256 + 1, size_t(sm_count()) * 4)));
+  cox_zero_words_kernel<<<zgrid, 256, 0, stream>>>(w.lookback, w.lookback_words, w.fallback);
+  MMBS_LAUNCH_CHECK();
   int rc = rs_histogram_enqueue(times, KEY_NEG_TIME_F32, n, 4, w.hist, w.digit_base, scores, w.max_enc, w.nan_flag,
-                                stream, enable);
+                                stream, w.fallback);
   if (rc) return rc;
-  return rs_sort_enqueue(times, KEY_NEG_TIME_F32, n, 4, sort_ws(w), perm_out, stream, status, w.nonbinary, enable);
+  return rs_sort_enqueue(times, KEY_NEG_TIME_F32, n, 4, sort_ws(w), perm_out, stream, status, w.nonbinary, w.fallback);
 }
 
 extern "C" int mmbs_risk_order(const float* times, int64_t n, int32_t* perm_out, void* workspace,
-                               size_t workspace_bytes, void* stream) {
+                               size_t workspace_bytes, void* stream_) {
   if (int rc = mmbs_device_check()) return rc;
   MMBS_REQUIRE(times && perm_out && workspace, "mmbs_risk_order: null pointer");
   MMBS_REQUIRE(n >= 1 && n <= RS_MAX_N, "mmbs_risk_order: n=%lld out of range", (long long)n);
@@ -630,7 +666,16 @@ extern "C" int mmbs_risk_order(const float* times, int64_t n, int32_t* perm_out,
     set_error("mmbs_risk_order: workspace %zu < %zu bytes", workspace_bytes, w.total_bytes);
     return MMBS_ERR_WORKSPACE;
   }
-  return cox_sort_common(nullptr, times, nullptr, n, perm_out, nullptr, w, static_cast<cudaStream_t>(stream));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MMBS_CUDA_TRY(cudaMemsetAsync(w.hist, 0, w.zero_bytes, stream));
+  if (use_bucketed(n)) {
+    if (int rc = fs_forward_enqueue(times, nullptr, nullptr, n, fast_ws(w), w.max_enc, w.nan_flag, w.nonbinary, perm_out,
+                                    nullptr, w.max_count, w.max_list, nullptr, nullptr, stream))
+      return rc;
+  } else {
+    MMBS_CUDA_TRY(cudaMemsetAsync(w.fallback, 0xff, sizeof(int32_t), stream));
+  }
+  return cox_lsd_sort(nullptr, times, nullptr, n, perm_out, w, stream);
 }
 
 extern "C" int mmbs_cox_forward(const float* scores, const float* times, const float* status,
@@ -658,22 +703,32 @@ extern "C" int mmbs_cox_forward(const float* scores, const float* times, const f
     set_error("mmbs_cox_forward: workspace %zu < %zu bytes", workspace_bytes, w.total_bytes);
     return MMBS_ERR_WORKSPACE;
   }
-  if (int rc = cox_sort_common(scores, times, status, n, perm_out, saved_s, w, stream)) return rc;
+  MMBS_CUDA_TRY(cudaMemsetAsync(w.hist, 0, w.zero_bytes, stream));
+  const float* lsd_scores = scores;
+  if (use_bucketed(n)) {
+    // bucketed pipeline: saved_w stays unwritten (its backward recomputes w from s~)
+    if (int rc = fs_forward_enqueue(times, status, scores, n, fast_ws(w), w.max_enc, w.nan_flag, w.nonbinary, perm_out,
+                                    saved_s, w.max_count, w.max_list, loss_out, flags_out, stream))
+      return rc;
+    lsd_scores = nullptr;   // max(scores) and the NaN flag are already known
+  } else {
+    MMBS_CUDA_TRY(cudaMemsetAsync(w.fallback, 0xff, sizeof(int32_t), stream));
+  }
+  // LSD pipeline: every kernel returns at once unless *w.fallback != 0
+  if (int rc = cox_lsd_sort(lsd_scores, times, status, n, perm_out, w, stream)) return rc;
   const int64_t tiles = cs_tiles(n);
-  // LSD path only (returns at once when the two-pass sort wrote s~): the gather through the permutation
   cox_gather_kernel<<<unsigned(tiles), CS_THREADS, 0, stream>>>(perm_out, scores, w.max_enc, n, saved_s,
-                                                               w.max_count + 1, w.max_list + COX_MAX_LIST,
-                                                               use_two_pass_sort(n) ? w.fallback : nullptr);
+                                                               w.max_count + 1, w.max_list + COX_MAX_LIST, w.fallback);
   MMBS_LAUNCH_CHECK();
-  cox_tilesum_kernel<<<unsigned(tiles), CS_THREADS, 0, stream>>>(saved_s, n, w.tile_sum);
+  cox_tilesum_kernel<<<unsigned(tiles), CS_THREADS, 0, stream>>>(saved_s, n, w.tile_sum, w.fallback);
   MMBS_LAUNCH_CHECK();
-  cox_tile_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_sum, w.tile_sum, tiles, 0);
+  cox_tile_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_sum, w.tile_sum, tiles, 0, w.fallback);
   MMBS_LAUNCH_CHECK();
   cox_loss_kernel<<<unsigned(tiles), CS_THREADS, 0, stream>>>(perm_out, status, saved_s, w.tile_sum, n,
                                                              saved_w, w.loss_partial, w.tile_wsum,
-                                                             w.nan_flag, w.nonbinary);
+                                                             w.nan_flag, w.nonbinary, w.fallback);
   MMBS_LAUNCH_CHECK();
-  cox_finalize_kernel<<<1, 256, 0, stream>>>(w.loss_partial, tiles, n, w.nan_flag, loss_out, flags_out);
+  cox_finalize_kernel<<<1, 256, 0, stream>>>(w.loss_partial, tiles, n, w.nan_flag, loss_out, flags_out, w.fallback);
   MMBS_LAUNCH_CHECK();
   return MMBS_OK;
 }
@@ -697,17 +752,22 @@ extern "C" int mmbs_cox_backward(const float* scores, const float* status, const
     return MMBS_OK;
   }
   MMBS_REQUIRE(workspace != nullptr, "mmbs_cox_backward: null workspace");
-  const CoxWorkspace w = carve_cox(workspace, n);  // must be the forward's workspace (tile sums, max list)
+  const CoxWorkspace w = carve_cox(workspace, n);  // must be the forward's workspace (bucket / tile sums, max list)
   if (workspace_bytes < w.total_bytes) {
     set_error("mmbs_cox_backward: workspace %zu < %zu bytes", workspace_bytes, w.total_bytes);
     return MMBS_ERR_WORKSPACE;
   }
+  if (use_bucketed(n)) {
+    if (int rc = fs_backward_enqueue(status, perm, saved_s, grad_loss, n, fast_ws(w), w.nonbinary, w.max_count,
+                                     w.max_list, w.gsum_total, grad_scores, stream))
+      return rc;
+  }
   const int64_t tiles = cs_tiles(n);
-  cox_tile_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_wsum, w.tile_suffix, tiles, 1);
+  cox_tile_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_wsum, w.tile_suffix, tiles, 1, w.fallback);
   MMBS_LAUNCH_CHECK();
   cox_grad_kernel<<<unsigned(tiles), CS_THREADS, 0, stream>>>(perm, status, saved_s, saved_w, w.tile_suffix,
                                                              grad_loss, n, grad_scores, w.gsum_partial,
-                                                             w.nonbinary);
+                                                             w.nonbinary, w.fallback);
   MMBS_LAUNCH_CHECK();
   cox_maxfix_list_kernel<<<1, 256, 0, stream>>>(w.gsum_partial, tiles, w.max_count, w.max_list, w.fallback,
                                                w.gsum_total, grad_scores);

@@ -1,46 +1,76 @@
-// Two-pass risk-set sort (MSD partition by an equalised-CDF bucket map + block-local sort with the forward gather
-// fused): see cox_sort.cu.  Used by the Cox loss for 2048 < n <= FS_MAX_N.
+// Bucketed risk-set pipeline of the Cox loss for 2048 < n <= FS_MAX_N (see cox_sort.cu): equalised-CDF partition into
+// buckets of ~5 K samples, one block per bucket sorts it in shared memory and runs the forward pass on it, one block
+// per bucket runs the backward pass.
 #pragma once
 
 #include "radix_sort.cuh"
 
 namespace mmbs {
 
-constexpr int FS_BINS = 4096;             // histogram of the top 12 key bits
-constexpr int FS_MAX_BUCKETS = 1024;
-constexpr int FS_CAP = 16384;             // samples one block sorts in shared memory
-constexpr int FS_TARGET = 8192;           // aimed bucket size (n <= 8.4 M); 10 M samples -> 9766 per bucket
-constexpr int FS_PART_TILE = 8192;        // keys per partition tile
-constexpr int FS_MAX_WORK = 2048;         // >= FS_MAX_BUCKETS + FS_MAX_N / FS_CAP + 1
-constexpr int64_t FS_MAX_N = 12000000;    // beyond: mean bucket size too close to FS_CAP -> LSD sort
+constexpr int FS_BINS = 4096;              // histogram of the top 12 key bits
+constexpr int FS_MAX_BUCKETS = 4096;
+constexpr int FS_CAP = 8192;               // samples one block sorts in shared memory (= slots per bucket region)
+constexpr int FS_TARGET = 5120;            // aimed bucket size: 1.6x head-room below FS_CAP
+constexpr int FS_LOG_S_MAX = 12;           // <= 4096 sub-buckets per bucket (~1.25 samples each)
+constexpr int FS_CMAX = 128;               // largest sub-bucket the rank-by-comparison finish accepts
+constexpr int FS_MAX_LIST = 1024;          // argmax positions remembered for the gradient through max(scores)
+constexpr int64_t FS_MAX_N = int64_t(FS_MAX_BUCKETS) * FS_TARGET;   // 20.97 M; beyond: LSD sort
 
-static inline int fs_num_buckets(int64_t n) {
-  const int64_t nb = (n + FS_TARGET - 1) / FS_TARGET;
-  return int(nb < 1 ? 1 : (nb > FS_MAX_BUCKETS ? FS_MAX_BUCKETS : nb));
+struct FsPlan {
+  int nb;            // buckets
+  int log_s;         // log2(sub-buckets per bucket)
+  uint32_t mult2;    // floor((nb << log_s) * 2^32 / n): rank estimate -> fine cell
+};
+static inline FsPlan fs_plan(int64_t n) {
+  FsPlan p;
+  int64_t nb = (n + FS_TARGET - 1) / FS_TARGET;
+  p.nb = int(nb < 1 ? 1 : (nb > FS_MAX_BUCKETS ? FS_MAX_BUCKETS : nb));
+  p.log_s = FS_LOG_S_MAX;
+  while (p.log_s > 0 && (int64_t(p.nb) << p.log_s) >= n) --p.log_s;
+  p.mult2 = uint32_t(((uint64_t(p.nb) << p.log_s) << 32) / uint64_t(n < 1 ? 1 : n));
+  return p;
 }
-static inline int64_t fs_tiles(int64_t n) { return n > 0 ? (n + FS_PART_TILE - 1) / FS_PART_TILE : 1; }
 
-struct FastSortWs {
-  // zeroed by the caller before every sort
-  uint32_t* hist12;        // [FS_BINS]
-  uint32_t* bucket_count;  // [FS_MAX_BUCKETS]
-  uint32_t* counters;      // [4]: blocks done (histogram, count), partition tile ticket
-  int32_t* fallback;       // [1] set when the bucket map could not balance the input: the LSD sort must run
-  uint32_t* lookback;      // [fs_tiles][FS_MAX_BUCKETS]
-  // not zeroed
-  uint2* lut;              // [FS_BINS] (exclusive prefix, count) of every 12-bit bin
-  uint32_t* bucket_base;   // [FS_MAX_BUCKETS + 1]
-  uint4* work;             // [FS_MAX_WORK] (bucket, first element, count, bucket size)
-  uint32_t* params;        // [4]: number of work items
-  uint32_t* keys;          // [n] partitioned keys
-  uint32_t* vals;          // [n] partitioned payloads (index | event << 31)
+struct FsEdge {       // the two 12-bit bins that hold the smallest / largest key are interpolated over the occupied
+  uint32_t lo_bin;    // key range only (a bin half covered by the data would otherwise give buckets of twice the size)
+  uint32_t lo_base;
+  float lo_scale;
+  uint32_t hi_bin;
+  uint32_t hi_base;
+  float hi_scale;
+  uint32_t pad[2];
 };
 
-// Enqueue histogram (+ max / NaN flag over `scores` when given), count, partition and local sort.  Writes
-// perm_out (index | event bit) and, when `scores` is given, saved_s = scores[perm] - max and the list of argmax
-// positions.  On inputs the bucket map cannot balance, *w.fallback is set instead (outputs undefined).
-int fs_sort_enqueue(const float* times, const float* status, const float* scores, int64_t n, const FastSortWs& w,
-                    uint32_t* max_enc, int32_t* nan_flag, int32_t* nonbinary_flag, int32_t* perm_out, float* saved_s,
-                    int32_t* max_count, int32_t* max_list, int max_list_cap, cudaStream_t stream);
+struct FastSortWs {
+  // zeroed by the caller before every forward pass
+  uint32_t* hist12;        // [FS_BINS]
+  uint32_t* kext;          // [2]: max(~key), max(key)
+  uint32_t* counters;      // [8]: 0 histogram blocks done, 1 bucket ticket, 2 forward blocks done, 3 backward blocks done
+  uint32_t* cursor;        // [FS_MAX_BUCKETS] samples written to every bucket region
+  double* agg_val;         // [FS_MAX_BUCKETS] sum of exp(s~) over the bucket; +0.0 = not published yet
+  int32_t* fallback;       // [1] set when this pipeline gave up: the LSD-sort pipeline must (re)do the work
+  // not zeroed
+  uint2* lut;              // [FS_BINS] (exclusive prefix, count) of every 12-bit bin
+  FsEdge* edge;            // [1]
+  double* exp_prefix;      // [FS_MAX_BUCKETS] sum of exp(s~) over all earlier buckets           (kept for backward)
+  double* wsum;            // [FS_MAX_BUCKETS] sum of w = status / (C + eps) over the bucket     (kept for backward)
+  double* loss_part;       // [FS_MAX_BUCKETS]
+  double* gsum_part;       // [FS_MAX_BUCKETS]
+  uint32_t* bucket_base;   // [FS_MAX_BUCKETS] first sorted position of the bucket               (kept for backward)
+  uint32_t* bucket_cnt;    // [FS_MAX_BUCKETS]                                                    (kept for backward)
+  uint2* pairs;            // [nb * FS_CAP] partitioned (key, index | event << 31)
+};
+
+// Forward: histogram (+ max / NaN flag over `scores`) -> partition -> per-bucket sort + gather + scan + loss.
+// With scores == nullptr only the permutation is produced (mmbs_risk_order).
+int fs_forward_enqueue(const float* times, const float* status, const float* scores, int64_t n, const FastSortWs& w,
+                       uint32_t* max_enc, int32_t* nan_flag, int32_t* nonbinary_flag, int32_t* perm_out, float* saved_s,
+                       int32_t* max_count, int32_t* max_list, float* loss_out, int32_t* flags_out, cudaStream_t stream);
+
+// Backward: per bucket, recompute C and w from s~, suffix sums, gradient scatter; the last block applies the gradient
+// through max(scores) when its argmax positions fit the list (otherwise cox_maxfix_full_kernel does, cox.cu).
+int fs_backward_enqueue(const float* status, const int32_t* perm, const float* saved_s, const float* grad_loss, int64_t n,
+                        const FastSortWs& w, const int32_t* nonbinary_flag, const int32_t* max_count,
+                        const int32_t* max_list, double* gsum_total, float* grad_scores, cudaStream_t stream);
 
 }  // namespace mmbs
