@@ -627,6 +627,62 @@ __global__ void __launch_bounds__(256) cox_zero_words_kernel(uint32_t* __restric
   if (blockIdx.x == 0 && threadIdx.x < words % 4) p[quads * 4 + threadIdx.x] = 0u;
 }
 
+
+// ---- device-side fallback (CUDA dynamic parallelism, tail launches): the bucketed pipeline raises `fallback` on the
+// device; ONE tiny kernel behind it enqueues the whole LSD pipeline when - and only when - the flag is set, so the common
+// path carries neither a host synchronisation nor a dozen parked no-op launches.
+struct CoxLsdForward {
+  const float* scores; const float* times; const float* status; int64_t n;
+  int32_t* perm_out; float* saved_s; float* saved_w; float* loss_out; int32_t* flags_out;
+  SortWorkspace sw; size_t lookback_words;
+  uint32_t* max_enc; int32_t* nan_flag; int32_t* max_count; int32_t* max_list; int32_t* nonbinary;
+  double* tile_sum; double* tile_wsum; double* loss_partial;
+  const int32_t* fallback;
+  int zero_grid, hist_grid; unsigned sort_grid; int64_t sort_tiles, scan_tiles;
+};
+
+__global__ void cox_lsd_forward_dispatch_kernel(CoxLsdForward a) {
+  if (*a.fallback == 0) return;
+  const unsigned tiles = unsigned(a.scan_tiles);
+  cox_zero_words_kernel<<<a.zero_grid, 256, 0, cudaStreamTailLaunch>>>(a.sw.lookback, a.lookback_words, a.fallback);
+  rs_sort_tail_launch(a.times, int(KEY_NEG_TIME_F32), a.n, 4, a.sw, a.perm_out, a.status, a.nonbinary, a.hist_grid,
+                      a.sort_grid, a.sort_tiles);
+  cox_gather_kernel<<<tiles, CS_THREADS, 0, cudaStreamTailLaunch>>>(a.perm_out, a.scores, a.max_enc, a.n, a.saved_s,
+                                                                    a.max_count + 1, a.max_list + COX_MAX_LIST, nullptr);
+  cox_tilesum_kernel<<<tiles, CS_THREADS, 0, cudaStreamTailLaunch>>>(a.saved_s, a.n, a.tile_sum, nullptr);
+  cox_tile_scan_kernel<<<1, 1024, 0, cudaStreamTailLaunch>>>(a.tile_sum, a.tile_sum, a.scan_tiles, 0, nullptr);
+  cox_loss_kernel<<<tiles, CS_THREADS, 0, cudaStreamTailLaunch>>>(a.perm_out, a.status, a.saved_s, a.tile_sum, a.n, a.saved_w,
+                                                                  a.loss_partial, a.tile_wsum, a.nan_flag, a.nonbinary,
+                                                                  nullptr);
+  cox_finalize_kernel<<<1, 256, 0, cudaStreamTailLaunch>>>(a.loss_partial, a.scan_tiles, a.n, a.nan_flag, a.loss_out,
+                                                           a.flags_out, nullptr);
+}
+
+struct CoxLsdBackward {
+  const float* scores; const float* status; const int32_t* perm; const float* saved_s; const float* saved_w;
+  const float* grad_loss; int64_t n; float* grad_scores;
+  uint32_t* max_enc; int32_t* max_count; int32_t* max_list; int32_t* nonbinary; const int32_t* fallback;
+  double* tile_wsum; double* tile_suffix; double* gsum_partial; double* gsum_total;
+  int64_t scan_tiles; int full_grid;
+};
+
+__global__ void cox_lsd_backward_dispatch_kernel(CoxLsdBackward a) {
+  const bool fb = *a.fallback != 0;
+  if (fb) {
+    const unsigned tiles = unsigned(a.scan_tiles);
+    cox_tile_scan_kernel<<<1, 1024, 0, cudaStreamTailLaunch>>>(a.tile_wsum, a.tile_suffix, a.scan_tiles, 1, nullptr);
+    cox_grad_kernel<<<tiles, CS_THREADS, 0, cudaStreamTailLaunch>>>(a.perm, a.status, a.saved_s, a.saved_w, a.tile_suffix,
+                                                                    a.grad_loss, a.n, a.grad_scores, a.gsum_partial,
+                                                                    a.nonbinary, nullptr);
+    cox_maxfix_list_kernel<<<1, 256, 0, cudaStreamTailLaunch>>>(a.gsum_partial, a.scan_tiles, a.max_count, a.max_list,
+                                                                a.fallback, a.gsum_total, a.grad_scores);
+  }
+  // more argmax positions than the list holds (e.g. all scores equal): a pass over `scores`, either pipeline
+  if (a.max_count[fb ? 1 : 0] > COX_MAX_LIST)
+    cox_maxfix_full_kernel<<<a.full_grid, 256, 0, cudaStreamTailLaunch>>>(a.scores, a.max_enc, a.max_count, a.fallback,
+                                                                          a.gsum_total, a.n, a.grad_scores);
+}
+
 }  // namespace mmbs
 
 using namespace mmbs;
@@ -644,17 +700,34 @@ static bool use_bucketed(int64_t n) {
   return !disabled && n <= FS_MAX_N;
 }
 
-// LSD pipeline up to the permutation (+ max(scores) / NaN flag when `scores` is given).  Runs when *w.fallback != 0.
+static int lsd_zero_grid(const CoxWorkspace& w) {
+  return int(std::max<size_t>(1, std::min<size_t>(w.lookback_words / 4 / 256 + 1, size_t(sm_count()) * 4)));
+}
+
+// LSD pipeline up to the permutation (+ max(scores) / NaN flag when `scores` is given), enqueued from the host.
 static int cox_lsd_sort(const float* scores, const float* times, const float* status, int64_t n, int32_t* perm_out,
                         const CoxWorkspace& w, cudaStream_t stream) {
-  const int zgrid = int(std::max<size_t>(1, std::min<size_t>(w.lookback_words / 4 / 256 + 1, size_t(sm_count()) * 4)));
-  cox_zero_words_kernel<<<zgrid, 256, 0, stream>>>(w.lookback, w.lookback_words, w.fallback);
+  cox_zero_words_kernel<<<lsd_zero_grid(w), 256, 0, stream>>>(w.lookback, w.lookback_words, w.fallback);
   MMBS_LAUNCH_CHECK();
   int rc = rs_histogram_enqueue(times, KEY_NEG_TIME_F32, n, 4, w.hist, w.digit_base, scores, w.max_enc, w.nan_flag,
-                                stream, w.fallback);
+                                stream, nullptr);
   if (rc) return rc;
-  return rs_sort_enqueue(times, KEY_NEG_TIME_F32, n, 4, sort_ws(w), perm_out, stream, status, w.nonbinary, w.fallback);
+  return rs_sort_enqueue(times, KEY_NEG_TIME_F32, n, 4, sort_ws(w), perm_out, stream, status, w.nonbinary, nullptr);
 }
+
+// mmbs_risk_order on the bucketed pipeline: the permutation only
+struct CoxLsdOrder {
+  const float* times; int64_t n; int32_t* perm_out; SortWorkspace sw; size_t lookback_words; int32_t* nonbinary;
+  const int32_t* fallback; int zero_grid, hist_grid; unsigned sort_grid; int64_t sort_tiles;
+};
+namespace mmbs {
+__global__ void cox_lsd_order_dispatch_kernel(CoxLsdOrder a) {
+  if (*a.fallback == 0) return;
+  cox_zero_words_kernel<<<a.zero_grid, 256, 0, cudaStreamTailLaunch>>>(a.sw.lookback, a.lookback_words, a.fallback);
+  rs_sort_tail_launch(a.times, int(KEY_NEG_TIME_F32), a.n, 4, a.sw, a.perm_out, nullptr, a.nonbinary, a.hist_grid,
+                      a.sort_grid, a.sort_tiles);
+}
+}  // namespace mmbs
 
 extern "C" int mmbs_risk_order(const float* times, int64_t n, int32_t* perm_out, void* workspace,
                                size_t workspace_bytes, void* stream_) {
@@ -672,9 +745,16 @@ extern "C" int mmbs_risk_order(const float* times, int64_t n, int32_t* perm_out,
     if (int rc = fs_forward_enqueue(times, nullptr, nullptr, n, fast_ws(w), w.max_enc, w.nan_flag, w.nonbinary, perm_out,
                                     nullptr, w.max_count, w.max_list, nullptr, nullptr, stream))
       return rc;
-  } else {
-    MMBS_CUDA_TRY(cudaMemsetAsync(w.fallback, 0xff, sizeof(int32_t), stream));
+    if (int rc = rs_configure()) return rc;
+    CoxLsdOrder a;
+    a.times = times; a.n = n; a.perm_out = perm_out; a.sw = sort_ws(w); a.lookback_words = w.lookback_words;
+    a.nonbinary = w.nonbinary; a.fallback = w.fallback; a.zero_grid = lsd_zero_grid(w); a.hist_grid = rs_hist_grid(n);
+    a.sort_grid = rs_sort_grid(n); a.sort_tiles = rs_tiles(n);
+    cox_lsd_order_dispatch_kernel<<<1, 1, 0, stream>>>(a);
+    MMBS_LAUNCH_CHECK();
+    return MMBS_OK;
   }
+  MMBS_CUDA_TRY(cudaMemsetAsync(w.fallback, 0xff, sizeof(int32_t), stream));
   return cox_lsd_sort(nullptr, times, nullptr, n, perm_out, w, stream);
 }
 
@@ -704,31 +784,42 @@ extern "C" int mmbs_cox_forward(const float* scores, const float* times, const f
     return MMBS_ERR_WORKSPACE;
   }
   MMBS_CUDA_TRY(cudaMemsetAsync(w.hist, 0, w.zero_bytes, stream));
-  const float* lsd_scores = scores;
+  const int64_t tiles = cs_tiles(n);
   if (use_bucketed(n)) {
     // bucketed pipeline: saved_w stays unwritten (its backward recomputes w from s~)
     if (int rc = fs_forward_enqueue(times, status, scores, n, fast_ws(w), w.max_enc, w.nan_flag, w.nonbinary, perm_out,
                                     saved_s, w.max_count, w.max_list, loss_out, flags_out, stream))
       return rc;
-    lsd_scores = nullptr;   // max(scores) and the NaN flag are already known
-  } else {
-    MMBS_CUDA_TRY(cudaMemsetAsync(w.fallback, 0xff, sizeof(int32_t), stream));
+    // ... unless it raised `fallback`: then this kernel enqueues the LSD pipeline from the device
+    if (int rc = rs_configure()) return rc;
+    CoxLsdForward a;
+    a.scores = scores; a.times = times; a.status = status; a.n = n;
+    a.perm_out = perm_out; a.saved_s = saved_s; a.saved_w = saved_w; a.loss_out = loss_out; a.flags_out = flags_out;
+    a.sw = sort_ws(w); a.lookback_words = w.lookback_words;
+    a.max_enc = w.max_enc; a.nan_flag = w.nan_flag; a.max_count = w.max_count; a.max_list = w.max_list;
+    a.nonbinary = w.nonbinary; a.tile_sum = w.tile_sum; a.tile_wsum = w.tile_wsum; a.loss_partial = w.loss_partial;
+    a.fallback = w.fallback;
+    a.zero_grid = lsd_zero_grid(w); a.hist_grid = rs_hist_grid(n); a.sort_grid = rs_sort_grid(n);
+    a.sort_tiles = rs_tiles(n); a.scan_tiles = tiles;
+    cox_lsd_forward_dispatch_kernel<<<1, 1, 0, stream>>>(a);
+    MMBS_LAUNCH_CHECK();
+    return MMBS_OK;
   }
-  // LSD pipeline: every kernel returns at once unless *w.fallback != 0
-  if (int rc = cox_lsd_sort(lsd_scores, times, status, n, perm_out, w, stream)) return rc;
-  const int64_t tiles = cs_tiles(n);
+  // LSD pipeline, enqueued from the host
+  MMBS_CUDA_TRY(cudaMemsetAsync(w.fallback, 0xff, sizeof(int32_t), stream));
+  if (int rc = cox_lsd_sort(scores, times, status, n, perm_out, w, stream)) return rc;
   cox_gather_kernel<<<unsigned(tiles), CS_THREADS, 0, stream>>>(perm_out, scores, w.max_enc, n, saved_s,
-                                                               w.max_count + 1, w.max_list + COX_MAX_LIST, w.fallback);
+                                                               w.max_count + 1, w.max_list + COX_MAX_LIST, nullptr);
   MMBS_LAUNCH_CHECK();
-  cox_tilesum_kernel<<<unsigned(tiles), CS_THREADS, 0, stream>>>(saved_s, n, w.tile_sum, w.fallback);
+  cox_tilesum_kernel<<<unsigned(tiles), CS_THREADS, 0, stream>>>(saved_s, n, w.tile_sum, nullptr);
   MMBS_LAUNCH_CHECK();
-  cox_tile_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_sum, w.tile_sum, tiles, 0, w.fallback);
+  cox_tile_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_sum, w.tile_sum, tiles, 0, nullptr);
   MMBS_LAUNCH_CHECK();
   cox_loss_kernel<<<unsigned(tiles), CS_THREADS, 0, stream>>>(perm_out, status, saved_s, w.tile_sum, n,
                                                              saved_w, w.loss_partial, w.tile_wsum,
-                                                             w.nan_flag, w.nonbinary, w.fallback);
+                                                             w.nan_flag, w.nonbinary, nullptr);
   MMBS_LAUNCH_CHECK();
-  cox_finalize_kernel<<<1, 256, 0, stream>>>(w.loss_partial, tiles, n, w.nan_flag, loss_out, flags_out, w.fallback);
+  cox_finalize_kernel<<<1, 256, 0, stream>>>(w.loss_partial, tiles, n, w.nan_flag, loss_out, flags_out, nullptr);
   MMBS_LAUNCH_CHECK();
   return MMBS_OK;
 }
@@ -757,24 +848,33 @@ extern "C" int mmbs_cox_backward(const float* scores, const float* status, const
     set_error("mmbs_cox_backward: workspace %zu < %zu bytes", workspace_bytes, w.total_bytes);
     return MMBS_ERR_WORKSPACE;
   }
+  const int64_t tiles = cs_tiles(n);
+  const int full_grid = int(std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256 * 8), int64_t(sm_count()) * 4)));
   if (use_bucketed(n)) {
     if (int rc = fs_backward_enqueue(status, perm, saved_s, grad_loss, n, fast_ws(w), w.nonbinary, w.max_count,
                                      w.max_list, w.gsum_total, grad_scores, stream))
       return rc;
+    CoxLsdBackward a;
+    a.scores = scores; a.status = status; a.perm = perm; a.saved_s = saved_s; a.saved_w = saved_w;
+    a.grad_loss = grad_loss; a.n = n; a.grad_scores = grad_scores;
+    a.max_enc = w.max_enc; a.max_count = w.max_count; a.max_list = w.max_list; a.nonbinary = w.nonbinary;
+    a.fallback = w.fallback; a.tile_wsum = w.tile_wsum; a.tile_suffix = w.tile_suffix;
+    a.gsum_partial = w.gsum_partial; a.gsum_total = w.gsum_total; a.scan_tiles = tiles; a.full_grid = full_grid;
+    cox_lsd_backward_dispatch_kernel<<<1, 1, 0, stream>>>(a);
+    MMBS_LAUNCH_CHECK();
+    return MMBS_OK;
   }
-  const int64_t tiles = cs_tiles(n);
-  cox_tile_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_wsum, w.tile_suffix, tiles, 1, w.fallback);
+  cox_tile_scan_kernel<<<1, 1024, 0, stream>>>(w.tile_wsum, w.tile_suffix, tiles, 1, nullptr);
   MMBS_LAUNCH_CHECK();
   cox_grad_kernel<<<unsigned(tiles), CS_THREADS, 0, stream>>>(perm, status, saved_s, saved_w, w.tile_suffix,
                                                              grad_loss, n, grad_scores, w.gsum_partial,
-                                                             w.nonbinary, w.fallback);
+                                                             w.nonbinary, nullptr);
   MMBS_LAUNCH_CHECK();
   cox_maxfix_list_kernel<<<1, 256, 0, stream>>>(w.gsum_partial, tiles, w.max_count, w.max_list, w.fallback,
                                                w.gsum_total, grad_scores);
   MMBS_LAUNCH_CHECK();
-  const int grid = int(std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256 * 8), int64_t(sm_count()) * 4)));
-  cox_maxfix_full_kernel<<<grid, 256, 0, stream>>>(scores, w.max_enc, w.max_count, w.fallback, w.gsum_total, n,
-                                                  grad_scores);
+  cox_maxfix_full_kernel<<<full_grid, 256, 0, stream>>>(scores, w.max_enc, w.max_count, w.fallback, w.gsum_total, n,
+                                                       grad_scores);
   MMBS_LAUNCH_CHECK();
   return MMBS_OK;
 }

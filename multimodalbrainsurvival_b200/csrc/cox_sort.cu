@@ -24,6 +24,7 @@
 // jumps inside a 12-bit bin) raise the device flag `fallback`; the LSD-sort pipeline of radix_sort.cu / cox.cu is
 // enqueued behind and only runs when the flag is set - the decision never costs a host synchronisation.
 #include <algorithm>
+#include <cstdlib>
 
 #include "cox_sort.cuh"
 
@@ -35,11 +36,8 @@ constexpr int P_ITEMS = 16;
 constexpr int P_TILE = P_THREADS * P_ITEMS;        // 8192
 constexpr int B_THREADS = 512;
 constexpr int B_ITEMS = FS_CAP / B_THREADS;        // 16 (the skew below assumes 16)
-constexpr int B_SKEW_WORDS = FS_CAP + FS_CAP / 16; // word p lives at p + p/16: 16-word runs start on distinct banks
 constexpr float FS_EPS = 1e-5f;
-static_assert(B_ITEMS == 16, "skewed shared-memory layout assumes 16 samples per thread");
-
-__device__ __forceinline__ int skew(int p) { return p + (p >> 4); }
+static_assert(B_ITEMS % 4 == 0, "blocked 16-byte loads");
 
 __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
   uint32_t v;
@@ -73,7 +71,8 @@ __device__ __forceinline__ uint32_t fs_rank(uint32_t key, const uint2* __restric
   const uint32_t bin = key >> 20;
   const uint2 e = __ldg(lut + bin);
   uint32_t in = uint32_t((uint64_t(key & 0xfffffu) * e.y) >> 20);
-  if (bin == lo_bin) in = min(e.y - 1u, __float2uint_rz(__uint2float_rz(key - E->lo_base) * E->lo_scale));
+  if (bin == lo_bin)   // (a sampled histogram may have missed smaller keys: they rank first)
+    in = key < E->lo_base ? 0u : min(e.y - 1u, __float2uint_rz(__uint2float_rz(key - E->lo_base) * E->lo_scale));
   else if (bin == hi_bin) in = min(e.y - 1u, __float2uint_rz(__uint2float_rz(key - E->hi_base) * E->hi_scale));
   return e.x + in;
 }
@@ -137,9 +136,9 @@ __device__ __forceinline__ double block_sum_f64(double v, double* s_red, int lan
 
 // ------------------------------------------------------------------------------------------ histogram + CDF table
 __global__ void __launch_bounds__(FS_HIST_THREADS, 6) fs_hist_kernel(
-    const float* __restrict__ times, int64_t n, const float* __restrict__ scores, uint32_t* __restrict__ hist,
-    uint32_t* __restrict__ kext, uint32_t* __restrict__ max_enc, int32_t* __restrict__ nan_flag, uint32_t* done_counter,
-    uint2* __restrict__ lut, FsEdge* __restrict__ edge) {
+    const float* __restrict__ times, int64_t n, int sample_shift, int nb, const float* __restrict__ scores,
+    uint32_t* __restrict__ hist, uint32_t* __restrict__ kext, uint32_t* __restrict__ max_enc, int32_t* __restrict__ nan_flag,
+    uint32_t* done_counter, uint2* __restrict__ lut, FsEdge* __restrict__ edge) {
   __shared__ uint32_t s_hist[FS_BINS];
   __shared__ uint32_t s_w[FS_HIST_THREADS / 32];
   __shared__ uint32_t s_max[FS_HIST_THREADS / 32];
@@ -153,7 +152,12 @@ __global__ void __launch_bounds__(FS_HIST_THREADS, 6) fs_hist_kernel(
   float vmax = -INFINITY;
   bool has_nan = false;
   uint32_t kmin = 0xffffffffu, kmax = 0u;
-  for (int64_t blk = blockIdx.x; blk * 1024 < n; blk += gridDim.x) {   // warp-uniform trip count
+  // chunks of 1024 samples; with sample_shift > 0 one pseudo-randomly placed chunk out of every 2^sample_shift
+  const int64_t nchunks = (n + 1023) / 1024;
+  const int64_t ngroups = (nchunks + (int64_t(1) << sample_shift) - 1) >> sample_shift;
+  for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {   // warp-uniform trip count
+    const int64_t blk = (grp << sample_shift) +
+                        (sample_shift ? int64_t((uint32_t(grp) * 2654435761u) >> (32 - sample_shift)) : 0);
     const int64_t base = blk * 1024 + int64_t(tid) * 4;
     const int cnt = int(max((long long)0, min((long long)4, (long long)(n - base))));
     uint32_t k[4] = {0u, 0u, 0u, 0u};
@@ -237,6 +241,10 @@ __global__ void __launch_bounds__(FS_HIST_THREADS, 6) fs_hist_kernel(
   }
   const uint2 sc = block_scan_u32<FS_HIST_THREADS / 32>(sum, s_w, lane, warp);
   uint32_t run = sc.x - sum;
+  if (tid == 0) {   // sc.y = m, the samples counted
+    edge->mult = (sc.y <= uint32_t(nb)) ? 0xffffffffu : uint32_t((uint64_t(nb) << 32) / uint64_t(sc.y));
+    edge->pad = 0u;
+  }
   const uint32_t gmin = ~ld_cg_u32(kext + 0), gmax = ld_cg_u32(kext + 1);
   const uint32_t lo_bin = gmin >> 20, hi_bin = gmax >> 20;
 #pragma unroll
@@ -266,39 +274,55 @@ __global__ void __launch_bounds__(FS_HIST_THREADS, 6) fs_hist_kernel(
 // ------------------------------------------------------------------------------------------ partition
 // dynamic shared memory: s_cnt[nbp] | s_start[nbp] | s_gbase[nbp] | staged pairs[P_TILE] | staged bucket ids[P_TILE] (u16)
 // (nbp = nb rounded up to a multiple of the block size)
-__global__ void __launch_bounds__(P_THREADS, 2) fs_partition_kernel(
-    const float* __restrict__ times, const float* __restrict__ status, int64_t n, const uint2* __restrict__ lut,
-    const FsEdge* __restrict__ edge, uint32_t mult2, int log_s, int nb, uint32_t* __restrict__ cursor,
-    uint2* __restrict__ pairs_out, int32_t* __restrict__ nonbinary_flag, int32_t* __restrict__ fallback) {
-  extern __shared__ __align__(16) uint32_t s_dyn[];
-  __shared__ uint32_t s_w[P_THREADS / 32];
+template <bool FULL>   // FULL: the tile holds P_TILE samples and `times` / `status` / `scores` are 16-byte aligned
+__device__ __forceinline__ void partition_tile(const float* __restrict__ times, const float* __restrict__ status,
+                                               const float* __restrict__ scores, uint32_t* __restrict__ max_enc,
+                                               int32_t* __restrict__ nan_flag, int64_t tile_base, int n_valid,
+                                               const uint2* __restrict__ lut, int nb, int per,
+                                               uint32_t* __restrict__ cursor, uint2* __restrict__ pairs_out,
+                                               int32_t* __restrict__ nonbinary_flag, int32_t* __restrict__ fallback,
+                                               uint32_t* s_cnt, uint32_t* s_start, uint32_t* s_delta, uint2* s_pairs,
+                                               uint16_t* s_bid, const FsEdge* s_E, uint32_t* s_w) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int per = (nb + P_THREADS - 1) / P_THREADS;
-  const int nbp = per * P_THREADS;
-  uint32_t* s_cnt = s_dyn;
-  uint32_t* s_start = s_dyn + nbp;
-  uint32_t* s_gbase = s_dyn + 2 * nbp;
-  uint2* s_pairs = reinterpret_cast<uint2*>(s_dyn + 3 * nbp);
-  uint16_t* s_bid = reinterpret_cast<uint16_t*>(s_dyn + 3 * nbp + 2 * P_TILE);
-  __shared__ FsEdge s_E;
-  if (tid < 8) reinterpret_cast<uint32_t*>(&s_E)[tid] = reinterpret_cast<const uint32_t*>(edge)[tid];
-  for (int i = tid; i < nbp; i += P_THREADS) s_cnt[i] = 0;
-  __syncthreads();
-  const uint32_t lo_bin = s_E.lo_bin, hi_bin = s_E.hi_bin;
-  const int64_t tile_base = int64_t(blockIdx.x) * P_TILE;
-  const int n_valid = int(min((long long)P_TILE, (long long)(n - tile_base)));
-
-  uint32_t key[P_ITEMS], br[P_ITEMS];   // br = bucket << 16 | rank inside (tile, bucket); all ones: no sample
+  const uint32_t lo_bin = s_E->lo_bin, hi_bin = s_E->hi_bin, mult = s_E->mult;
+  uint32_t key[P_ITEMS], br[P_ITEMS];   // br = bucket << 16 | rank inside (tile, bucket)
   uint32_t ev = 0;                      // event bits of the thread's samples
   bool nonbinary = false;
-  const bool vec = n_valid == P_TILE && (reinterpret_cast<uintptr_t>(times) & 15) == 0 &&
-                   (status == nullptr || (reinterpret_cast<uintptr_t>(status) & 15) == 0);
+  if (scores != nullptr) {   // max(scores) and the NaN flag (when the histogram only sampled, it left them to this pass)
+    const uint64_t pol = make_evict_last_policy();   // the sort kernel gathers from `scores` next
+    float vmax = -INFINITY;
+    bool has_nan = false;
+#pragma unroll
+    for (int q = 0; q < P_ITEMS / 4; ++q) {
+      const int e0 = 4 * (q * P_THREADS + tid);
+      float s4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (FULL) {
+        const float4 v = ld_f32x4_hint(scores + tile_base + e0, pol);
+        s4[0] = v.x; s4[1] = v.y; s4[2] = v.z; s4[3] = v.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (e0 + k < n_valid) s4[k] = ld_f32_hint(scores + tile_base + e0 + k, pol);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        has_nan |= (s4[k] != s4[k]);
+        vmax = fmaxf(vmax, s4[k]);
+      }
+    }
+    vmax = warp_max(vmax);
+    const unsigned any_nan = __ballot_sync(0xffffffffu, has_nan);
+    if (lane == 0) {
+      atomicMax(max_enc, float_order_enc(vmax));
+      if (any_nan) atomicOr(nan_flag, 1);
+    }
+  }
   // sample (q, k) of the thread is tile element 4 * (q * P_THREADS + tid) + k
 #pragma unroll
   for (int q = 0; q < P_ITEMS / 4; ++q) {
     const int e0 = 4 * (q * P_THREADS + tid);
     float t4[4], s4[4] = {0.f, 0.f, 0.f, 0.f};
-    if (vec) {
+    if (FULL) {
       const float4 a = __ldg(reinterpret_cast<const float4*>(times + tile_base + e0));
       t4[0] = a.x; t4[1] = a.y; t4[2] = a.z; t4[3] = a.w;
       if (status != nullptr) {
@@ -324,11 +348,11 @@ __global__ void __launch_bounds__(P_THREADS, 2) fs_partition_kernel(
 #pragma unroll
   for (int j = 0; j < P_ITEMS; ++j) {
     const int e = 4 * ((j >> 2) * P_THREADS + tid) + (j & 3);
-    if (e < n_valid) {
-      const uint32_t b = __umulhi(fs_rank(key[j], lut, lo_bin, hi_bin, &s_E), mult2) >> log_s;
+    if (FULL || e < n_valid) {
+      const uint32_t b = min(__umulhi(fs_rank(key[j], lut, lo_bin, hi_bin, s_E), mult), uint32_t(nb - 1));
       br[j] = (b << 16) | atomicAdd(&s_cnt[b], 1u);
     } else {
-      br[j] = 0xffffffffu;
+      br[j] = 0xffffffffu;   // no sample
     }
   }
   if (nonbinary) atomicOr(nonbinary_flag, 1);
@@ -344,14 +368,14 @@ __global__ void __launch_bounds__(P_THREADS, 2) fs_partition_kernel(
       const int b = tid * per + k;
       const uint32_t c = s_cnt[b];
       s_start[b] = run;
+      if (c != 0u) s_delta[b] = atomicAdd(cursor + b, c) - run;   // slot in the bucket region = tile position + delta
       run += c;
-      if (c != 0u) s_gbase[b] = atomicAdd(cursor + b, c);
     }
   }
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < P_ITEMS; ++j) {
-    if (br[j] != 0xffffffffu) {
+    if (FULL || br[j] != 0xffffffffu) {
       const int e = 4 * ((j >> 2) * P_THREADS + tid) + (j & 3);
       const uint32_t b = br[j] >> 16;
       const uint32_t pos = s_start[b] + (br[j] & 0xffffu);
@@ -361,54 +385,113 @@ __global__ void __launch_bounds__(P_THREADS, 2) fs_partition_kernel(
   }
   __syncthreads();
   bool overflow = false;
-#pragma unroll 4
-  for (int i = tid; i < n_valid; i += P_THREADS) {
-    const uint2 pr = s_pairs[i];
-    const uint32_t b = s_bid[i];
-    const uint32_t dst = s_gbase[b] + (uint32_t(i) - s_start[b]);
-    if (dst < uint32_t(FS_CAP)) pairs_out[size_t(b) * FS_CAP + dst] = pr;
-    else overflow = true;
+#pragma unroll
+  for (int j = 0; j < P_ITEMS; ++j) {
+    const int i = j * P_THREADS + tid;
+    if (FULL || i < n_valid) {
+      const uint2 pr = s_pairs[i];
+      const uint32_t b = s_bid[i];
+      const uint32_t dst = uint32_t(i) + s_delta[b];
+      // (3 slots stay free: the blocked 16-byte loads of the loss / backward kernels start at base & ~3)
+      if (dst < uint32_t(FS_CAP - 3)) pairs_out[size_t(b) * FS_CAP + dst] = pr;
+      else overflow = true;
+    }
   }
   if (overflow) atomicExch(fallback, 1);
 }
 
-// ------------------------------------------------------------------------------------------ per-bucket forward
-// dynamic shared memory: s_a[B_SKEW_WORDS] | s_b[B_SKEW_WORDS] | s_cnt[4097]
-constexpr int B_DYN_SMEM = (2 * B_SKEW_WORDS + (1 << FS_LOG_S_MAX) + 8) * 4;
+__global__ void __launch_bounds__(P_THREADS, 2) fs_partition_kernel(
+    const float* __restrict__ times, const float* __restrict__ status, const float* __restrict__ scores,
+    uint32_t* __restrict__ max_enc, int32_t* __restrict__ nan_flag, int64_t n, const uint2* __restrict__ lut,
+    const FsEdge* __restrict__ edge, int nb, uint32_t* __restrict__ cursor, uint2* __restrict__ pairs_out,
+    int32_t* __restrict__ nonbinary_flag, int32_t* __restrict__ fallback) {
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  __shared__ uint32_t s_w[P_THREADS / 32];
+  __shared__ FsEdge s_E;
+  const int tid = threadIdx.x;
+  const int per = (nb + P_THREADS - 1) / P_THREADS;
+  const int nbp = per * P_THREADS;
+  uint32_t* s_cnt = s_dyn;
+  uint32_t* s_start = s_dyn + nbp;
+  uint32_t* s_delta = s_dyn + 2 * nbp;
+  uint2* s_pairs = reinterpret_cast<uint2*>(s_dyn + 3 * nbp);
+  uint16_t* s_bid = reinterpret_cast<uint16_t*>(s_dyn + 3 * nbp + 2 * P_TILE);
+  if (tid < 8) reinterpret_cast<uint32_t*>(&s_E)[tid] = reinterpret_cast<const uint32_t*>(edge)[tid];
+  for (int i = tid; i < nbp; i += P_THREADS) s_cnt[i] = 0;
+  __syncthreads();
+  const int64_t tile_base = int64_t(blockIdx.x) * P_TILE;
+  const int n_valid = int(min((long long)P_TILE, (long long)(n - tile_base)));
+  const bool full = n_valid == P_TILE && (reinterpret_cast<uintptr_t>(times) & 15) == 0 &&
+                    (status == nullptr || (reinterpret_cast<uintptr_t>(status) & 15) == 0) &&
+                    (scores == nullptr || (reinterpret_cast<uintptr_t>(scores) & 15) == 0);
+  if (full)
+    partition_tile<true>(times, status, scores, max_enc, nan_flag, tile_base, n_valid, lut, nb, per, cursor, pairs_out,
+                         nonbinary_flag, fallback, s_cnt, s_start, s_delta, s_pairs, s_bid, &s_E, s_w);
+  else
+    partition_tile<false>(times, status, scores, max_enc, nan_flag, tile_base, n_valid, lut, nb, per, cursor, pairs_out,
+                          nonbinary_flag, fallback, s_cnt, s_start, s_delta, s_pairs, s_bid, &s_E, s_w);
+}
 
-__global__ void __launch_bounds__(B_THREADS, 2) fs_bucket_forward_kernel(
-    const uint2* __restrict__ pairs, const uint32_t* __restrict__ cursor, const uint2* __restrict__ lut,
-    const FsEdge* __restrict__ edge, uint32_t mult2, int log_s, int nb, int64_t n, uint32_t* counters,
-    const float* __restrict__ scores, const float* __restrict__ status, const uint32_t* __restrict__ max_enc,
-    int32_t* nan_flag, const int32_t* __restrict__ nonbinary_flag, int32_t* __restrict__ perm_out,
-    float* __restrict__ saved_s, int32_t* max_count, int32_t* __restrict__ max_list, double* agg_val,
-    double* __restrict__ exp_prefix, double* __restrict__ wsum, double* loss_part, uint32_t* __restrict__ bucket_base,
-    uint32_t* __restrict__ bucket_cnt, float* __restrict__ loss_out, int32_t* __restrict__ flags_out, int32_t* fallback) {
+// ------------------------------------------------------------------------------------------ per-bucket sort + gather
+// Row j of a block holds the samples j * B_THREADS + tid.  f(j, ok) runs for every row of the 4-row groups that hold
+// samples: groups of full rows with ok == true as a compile-time constant (no per-sample predicate), the one partial
+// group with ok = (sample exists); empty groups are skipped by a block-uniform branch.
+template <typename F>
+__device__ __forceinline__ void for_rows(int cnt, int tid, F&& f) {
+  const int nfull = cnt / B_THREADS;
+#pragma unroll
+  for (int g = 0; g < B_ITEMS / 4; ++g) {
+    if (4 * g + 4 <= nfull) {
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) f(4 * g + jj, true);
+    } else if (4 * g * B_THREADS < cnt) {
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) f(4 * g + jj, (4 * g + jj) * B_THREADS + tid < cnt);
+    }
+  }
+}
+
+// One block per bucket.  dynamic shared memory: s_a[FS_CAP + S_PAD] | s_b[FS_CAP + S_PAD] | s_cnt[S_SUB + 1]
+constexpr int S_SUB = 1 << FS_LOG_S;   // sub-buckets of the counting sort
+constexpr int S_PAD = 160;             // >= FS_CMAX sentinel keys behind the bucket (the finish reads past sub-bucket ends)
+constexpr int S_KU = 8;                // unrolled trip count of the finish (largest sub-bucket of a typical block)
+constexpr int S_DYN_SMEM = (2 * (FS_CAP + S_PAD) + S_SUB + 8) * 4;
+static_assert(S_PAD >= FS_CMAX + 8, "sentinel padding must cover the largest accepted sub-bucket");
+
+// rank of (key, me) among the members [lo, hi) of its sub-bucket, in the total order (key, original index); kept out of
+// line: taken only for sub-buckets over S_KU samples and for tied survival times
+__device__ __noinline__ uint32_t finish_slow(const uint32_t* s_a, const uint32_t* s_b, uint32_t lo, uint32_t hi, uint32_t key,
+                                             uint32_t me) {
+  uint32_t rank = lo;
+  for (uint32_t q = lo; q < hi; ++q) {
+    const uint32_t k2 = s_a[q];
+    if (k2 < key || (k2 == key && (s_b[q] & 0x7fffffffu) < me)) ++rank;
+  }
+  return rank;
+}
+
+__global__ void __launch_bounds__(B_THREADS, 2) fs_bucket_sort_kernel(
+    const uint2* __restrict__ pairs, const uint32_t* __restrict__ cursor, int nb, const float* __restrict__ scores,
+    const uint32_t* __restrict__ max_enc, int32_t* __restrict__ perm_out, float* __restrict__ saved_s, int32_t* max_count,
+    int32_t* __restrict__ max_list, double* __restrict__ agg_val, uint32_t* __restrict__ bucket_base,
+    uint32_t* __restrict__ bucket_cnt, int32_t* fallback) {
   extern __shared__ __align__(16) uint32_t s_dyn[];
   __shared__ double s_red[B_THREADS / 32];
   __shared__ uint32_t s_w[B_THREADS / 32];
   __shared__ uint32_t s_w2[B_THREADS / 32];
-  __shared__ uint32_t s_misc[2];
-  uint32_t* s_a = s_dyn;                       // keys, then the sorted payloads (skewed)
-  uint32_t* s_b = s_dyn + B_SKEW_WORDS;        // payloads, then s~ | event << 31 (skewed)
-  uint32_t* s_cnt = s_dyn + 2 * B_SKEW_WORDS;  // sub-bucket counters / starts, one sentinel
+  __shared__ uint32_t s_misc[4];   // 0: stop flag, 1: smallest key, 2: largest key
+  uint32_t* s_a = s_dyn;                          // keys in sub-bucket order, then the sorted payloads
+  uint32_t* s_b = s_dyn + (FS_CAP + S_PAD);       // payloads in sub-bucket order
+  uint32_t* s_cnt = s_dyn + 2 * (FS_CAP + S_PAD); // sub-bucket counters / starts, one sentinel
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = B_THREADS / 32;
-  // one thread decides for the block (the flag may be raised by a running block at any time) and takes the ticket:
-  // buckets are handed out in ticket order, so every predecessor of a bucket is running or done
-  if (tid == 0) {
-    const bool stop = *reinterpret_cast<volatile int32_t*>(fallback) != 0;   // the pipeline already gave up
-    s_misc[1] = stop ? 1u : 0u;
-    if (!stop) s_misc[0] = atomicAdd(counters + 1, 1u);
+  const int b = blockIdx.x;
+  if (tid == 0) {   // one thread decides for the block: the flag may be raised by a running block at any time
+    s_misc[0] = (*reinterpret_cast<volatile int32_t*>(fallback) != 0) ? 1u : 0u;
+    s_misc[1] = 0xffffffffu;
+    s_misc[2] = 0u;
   }
-  __shared__ FsEdge s_E;
-  if (tid < 8) reinterpret_cast<uint32_t*>(&s_E)[tid] = reinterpret_cast<const uint32_t*>(edge)[tid];
-  const int S = 1 << log_s;
-  for (int i = tid; i <= S; i += B_THREADS) s_cnt[i] = 0;
-  __syncthreads();
-  if (s_misc[1] != 0u) return;
-  const uint32_t lo_bin = s_E.lo_bin, hi_bin = s_E.hi_bin;
-  const int b = int(s_misc[0]);
+  for (int i = tid; i <= S_SUB; i += B_THREADS) s_cnt[i] = 0;
   const int cnt = int(min(__ldg(cursor + b), uint32_t(FS_CAP)));
   uint32_t base;
   {
@@ -416,211 +499,267 @@ __global__ void __launch_bounds__(B_THREADS, 2) fs_bucket_forward_kernel(
     for (int q = tid; q < b; q += B_THREADS) part += min(__ldg(cursor + q), uint32_t(FS_CAP));
     part = __reduce_add_sync(0xffffffffu, part);
     if (lane == 0) s_w[warp] = part;
-    __syncthreads();
-    base = 0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) base += s_w[w];
   }
-
-  // ---- counting sort over the sub-buckets of the rank estimate
+  // ---- load the bucket, its smallest and largest key
   uint32_t key[B_ITEMS], val[B_ITEMS], dr[B_ITEMS];   // dr = sub-bucket << 16 | arrival rank inside it
   const uint2* src = pairs + size_t(b) * FS_CAP;
-#pragma unroll
-  for (int j = 0; j < B_ITEMS; ++j) {
-    const int i = j * B_THREADS + tid;
-    const uint2 pr = (i < cnt) ? __ldg(src + i) : make_uint2(0xffffffffu, 0xffffffffu);
+  uint32_t kmin = 0xffffffffu, kmax = 0u;
+  for_rows(cnt, tid, [&](int j, bool ok) {
+    const uint2 pr = ok ? __ldg(src + j * B_THREADS + tid) : make_uint2(0xffffffffu, 0u);
     key[j] = pr.x;
     val[j] = pr.y;
+    kmin = min(kmin, pr.x);
+    if (ok) kmax = max(kmax, pr.x);
+  });
+  kmin = __reduce_min_sync(0xffffffffu, kmin);
+  kmax = __reduce_max_sync(0xffffffffu, kmax);
+  __syncthreads();   // s_misc initialised, s_cnt cleared, s_w written
+  if (s_misc[0] != 0u) return;   // the pipeline already gave up
+  if (lane == 0) {
+    atomicMin(&s_misc[1], kmin);
+    atomicMax(&s_misc[2], kmax);
   }
+  base = 0;
 #pragma unroll
-  for (int j = 0; j < B_ITEMS; ++j) {
-    const int i = j * B_THREADS + tid;
-    if (i < cnt) {
-      const uint32_t d = __umulhi(fs_rank(key[j], lut, lo_bin, hi_bin, &s_E), mult2) & uint32_t(S - 1);
-      dr[j] = (d << 16) | atomicAdd(&s_cnt[d], 1u);
-    } else {
-      dr[j] = 0xffffffffu;
-    }
-  }
+  for (int w = 0; w < NW; ++w) base += s_w[w];
   __syncthreads();
-  uint32_t kmax;   // largest sub-bucket of the block
+  kmin = s_misc[1];
+  // sub-bucket = floor(S_SUB * (key - kmin) / (range + 1)): monotone in the key; keys of a bucket are near-uniform
+  const uint32_t range = s_misc[2] - kmin;
+  const uint64_t sc64 = (uint64_t(S_SUB) << 32) / (uint64_t(range) + 1u);
+  const uint32_t scale = sc64 > 0xffffffffull ? 0xffffffffu : uint32_t(sc64);
+  for_rows(cnt, tid, [&](int j, bool ok) {
+    if (ok) {
+      const uint32_t d = __umulhi(key[j] - kmin, scale);
+      dr[j] = (d << 16) | atomicAdd(&s_cnt[d], 1u);
+    }
+  });
+  if (tid < S_PAD) s_a[cnt + tid] = 0xffffffffu;   // sentinels: larger than every key of the bucket
+  __syncthreads();
+  uint32_t cmax;   // largest sub-bucket of the block
   {
-    const int per = (S + B_THREADS - 1) / B_THREADS;
-    uint32_t sum = 0, big = 0;
-    for (int k = 0; k < per; ++k) {
-      const int d = tid * per + k;
-      const uint32_t c = (d < S) ? s_cnt[d] : 0u;
-      sum += c;
-      big = max(big, c);
+    constexpr int PER = S_SUB / B_THREADS;
+    uint32_t c[PER], sum = 0, big = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      c[k] = s_cnt[tid * PER + k];
+      sum += c[k];
+      big = max(big, c[k]);
     }
     big = __reduce_max_sync(0xffffffffu, big);
     if (lane == 0) s_w2[warp] = big;
     const uint2 sc = block_scan_u32<NW>(sum, s_w, lane, warp);   // (its barriers also publish s_w2)
     uint32_t run = sc.x - sum;
-    for (int k = 0; k < per; ++k) {
-      const int d = tid * per + k;
-      if (d < S) {
-        const uint32_t c = s_cnt[d];
-        s_cnt[d] = run;
-        run += c;
-      }
-    }
-    if (tid == 0) s_cnt[S] = uint32_t(cnt);
-    kmax = 0;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) kmax = max(kmax, s_w2[w]);
-    // heavy ties / a density jump inside a bin: the finish below would be quadratic.  Give the whole input up (the LSD
-    // pipeline redoes it) - but publish, so that successors waiting on this bucket's sum are released.
-    if (kmax > uint32_t(FS_CMAX)) {
-      if (tid == 0) {
-        atomicExch(fallback, 1);
-        st_relaxed_f64(agg_val + b, -0.0);
-      }
+    for (int k = 0; k < PER; ++k) {
+      s_cnt[tid * PER + k] = run;
+      run += c[k];
+    }
+    if (tid == 0) s_cnt[S_SUB] = uint32_t(cnt);
+    cmax = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) cmax = max(cmax, s_w2[w]);
+    // heavy ties / a density jump inside the bucket: the finish below would be quadratic.  Give the whole input up:
+    // the LSD pipeline redoes it.
+    if (cmax > uint32_t(FS_CMAX)) {
+      if (tid == 0) atomicExch(fallback, 1);
       return;
     }
   }
   __syncthreads();
-#pragma unroll
-  for (int j = 0; j < B_ITEMS; ++j) {
-    if (dr[j] != 0xffffffffu) {
-      const uint32_t pos = s_cnt[dr[j] >> 16] + (dr[j] & 0xffffu);
+  for_rows(cnt, tid, [&](int j, bool ok) {
+    if (ok) {
+      const uint32_t lo = s_cnt[dr[j] >> 16];
+      const uint32_t pos = lo + (dr[j] & 0xffffu);
       s_a[pos] = key[j];
       s_b[pos] = val[j];
+      dr[j] = lo | (dr[j] & 0xffff0000u);   // sub-bucket << 16 | its first slot (< 8192)
     }
-  }
+  });
   __syncthreads();
-  // ---- final rank = sub-bucket start + members that precede in the total order (key, index).  The trip count is the
-  // block's largest sub-bucket (~8 at 1.25 samples per sub-bucket), the 16 samples of a thread advance together.
-  // Per sample: dr = sub-bucket << 16 | arrival rank << 8 | members found to precede; lohi = start | end << 13.
-  {
-    uint32_t lohi[B_ITEMS];
+  // ---- final rank = first slot of the sub-bucket + members that precede in the total order (key, index).  Slots behind
+  // the sub-bucket hold larger keys (sub-buckets are ordered, the bucket ends in sentinels), so S_KU slots are compared
+  // unconditionally; equal keys (counted on the way: the sample itself is one) order by original index - the stable
+  // order, whatever order the atomics produced.
+  for_rows(cnt, tid, [&](int j, bool ok) {
+    if (ok) {
+      const uint32_t lo = dr[j] & 0xffffu;
+      const uint32_t* row = s_a + lo;
+      uint32_t k2[S_KU];
 #pragma unroll
-    for (int j = 0; j < B_ITEMS; ++j) {
-      const bool ok = dr[j] != 0xffffffffu;
-      const uint32_t d = ok ? (dr[j] >> 16) : 0u;
-      const uint32_t lo = s_cnt[d], hi = s_cnt[d + 1];
-      lohi[j] = ok ? (lo | (hi << 13)) : 0u;                         // no sample: empty range
-      dr[j] = ok ? ((d << 16) | ((dr[j] & 0xffffu) << 8)) : 0u;      // arrival rank < FS_CMAX = 128
-    }
-    for (uint32_t k = 0; k < kmax; ++k) {
+      for (int k = 0; k < S_KU; ++k) k2[k] = row[k];
+      uint32_t rank = lo, same = 0;
 #pragma unroll
-      for (int j = 0; j < B_ITEMS; ++j) {
-        const uint32_t q = (lohi[j] & 0x1fffu) + k;
-        const bool act = q < (lohi[j] >> 13);
-        const uint32_t k2 = s_a[act ? q : 0u];
-        if (act && k2 <= key[j]) {
-          if (k2 < key[j]) {
-            ++dr[j];
-          } else {   // equal keys: ascending original index (the stable order)
-            const uint32_t mine = s_b[(lohi[j] & 0x1fffu) + ((dr[j] >> 8) & 0xffu)];
-            if ((s_b[q] & 0x7fffffffu) < (mine & 0x7fffffffu)) ++dr[j];
-          }
-        }
+      for (int k = 0; k < S_KU; ++k) {
+        rank += (k2[k] < key[j]) ? 1u : 0u;
+        same += (k2[k] == key[j]) ? 1u : 0u;
       }
+      // a sub-bucket over S_KU samples, or tied survival times (rare): compare (key, index) with every member
+      if (cmax > uint32_t(S_KU) || same > 1u) {
+        const uint32_t hi = s_cnt[(dr[j] >> 16) + 1];
+        if (hi - lo > uint32_t(S_KU) || same > 1u) rank = finish_slow(s_a, s_b, lo, hi, key[j], val[j] & 0x7fffffffu);
+      }
+      dr[j] = rank;
     }
-    // final position and payload (re-read from the sub-bucket order; s_b is not overwritten before the next barrier)
-#pragma unroll
-    for (int j = 0; j < B_ITEMS; ++j) {
-      const bool ok = (lohi[j] >> 13) != 0u;
-      const uint32_t lo = lohi[j] & 0x1fffu;
-      val[j] = ok ? s_b[lo + ((dr[j] >> 8) & 0xffu)] : 0u;
-      dr[j] = ok ? (lo + (dr[j] & 0xffu)) : 0xffffffffu;
-    }
-  }
+  });
   __syncthreads();
-#pragma unroll
-  for (int j = 0; j < B_ITEMS; ++j)
-    if (dr[j] != 0xffffffffu) s_a[skew(int(dr[j]))] = val[j];
+  for_rows(cnt, tid, [&](int j, bool ok) {
+    if (ok) s_a[dr[j]] = val[j];
+  });
   __syncthreads();
 
   if (scores == nullptr) {   // mmbs_risk_order: the permutation only
-#pragma unroll
-    for (int j = 0; j < B_ITEMS; ++j) {
-      const int i = j * B_THREADS + tid;
-      if (i < cnt) perm_out[base + i] = int32_t(s_a[skew(i)]);
-    }
+    for_rows(cnt, tid, [&](int j, bool ok) {
+      if (ok) perm_out[base + j * B_THREADS + tid] = int32_t(s_a[j * B_THREADS + tid]);
+    });
     return;
   }
-
-  // ---- gather s~ = scores[index] - max through the sorted payloads (scores L2-resident: evict_last since the histogram)
+  // ---- gather s~ = scores[index] - max through the sorted payloads (scores L2-resident: evict_last since the histogram);
+  // saved_s keeps |s~| with the event bit in the sign position (s~ <= 0 always)
   const float smax = float_order_dec(__ldg(max_enc));
   const uint64_t pol = make_evict_last_policy();
-  {
-    uint32_t v[B_ITEMS];
-    float st[B_ITEMS];
-#pragma unroll
-    for (int j = 0; j < B_ITEMS; ++j) {
-      const int i = j * B_THREADS + tid;
-      v[j] = (i < cnt) ? s_a[skew(i)] : 0u;
-    }
-#pragma unroll
-    for (int j = 0; j < B_ITEMS; ++j) {
-      const int i = j * B_THREADS + tid;
-      st[j] = (i < cnt) ? ld_f32_hint(scores + (v[j] & 0x7fffffffu), pol) : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < B_ITEMS; ++j) {
-      const int i = j * B_THREADS + tid;
-      uint32_t enc = 0x7f800000u;   // no sample: s~ = -inf, no event
-      if (i < cnt) {
-        const float s = st[j] - smax;
-        perm_out[base + i] = int32_t(v[j]);
-        saved_s[base + i] = s;
-        enc = (__float_as_uint(s) & 0x7fffffffu) | (v[j] & 0x80000000u);
-        if (s == 0.f) {   // an argmax position (gradient through max(scores) in the backward pass)
-          const int pos = atomicAdd(max_count, 1);
-          if (pos < FS_MAX_LIST) max_list[pos] = int32_t(v[j] & 0x7fffffffu);
-        }
+  float esum = 0.f;
+  int32_t* po = perm_out + base + tid;
+  uint32_t* so = reinterpret_cast<uint32_t*>(saved_s) + base + tid;
+  for_rows(cnt, tid, [&](int j, bool ok) {   // (val / key are dead: their registers carry the gather)
+    val[j] = ok ? s_a[j * B_THREADS + tid] : 0u;
+  });
+  for_rows(cnt, tid, [&](int j, bool ok) {
+    key[j] = ok ? __float_as_uint(ld_f32_hint(scores + (val[j] & 0x7fffffffu), pol)) : 0u;
+  });
+  for_rows(cnt, tid, [&](int j, bool ok) {
+    if (ok) {
+      const float sv = __uint_as_float(key[j]) - smax;
+      po[j * B_THREADS] = int32_t(val[j]);
+      so[j * B_THREADS] = (__float_as_uint(sv) & 0x7fffffffu) | (val[j] & 0x80000000u);
+      esum += fs_exp(sv);
+      if (sv == 0.f) {   // an argmax position (gradient through max(scores) in the backward pass)
+        const int pos = atomicAdd(max_count, 1);
+        if (pos < FS_MAX_LIST) max_list[pos] = int32_t(val[j] & 0x7fffffffu);
       }
-      s_b[skew(i)] = enc;
     }
+  });
+  const double tot = block_sum_f64<NW>(double(esum), s_red, lane, warp);
+  if (tid == 0) {
+    agg_val[b] = tot;
+    bucket_base[b] = base;
+    bucket_cnt[b] = uint32_t(cnt);
   }
-  __syncthreads();
+}
 
-  // ---- blocked arrangement: thread t owns sorted positions 16 t .. 16 t + 15
-  float st[B_ITEMS], c[B_ITEMS];
-  uint32_t evm = 0;
-  float run = 0.f;
+// ------------------------------------------------------------------------------------------ per-bucket loss / gradient
+// Both kernels read their bucket in the BLOCKED arrangement straight from global memory: thread t owns 16 consecutive
+// sorted positions, fetched as four 16-byte loads from the 16-byte aligned address below the bucket's first position
+// (positions in front of the bucket / behind it are masked).  No shared-memory staging.  (1024 threads x 8 samples,
+// one block per SM, measured slower: 97 / 186 us against 55 / 141 us - a lone block stalls the SM at every barrier.)
+constexpr int L_THREADS = 512;
+constexpr int L_ITEMS = FS_CAP / L_THREADS;   // 16
+static_assert(L_ITEMS % 4 == 0, "blocked 16-byte loads");
+struct BucketSlice {
+  uint32_t a0;     // first position covered by the block: bucket base rounded down to a multiple of 4
+  int lead;        // masked positions in front of the bucket (0..3)
+  int end;         // lead + samples of the bucket: thread-local positions [lead, end) are real
+};
+__device__ __forceinline__ BucketSlice bucket_slice(const uint32_t* __restrict__ bucket_base,
+                                                    const uint32_t* __restrict__ bucket_cnt, int b) {
+  const uint32_t base = __ldg(bucket_base + b);
+  BucketSlice s;
+  s.a0 = base & ~3u;
+  s.lead = int(base - s.a0);
+  s.end = s.lead + int(__ldg(bucket_cnt + b));
+  return s;
+}
+// L_ITEMS consecutive words of the thread (zeros where no 16-byte group of the bucket lies)
+__device__ __forceinline__ void load_items(const uint32_t* __restrict__ p, int first, int end, uint32_t (&v)[L_ITEMS]) {
 #pragma unroll
-  for (int j = 0; j < B_ITEMS; ++j) {
-    const uint32_t enc = s_b[tid * 17 + j];
-    st[j] = __uint_as_float(enc | 0x80000000u);   // s~ <= 0
-    evm |= (enc >> 31) << j;
-    run += fs_exp(st[j]);                         // exp(-inf) = 0 beyond the bucket
-    c[j] = run;
+  for (int q = 0; q < L_ITEMS / 4; ++q) {
+    uint4 x = make_uint4(0u, 0u, 0u, 0u);
+    if (first + 4 * q < end) x = __ldg(reinterpret_cast<const uint4*>(p + first + 4 * q));
+    v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
   }
+}
+
+// A thread is INTERIOR when all L_ITEMS of its positions are samples of the bucket (every thread but the one or two at the
+// bucket's ends and the idle ones behind it): its loops carry no per-sample predicate.  `sel(ok_true_type, f)` style:
+// f(j, ok) is instantiated once with ok == true as a constant and once with the real test.
+template <typename F>
+__device__ __forceinline__ void for_items(bool interior, int first, int lead, int end, F&& f) {
+  if (interior) {
+#pragma unroll
+    for (int j = 0; j < L_ITEMS; ++j) f(j, true);
+  } else if (first < end) {
+#pragma unroll
+    for (int j = 0; j < L_ITEMS; ++j) f(j, first + j >= lead && first + j < end);
+  }
+}
+template <typename F>
+__device__ __forceinline__ void for_items_rev(bool interior, int first, int lead, int end, F&& f) {
+  if (interior) {
+#pragma unroll
+    for (int j = L_ITEMS - 1; j >= 0; --j) f(j, true);
+  } else if (first < end) {
+#pragma unroll
+    for (int j = L_ITEMS - 1; j >= 0; --j) f(j, first + j >= lead && first + j < end);
+  }
+}
+
+__global__ void __launch_bounds__(L_THREADS, 2) fs_bucket_loss_kernel(
+    const float* __restrict__ saved_s, const int32_t* __restrict__ perm, const float* __restrict__ status, int nb, int64_t n,
+    const uint32_t* __restrict__ bucket_base, const uint32_t* __restrict__ bucket_cnt, const double* __restrict__ agg_val,
+    double* __restrict__ exp_prefix, double* __restrict__ wsum, double* loss_part, uint32_t* counters, int32_t* nan_flag,
+    const int32_t* __restrict__ nonbinary_flag, float* __restrict__ loss_out, int32_t* __restrict__ flags_out,
+    const int32_t* __restrict__ fallback) {
+  __shared__ double s_red[L_THREADS / 32];
+  __shared__ uint32_t s_last;
+  constexpr int NW = L_THREADS / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (*fallback != 0) return;   // final by now: the kernels that raise it have finished
+  const int b = blockIdx.x;
+  const BucketSlice sl = bucket_slice(bucket_base, bucket_cnt, b);
+  double pre = 0.0;
+  for (int q = tid; q < b; q += L_THREADS) pre += __ldg(agg_val + q);
+  const int first = tid * L_ITEMS;
+  const bool interior = first >= sl.lead && first + L_ITEMS <= sl.end;
+  uint32_t enc[L_ITEMS];
+  load_items(reinterpret_cast<const uint32_t*>(saved_s) + sl.a0, first, sl.end, enc);
+  const double P = block_sum_f64<NW>(pre, s_red, lane, warp);   // sum of exp(s~) over all earlier buckets
+  float c[L_ITEMS];
+  float run = 0.f;
+  for_items(interior, first, sl.lead, sl.end, [&](int j, bool ok) {
+    run += ok ? fs_exp(__uint_as_float(enc[j] | 0x80000000u)) : 0.f;   // s~ = -|s~|
+    c[j] = run;
+  });
   double total;
   const double incl = block_scan_f64<NW, false>(double(run), s_red, lane, warp, &total);
-  const double off_in = incl - double(run);
-  // publish the bucket's sum, then fetch the sum over all earlier buckets (every one of them holds an earlier ticket).
-  // One 8-byte word is value and flag at once: the workspace is zeroed, a published sum is never +0.0 (an empty sum is
-  // stored as -0.0), so there is nothing to order and no fence / cache invalidation on the spinning side.
-  if (tid == 0) st_relaxed_f64(agg_val + b, total == 0.0 ? -0.0 : total);
-  double pre = 0.0;
-  for (int q = tid; q < b; q += B_THREADS) {
-    unsigned long long bits;
-    while ((bits = ld_relaxed_u64(reinterpret_cast<const unsigned long long*>(agg_val + q))) == 0ull) __nanosleep(40);
-    pre += __longlong_as_double((long long)bits);
-  }
-  const double P = block_sum_f64<NW>(pre, s_red, lane, warp);
-  const double off = P + off_in;
+  const double off = P + (incl - double(run));
   // C = off + c[j], rounded to fp32 once: off as a (hi, lo) float pair (2 FADD per sample instead of fp64 converts)
   const float off_hi = float(off), off_lo = float(off - double(off_hi));
-
-  const bool gather_status = (*nonbinary_flag != 0);
   float lsum = 0.f, ws = 0.f;
   bool bad = false;
+  if (*nonbinary_flag == 0) {
+    for_items(interior, first, sl.lead, sl.end, [&](int j, bool ok) {
+      if (ok && (enc[j] >> 31)) {
+        const float den = ((off_hi + c[j]) + off_lo) + FS_EPS;                        // cumsum + eps (models.py:104)
+        const float term = fs_log(den) - __uint_as_float(enc[j] | 0x80000000u);       // -(s~ - log(.)) (models.py:104-105)
+        lsum += term;
+        ws += __fdividef(1.f, den);
+        bad |= (term != term);
+      }
+    });
+  } else if (first < sl.end) {   // general status weights: gathered through the permutation
+    uint32_t pv[L_ITEMS];
+    load_items(reinterpret_cast<const uint32_t*>(perm) + sl.a0, first, sl.end, pv);
 #pragma unroll
-  for (int j = 0; j < B_ITEMS; ++j) {
-    const int p = tid * B_ITEMS + j;
-    if (p < cnt) {
-      float dl = float((evm >> j) & 1u);
-      if (gather_status) dl = __ldg(status + (s_a[tid * 17 + j] & 0x7fffffffu));
-      const float den = ((off_hi + c[j]) + off_lo) + FS_EPS;   // cumsum + eps (models.py:104)
-      const float term = -(st[j] - fs_log(den)) * dl;          // models.py:104-105
-      lsum += term;
-      ws += __fdividef(dl, den);
-      bad |= (term != term);
+    for (int j = 0; j < L_ITEMS; ++j) {
+      const bool ok = first + j >= sl.lead && first + j < sl.end;
+      if (ok) {
+        const float dl = __ldg(status + (pv[j] & 0x7fffffffu));
+        const float den = ((off_hi + c[j]) + off_lo) + FS_EPS;
+        const float term = -(__uint_as_float(enc[j] | 0x80000000u) - fs_log(den)) * dl;
+        lsum += term;
+        ws += __fdividef(dl, den);
+        bad |= (term != term);
+      }
     }
   }
   const unsigned any_bad = __ballot_sync(0xffffffffu, bad);
@@ -631,125 +770,135 @@ __global__ void __launch_bounds__(B_THREADS, 2) fs_bucket_forward_kernel(
     exp_prefix[b] = P;
     wsum[b] = tw;
     loss_part[b] = tl;
-    bucket_base[b] = base;
-    bucket_cnt[b] = uint32_t(cnt);
     __threadfence();
-    s_misc[0] = (atomicAdd(counters + 2, 1u) == uint32_t(nb) - 1u) ? 1u : 0u;
+    s_last = (atomicAdd(counters + 2, 1u) == uint32_t(nb) - 1u) ? 1u : 0u;
   }
   __syncthreads();
-  if (s_misc[0] == 0u) return;
+  if (s_last == 0u) return;
   // the last block: loss = sum of the bucket partials / n   (.mean() over N, models.py:111)
   __threadfence();
   double t = 0.0;
-  for (int q = tid; q < nb; q += B_THREADS) t += ld_volatile_f64(loss_part + q);
+  for (int q = tid; q < nb; q += L_THREADS) t += ld_volatile_f64(loss_part + q);
   t = block_sum_f64<NW>(t, s_red, lane, warp);
   if (tid == 0) {
     const int f = *reinterpret_cast<const volatile int32_t*>(nan_flag);
-    if (*reinterpret_cast<volatile int32_t*>(fallback) == 0) {   // otherwise the LSD pipeline writes the result
-      loss_out[0] = f ? __int_as_float(0x7fc00000) : float(t / double(n));
-      if (flags_out) flags_out[0] = f;
-    }
+    loss_out[0] = f ? __int_as_float(0x7fc00000) : float(t / double(n));
+    if (flags_out) flags_out[0] = f;
   }
 }
 
-// ------------------------------------------------------------------------------------------ per-bucket backward
-constexpr int G_DYN_SMEM = 2 * B_SKEW_WORDS * 4;
-
-__global__ void __launch_bounds__(B_THREADS, 2) fs_bucket_backward_kernel(
-    const int32_t* __restrict__ perm, const float* __restrict__ saved_s, const float* __restrict__ status,
-    const float* __restrict__ grad_loss, int64_t n, int nb, const uint32_t* __restrict__ bucket_base,
-    const uint32_t* __restrict__ bucket_cnt, const double* __restrict__ exp_prefix, const double* __restrict__ wsum,
-    double* gsum_part, uint32_t* counters, const int32_t* __restrict__ nonbinary_flag, const int32_t* __restrict__ max_count,
-    const int32_t* __restrict__ max_list, double* __restrict__ gsum_total, float* grad_scores,
-    const int32_t* __restrict__ fallback) {
-  extern __shared__ __align__(16) uint32_t s_dyn[];
-  __shared__ double s_red[B_THREADS / 32];
-  __shared__ uint32_t s_misc[2];
-  uint32_t* s_v = s_dyn;                   // perm words (skewed)
-  uint32_t* s_s = s_dyn + B_SKEW_WORDS;    // s~ bits (skewed)
-  constexpr int NW = B_THREADS / 32;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (*fallback != 0) return;
-  const int b = blockIdx.x;
-  const uint32_t base = __ldg(bucket_base + b);
-  const int cnt = int(__ldg(bucket_cnt + b));
-  const double P = __ldg(exp_prefix + b);
-  double later = 0.0;
-  for (int q = b + 1 + tid; q < nb; q += B_THREADS) later += __ldg(wsum + q);
-#pragma unroll
-  for (int j = 0; j < B_ITEMS; ++j) {
-    const int i = j * B_THREADS + tid;
-    uint32_t v = 0u, sb = 0xff800000u;   // no sample: s~ = -inf
-    if (i < cnt) {
-      v = uint32_t(__ldg(perm + base + i));
-      sb = __float_as_uint(__ldg(saved_s + base + i));
-    }
-    s_v[skew(i)] = v;
-    s_s[skew(i)] = sb;
-  }
-  const double S_later = block_sum_f64<NW>(later, s_red, lane, warp);   // (its barriers also publish s_v / s_s)
-  const bool gather_status = (*nonbinary_flag != 0);
-  const float scale = float(double(grad_loss[0]) / double(n));
-  float e[B_ITEMS], cw[B_ITEMS];
+// the per-sample part of the backward pass; GATHER: general (non-binary) status weights, read through the permutation
+template <bool GATHER>
+__device__ __forceinline__ double bucket_backward_body(const BucketSlice sl, const int32_t* __restrict__ perm,
+                                                       const float* __restrict__ saved_s, const float* __restrict__ status,
+                                                       double P, double S_later, float scale, float* grad_scores,
+                                                       double* s_red, int tid, int lane, int warp) {
+  constexpr int NW = L_THREADS / 32;
+  const int first = tid * L_ITEMS;
+  const bool interior = first >= sl.lead && first + L_ITEMS <= sl.end;
+  float e[L_ITEMS], cw[L_ITEMS], dl[GATHER ? L_ITEMS : 1];
   uint32_t evm = 0;
   float run = 0.f;
 #pragma unroll
-  for (int j = 0; j < B_ITEMS; ++j) {
-    evm |= (s_v[tid * 17 + j] >> 31) << j;
-    e[j] = fs_exp(__uint_as_float(s_s[tid * 17 + j]));
-    run += e[j];
-    cw[j] = run;
+  for (int j = 0; j < L_ITEMS; ++j) e[j] = cw[j] = 0.f;
+  {
+    uint32_t enc[L_ITEMS];
+    load_items(reinterpret_cast<const uint32_t*>(saved_s) + sl.a0, first, sl.end, enc);
+    for_items(interior, first, sl.lead, sl.end, [&](int j, bool ok) {
+      e[j] = ok ? fs_exp(__uint_as_float(enc[j] | 0x80000000u)) : 0.f;   // s~ = -|s~|; no sample: 0
+      evm |= (ok ? (enc[j] >> 31) : 0u) << j;
+      run += e[j];
+      cw[j] = run;
+    });
+  }
+  if (GATHER) {
+    uint32_t pv[L_ITEMS];
+    load_items(reinterpret_cast<const uint32_t*>(perm) + sl.a0, first, sl.end, pv);
+#pragma unroll
+    for (int j = 0; j < L_ITEMS; ++j) {
+      const bool ok = first + j >= sl.lead && first + j < sl.end;
+      dl[GATHER ? j : 0] = ok ? __ldg(status + (pv[j] & 0x7fffffffu)) : 0.f;
+    }
   }
   double total;
   const double incl = block_scan_f64<NW, false>(double(run), s_red, lane, warp, &total);
   const double off = P + (incl - double(run));
   const float off_hi = float(off), off_lo = float(off - double(off_hi));   // the same C as the forward pass
   float wrun = 0.f;
-#pragma unroll
-  for (int j = B_ITEMS - 1; j >= 0; --j) {
-    float w = 0.f;
-    if (tid * B_ITEMS + j < cnt) {
-      float dl = float((evm >> j) & 1u);
-      if (gather_status) dl = __ldg(status + (s_v[tid * 17 + j] & 0x7fffffffu));
-      w = __fdividef(dl, ((off_hi + cw[j]) + off_lo) + FS_EPS);
-    }
+  for_items_rev(interior, first, sl.lead, sl.end, [&](int j, bool ok) {
+    const float den = ((off_hi + cw[j]) + off_lo) + FS_EPS;
+    float w;
+    if (GATHER) w = __fdividef(dl[GATHER ? j : 0], den);            // 0 where there is no sample
+    else w = ((evm >> j) & 1u) ? __fdividef(1.f, den) : 0.f;
     wrun += w;
     cw[j] = wrun;   // inclusive suffix of w inside the thread
-  }
+  });
   const double sincl = block_scan_f64<NW, true>(double(wrun), s_red, lane, warp, &total);
   const double soff = S_later + (sincl - double(wrun));
   const float soff_hi = float(soff), soff_lo = float(soff - double(soff_hi));
+  uint32_t pv[L_ITEMS];
+  load_items(reinterpret_cast<const uint32_t*>(perm) + sl.a0, first, sl.end, pv);
   float gs = 0.f;
-#pragma unroll
-  for (int j = 0; j < B_ITEMS; ++j) {
-    if (tid * B_ITEMS + j < cnt) {
-      const uint32_t idx = s_v[tid * 17 + j] & 0x7fffffffu;
-      float dl = float((evm >> j) & 1u);
-      if (gather_status) dl = __ldg(status + idx);
+  for_items(interior, first, sl.lead, sl.end, [&](int j, bool ok) {
+    if (ok) {
+      const float d = GATHER ? dl[GATHER ? j : 0] : float((evm >> j) & 1u);
       const float W = (soff_hi + cw[j]) + soff_lo;   // sum of w over this and all later positions
-      const float g = -(dl - e[j] * W) * scale;
-      grad_scores[idx] = g;                          // un-permute
+      const float g = -(d - e[j] * W) * scale;
+      grad_scores[pv[j] & 0x7fffffffu] = g;          // un-permute
       gs += g;
     }
-  }
-  const double tg = block_sum_f64<NW>(double(gs), s_red, lane, warp);
+  });
+  return block_sum_f64<NW>(double(gs), s_red, lane, warp);
+}
+
+__device__ __noinline__ double bucket_backward_gather(const BucketSlice sl, const int32_t* __restrict__ perm,
+                                                      const float* __restrict__ saved_s, const float* __restrict__ status,
+                                                      double P, double S_later, float scale, float* grad_scores,
+                                                      double* s_red, int tid, int lane, int warp) {
+  return bucket_backward_body<true>(sl, perm, saved_s, status, P, S_later, scale, grad_scores, s_red, tid, lane, warp);
+}
+
+__global__ void __launch_bounds__(L_THREADS, 2) fs_bucket_backward_kernel(
+    const int32_t* __restrict__ perm, const float* __restrict__ saved_s, const float* __restrict__ status,
+    const float* __restrict__ grad_loss, int64_t n, int nb, const uint32_t* __restrict__ bucket_base,
+    const uint32_t* __restrict__ bucket_cnt, const double* __restrict__ exp_prefix, const double* __restrict__ wsum,
+    double* gsum_part, uint32_t* counters, const int32_t* __restrict__ nonbinary_flag, const int32_t* __restrict__ max_count,
+    const int32_t* __restrict__ max_list, double* __restrict__ gsum_total, float* grad_scores,
+    const int32_t* __restrict__ fallback) {
+  __shared__ double s_red[L_THREADS / 32];
+  __shared__ uint32_t s_last;
+  constexpr int NW = L_THREADS / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (*fallback != 0) return;
+  const int b = blockIdx.x;
+  const BucketSlice sl = bucket_slice(bucket_base, bucket_cnt, b);
+  const double P = __ldg(exp_prefix + b);
+  double later = 0.0;
+  for (int q = b + 1 + tid; q < nb; q += L_THREADS) later += __ldg(wsum + q);
+  const double S_later = block_sum_f64<NW>(later, s_red, lane, warp);   // sum of w over all later buckets
+  const float scale = float(double(grad_loss[0]) / double(n));
+  double tg;
+  if (*nonbinary_flag != 0)   // (rare, and out of line: its extra live array must not cost the common path registers)
+    tg = bucket_backward_gather(sl, perm, saved_s, status, P, S_later, scale, grad_scores, s_red, tid, lane, warp);
+  else
+    tg = bucket_backward_body<false>(sl, perm, saved_s, status, P, S_later, scale, grad_scores, s_red, tid, lane, warp);
   if (tid == 0) {
     gsum_part[b] = tg;
     __threadfence();
-    s_misc[0] = (atomicAdd(counters + 3, 1u) == uint32_t(nb) - 1u) ? 1u : 0u;
+    s_last = (atomicAdd(counters + 3, 1u) == uint32_t(nb) - 1u) ? 1u : 0u;
   }
   __syncthreads();
-  if (s_misc[0] == 0u) return;
+  if (s_last == 0u) return;
   // the last block: gradient through "- max(scores)": every argmax position receives -(sum_k g~_k) / count
   __threadfence();
   double t = 0.0;
-  for (int q = tid; q < nb; q += B_THREADS) t += ld_volatile_f64(gsum_part + q);
+  for (int q = tid; q < nb; q += L_THREADS) t += ld_volatile_f64(gsum_part + q);
   t = block_sum_f64<NW>(t, s_red, lane, warp);
   if (tid == 0) gsum_total[0] = t;
   const int mc = *max_count;
   if (mc <= FS_MAX_LIST) {
     const float fix = float(t / double(mc));
-    for (int i = tid; i < mc; i += B_THREADS) {
+    for (int i = tid; i < mc; i += L_THREADS) {
       float* p = grad_scores + max_list[i];
       *reinterpret_cast<volatile float*>(p) = *reinterpret_cast<volatile float*>(p) - fix;
     }
@@ -758,13 +907,30 @@ __global__ void __launch_bounds__(B_THREADS, 2) fs_bucket_backward_kernel(
 }
 
 // ------------------------------------------------------------------------------------------ host side
+int fs_sample_shift(int64_t n) {
+  static const int forced = []() {
+    const char* e = getenv("MMBS_COX_HIST_SAMPLE");
+    return (e && e[0] >= '0' && e[0] <= '5') ? int(e[0] - '0') : -1;
+  }();
+  if (forced >= 0) return forced;
+  return n >= (int64_t(1) << 21) ? 3 : 0;   // >= 2 M samples: one chunk in 8 (>= 256 K samples counted)
+}
+
+int fs_target() {
+  static const int t = []() {
+    const char* e = getenv("MMBS_COX_TARGET");
+    const int v = e ? atoi(e) : 0;
+    return (v >= 1024 && v <= FS_TARGET) ? v : FS_TARGET;   // never above FS_TARGET: FS_MAX_N assumes it
+  }();
+  return t;
+}
+
 static int fs_configure() {
   static PerDeviceOnce configured;
   if (configured.first()) {
     MMBS_CUDA_TRY(cudaFuncSetAttribute(fs_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (3 * FS_MAX_BUCKETS + 2 * P_TILE) * 4 + P_TILE * 2));
-    MMBS_CUDA_TRY(cudaFuncSetAttribute(fs_bucket_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_DYN_SMEM));
-    MMBS_CUDA_TRY(cudaFuncSetAttribute(fs_bucket_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_DYN_SMEM));
+    MMBS_CUDA_TRY(cudaFuncSetAttribute(fs_bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_DYN_SMEM));
   }
   return MMBS_OK;
 }
@@ -776,20 +942,29 @@ int fs_forward_enqueue(const float* times, const float* status, const float* sco
   if (int rc = fs_configure()) return rc;
   const FsPlan p = fs_plan(n);
   const int sms = sm_count();
-  const int hist_grid = int(std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 1024 * 2), int64_t(sms) * 8)));
-  fs_hist_kernel<<<hist_grid, FS_HIST_THREADS, 0, stream>>>(times, n, scores, w.hist12, w.kext, max_enc, nan_flag,
-                                                            w.counters + 0, w.lut, w.edge);
+  // a sampling histogram leaves max(scores) / the NaN flag to the partition pass
+  const bool sampled = p.sample_shift > 0;
+  const int64_t groups = ceil_div(ceil_div(n, 1024), int64_t(1) << p.sample_shift);
+  const int hist_grid = int(std::max<int64_t>(1, std::min<int64_t>(ceil_div(groups, 2), int64_t(sms) * 6)));
+  fs_hist_kernel<<<hist_grid, FS_HIST_THREADS, 0, stream>>>(times, n, p.sample_shift, p.nb, sampled ? nullptr : scores,
+                                                            w.hist12, w.kext, max_enc, nan_flag, w.counters + 0, w.lut,
+                                                            w.edge);
   MMBS_LAUNCH_CHECK();
   const int64_t tiles = ceil_div(n, P_TILE);
   const int nbp = int(ceil_div(p.nb, P_THREADS)) * P_THREADS;
   const int p_smem = (3 * nbp + 2 * P_TILE) * 4 + P_TILE * 2;
-  fs_partition_kernel<<<unsigned(tiles), P_THREADS, p_smem, stream>>>(times, status, n, w.lut, w.edge, p.mult2, p.log_s,
-                                                                     p.nb, w.cursor, w.pairs, nonbinary_flag, w.fallback);
+  fs_partition_kernel<<<unsigned(tiles), P_THREADS, p_smem, stream>>>(times, status, sampled ? scores : nullptr, max_enc,
+                                                                     nan_flag, n, w.lut, w.edge, p.nb, w.cursor, w.pairs,
+                                                                     nonbinary_flag, w.fallback);
   MMBS_LAUNCH_CHECK();
-  fs_bucket_forward_kernel<<<p.nb, B_THREADS, B_DYN_SMEM, stream>>>(
-      w.pairs, w.cursor, w.lut, w.edge, p.mult2, p.log_s, p.nb, n, w.counters, scores, status, max_enc, nan_flag,
-      nonbinary_flag, perm_out, saved_s, max_count, max_list, w.agg_val, w.exp_prefix, w.wsum, w.loss_part,
-      w.bucket_base, w.bucket_cnt, loss_out, flags_out, w.fallback);
+  fs_bucket_sort_kernel<<<p.nb, B_THREADS, S_DYN_SMEM, stream>>>(w.pairs, w.cursor, p.nb, scores, max_enc, perm_out,
+                                                                saved_s, max_count, max_list, w.agg_val, w.bucket_base,
+                                                                w.bucket_cnt, w.fallback);
+  MMBS_LAUNCH_CHECK();
+  if (scores == nullptr) return MMBS_OK;   // mmbs_risk_order
+  fs_bucket_loss_kernel<<<p.nb, L_THREADS, 0, stream>>>(saved_s, perm_out, status, p.nb, n, w.bucket_base, w.bucket_cnt,
+                                                       w.agg_val, w.exp_prefix, w.wsum, w.loss_part, w.counters, nan_flag,
+                                                       nonbinary_flag, loss_out, flags_out, w.fallback);
   MMBS_LAUNCH_CHECK();
   return MMBS_OK;
 }
@@ -797,9 +972,8 @@ int fs_forward_enqueue(const float* times, const float* status, const float* sco
 int fs_backward_enqueue(const float* status, const int32_t* perm, const float* saved_s, const float* grad_loss, int64_t n,
                         const FastSortWs& w, const int32_t* nonbinary_flag, const int32_t* max_count,
                         const int32_t* max_list, double* gsum_total, float* grad_scores, cudaStream_t stream) {
-  if (int rc = fs_configure()) return rc;
   const FsPlan p = fs_plan(n);
-  fs_bucket_backward_kernel<<<p.nb, B_THREADS, G_DYN_SMEM, stream>>>(
+  fs_bucket_backward_kernel<<<p.nb, L_THREADS, 0, stream>>>(
       perm, saved_s, status, grad_loss, n, p.nb, w.bucket_base, w.bucket_cnt, w.exp_prefix, w.wsum, w.gsum_part, w.counters,
       nonbinary_flag, max_count, max_list, gsum_total, grad_scores, w.fallback);
   MMBS_LAUNCH_CHECK();

@@ -10,24 +10,28 @@ namespace mmbs {
 constexpr int FS_BINS = 4096;              // histogram of the top 12 key bits
 constexpr int FS_MAX_BUCKETS = 4096;
 constexpr int FS_CAP = 8192;               // samples one block sorts in shared memory (= slots per bucket region)
-constexpr int FS_TARGET = 5120;            // aimed bucket size: 1.6x head-room below FS_CAP
-constexpr int FS_LOG_S_MAX = 12;           // <= 4096 sub-buckets per bucket (~1.25 samples each)
+constexpr int FS_TARGET = 6144;            // aimed bucket size (12 of the 16 rows of a block): 1.33x head-room below FS_CAP
+constexpr int FS_LOG_S = 12;               // 4096 sub-buckets per bucket (~1.25 samples each)
 constexpr int FS_CMAX = 128;               // largest sub-bucket the rank-by-comparison finish accepts
 constexpr int FS_MAX_LIST = 1024;          // argmax positions remembered for the gradient through max(scores)
-constexpr int64_t FS_MAX_N = int64_t(FS_MAX_BUCKETS) * FS_TARGET;   // 20.97 M; beyond: LSD sort
+constexpr int64_t FS_MAX_N = int64_t(FS_MAX_BUCKETS) * FS_TARGET;   // 25.2 M; beyond: LSD sort
+
+// MMBS_COX_HIST_SAMPLE=<shift> overrides (0 = read everything)
+int fs_sample_shift(int64_t n);
+// aimed bucket size: FS_TARGET unless MMBS_COX_TARGET=<samples> overrides it (experiments)
+int fs_target();
 
 struct FsPlan {
-  int nb;            // buckets
-  int log_s;         // log2(sub-buckets per bucket)
-  uint32_t mult2;    // floor((nb << log_s) * 2^32 / n): rank estimate -> fine cell
+  int nb;             // buckets
+  int sample_shift;   // the histogram reads one 1024-sample chunk out of 2^sample_shift (large n: the CDF table only has
+                      // to balance the buckets, ~5 % noise on 5 K-sample buckets is far inside the 1.6x head-room)
 };
 static inline FsPlan fs_plan(int64_t n) {
   FsPlan p;
-  int64_t nb = (n + FS_TARGET - 1) / FS_TARGET;
+  const int64_t target = fs_target();
+  int64_t nb = (n + target - 1) / target;
   p.nb = int(nb < 1 ? 1 : (nb > FS_MAX_BUCKETS ? FS_MAX_BUCKETS : nb));
-  p.log_s = FS_LOG_S_MAX;
-  while (p.log_s > 0 && (int64_t(p.nb) << p.log_s) >= n) --p.log_s;
-  p.mult2 = uint32_t(((uint64_t(p.nb) << p.log_s) << 32) / uint64_t(n < 1 ? 1 : n));
+  p.sample_shift = fs_sample_shift(n);
   return p;
 }
 
@@ -38,20 +42,21 @@ struct FsEdge {       // the two 12-bit bins that hold the smallest / largest ke
   uint32_t hi_bin;
   uint32_t hi_base;
   float hi_scale;
-  uint32_t pad[2];
+  uint32_t mult;      // floor(nb * 2^32 / m): rank estimate in [0, m) -> bucket; m = samples the histogram counted
+  uint32_t pad;
 };
 
 struct FastSortWs {
   // zeroed by the caller before every forward pass
   uint32_t* hist12;        // [FS_BINS]
   uint32_t* kext;          // [2]: max(~key), max(key)
-  uint32_t* counters;      // [8]: 0 histogram blocks done, 1 bucket ticket, 2 forward blocks done, 3 backward blocks done
+  uint32_t* counters;      // [8]: 0 histogram blocks done, 2 loss blocks done, 3 backward blocks done
   uint32_t* cursor;        // [FS_MAX_BUCKETS] samples written to every bucket region
-  double* agg_val;         // [FS_MAX_BUCKETS] sum of exp(s~) over the bucket; +0.0 = not published yet
   int32_t* fallback;       // [1] set when this pipeline gave up: the LSD-sort pipeline must (re)do the work
   // not zeroed
   uint2* lut;              // [FS_BINS] (exclusive prefix, count) of every 12-bit bin
   FsEdge* edge;            // [1]
+  double* agg_val;         // [FS_MAX_BUCKETS] sum of exp(s~) over the bucket
   double* exp_prefix;      // [FS_MAX_BUCKETS] sum of exp(s~) over all earlier buckets           (kept for backward)
   double* wsum;            // [FS_MAX_BUCKETS] sum of w = status / (C + eps) over the bucket     (kept for backward)
   double* loss_part;       // [FS_MAX_BUCKETS]

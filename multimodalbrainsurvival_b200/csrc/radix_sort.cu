@@ -304,11 +304,49 @@ __global__ void __launch_bounds__(RS_THREADS, RS_BLOCKS_PER_SM) rs_onesweep_kern
   }  // persistent tile loop
 }
 
+// Device-side twin of rs_histogram_enqueue + rs_sort_enqueue: one thread of a running kernel enqueues the whole sort
+// behind its own grid (CUDA dynamic parallelism, tail-launch stream: the grids run in launch order once the launching
+// grid has finished and before the next kernel of the host stream starts).  Used by the Cox loss to fall back from the
+// bucketed pipeline without a host synchronisation and without parking no-op launches in the stream (cox.cu).
+__device__ void rs_sort_tail_launch(const void* src, int kind, int64_t n, int num_passes, SortWorkspace ws,
+                                    int32_t* perm_out, const float* status, int32_t* nonbinary_flag, int hist_grid,
+                                    unsigned sort_grid, int64_t tiles) {
+  rs_histogram_kernel<<<hist_grid, 256, 0, cudaStreamTailLaunch>>>(src, kind, n, num_passes, ws.hist, nullptr, nullptr,
+                                                                   nullptr, nullptr);
+  rs_digit_base_kernel<<<num_passes, RS_RADIX, 0, cudaStreamTailLaunch>>>(ws.hist, ws.digit_base, nullptr);
+  const uint32_t* kin = nullptr;
+  const uint32_t* vin = nullptr;
+  for (int p = 0; p < num_passes; ++p) {
+    const bool first = (p == 0), last = (p == num_passes - 1);
+    uint32_t* kout = (p & 1) ? ws.keys_b : ws.keys_a;
+    uint32_t* vout = last ? reinterpret_cast<uint32_t*>(perm_out) : ((p & 1) ? ws.vals_b : ws.vals_a);
+    rs_onesweep_kernel<<<sort_grid, RS_THREADS, RS_DYN_SMEM, cudaStreamTailLaunch>>>(
+        src, kind, kin, vin, kout, vout, n, 8 * p, ws.digit_base + p * RS_RADIX, ws.lookback + int64_t(p) * tiles * RS_RADIX,
+        ws.counters + p, first ? 1 : 0, last ? 1 : 0, first ? status : nullptr, nonbinary_flag, nullptr);
+    kin = kout;
+    vin = vout;
+  }
+}
+
+int rs_configure() {
+  static PerDeviceOnce configured;
+  if (configured.first())
+    MMBS_CUDA_TRY(cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_DYN_SMEM));
+  return MMBS_OK;
+}
+int rs_hist_grid(int64_t n) {
+  const int64_t want = ceil_div(n, 256 * 8);
+  return int(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(sm_count()) * 8)));
+}
+unsigned rs_sort_grid(int64_t n) {
+  const int64_t tiles = rs_tiles(n);
+  return RS_PERSISTENT ? unsigned(std::min<int64_t>(tiles, int64_t(sm_count()) * RS_BLOCKS_PER_SM)) : unsigned(tiles);
+}
+
 int rs_histogram_enqueue(const void* src, KeyKind kind, int64_t n, int num_passes, uint32_t* hist,
                          uint32_t* digit_base, const float* scores, uint32_t* max_enc,
                          int32_t* nan_flag, cudaStream_t stream, const int32_t* enable) {
-  const int64_t want = ceil_div(n, 256 * 8);
-  const int grid = int(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(sm_count()) * 8)));
+  const int grid = rs_hist_grid(n);
   rs_histogram_kernel<<<grid, 256, 0, stream>>>(src, int(kind), n, num_passes, hist, scores, max_enc,
                                                 nan_flag, enable);
   MMBS_LAUNCH_CHECK();
@@ -323,11 +361,8 @@ int rs_sort_enqueue(const void* src, KeyKind kind, int64_t n, int num_passes,
   MMBS_REQUIRE(n >= 1 && n <= RS_MAX_N, "radix sort: n=%lld out of range [1, 2^30)", (long long)n);
   MMBS_REQUIRE(num_passes >= 1 && num_passes <= 4, "radix sort: num_passes=%d", num_passes);
   const int64_t tiles = rs_tiles(n);
-  static PerDeviceOnce configured;
-  if (configured.first())
-    MMBS_CUDA_TRY(cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_DYN_SMEM));
-  const unsigned grid = RS_PERSISTENT ? unsigned(std::min<int64_t>(tiles, int64_t(sm_count()) * RS_BLOCKS_PER_SM))
-                                      : unsigned(tiles);
+  if (int rc = rs_configure()) return rc;
+  const unsigned grid = rs_sort_grid(n);
   const uint32_t* kin = nullptr;
   const uint32_t* vin = nullptr;
   for (int p = 0; p < num_passes; ++p) {

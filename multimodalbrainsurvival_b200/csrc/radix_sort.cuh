@@ -73,7 +73,18 @@ int rs_histogram_enqueue(const void* src, KeyKind kind, int64_t n, int num_passe
                          uint32_t* digit_base, const float* scores, uint32_t* max_enc,
                          int32_t* nan_flag, cudaStream_t stream, const int32_t* enable = nullptr);
 
+// launch geometry / one-time kernel configuration, for callers that enqueue the sort from the device (below)
+int rs_configure();
+int rs_hist_grid(int64_t n);
+unsigned rs_sort_grid(int64_t n);
+
 #ifdef __CUDACC__
+// Device-side twin of rs_histogram_enqueue + rs_sort_enqueue (tail launches behind the calling grid); the caller has
+// cleared ws.hist / ws.counters / ws.lookback and run rs_configure() on the host.  Needs -rdc=true.
+__device__ void rs_sort_tail_launch(const void* src, int kind, int64_t n, int num_passes, SortWorkspace ws,
+                                    int32_t* perm_out, const float* status, int32_t* nonbinary_flag, int hist_grid,
+                                    unsigned sort_grid, int64_t tiles);
+
 __device__ __forceinline__ uint32_t rs_load_key(const void* src, int kind, int64_t i) {
   if (kind == KEY_NEG_TIME_F32) return time_key(__ldg(static_cast<const float*>(src) + i));
   return __ldg(static_cast<const uint32_t*>(src) + i);
