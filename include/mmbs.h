@@ -307,6 +307,8 @@ int mmbs_concordance_counts(const double* event_times, const double* predicted, 
 #define MMBS_ADAM_MAX_GROUPS 8
 typedef struct {
   float step_size, beta1, beta2, eps, weight_decay, bias_correction2_sqrt;
+  float one_minus_beta1, one_minus_beta2;   /* rounded from the caller's double 1 - beta, like torch's scalars
+                                               (1.0f - 0.999f differs from float(1 - 0.999) by 1.3e-5 relative) */
 } mmbs_adam_group;
 typedef struct {
   void* p;          /* parameter, updated in place */

@@ -47,7 +47,8 @@ class BnTrainDesc(ctypes.Structure):
 class AdamGroup(ctypes.Structure):
     """mmbs_adam_group (include/mmbs.h)."""
     _fields_ = [("step_size", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
-                ("weight_decay", c_float), ("bias_correction2_sqrt", c_float)]
+                ("weight_decay", c_float), ("bias_correction2_sqrt", c_float),
+                ("one_minus_beta1", c_float), ("one_minus_beta2", c_float)]
 
 
 class AdamTensor(ctypes.Structure):

@@ -31,8 +31,8 @@ struct AdamLaunch {
 __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, const mmbs_adam_group& h) {
   // same operation order as torch._multi_tensor_adam (add, lerp, mul + addcmul, sqrt / bc2_sqrt + eps, addcdiv)
   g = fmaf(h.weight_decay, p, g);
-  m = fmaf(1.0f - h.beta1, g - m, m);
-  v = fmaf((1.0f - h.beta2) * g, g, v * h.beta2);
+  m = fmaf(h.one_minus_beta1, g - m, m);
+  v = fmaf(h.one_minus_beta2 * g, g, v * h.beta2);
   const float denom = sqrtf(v) / h.bias_correction2_sqrt + h.eps;
   p = p - h.step_size * (m / denom);
 }

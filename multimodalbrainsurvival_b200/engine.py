@@ -218,21 +218,41 @@ class ResNetEngine:
         self._keep.append(pl)
         return pl
 
+    @staticmethod
+    def _is_basic(blk):
+        return not hasattr(blk, "conv3")   # BasicBlock (ResNet-18/34): two 3x3 convs; Bottleneck: 1x1 -> 3x3 -> 1x1
+
+    @classmethod
+    def _out_channels(cls, blk):
+        return blk.conv2.out_channels if cls._is_basic(blk) else blk.conv3.out_channels
+
+    @classmethod
+    def _block_stride(cls, blk):
+        return blk.conv1.stride[0] if cls._is_basic(blk) else blk.conv2.stride[0]
+
     def _block_steps(self, blk, w, x, out):
-        """Steps of one Bottleneck on input buffer x writing `out` (scratch allocated here)."""
+        """Steps of one residual block on input buffer x writing `out` (scratch allocated here)."""
         B, H, W, Cin = x.shape
         planes = blk.conv1.out_channels
-        s = blk.conv2.stride[0]
+        s = self._block_stride(blk)
         Ho, Wo = H // s, W // s
-        t1 = self._buf(B, H, W, planes)
-        t2 = self._buf(B, Ho, Wo, planes)
         steps = []
         if blk.downsample is not None:
-            res = self._buf(B, Ho, Wo, planes * 4)
+            res = self._buf(B, Ho, Wo, self._out_channels(blk))
             steps.append(self._plan(x, w["wd"], res, ksize=1, stride=blk.downsample[0].stride[0], c_in=Cin,
                                     scale=w["scd"], shift=w["shd"], relu=False).run)
         else:
             res = x
+        if self._is_basic(blk):
+            # BasicBlock.forward (reference resnet.py:23-51): 3x3 (stride) -> BN -> ReLU -> 3x3 -> BN -> (+shortcut) -> ReLU
+            t1 = self._buf(B, Ho, Wo, planes)
+            steps.append(self._plan(x, w["w1"], t1, ksize=3, stride=s, c_in=Cin, scale=w["sc1"], shift=w["sh1"],
+                                    relu=True, halo_weights=w["halo1"]).run)
+            steps.append(self._plan(t1, w["w2"], out, ksize=3, stride=1, c_in=planes, scale=w["sc2"], shift=w["sh2"],
+                                    residual=res, relu=True, halo_weights=w["halo2"]).run)
+            return steps
+        t1 = self._buf(B, H, W, planes)
+        t2 = self._buf(B, Ho, Wo, planes)
         steps.append(self._plan(x, w["w1"], t1, ksize=1, stride=1, c_in=Cin, scale=w["sc1"], shift=w["sh1"],
                                 relu=True).run)
         steps.append(self._plan(t1, w["w2"], t2, ksize=3, stride=s, c_in=planes, scale=w["sc2"], shift=w["sh2"],
@@ -241,14 +261,24 @@ class ResNetEngine:
                                 residual=res, relu=True).run)
         return steps
 
-    @staticmethod
-    def _block_weights(blk):
-        halo2 = halo_eligible(blk.conv2) and os.environ.get("MMBS_CONV_HALO", "1") == "1"
-        w = {"w1": pack_conv_weight(blk.conv1.weight), "w3": pack_conv_weight(blk.conv3.weight), "halo2": halo2,
-             "w2": pack_conv_weight_halo(blk.conv2.weight) if halo2 else pack_conv_weight(blk.conv2.weight)}
+    @classmethod
+    def _block_weights(cls, blk):
+        use_halo = os.environ.get("MMBS_CONV_HALO", "1") == "1"
+        w = {}
+        if cls._is_basic(blk):
+            # (the residual epilogue of the weights-resident halo variant is not instantiated: conv2 streams its weights)
+            w["halo1"] = halo_eligible(blk.conv1) and use_halo
+            w["halo2"] = False
+            w["w1"] = pack_conv_weight_halo(blk.conv1.weight) if w["halo1"] else pack_conv_weight(blk.conv1.weight)
+            w["w2"] = pack_conv_weight(blk.conv2.weight)
+        else:
+            w["halo2"] = halo_eligible(blk.conv2) and use_halo
+            w["w1"] = pack_conv_weight(blk.conv1.weight)
+            w["w2"] = pack_conv_weight_halo(blk.conv2.weight) if w["halo2"] else pack_conv_weight(blk.conv2.weight)
+            w["w3"] = pack_conv_weight(blk.conv3.weight)
+            w["sc3"], w["sh3"] = bn_fold(blk.bn3)
         w["sc1"], w["sh1"] = bn_fold(blk.bn1)
         w["sc2"], w["sh2"] = bn_fold(blk.bn2)
-        w["sc3"], w["sh3"] = bn_fold(blk.bn3)
         if blk.downsample is not None:
             w["wd"] = pack_conv_weight(blk.downsample[0].weight)
             w["scd"], w["shd"] = bn_fold(blk.downsample[1])
@@ -267,7 +297,7 @@ class ResNetEngine:
             self._keep += [w_stem, sc0, sh0, fw, bw]
 
             self.x_s2d = self._buf(B, 116, 116, 16)
-            mid = self._buf(B, 28, 28, front_blocks[-1].conv3.out_channels)  # layer2 output, whole chunk
+            mid = self._buf(B, 28, 28, self._out_channels(front_blocks[-1]))  # layer2 output, whole chunk
             # ---- front: per sub-chunk, on scratch buffers shared by all sub-chunks
             stem_out = self._buf(F, 112, 112, 64)
             pool_out = self._buf(F, 56, 56, 64)
@@ -282,8 +312,8 @@ class ResNetEngine:
                     scratch_steps = []
                     x = pool_out
                     for blk, w in zip(front_blocks[:-1], fw[:-1]):
-                        s = blk.conv2.stride[0]
-                        out = self._buf(F, x.shape[1] // s, x.shape[2] // s, blk.conv3.out_channels)
+                        s = self._block_stride(blk)
+                        out = self._buf(F, x.shape[1] // s, x.shape[2] // s, self._out_channels(blk))
                         scratch_steps += self._block_steps(blk, w, x, out)
                         x = out
                     self._front_last_in = x
@@ -293,15 +323,15 @@ class ResNetEngine:
             x = mid
             for bi, (blk, w) in enumerate(zip(back_blocks, bw)):
                 last = bi == len(back_blocks) - 1
-                s = blk.conv2.stride[0]
+                s = self._block_stride(blk)
                 # the final block's output stays bf16 like every other activation (TMA-store epilogue); the
                 # average pool accumulates the 49 positions in fp32 (MMBS_RESNET_FINAL_F32=1: fp32 output)
                 final_f32 = last and os.environ.get("MMBS_RESNET_FINAL_F32", "0") == "1"
-                out = self._buf(B, x.shape[1] // s, x.shape[2] // s, blk.conv3.out_channels,
+                out = self._buf(B, x.shape[1] // s, x.shape[2] // s, self._out_channels(blk),
                                 dtype=torch.float32 if final_f32 else torch.bfloat16)
                 self._steps += self._block_steps(blk, w, x, out)
                 x = out
-            self.final = x  # [B,7,7,2048]
+            self.final = x  # [B,7,7,2048] (512 for the BasicBlock depths)
         self._weights_version = self.weights_version(net)
         self.n_kernels = len(self._steps) + 2
 
@@ -321,11 +351,11 @@ class ResNetEngine:
                        "mmbs_stem_pack_input")
         self._run_body()
         if self.final.dtype == torch.float32:
-            _lib.check(L.mmbs_avgpool_global_f32(_lib.ptr(self.final), _lib.ptr(out), B, 49, 2048,
+            _lib.check(L.mmbs_avgpool_global_f32(_lib.ptr(self.final), _lib.ptr(out), B, 49, self.final.shape[3],
                                                  _lib.stream_ptr()), "mmbs_avgpool_global_f32")
         else:
-            _lib.check(L.mmbs_avgpool_global(_lib.ptr(self.final), _lib.ptr(out), B, 49, 2048, _lib.stream_ptr()),
-                       "mmbs_avgpool_global")
+            _lib.check(L.mmbs_avgpool_global(_lib.ptr(self.final), _lib.ptr(out), B, 49, self.final.shape[3],
+                                             _lib.stream_ptr()), "mmbs_avgpool_global")
 
 
 GRAPH_LAUNCHES = 0  # kernels launched through CUDA-graph replays (not seen by mmbs_launch_count)

@@ -78,6 +78,7 @@ def _fused_step(opt) -> bool:
         beta1, beta2 = group["betas"]
         hyper[r].step_size = float(group["lr"]) / (1.0 - beta1 ** t)
         hyper[r].beta1, hyper[r].beta2 = beta1, beta2
+        hyper[r].one_minus_beta1, hyper[r].one_minus_beta2 = 1.0 - beta1, 1.0 - beta2   # in double, then rounded
         hyper[r].eps, hyper[r].weight_decay = group["eps"], group["weight_decay"]
         hyper[r].bias_correction2_sqrt = math.sqrt(1.0 - beta2 ** t)
     tensors = (_lib.AdamTensor * len(work))()

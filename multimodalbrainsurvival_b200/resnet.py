@@ -151,7 +151,7 @@ class ResNet(_Trunk):
             from . import train_engine
             with torch.cuda.device(x.device):   # the kernels launch on the CURRENT device's stream
                 return train_engine.run_train(self, x, self._engines)
-        if not x.is_cuda and os.environ.get("MMBS_DISABLE_KERNELS", "0") != "1" and isinstance(self.layer1[0], Bottleneck):
+        if not x.is_cuda and os.environ.get("MMBS_DISABLE_KERNELS", "0") != "1":
             # north_star: no CPU fallback.  (MMBS_DISABLE_KERNELS=1 keeps the stock module graph reachable for
             # host-side tooling: checkpoint round-trips, oracle pinning.)
             raise RuntimeError("ResNet.forward_extract: input must be a CUDA tensor (this build has no CPU path; "
@@ -165,9 +165,11 @@ class ResNet(_Trunk):
     def _can_accelerate(self, x):
         if os.environ.get("MMBS_DISABLE_KERNELS", "0") == "1":
             return False
+        # every depth of the reference's resnet.py (18/34: BasicBlock, 50/101/152: Bottleneck; resnet.py:167-337)
         return (x.is_cuda and not self.training and not torch.is_grad_enabled()
                 and x.dim() == 4 and tuple(x.shape[1:]) == (3, 224, 224)
-                and isinstance(self.layer1[0], Bottleneck) and self.fc.in_features == 2048)
+                and isinstance(self.layer1[0], (Bottleneck, BasicBlock))
+                and self.fc.in_features == 512 * type(self.layer1[0]).expansion)
 
     def _can_accelerate_train(self, x):
         """model.train() on CUDA, fp32 224x224 patches, ResNet-50, gradients (if any) confined to layer4."""
@@ -201,7 +203,7 @@ class ResNet(_Trunk):
         from . import engine
         B = x.shape[0]
         x = x.contiguous() if x.dtype == torch.uint8 else x.float().contiguous()
-        out = torch.empty((B, 2048), dtype=torch.float32, device=x.device)
+        out = torch.empty((B, self.fc.in_features), dtype=torch.float32, device=x.device)
         done = 0
         while done < B:
             chunk = engine.default_chunk(B - done)

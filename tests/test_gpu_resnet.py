@@ -118,3 +118,33 @@ def test_full_batch_properties_512():
     for i in range(8):
         assert float((got[i] - ref32[i]).norm() / ref32[i].norm()) < 1e-2, f"row {int(rows[i])} vs fp32 oracle"
         assert float((got[i] - refbf[i]).norm() / refbf[i].norm()) < 3e-3, f"row {int(rows[i])} vs bf16 oracle"
+
+
+@pytest.mark.parametrize("name", ["resnet18", "resnet34", "resnet101", "resnet152"])
+def test_other_depths_run_on_the_kernels(name):
+    """the other depths of the reference's resnet.py (:167-337; BasicBlock for 18/34, deeper
+    Bottleneck stacks for 101/152) go through the same tcgen05 conv engine.  Reference: the identical module graph
+    evaluated by torch in fp32 on the same weights (a floating-point kernel: torch fp32 is the allowed reference);
+    tolerance 1e-2 relative L2 (bf16 storage, north_star)."""
+    from multimodalbrainsurvival_b200 import resnet
+    torch.manual_seed({"resnet18": 18, "resnet34": 34, "resnet101": 101, "resnet152": 152}[name])
+    net = getattr(resnet, name)(pretrained=False)
+    g = torch.Generator().manual_seed(5)
+    for m in net.modules():   # folded BatchNorm with non-trivial statistics; small last-BN gamma like a trained net
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data = 0.5 + torch.rand(m.num_features, generator=g)
+            m.bias.data = 0.1 * torch.randn(m.num_features, generator=g)
+            m.running_mean.data = 0.1 * torch.randn(m.num_features, generator=g)
+            m.running_var.data = 0.5 + torch.rand(m.num_features, generator=g)
+    for blk in [b for l in (net.layer1, net.layer2, net.layer3, net.layer4) for b in l]:
+        last_bn = blk.bn3 if hasattr(blk, "bn3") else blk.bn2
+        last_bn.weight.data *= 0.2
+    net = net.cuda().eval()
+    x = torch.randn(3, 3, 224, 224, generator=g).cuda()
+    with torch.no_grad():
+        f = net.forward_extract(x)
+        assert net._engines, "the CUDA engine did not run"
+        ref = net._features_torch(x)   # stock module graph, fp32
+    assert f.shape == ref.shape == (3, net.fc.in_features)
+    rel = float((f - ref).norm() / ref.norm())
+    assert rel < 1e-2, f"{name}: relative L2 error {rel}"

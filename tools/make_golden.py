@@ -263,6 +263,58 @@ def gen_mlp():
     print("mlp: rna", tuple(y.shape), "early", tuple(ye.shape), "joint", tuple(yj.shape))
 
 
+# ------------------------------------------------------------------------- rna script
+def gen_rna_script():
+    """Runs the UNMODIFIED 2_GeneExpression/1_GeneExpress_train.py on CPU (synthetic CSVs of tests/_rna_script.py, the
+    shipped config values, 2 epochs) with a concordance stub that records its arguments, then the call-sequence mirror
+    of tests/_rna_script.py with the reference's own `models` module, and requires both recordings to be identical."""
+    import json
+    import runpy
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _rna_script as R
+    _stub_third_party()
+    recorded = []
+
+    def recorder(months, neg_scores, vital):
+        recorded.append((np.array(months), np.array(neg_scores), np.array(vital)))
+        return 0.5
+
+    sys.modules["lifelines.utils"].concordance_index = recorder
+    tmp = tempfile.mkdtemp(prefix="rna_script_")
+    paths = R.write_csvs(tmp)
+    cfg = dict(R.CONFIG, use_cuda=False, train_csv_path=paths["train"], val_csv_path=paths["val"],
+               test_csv_path=paths["test"], checkpoint_path=os.path.join(tmp, "out"),
+               summary_path=os.path.join(tmp, "out", "summary"))
+    cfg_path = os.path.join(tmp, "config_rna_train.json")
+    with open(cfg_path, "w") as f:
+        json.dump(cfg, f)
+    script_dir = os.path.join(REF, "2_GeneExpression")
+    for k in ("resnet", "models", "datasets"):
+        sys.modules.pop(k, None)
+    sys.path.insert(0, script_dir)
+    argv = sys.argv
+    sys.argv = ["1_GeneExpress_train.py", "--config", cfg_path]
+    try:
+        runpy.run_path(os.path.join(script_dir, "1_GeneExpress_train.py"), run_name="__main__")
+    finally:
+        sys.argv = argv
+        sys.path.remove(script_dir)
+    script_rec = list(recorded)
+    ref_models = load_ref("2_GeneExpression/models.py", "ref_rna_models_script")
+    mirror_rec, train_losses, last_state = R.run_like_script(ref_models, torch.device("cpu"))
+    assert len(script_rec) == len(mirror_rec) == 2 * R.CONFIG["num_epochs"] + 3, (len(script_rec), len(mirror_rec))
+    for a, b in zip(script_rec, mirror_rec):
+        for x, y in zip(a, b):
+            assert np.array_equal(np.asarray(x), np.asarray(y)), "the mirror does not reproduce the script"
+    out = {"train_losses": np.array(train_losses), "n_calls": np.array(len(script_rec)),
+           "final_head_weight": last_state["final_mlp.0.weight"].numpy()}
+    for i, (m, s, v) in enumerate(script_rec):
+        out[f"call{i}/months"], out[f"call{i}/neg_score"], out[f"call{i}/vital"] = m, s, v
+    np.savez_compressed(os.path.join(OUT, "rna_script_reference.npz"), **out)
+    print("rna_script: mirror == unmodified script on", len(script_rec), "evaluate calls; TRAIN losses", train_losses)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     which = sys.argv[1:] or ["cox", "aggregate", "resnet", "resnet_train", "mlp"]
