@@ -322,6 +322,14 @@ typedef struct {
 int mmbs_adam_step(const mmbs_adam_tensor* tensors_host, int32_t n_tensors, const mmbs_adam_group* groups_host,
                    int32_t n_groups, void* stream);
 
+/* ------------------------------------------------ feature-matrix writer (host code, no GPU needed)
+ * Replaces np.savetxt(path, features, delimiter=",") of
+ *   /root/reference/1_HistoPathology/4_HistoPath_extractfeatures.py:184-192,
+ *   /root/reference/2_GeneExpression/3_GeneExpress_extractfeatures.py:143-149
+ * byte for byte ('%.18e', ',' between columns, '\n' per row).  data: rows x cols float64, row-major, HOST memory.
+ * threads <= 0: one per hardware thread (at most 64). */
+int mmbs_write_matrix_csv(const double* data, int64_t rows, int64_t cols, const char* path, int32_t threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -141,3 +141,20 @@ def get_survival_CI(output_list, ids_list, survival_months, vital_status, concor
     pandas_output = pd.DataFrame({'id': ids_unique, 'score': score_list, 'survival_months': sm,
                                   'vital_status': vs})
     return CI, pandas_output
+
+
+def save_features_csv(path, features, threads: int = 0) -> None:
+    """Drop-in for ``np.savetxt(path, features, delimiter=",")`` as the extraction scripts call it
+    (/root/reference/1_HistoPathology/4_HistoPath_extractfeatures.py:184-192,
+    /root/reference/2_GeneExpression/3_GeneExpress_extractfeatures.py:143-149): the same bytes ('%.18e' per value),
+    written by the multi-threaded formatter of csrc/csv.cu (host code)."""
+    import ctypes
+    a = np.ascontiguousarray(np.asarray(features, dtype=np.float64))
+    if a.ndim == 1:               # np.savetxt writes a 1-D array as one value per row
+        a = a.reshape(-1, 1)
+    if a.ndim != 2:
+        raise ValueError(f"save_features_csv: expected a 1-D or 2-D array, got shape {a.shape}")
+    if a.shape[1] == 0:
+        raise ValueError("save_features_csv: no columns")
+    _lib.check(_lib.lib().mmbs_write_matrix_csv(a.ctypes.data_as(ctypes.c_void_p), a.shape[0], a.shape[1],
+                                                str(path).encode(), int(threads)), "mmbs_write_matrix_csv")

@@ -30,6 +30,14 @@ from . import _lib
 _MAX_GROUPS = 8
 
 
+def _bump_versions(tensors) -> None:
+    try:
+        torch._C._increment_version(tensors)          # torch >= 2.3: an iterable of tensors
+    except TypeError:
+        for t in tensors:
+            torch._C._increment_version(t)
+
+
 def _fusable_group(group) -> bool:
     return not (group.get("amsgrad") or group.get("maximize") or group.get("differentiable")
                 or group.get("capturable"))
@@ -93,6 +101,14 @@ def _fused_step(opt) -> bool:
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().mmbs_adam_step(tensors, len(work), hyper, n_rows, _lib.stream_ptr()),
                    "mmbs_adam_step")
+    # the kernel wrote through raw pointers: bump the version counters like an in-place torch op would, so that
+    # autograd's saved-tensor checks and the packed-weight caches keyed on `_version` (mlp.py, engine.py,
+    # train_engine.py) see the update
+    touched = []
+    for _, p, _ in work:
+        st = opt.state[p]
+        touched += [p, st["exp_avg"], st["exp_avg_sq"]]
+    _bump_versions(touched)
     return True
 
 

@@ -14,6 +14,12 @@ copied into this repository), and the drop-in has no CPU path to run the script 
 `tools/make_golden.py rna_script` runs the unmodified script on CPU (third-party imports stubbed, the concordance stub
 recording its arguments), runs this mirror with the reference's own `models` module on the same inputs, and asserts that
 both recordings are IDENTICAL before writing tests/golden/rna_script_reference.npz.
+
+Dropout: the script trains with nn.Dropout() and Adam's first steps move every weight by +-lr whatever the gradient's
+size, so after one step on 24 samples the scores depend on the dropout masks at the 10 % level (measured: 9.2 % between
+torch's CPU stream and the kernels' Philox stream) - a run with dropout cannot be compared tighter than that with ANY
+other random stream.  The golden therefore also holds the mirror's recording with dropout_p = 0 (same initial weights,
+same sampler order, reference `models` module, CPU): that variant is deterministic and is compared at 1e-2.
 """
 import os
 
@@ -106,11 +112,14 @@ def _evaluate(models, model, loader, device, record):
     return float(np.mean(losses))
 
 
-def run_like_script(models, device, optimizer_hook=None):
-    """Returns (recorded concordance arguments per evaluate call, printed TRAIN losses, final state_dict)."""
+def run_like_script(models, device, optimizer_hook=None, dropout_p=0.5):
+    """Returns (recorded concordance arguments per evaluate call, printed TRAIN losses, final state_dict).
+    dropout_p = 0.5 is the script (nn.Dropout()); 0.0 is the deterministic variant of the parity test (dropout draws
+    nothing from the generator, so the initial weights and the sampler order are those of the script)."""
     np.random.seed(SEED)
     torch.random.manual_seed(SEED)
-    model_rna = nn.Sequential(nn.Dropout(), nn.Linear(N_GENES, 4096), nn.ReLU(), nn.Dropout(), nn.Linear(4096, 2048))
+    model_rna = nn.Sequential(nn.Dropout(dropout_p), nn.Linear(N_GENES, 4096), nn.ReLU(), nn.Dropout(dropout_p),
+                              nn.Linear(4096, 2048))
     combine_mlp = nn.Sequential(nn.Linear(2048, 1))
     model = models.RNAOnlyModel(model_rna, combine_mlp)
     datasets = {x: _RNADataset(x) for x in ("train", "val", "test")}

@@ -53,6 +53,18 @@ def test_fused_adam_matches_torch_adam_over_10_steps():
         _close(sa["exp_avg_sq"], sb["exp_avg_sq"], 1e-6, f"exp_avg_sq {i}")
 
 
+def test_fused_step_bumps_version_counters():
+    """The packed bf16 weight caches of the MLP / ResNet engines are keyed on `_version`: a fused step that left it
+    alone would let the next forward run on stale weights (found by tests/test_gpu_script_rna.py)."""
+    from multimodalbrainsurvival_b200 import optim
+    p = torch.randn(1000, device=DEV, requires_grad=True)
+    o = optim.accelerate_optimizer(torch.optim.Adam([p], lr=1e-2))
+    p.grad = torch.ones_like(p)
+    v0 = p._version
+    o.step()
+    assert p._version > v0 and o.state[p]["exp_avg"]._version > 0
+
+
 def test_state_dict_round_trips_between_fused_and_stock():
     from multimodalbrainsurvival_b200 import optim
     pa = _make(3)
@@ -66,10 +78,11 @@ def test_state_dict_round_trips_between_fused_and_stock():
     assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
     pb = [a.detach().clone().requires_grad_(True) for a in pa]
     ob = torch.optim.Adam(_groups(pb), weight_decay=1e-5)
-    ob.load_state_dict(sd)                         # a checkpoint written by the fused path resumes on stock torch
+    # (load_state_dict does not clone: every optimizer gets its own copy of the checkpoint's tensors)
+    ob.load_state_dict(copy.deepcopy(sd))          # a checkpoint written by the fused path resumes on stock torch
     pc = [a.detach().clone().requires_grad_(True) for a in pa]
     oc = optim.accelerate_optimizer(torch.optim.Adam(_groups(pc), weight_decay=1e-5))
-    oc.load_state_dict(sd)                         # ... and the other way round
+    oc.load_state_dict(copy.deepcopy(sd))          # ... and the other way round
     for _ in range(2):
         for a, b, c in zip(pa, pb, pc):
             gr = torch.randn(a.shape, device=DEV, generator=g)

@@ -168,3 +168,18 @@ def test_accelerate_optimizer_keeps_the_torch_object_and_state_layout():
     s1, s2 = o1.state_dict(), o2.state_dict()
     assert s1["param_groups"] == s2["param_groups"]
     assert {k: sorted(v) for k, v in s1["state"].items()} == {k: sorted(v) for k, v in s2["state"].items()}
+
+
+def test_feature_csv_writer_is_byte_identical_to_savetxt(tmp_path):
+    """np.savetxt(path, features, delimiter=",") of 4_HistoPath_extractfeatures.py:184-192 vs the multi-threaded
+    writer (csrc/csv.cu, host code): identical bytes, including non-finite values, 1-D input and float32 input."""
+    from multimodalbrainsurvival_b200 import aggregate
+    rng = np.random.default_rng(3)
+    cases = [rng.standard_normal((37, 2048)) * 10.0 ** rng.integers(-30, 30, (37, 2048)),
+             np.array([[0.0, -0.0, np.inf, -np.inf, np.nan, 1e-320, 1.7976931348623157e308, 5e-324]]),
+             rng.standard_normal(11), rng.standard_normal((700, 3)).astype(np.float32)]
+    for i, a in enumerate(cases):
+        ref, out = tmp_path / f"ref{i}.csv", tmp_path / f"out{i}.csv"
+        np.savetxt(ref, a, delimiter=",")
+        aggregate.save_features_csv(out, a, threads=1 + i)
+        assert ref.read_bytes() == out.read_bytes(), f"case {i}"

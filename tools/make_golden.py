@@ -311,6 +311,13 @@ def gen_rna_script():
            "final_head_weight": last_state["final_mlp.0.weight"].numpy()}
     for i, (m, s, v) in enumerate(script_rec):
         out[f"call{i}/months"], out[f"call{i}/neg_score"], out[f"call{i}/vital"] = m, s, v
+    # the deterministic variant (dropout_p = 0): same call sequence, same weights / sampler order
+    nd_rec, nd_losses, nd_state = R.run_like_script(ref_models, torch.device("cpu"), dropout_p=0.0)
+    out["nodrop/train_losses"] = np.array(nd_losses)
+    out["nodrop/final_head_weight"] = nd_state["final_mlp.0.weight"].numpy()
+    for i, (m, s, v) in enumerate(nd_rec):
+        assert np.array_equal(m, script_rec[i][0]) and np.array_equal(v, script_rec[i][2])
+        out[f"nodrop/call{i}/neg_score"] = s
     np.savez_compressed(os.path.join(OUT, "rna_script_reference.npz"), **out)
     print("rna_script: mirror == unmodified script on", len(script_rec), "evaluate calls; TRAIN losses", train_losses)
 
