@@ -134,6 +134,12 @@ typedef struct {
 
 int mmbs_conv_plan_create(const mmbs_conv_desc* desc, mmbs_conv_plan** plan_out);
 void mmbs_conv_plan_destroy(mmbs_conv_plan* plan);
+/* Dropout fused into a LINEAR plan's epilogue (mmbs_linear_plan_create): after bias / ReLU the output is multiplied
+ * by the keep-mask of probability 1 - p and 1 / (1 - p) - the nn.Dropout in front of the NEXT Linear of the reference
+ * MLPs (/root/reference/2_GeneExpression/1_GeneExpress_train.py:247-257).  Mask = Philox-4x32-10 keyed by (seed, tag)
+ * at (row, column / 8), the same function mmbs_dropout_cast_bf16 / mmbs_mlp_bwd_elementwise use, so the backward pass
+ * regenerates it.  p = 0 switches the dropout off; the setting holds from the next mmbs_conv_run on. */
+int mmbs_plan_set_dropout(mmbs_conv_plan* plan, float p, uint64_t seed, uint32_t tag);
 int mmbs_conv_run(const mmbs_conv_plan* plan, void* stream);
 
 /* Linear: y[M,N] = act(x[M,K] W[N,K]^T + bias[N]); x/W bf16 with K % 64 == 0 (pad
@@ -321,6 +327,19 @@ typedef struct {
 } mmbs_adam_tensor;
 int mmbs_adam_step(const mmbs_adam_tensor* tensors_host, int32_t n_tensors, const mmbs_adam_group* groups_host,
                    int32_t n_groups, void* stream);
+
+/* ------------------------------------------------ discrete-time survival NLL
+ * Replaces nll_loss() / NLLSurvLoss (/root/reference/1_HistoPathology/models.py:120-232; `survival_bin` task):
+ * hazards = sigmoid(h), S = cumprod(1 - hazards), loss_i = -(1-c)(log S_padded[y] + log hazards[y])
+ * - (1-alpha) c log S_padded[y+1] with every log argument clamped at eps; mean (reduction_mean = 1) or sum over n.
+ * h fp32 [n, n_bins], y int64 [n] (bin index in [0, n_bins)), c fp32 [n] (1 = censored).  The forward also writes
+ * grad_unit[n, n_bins] = d loss_i / d h_i (saved for backward) and the per-sample losses; flags_out[0] != 0: some
+ * y was out of range (those samples are NaN).  backward: grad_h = grad_unit * grad_loss (/ n for the mean). */
+int mmbs_nll_surv_forward(const float* h, const int64_t* y, const float* c, int64_t n, int32_t n_bins, float alpha,
+                          float eps, int32_t reduction_mean, float* loss_i, float* grad_unit, float* loss_out,
+                          int32_t* flags_out, void* stream);
+int mmbs_nll_surv_backward(const float* grad_unit, const float* grad_loss, int64_t n, int32_t n_bins,
+                           int32_t reduction_mean, float* grad_h, void* stream);
 
 /* ------------------------------------------------ feature-matrix writer (host code, no GPU needed)
  * Replaces np.savetxt(path, features, delimiter=",") of

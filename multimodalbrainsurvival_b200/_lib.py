@@ -123,6 +123,10 @@ SIGNATURES = {
     "mmbs_bn_train_relu_maxpool_3x3s2": (ctypes.c_int, [ctypes.POINTER(BnTrainDesc), c_void_p, c_void_p, c_i64, c_i64,
                                                         c_i64, c_void_p]),
     "mmbs_concordance_counts": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
+    "mmbs_plan_set_dropout": (ctypes.c_int, [c_void_p, c_float, ctypes.c_uint64, ctypes.c_uint32]),
+    "mmbs_nll_surv_forward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i32, c_float, c_float, c_i32,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmbs_nll_surv_backward": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, c_void_p, c_void_p]),
     "mmbs_write_matrix_csv": (ctypes.c_int, [c_void_p, c_i64, c_i64, ctypes.c_char_p, c_i32]),
     "mmbs_adam_step": (ctypes.c_int, [ctypes.POINTER(AdamTensor), c_i32, ctypes.POINTER(AdamGroup), c_i32, c_void_p]),
 }

@@ -96,6 +96,45 @@ __device__ __forceinline__ uint32_t time_key(float t) {
   uint32_t b = __float_as_uint(__fsub_rn(0.0f, t));
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
+// ---- dropout masks: Philox-4x32-10 keyed by (seed, tag), counter = (column / 8, row).  Every kernel that applies or
+// re-applies a mask (the GEMM epilogue, the cast kernels, the MLP backward) derives it from dropout_keep8.
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
+  uint32_t c2 = 0x5851f42du, c3 = 0x14057b7eu;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+// keep-mask of the 8 elements [8*q8, 8*q8+8) of row `row`: one Philox call yields eight 16-bit uniforms, element j is
+// kept when its uniform is >= thresh16 = round(p * 65536).  Every kernel (forward / backward, scalar / vector)
+// derives its mask from this function, so the backward pass regenerates exactly the forward mask.
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t tag, uint32_t row, uint32_t q8,
+                                                  uint32_t thresh16) {
+  const uint4 r = philox4x32(q8, row, uint32_t(seed) ^ tag, uint32_t(seed >> 32));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t keep = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    keep |= ((w[i] & 0xffffu) >= thresh16 ? 1u : 0u) << (2 * i);
+    keep |= ((w[i] >> 16) >= thresh16 ? 1u : 0u) << (2 * i + 1);
+  }
+  return keep;
+}
+// keep-mask of the 4 elements [4*q, 4*q+4) of row `row` (q = column / 4): one nibble of the 8-element group
+__device__ __forceinline__ uint32_t dropout_keep4(uint64_t seed, uint32_t tag, uint32_t row, uint32_t q,
+                                                  uint32_t thresh16) {
+  return (dropout_keep8(seed, tag, row, q >> 1, thresh16) >> (4 * (q & 1u))) & 0xfu;
+}
+__device__ __forceinline__ uint32_t drop_threshold(float p) {
+  const float t = p * 65536.0f + 0.5f;
+  return t >= 65535.0f ? 65535u : uint32_t(t);
+}
+
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));

@@ -106,6 +106,12 @@ struct ConvParams {
   const __nv_bfloat16* residual;
   void* out;
   float* stats;   // training-mode BatchNorm: [2][c_out] per-channel sum / sum of squares of the bf16 output
+  // dropout fused into the epilogue of a linear layer (after bias / ReLU; nn.Dropout in front of the NEXT Linear of the
+  // reference MLPs, 1_GeneExpress_train.py:247-257): keep-mask of common.cuh dropout_keep8 at (row, column / 8)
+  uint32_t drop_thresh;   // 0: no dropout; otherwise round(p * 65536)
+  uint32_t drop_tag;
+  float drop_scale;       // 1 / (1 - p)
+  uint64_t drop_seed;
 };
 
 // Shared-memory carve-up (offsets from a 1024-B aligned base):
@@ -169,7 +175,8 @@ __device__ __forceinline__ KRange k_range(const ConvParams& p, int tile) {
 template <int N_TILE>
 __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32_t (&accr)[32], int c0,
                                                const float* s_scale, const float* s_shift, uint32_t stg, int r,
-                                               bool use_tma_store, bool tma_res, bool row_ok, int64_t row_off) {
+                                               bool use_tma_store, bool tma_res, bool row_ok, int64_t row_off,
+                                               int grow, int gcol0) {
   {
     float v[32];
 #pragma unroll
@@ -180,6 +187,19 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
       v[j + 1] = __uint_as_float(accr[j + 1]) * sc.y + sh.y;
       v[j + 2] = __uint_as_float(accr[j + 2]) * sc.z + sh.z;
       v[j + 3] = __uint_as_float(accr[j + 3]) * sc.w + sh.w;
+    }
+    if (p.drop_thresh != 0u) {   // linear layers only (no residual): bias, ReLU, then the dropout of the next layer's input
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t keep = dropout_keep8(p.drop_seed, p.drop_tag, uint32_t(grow), uint32_t(gcol0 + c0) / 8u + g,
+                                            p.drop_thresh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float x = v[g * 8 + j];
+          if (p.relu) x = fmaxf(x, 0.0f);
+          v[g * 8 + j] = ((keep >> j) & 1u) ? x * p.drop_scale : 0.0f;
+        }
+      }
     }
     if (use_tma_store) {
       // staging tile: column block (c0/64), row r, 16-B chunk index XOR-swizzled by (r & 7)
@@ -270,7 +290,8 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
 template <int N_TILE>
 __device__ __forceinline__ void epilogue_columns(const ConvParams& p, uint32_t t_addr, int c_begin, int c_end,
                                                  const float* s_scale, const float* s_shift, uint32_t stg, int r,
-                                                 bool use_tma_store, bool tma_res, bool row_ok, int64_t row_off) {
+                                                 bool use_tma_store, bool tma_res, bool row_ok, int64_t row_off,
+                                                 int grow, int gcol0) {
   uint32_t acc_a[32], acc_b[32];
   tc::tmem_ld_32x32(t_addr + uint32_t(c_begin), acc_a);
 #pragma unroll 1
@@ -278,11 +299,12 @@ __device__ __forceinline__ void epilogue_columns(const ConvParams& p, uint32_t t
     tc::tmem_ld_wait();
     const bool more1 = c0 + 32 < c_end;
     if (more1) tc::tmem_ld_32x32(t_addr + uint32_t(c0 + 32), acc_b);
-    epilogue_chunk<N_TILE>(p, acc_a, c0, s_scale, s_shift, stg, r, use_tma_store, tma_res, row_ok, row_off);
+    epilogue_chunk<N_TILE>(p, acc_a, c0, s_scale, s_shift, stg, r, use_tma_store, tma_res, row_ok, row_off, grow, gcol0);
     if (more1) {
       tc::tmem_ld_wait();
       if (c0 + 64 < c_end) tc::tmem_ld_32x32(t_addr + uint32_t(c0 + 64), acc_a);
-      epilogue_chunk<N_TILE>(p, acc_b, c0 + 32, s_scale, s_shift, stg, r, use_tma_store, tma_res, row_ok, row_off);
+      epilogue_chunk<N_TILE>(p, acc_b, c0 + 32, s_scale, s_shift, stg, r, use_tma_store, tma_res, row_ok, row_off, grow,
+                             gcol0);
     }
   }
 }
@@ -652,7 +674,7 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
         if (tma_res) tc::mbar_wait(res_bar + 8 * grp, use & 1u);
         const uint32_t t_addr = tmem_base + uint32_t(grp) * N_TILE + (uint32_t(q * 32) << 16);
         epilogue_columns<N_TILE>(p, t_addr, 0, N_TILE, g_scale, g_shift, stg, r, use_tma_store, tma_res, row_ok,
-                                 row_off);
+                                 row_off, tcd.w0 + r_w, tcd.nt * N_TILE);
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(tempty_bar + 8 * grp);
@@ -729,7 +751,7 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
             const int blk = grp * 2 + b;
             tc::mbar_wait(blk_in_bar + 8 * blk, tl & 1u);   // previous store read out (+ this tile's residual landed)
             epilogue_columns<N_TILE>(p, t_addr, blk * 64, blk * 64 + 64, s_scale, s_shift, stg, r, true, tma_res, false,
-                                     0);
+                                     0, tcd.w0 + r_w, tcd.nt * N_TILE);
             if (b == 1) {   // accumulator fully read: hand it back to the MMA warp
               tc::tc_fence_before();
               __syncwarp();
@@ -743,7 +765,7 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
         }
         if (active)
           epilogue_columns<N_TILE>(p, t_addr, col_lo, col_lo + COLS_PER_HALF, s_scale, s_shift, stg, r,
-                                   use_tma_store, tma_res, row_ok, row_off);
+                                   use_tma_store, tma_res, row_ok, row_off, tcd.w0 + r_w, tcd.nt * N_TILE);
         // accumulator fully read: hand it back to the MMA warp before the stores drain
         tc::tc_fence_before();
         __syncwarp();
@@ -877,6 +899,23 @@ extern "C" int mmbs_conv_run(const mmbs_conv_plan* plan, void* stream_) {
 }
 
 extern "C" void mmbs_conv_plan_destroy(mmbs_conv_plan* plan) { delete plan; }
+
+// Dropout of the NEXT layer's input, applied by this linear layer's epilogue (after bias / ReLU).  p = 0 switches it
+// off.  Takes effect from the next mmbs_conv_run; the mask is common.cuh dropout_keep8(seed, tag, row, column / 8).
+extern "C" int mmbs_plan_set_dropout(mmbs_conv_plan* plan, float p, uint64_t seed, uint32_t tag) {
+  MMBS_REQUIRE(plan != nullptr, "mmbs_plan_set_dropout: null plan");
+  MMBS_REQUIRE(p >= 0.f && p < 1.f, "mmbs_plan_set_dropout: p=%f", double(p));
+  ConvParams& q = plan->p;
+  MMBS_REQUIRE(p == 0.f || (q.out_h == 1 && q.batch == 1 && q.th == 1 && q.tn == 1 && q.residual == nullptr &&
+                            q.stats == nullptr && q.k_split <= 1 && !q.wg_conv),
+               "mmbs_plan_set_dropout: only plain linear layers (rows x features) take a fused dropout");
+  const float t = p * 65536.0f + 0.5f;
+  q.drop_thresh = p > 0.f ? (t >= 65535.0f ? 65535u : uint32_t(t)) : 0u;
+  q.drop_scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  q.drop_seed = seed;
+  q.drop_tag = tag;
+  return MMBS_OK;
+}
 
 // choose the (tw, th, tn) output-pixel box (product 128) that wastes the fewest rows
 // (exact_spatial: only boxes that tile the image exactly - the batch-statistics epilogue counts every tile row)

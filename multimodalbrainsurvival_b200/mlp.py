@@ -136,8 +136,9 @@ class _MLPTrainEngine:
                 self.b.append(E(self.np_[i], dtype=f32))
                 self.act.append(E(M, self.np_[i], dtype=f32 if last else bf))
                 if not last:
-                    nxt_p = layers[i + 1][2]
-                    self.hin.append(E(M, self.np_[i]) if nxt_p > 0 else self.act[i])
+                    # the dropout in front of the NEXT Linear is applied by THIS layer's GEMM epilogue
+                    # (mmbs_plan_set_dropout): the layer writes the next layer's input directly
+                    self.hin.append(self.act[i])
                 self.dz.append(E(M, self.np_[i]))
                 self.dW.append(E(self.np_[i], self.kp[i], dtype=f32))
                 self.db.append(E(self.np_[i], dtype=f32))
@@ -198,11 +199,12 @@ class _MLPTrainEngine:
                                             _lib.ptr(self.hin[0]), self.m, x.shape[1],
                                             self.kp[0], ps[0], seed, 0, _lib.stream_ptr()), "mmbs_dropout_cast_bf16")
         for i in range(len(self.layers)):
+            # bias + ReLU + the dropout of layer i+1's input in one epilogue (north_star (2)); mask (seed, tag i+1) is
+            # the one mmbs_mlp_bwd_elementwise regenerates.  act[i] then holds the DROPPED activations: the backward's
+            # ReLU test (act > 0) is unaffected - a dropped element carries no gradient either way.
+            p_next = ps[i + 1] if i + 1 < len(self.layers) else 0.0
+            _lib.check(L.mmbs_plan_set_dropout(self.fwd[i]._h, float(p_next), seed, i + 1), "mmbs_plan_set_dropout")
             self.fwd[i].run()
-            if i + 1 < len(self.layers) and self.hin[i + 1] is not self.act[i]:
-                _lib.check(L.mmbs_dropout_cast_bf16(_lib.ptr(self.act[i]), 1, self.np_[i], _lib.ptr(self.hin[i + 1]),
-                                                    self.m, self.np_[i], self.np_[i], ps[i + 1], seed, i + 1,
-                                                    _lib.stream_ptr()), "mmbs_dropout_cast_bf16")
         return self.act[-1][:, :self.layers[-1][0].out_features].clone()
 
     def backward(self, dy, seed):

@@ -142,10 +142,8 @@ def accelerate(module: nn.Module) -> nn.Module:
 
 
 # --------------------------------------------------------------------------- NLL survival loss
-def nll_loss(h, y, c, alpha=0.0, eps=1e-7, reduction='mean'):
-    """Discrete-time survival negative log-likelihood (Zadeh & Schmid 2020); ``survival_bin``
-    task of the histopathology scripts - not on the Cox hot path, kept as plain torch.
-    h: (n, n_bins) logits; y: (n, 1) int64 bin; c: (n, 1) censoring indicator (1 = censored)."""
+def _nll_loss_torch(h, y, c, alpha, eps, reduction):
+    """The reference's formula evaluated by torch (CPU tensors / dtypes the kernel does not take)."""
     n = len(y)
     y = y.view(n, 1)
     c = c.view(n, 1).float()
@@ -154,14 +152,54 @@ def nll_loss(h, y, c, alpha=0.0, eps=1e-7, reduction='mean'):
     log_s_prev = torch.log(torch.gather(surv, 1, y).clamp(min=eps))
     log_h_this = torch.log(torch.gather(hazards, 1, y).clamp(min=eps))
     log_s_this = torch.log(torch.gather(surv, 1, y + 1).clamp(min=eps))
-    uncensored = -(1 - c) * (log_s_prev + log_h_this)
-    censored = -c * log_s_this
-    loss = (1 - alpha) * censored + uncensored
-    if reduction == 'mean':
-        return loss.mean()
-    if reduction == 'sum':
-        return loss.sum()
-    raise ValueError("Bad input for reduction: {}".format(reduction))
+    loss = (1 - alpha) * (-c * log_s_this) - (1 - c) * (log_s_prev + log_h_this)
+    return loss.mean() if reduction == 'mean' else loss.sum()
+
+
+class _NLLSurvFn(torch.autograd.Function):
+    """csrc/nll.cu: one pass writes the loss and d loss_i / d h; backward only scales."""
+
+    @staticmethod
+    def forward(ctx, h, y, c, alpha, eps, mean):
+        from . import _lib
+        n, k = h.shape
+        hc = h.detach().contiguous()
+        yc = y.detach().reshape(-1).to(torch.int64).contiguous()
+        cc = c.detach().reshape(-1).float().contiguous()
+        buf = torch.empty(n * (k + 1) + 2, dtype=torch.float32, device=h.device)
+        loss_i, grad_unit, out = buf[:n], buf[n:n * (k + 1)], buf[n * (k + 1):]
+        with torch.cuda.device(h.device):
+            _lib.check(_lib.lib().mmbs_nll_surv_forward(_lib.ptr(hc), _lib.ptr(yc), _lib.ptr(cc), n, k, float(alpha),
+                                                        float(eps), int(mean), _lib.ptr(loss_i), _lib.ptr(grad_unit),
+                                                        _lib.ptr(out), _lib.ptr(out[1:]), _lib.stream_ptr()),
+                       "mmbs_nll_surv_forward")
+        ctx.save_for_backward(grad_unit)
+        ctx.shape, ctx.mean = (n, k), bool(mean)
+        return out[0].clone().reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        from . import _lib
+        (grad_unit,) = ctx.saved_tensors
+        n, k = ctx.shape
+        g = grad_loss.detach().reshape(1).float().contiguous()
+        grad_h = torch.empty((n, k), dtype=torch.float32, device=grad_unit.device)
+        with torch.cuda.device(grad_unit.device):
+            _lib.check(_lib.lib().mmbs_nll_surv_backward(_lib.ptr(grad_unit), _lib.ptr(g), n, k, int(ctx.mean),
+                                                         _lib.ptr(grad_h), _lib.stream_ptr()), "mmbs_nll_surv_backward")
+        return grad_h, None, None, None, None, None
+
+
+def nll_loss(h, y, c, alpha=0.0, eps=1e-7, reduction='mean'):
+    """Discrete-time survival negative log-likelihood (Zadeh & Schmid 2020), the ``survival_bin`` task of the
+    histopathology scripts (/root/reference/1_HistoPathology/models.py:155-232).
+    h: (n, n_bins) logits; y: (n, 1) int64 bin; c: (n, 1) censoring indicator (1 = censored).
+    CUDA fp32 logits run csrc/nll.cu (forward + gradient in one pass); anything else evaluates the same formula in torch."""
+    if reduction not in ('mean', 'sum'):
+        raise ValueError("Bad input for reduction: {}".format(reduction))
+    if h.is_cuda and h.dtype == torch.float32 and h.dim() == 2 and h.shape[0] >= 1 and len(y) == h.shape[0]:
+        return _NLLSurvFn.apply(h, y, c, alpha, eps, reduction == 'mean')
+    return _nll_loss_torch(h, y, c, alpha, eps, reduction)
 
 
 class NLLSurvLoss(nn.Module):

@@ -322,8 +322,30 @@ def gen_rna_script():
     print("rna_script: mirror == unmodified script on", len(script_rec), "evaluate calls; TRAIN losses", train_losses)
 
 
+# ------------------------------------------------------------------------------- nll
+def gen_nll():
+    """nll_loss / NLLSurvLoss of 1_HistoPathology/models.py:120-232 on seeded inputs: loss and d loss / d h (autograd),
+    mean and sum reductions, alpha 0 and 0.4, including logits extreme enough to hit the eps clamps."""
+    _stub_third_party()
+    m = load_ref("1_HistoPathology/models.py", "ref_histo_models_nll")
+    rng = np.random.default_rng(21)
+    out = {}
+    for ci, (n, k, alpha, reduction, scale) in enumerate([(128, 4, 0.0, "mean", 1.0), (37, 4, 0.4, "sum", 1.0),
+                                                          (64, 8, 0.0, "mean", 12.0), (5, 1, 0.0, "mean", 1.0)]):
+        h = torch.tensor((rng.standard_normal((n, k)) * scale).astype(np.float32), requires_grad=True)
+        y = torch.tensor(rng.integers(0, k, n).astype(np.int64))
+        c = torch.tensor((rng.uniform(size=n) < 0.4).astype(np.float32))
+        loss = m.NLLSurvLoss(alpha=alpha, reduction=reduction)(h, y, c)
+        loss.backward()
+        out[f"case{ci}/h"], out[f"case{ci}/y"], out[f"case{ci}/c"] = h.detach().numpy(), y.numpy(), c.numpy()
+        out[f"case{ci}/alpha"], out[f"case{ci}/mean"] = np.float32(alpha), np.int32(reduction == "mean")
+        out[f"case{ci}/loss"], out[f"case{ci}/grad"] = loss.detach().numpy(), h.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "nll_reference.npz"), **out)
+    print("nll: 4 cases")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["cox", "aggregate", "resnet", "resnet_train", "mlp"]
+    which = sys.argv[1:] or ["cox", "aggregate", "resnet", "resnet_train", "mlp", "nll", "rna_script"]
     for w in which:
         globals()["gen_" + w]()
