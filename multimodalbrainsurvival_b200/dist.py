@@ -17,6 +17,28 @@ import torch
 import torch.distributed as dist
 
 
+# ---- weight gradients of wide linear layers from all-gathered OPERANDS ----------------------------------------------
+# dW = dz^T h is a sum over the batch, so SUM-all-reducing the (out x in) fp32 gradient of every rank (243 MB for the
+# RNA model at batch 128 per GPU) can be replaced by all-gathering its two thin factors - dz [batch, out] and
+# h [batch, in] in bf16 (1 + 3.3 MB per rank for the 12778 -> 4096 layer) - and running the weight-gradient GEMM over
+# the GLOBAL batch on every rank: 8x the wgrad flops (still an HBM-bound outer product), ~50x fewer bytes on NVLink.
+# mlp._MLPTrainEngine does this for every layer where it pays once enable_factored_mlp_gradients() was called; those
+# weights come out of backward already summed over ranks and allreduce_gradients() skips them.
+_FACTORED = {"enabled": False, "group": None}
+GLOBAL_GRAD_ATTR = "_mmbs_grad_is_global"
+
+
+def enable_factored_mlp_gradients(enabled=True, group=None):
+    _FACTORED["enabled"], _FACTORED["group"] = bool(enabled), group
+
+
+def factored_mlp_world():
+    """(world size, group) when MLP weight gradients are to be built from all-gathered operands, else (1, None)."""
+    if not _FACTORED["enabled"] or not (dist.is_available() and dist.is_initialized()):
+        return 1, None
+    return dist.get_world_size(_FACTORED["group"]), _FACTORED["group"]
+
+
 def _world(group=None):
     if not (dist.is_available() and dist.is_initialized()):
         return 1, 0
@@ -72,7 +94,8 @@ def allreduce_gradients(params, group=None, bucket_bytes=256 << 20):
     """SUM-all-reduce ``.grad`` of ``params`` in flat fp32 buckets (NVSwitch: size buckets for
     launch latency, not link count)."""
     world, _ = _world(group)
-    grads = [p.grad for p in params if p.grad is not None]
+    # (weights whose gradient was built from all-gathered operands are already summed over the ranks)
+    grads = [p.grad for p in params if p.grad is not None and not getattr(p, GLOBAL_GRAD_ATTR, False)]
     if world == 1 or not grads:
         return
     if dist.get_backend(group) == "nccl" and hasattr(dist, "_coalescing_manager"):

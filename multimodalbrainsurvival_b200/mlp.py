@@ -111,9 +111,10 @@ def _pad64(n):
 class _MLPTrainEngine:
     """Buffers + GEMM plans of one MLP for a fixed batch size M (forward, dgrad, wgrad)."""
 
-    def __init__(self, layers, m_rows, device, need_dx):
+    def __init__(self, layers, m_rows, device, need_dx, world=1, group=None):
         from . import _lib
         self.layers = layers
+        self.world, self.group = int(world), group
         self.m, self.mp = m_rows, _pad64(m_rows)
         self.device = device
         self.need_dx = need_dx
@@ -145,8 +146,19 @@ class _MLPTrainEngine:
                 self.dh.append(E(M, self.kp[i]) if (i > 0 or need_dx) else None)
             self.fwd = [engine.linear_plan(self.hin[i], self.w[i], self.b[i], self.act[i], relu=layers[i][1])
                         for i in range(L)]
-            # dW[n, k] = sum_m dz[m, n] hin[m, k]: a TN GEMM on the row-major tensors themselves (MN-major operands)
-            self.wgrad = [engine.linear_tn_plan(self.dz[i], self.hin[i], self.dW[i]) for i in range(L)]
+            # dW[n, k] = sum_m dz[m, n] hin[m, k]: a TN GEMM on the row-major tensors themselves (MN-major operands).
+            # Data parallel (dist.enable_factored_mlp_gradients): where the two factors of all ranks are smaller than
+            # the gradient itself, they are all-gathered and the GEMM runs over the GLOBAL batch - the result is the
+            # rank-summed gradient, nothing is left to all-reduce for that weight.
+            self.dz_all, self.hin_all = [None] * L, [None] * L
+            for i in range(L):
+                factors = self.world * M * (self.np_[i] + self.kp[i]) * 2          # bf16 bytes gathered per rank
+                if self.world > 1 and 4 * factors < self.np_[i] * self.kp[i] * 4:  # vs the fp32 gradient
+                    self.dz_all[i] = E(self.world * M, self.np_[i])
+                    self.hin_all[i] = E(self.world * M, self.kp[i])
+            self.wgrad = [engine.linear_tn_plan(self.dz[i] if self.dz_all[i] is None else self.dz_all[i],
+                                                self.hin[i] if self.hin_all[i] is None else self.hin_all[i], self.dW[i])
+                          for i in range(L)]
             # dh[m, k] = sum_n dz[m, n] W[n, k]: an NN GEMM on the forward weight matrix itself (MN-major B operand)
             self.dgrad = [engine.linear_nn_plan(self.dz[i], self.w[i], None, self.dh[i]) if self.dh[i] is not None
                           else None for i in range(L)]
@@ -221,6 +233,10 @@ class _MLPTrainEngine:
                                                   int(relu), p_after, seed, i + 1, self.m, lin.out_features,
                                                   self.np_[i], self.mp, _lib.ptr(self.dz[i]), None,
                                                   _lib.ptr(self.db[i]), _lib.stream_ptr()), "mmbs_mlp_bwd_elementwise")
+            if self.dz_all[i] is not None:   # global-batch weight gradient from the gathered factors
+                import torch.distributed as tdist
+                tdist.all_gather_into_tensor(self.dz_all[i], self.dz[i], group=self.group)
+                tdist.all_gather_into_tensor(self.hin_all[i], self.hin[i], group=self.group)
             self.wgrad[i].run()
             if self.dgrad[i] is not None:
                 self.dgrad[i].run()
@@ -272,8 +288,10 @@ class _MLPTrainFn(torch.autograd.Function):
 
 
 def _run_train(seq, layers, x):
+    from . import dist as _dist
     need_dx = bool(x.requires_grad)
-    key = (id(seq), x.shape[0], x.device.index, need_dx)
+    world, group = _dist.factored_mlp_world()
+    key = (id(seq), x.shape[0], x.device.index, need_dx, world)
     pool = _TRAIN_ENGINES.get(key)
     if pool is None or any(a[0] is not b[0] for a, b in zip(pool[0].layers, layers)):
         if len(_TRAIN_ENGINES) > 32:
@@ -284,10 +302,12 @@ def _run_train(seq, layers, x):
         if len(pool) >= _MAX_ENGINES_PER_KEY:
             raise RuntimeError(f"fused MLP: {len(pool)} forwards of the same module are waiting for their backward; "
                                "run backward (or drop the outputs) before calling it again, or set MMBS_MLP_TRAIN=0")
-        eng = _MLPTrainEngine(layers, x.shape[0], x.device, need_dx)
+        eng = _MLPTrainEngine(layers, x.shape[0], x.device, need_dx, world, group)
         pool.append(eng)
     params = []
-    for lin, _, _ in layers:
+    for i, (lin, _, _) in enumerate(layers):
+        # (allreduce_gradients skips weights whose gradient already is the sum over the ranks)
+        setattr(lin.weight, _dist.GLOBAL_GRAD_ATTR, eng.dz_all[i] is not None)
         params.append(lin.weight)
         if lin.bias is not None:
             params.append(lin.bias)

@@ -41,6 +41,46 @@ for n_all in (1024, 200_003):
     ok &= good
     print(f"[rank {rank}] n={n_all}: global loss {float(loss.detach()):.7f} ref {float(ref.detach()):.7f} "
           f"rel grad err {dg:.2e} {'OK' if good else 'MISMATCH'}", flush=True)
+# data-parallel MLP training: weight gradients built from all-gathered operands (dist.enable_factored_mlp_gradients)
+# + SUM all-reduce of what is left must equal the single-GPU gradients of the whole batch
+import torch.nn as nn  # noqa: E402
+from multimodalbrainsurvival_b200 import mlp, models  # noqa: E402
+mdist.enable_factored_mlp_gradients()
+torch.manual_seed(11)                                   # same weights on every rank
+def make():
+    torch.manual_seed(11)
+    return (nn.Sequential(nn.Dropout(0.0), nn.Linear(2048, 1024), nn.ReLU(), nn.Dropout(0.0), nn.Linear(1024, 256)),
+            nn.Sequential(nn.Linear(256, 1)))
+per = 128
+g = torch.Generator().manual_seed(5)
+x_all = torch.randn(per * world, 2048, generator=g)
+t_all = torch.rand(per * world, generator=g) * 100
+e_all = (torch.rand(per * world, generator=g) < 0.6).float()
+rna, head = make()
+model = models.RNAOnlyModel(rna, head).to(dev).train()
+sl = slice(per * rank, per * (rank + 1))
+out = model(x_all[sl].to(dev))
+loss = mdist.global_cox_loss(out.view(-1), t_all[sl].to(dev), e_all[sl].to(dev), equal_sizes=True)
+loss.backward()
+n_global = sum(bool(getattr(p_, mdist.GLOBAL_GRAD_ATTR, False)) for p_ in model.parameters())
+mdist.allreduce_gradients(list(model.parameters()))
+rna1, head1 = make()
+ref_model = nn.Sequential(rna1, head1).to(dev).train()   # stock torch modules, fp32, the whole batch on one GPU
+ref_loss = cox.cox_loss(ref_model(x_all.to(dev)).view(-1), t_all.to(dev), e_all.to(dev))
+ref_loss.backward()
+good = n_global >= 1 and abs(float(loss.detach()) - float(ref_loss.detach())) <= 2e-2 * abs(float(ref_loss.detach()))
+# (the Cox loss is shift invariant: the bias gradients of the last layers are ~0 - errors are measured against the
+#  largest gradient norm of the model, not against those)
+gmax = max(float(p2.grad.norm()) for p2 in ref_model.parameters())
+for (n1, p1), (n2, p2) in zip(model.named_parameters(), ref_model.named_parameters()):
+    rel = float((p1.grad - p2.grad).norm() / max(float(p2.grad.norm()), 1e-2 * gmax))
+    good &= rel <= 6e-2   # bf16 operands through two layers (the all-reduced first-layer bias shows the same level)
+    if rank == 0:
+        print(f"[rank 0] factored-gradient MLP {n1}: rel err {rel:.2e} (global-batch wgrad: {getattr(p1, mdist.GLOBAL_GRAD_ATTR, False)})", flush=True)
+ok &= good
+print(f"[rank {rank}] data-parallel MLP gradients {'OK' if good else 'MISMATCH'}", flush=True)
+mdist.enable_factored_mlp_gradients(False)
+
 # distributed per-case aggregation (cases split across ranks)
 n, d = 5000, 256
 g = torch.Generator().manual_seed(3)
