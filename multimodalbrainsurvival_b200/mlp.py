@@ -153,7 +153,8 @@ class _MLPTrainEngine:
             self.dz_all, self.hin_all = [None] * L, [None] * L
             for i in range(L):
                 factors = self.world * M * (self.np_[i] + self.kp[i]) * 2          # bf16 bytes gathered per rank
-                if self.world > 1 and 4 * factors < self.np_[i] * self.kp[i] * 4:  # vs the fp32 gradient
+                # vs the fp32 gradient (whose all-reduce moves it twice: reduce-scatter + all-gather)
+                if self.world > 1 and factors < self.np_[i] * self.kp[i] * 4:
                     self.dz_all[i] = E(self.world * M, self.np_[i])
                     self.hin_all[i] = E(self.world * M, self.kp[i])
             self.wgrad = [engine.linear_tn_plan(self.dz[i] if self.dz_all[i] is None else self.dz_all[i],
@@ -225,6 +226,7 @@ class _MLPTrainEngine:
         L = _lib.lib()
         g, g_bf16, g_stride = dy.detach().float().contiguous(), 0, dy.shape[1]
         n_layers = len(self.layers)
+        # 1. the chain dz[L-1] -> dgrad -> dz[L-2] -> ... (the weight gradients hang off it, nothing waits for them)
         for i in range(n_layers - 1, -1, -1):
             lin, relu, _ = self.layers[i]
             p_after = self.ps[i + 1] if i + 1 < n_layers else 0.0   # dropout applied to this layer's output
@@ -233,16 +235,29 @@ class _MLPTrainEngine:
                                                   int(relu), p_after, seed, i + 1, self.m, lin.out_features,
                                                   self.np_[i], self.mp, _lib.ptr(self.dz[i]), None,
                                                   _lib.ptr(self.db[i]), _lib.stream_ptr()), "mmbs_mlp_bwd_elementwise")
-            if self.dz_all[i] is not None:   # global-batch weight gradient from the gathered factors
-                import torch.distributed as tdist
-                # (issuing the input gather asynchronously behind the forward pass measured slower at N = 2:
-                #  1.79 vs 1.57 ms per RNA step - the NCCL kernel then competes with the forward GEMMs for SMs)
-                tdist.all_gather_into_tensor(self.dz_all[i], self.dz[i], group=self.group)
-                tdist.all_gather_into_tensor(self.hin_all[i], self.hin[i], group=self.group)
-            self.wgrad[i].run()
             if self.dgrad[i] is not None:
                 self.dgrad[i].run()
                 g, g_bf16, g_stride = self.dh[i], 1, self.kp[i]
+        # 2. data parallel: ONE coalesced all-gather of the (dz, h) factors of every factored layer
+        pairs = [(self.dz_all[i], self.dz[i]) for i in range(n_layers) if self.dz_all[i] is not None]
+        pairs += [(self.hin_all[i], self.hin[i]) for i in range(n_layers) if self.hin_all[i] is not None]
+        if pairs:
+            import torch.distributed as tdist
+            done = False
+            if tdist.get_backend(self.group) == "nccl" and hasattr(tdist, "_coalescing_manager"):
+                try:
+                    with tdist._coalescing_manager(group=self.group, device=pairs[0][0].device, async_ops=False):
+                        for out_t, in_t in pairs:
+                            tdist.all_gather_into_tensor(out_t, in_t, group=self.group)
+                    done = True
+                except TypeError:   # private API signature moved (raised before any collective)
+                    pass
+            if not done:
+                for out_t, in_t in pairs:
+                    tdist.all_gather_into_tensor(out_t, in_t, group=self.group)
+        # 3. weight gradients (over the global batch where the factors were gathered)
+        for i in range(n_layers):
+            self.wgrad[i].run()
         dx = None
         if self.need_dx:
             k0 = self.layers[0][0].in_features
