@@ -77,6 +77,12 @@ int mmbs_cox_backward(const float* scores, const float* status, const int32_t* p
  * the multi-GPU all-gathered risk set. */
 int mmbs_risk_order(const float* times, int64_t n, int32_t* perm_out, void* workspace,
                     size_t workspace_bytes, void* stream);
+/* Diagnostics of the last mmbs_cox_forward / mmbs_risk_order that used `workspace` (synchronises the device):
+ * out_host[0] = pipeline state (0: bucketed pipeline; bit 0: a bucket overflowed in the partition, bit 1: a sub-bucket
+ * was too large for the rank-by-comparison finish - either bit means the LSD-sort pipeline redid the work; -1: n is
+ * outside the bucketed pipeline's range), out_host[1] = largest bucket, out_host[2] = buckets, out_host[3] = bucket
+ * capacity.  For tests and tools/cox_fallback_scan.py. */
+int mmbs_cox_debug_state(const void* workspace, size_t workspace_bytes, int64_t n, int32_t* out_host);
 
 /* ------------------------------------------------------- per-patient aggregation
  * Replaces the aggregation tails of

@@ -69,6 +69,7 @@ SIGNATURES = {
     "mmbs_cox_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64,
                                          c_void_p, c_void_p, c_size, c_void_p]),
     "mmbs_risk_order": (ctypes.c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_size, c_void_p]),
+    "mmbs_cox_debug_state": (ctypes.c_int, [c_void_p, c_size, c_i64, c_void_p]),
     "mmbs_segmented_mean_workspace_bytes": (c_size, [c_i64, c_i64]),
     "mmbs_segmented_mean": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p,
                                            c_void_p, c_void_p, c_size, c_void_p]),

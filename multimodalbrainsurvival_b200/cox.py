@@ -59,6 +59,26 @@ def risk_order(times: torch.Tensor) -> torch.Tensor:
     return perm
 
 
+def pipeline_state(times: torch.Tensor) -> dict:
+    """Diagnostics: sort `times` like cox_loss would and report whether the bucketed pipeline kept the input
+    (``state`` 0) or handed it to the LSD-sort pipeline (bit 0: bucket overflow, bit 1: oversized sub-bucket;
+    -1: n outside the bucketed range).  Synchronises the device; for tests and tools/cox_fallback_scan.py."""
+    import ctypes
+    t = _prep(times, "times")
+    n = t.numel()
+    perm = torch.empty(n, dtype=torch.int32, device=t.device)
+    L = _lib.lib()
+    out = (ctypes.c_int32 * 4)()
+    with torch.cuda.device(t.device):
+        nbytes = L.mmbs_cox_workspace_bytes(n)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=t.device)
+        _lib.check(L.mmbs_risk_order(_lib.ptr(t), n, _lib.ptr(perm), _lib.ptr(ws), nbytes, _lib.stream_ptr()),
+                   "mmbs_risk_order")
+        _lib.check(L.mmbs_cox_debug_state(_lib.ptr(ws), nbytes, n, ctypes.cast(out, ctypes.c_void_p)),
+                   "mmbs_cox_debug_state")
+    return {"state": int(out[0]), "largest_bucket": int(out[1]), "buckets": int(out[2]), "capacity": int(out[3])}
+
+
 class _CoxLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cox_scores, times, status):

@@ -525,6 +525,7 @@ struct CoxWorkspace {
   uint32_t* fs_counters;   // [8]
   uint32_t* fs_cursor;     // [FS_MAX_BUCKETS]
   double* fs_agg_val;      // [FS_MAX_BUCKETS]
+  uint32_t* fs_row_done;   // [FS_MAX_BUCKETS]
   size_t zero_bytes;
   // zeroed by the LSD pipeline itself, only when it runs
   uint32_t* lookback;      // [4][rs_tiles][256]
@@ -539,6 +540,10 @@ struct CoxWorkspace {
   double* fs_gsum_part;
   uint32_t* fs_bucket_base;
   uint32_t* fs_bucket_cnt;
+  float* fs_part32;        // [FS_MAX_BUCKETS * FS_PART]
+  double* fs_row_loss;     // [FS_MAX_BUCKETS * 16] each
+  double* fs_row_w;
+  double* fs_row_g;
   int32_t* max_list;       // [2][COX_MAX_LIST]
   double* gsum_total;      // [1]
   double* tile_sum;        // [cs_tiles] sums of exp(s~), scanned in place
@@ -549,6 +554,7 @@ struct CoxWorkspace {
   // the two pipelines never hold sort buffers at the same time: the bucket regions alias the LSD ping-pong arrays
   uint32_t* keys_a; uint32_t* keys_b; uint32_t* vals_a; uint32_t* vals_b;
   uint2* fs_pairs;         // [nb * FS_CAP]
+  float* fs_sc_part;       // [nb * FS_CAP]
   size_t total_bytes;
 };
 
@@ -569,6 +575,7 @@ static CoxWorkspace carve_cox(void* base, int64_t n) {
   w.fs_counters = c.take<uint32_t>(8);
   w.fs_cursor = c.take<uint32_t>(FS_MAX_BUCKETS);
   w.fs_agg_val = c.take<double>(FS_MAX_BUCKETS);
+  w.fs_row_done = c.take<uint32_t>(FS_MAX_BUCKETS);
   w.zero_bytes = align_up(c.off, 256);
   w.lookback_words = size_t(4) * rt * RS_RADIX;
   w.lookback = c.take<uint32_t>(w.lookback_words);
@@ -581,6 +588,10 @@ static CoxWorkspace carve_cox(void* base, int64_t n) {
   w.fs_gsum_part = c.take<double>(FS_MAX_BUCKETS);
   w.fs_bucket_base = c.take<uint32_t>(FS_MAX_BUCKETS);
   w.fs_bucket_cnt = c.take<uint32_t>(FS_MAX_BUCKETS);
+  w.fs_part32 = c.take<float>(size_t(FS_MAX_BUCKETS) * FS_PART);
+  w.fs_row_loss = c.take<double>(size_t(FS_MAX_BUCKETS) * 16);
+  w.fs_row_w = c.take<double>(size_t(FS_MAX_BUCKETS) * 16);
+  w.fs_row_g = c.take<double>(size_t(FS_MAX_BUCKETS) * 16);
   w.max_list = c.take<int32_t>(2 * COX_MAX_LIST);
   w.gsum_total = c.take<double>(1);
   w.tile_sum = c.take<double>(ct);
@@ -589,13 +600,14 @@ static CoxWorkspace carve_cox(void* base, int64_t n) {
   w.loss_partial = c.take<double>(ct);
   w.gsum_partial = c.take<double>(ct);
   const size_t lsd_words = size_t(4) * size_t(n);
-  const size_t fs_words = fast ? size_t(fs_plan(n).nb) * FS_CAP * 2 : 0;
+  const size_t fs_words = fast ? size_t(fs_plan(n).nb) * FS_CAP * 3 : 0;
   uint32_t* sortbuf = c.take<uint32_t>(std::max(lsd_words, fs_words));
   w.keys_a = sortbuf;
   w.keys_b = sortbuf + n;
   w.vals_a = sortbuf + 2 * n;
   w.vals_b = sortbuf + 3 * n;
   w.fs_pairs = reinterpret_cast<uint2*>(sortbuf);
+  w.fs_sc_part = reinterpret_cast<float*>(sortbuf) + (fast ? size_t(fs_plan(n).nb) * FS_CAP * 2 : 0);
   w.total_bytes = align_up(c.off, 256);
   return w;
 }
@@ -613,6 +625,8 @@ static FastSortWs fast_ws(const CoxWorkspace& w) {
   f.agg_val = w.fs_agg_val; f.fallback = w.fallback; f.lut = w.fs_lut; f.edge = w.fs_edge;
   f.exp_prefix = w.fs_exp_prefix; f.wsum = w.fs_wsum; f.loss_part = w.fs_loss_part; f.gsum_part = w.fs_gsum_part;
   f.bucket_base = w.fs_bucket_base; f.bucket_cnt = w.fs_bucket_cnt; f.pairs = w.fs_pairs;
+  f.sc_part = w.fs_sc_part; f.row_done = w.fs_row_done; f.part32 = w.fs_part32;
+  f.row_loss = w.fs_row_loss; f.row_w = w.fs_row_w; f.row_g = w.fs_row_g;
   return f;
 }
 
@@ -728,6 +742,24 @@ __global__ void cox_lsd_order_dispatch_kernel(CoxLsdOrder a) {
                       a.sort_grid, a.sort_tiles);
 }
 }  // namespace mmbs
+
+extern "C" int mmbs_cox_debug_state(const void* workspace, size_t workspace_bytes, int64_t n, int32_t* out_host) {
+  MMBS_REQUIRE(workspace && out_host && n >= 1, "mmbs_cox_debug_state: bad argument");
+  const CoxWorkspace w = carve_cox(const_cast<void*>(workspace), n);
+  MMBS_REQUIRE(workspace_bytes >= w.total_bytes, "mmbs_cox_debug_state: workspace too small");
+  out_host[0] = -1; out_host[1] = 0; out_host[2] = 0; out_host[3] = FS_CAP;
+  if (n <= SM_MAX || n > FS_MAX_N) return MMBS_OK;
+  MMBS_CUDA_TRY(cudaDeviceSynchronize());
+  MMBS_CUDA_TRY(cudaMemcpy(out_host, w.fallback, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  static uint32_t host_cursor[FS_MAX_BUCKETS];
+  const int nb = fs_plan(n).nb;
+  MMBS_CUDA_TRY(cudaMemcpy(host_cursor, w.fs_cursor, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost));
+  uint32_t big = 0;
+  for (int i = 0; i < nb; ++i) big = std::max(big, host_cursor[i]);
+  out_host[1] = int32_t(big);
+  out_host[2] = nb;
+  return MMBS_OK;
+}
 
 extern "C" int mmbs_risk_order(const float* times, int64_t n, int32_t* perm_out, void* workspace,
                                size_t workspace_bytes, void* stream_) {

@@ -20,7 +20,7 @@
 // Replaces  _, idx = torch.sort(-times); scores[idx]; status[idx]; exp; cumsum; log; mask; mean  of cox_loss()
 //   /root/reference/1_HistoPathology/models.py:99-111 (and its three textual copies).
 //
-// Inputs this map cannot balance (a bucket over FS_CAP samples, a sub-bucket over FS_CMAX: heavy ties, densities with
+// Inputs this map cannot balance (a bucket over FS_CAP samples, sub-buckets whose squared sizes add up to more than FS_SQ_BUDGET: heavy ties, densities with
 // jumps inside a 12-bit bin) raise the device flag `fallback`; the LSD-sort pipeline of radix_sort.cu / cox.cu is
 // enqueued behind and only runs when the flag is set - the decision never costs a host synchronisation.
 #include <algorithm>
@@ -60,9 +60,24 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 __device__ __forceinline__ void st_relaxed_f64(double* p, double v) {
   asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
-// exp / log of the scan: MUFU-based (2^-21 relative; the loss and its gradient are specified to 1e-5)
-__device__ __forceinline__ float fs_exp(float x) { return __expf(x); }
-__device__ __forceinline__ float fs_log(float x) { return __logf(x); }
+// exp / log / reciprocal of the scan: bare MUFU operations (2^-21 relative; the loss and its gradient are specified to
+// 1e-5).  No denormal fix-ups: the arguments of log / reciprocal are >= eps = 1e-5, exp results below 2^-126 count as 0.
+__device__ __forceinline__ float fs_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+__device__ __forceinline__ float fs_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fs_log(float x) { return fs_lg2(x) * 0.6931471805599453f; }
+__device__ __forceinline__ float fs_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // rank estimate of a key in [0, n): piecewise-linear CDF over the 12-bit bins.  E: the edge-bin record in SHARED memory
 // (read only by the few keys that fall into the two edge bins; lo_bin / hi_bin are register copies)
@@ -272,51 +287,27 @@ __global__ void __launch_bounds__(FS_HIST_THREADS, 6) fs_hist_kernel(
 }
 
 // ------------------------------------------------------------------------------------------ partition
-// dynamic shared memory: s_cnt[nbp] | s_start[nbp] | s_gbase[nbp] | staged pairs[P_TILE] | staged bucket ids[P_TILE] (u16)
-// (nbp = nb rounded up to a multiple of the block size)
+// dynamic shared memory: s_cnt[nbp] (re-used for the slot deltas) | s_start[nbp] | staged pairs[P_TILE] | staged scores[P_TILE]
+// (nbp = nb rounded up to a multiple of the block size).  A staged pair is (key, e | event << 13 | bucket << 14) with e the
+// sample's position inside the tile: the write-out pass needs no separate bucket-id array.
+constexpr uint32_t P_E_MASK = P_TILE - 1;
+static_assert(P_TILE == 8192 && FS_MAX_BUCKETS <= 4096, "staged payload packs 13 + 1 + 12 bits");
+
 template <bool FULL>   // FULL: the tile holds P_TILE samples and `times` / `status` / `scores` are 16-byte aligned
 __device__ __forceinline__ void partition_tile(const float* __restrict__ times, const float* __restrict__ status,
-                                               const float* __restrict__ scores, uint32_t* __restrict__ max_enc,
+                                               const float* __restrict__ scores, bool do_max, uint32_t* __restrict__ max_enc,
                                                int32_t* __restrict__ nan_flag, int64_t tile_base, int n_valid,
                                                const uint2* __restrict__ lut, int nb, int per,
                                                uint32_t* __restrict__ cursor, uint2* __restrict__ pairs_out,
-                                               int32_t* __restrict__ nonbinary_flag, int32_t* __restrict__ fallback,
-                                               uint32_t* s_cnt, uint32_t* s_start, uint32_t* s_delta, uint2* s_pairs,
-                                               uint16_t* s_bid, const FsEdge* s_E, uint32_t* s_w) {
+                                               float* __restrict__ sc_out, int32_t* __restrict__ nonbinary_flag,
+                                               int32_t* __restrict__ fallback, uint32_t* s_cnt, uint32_t* s_start,
+                                               uint2* s_pairs, float* s_sc, const FsEdge* s_E, uint32_t* s_w) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lo_bin = s_E->lo_bin, hi_bin = s_E->hi_bin, mult = s_E->mult;
+  uint32_t* s_delta = s_cnt;            // a bucket's count is dead once its start / slot delta are known
   uint32_t key[P_ITEMS], br[P_ITEMS];   // br = bucket << 16 | rank inside (tile, bucket)
   uint32_t ev = 0;                      // event bits of the thread's samples
   bool nonbinary = false;
-  if (scores != nullptr) {   // max(scores) and the NaN flag (when the histogram only sampled, it left them to this pass)
-    const uint64_t pol = make_evict_last_policy();   // the sort kernel gathers from `scores` next
-    float vmax = -INFINITY;
-    bool has_nan = false;
-#pragma unroll
-    for (int q = 0; q < P_ITEMS / 4; ++q) {
-      const int e0 = 4 * (q * P_THREADS + tid);
-      float s4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      if (FULL) {
-        const float4 v = ld_f32x4_hint(scores + tile_base + e0, pol);
-        s4[0] = v.x; s4[1] = v.y; s4[2] = v.z; s4[3] = v.w;
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (e0 + k < n_valid) s4[k] = ld_f32_hint(scores + tile_base + e0 + k, pol);
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        has_nan |= (s4[k] != s4[k]);
-        vmax = fmaxf(vmax, s4[k]);
-      }
-    }
-    vmax = warp_max(vmax);
-    const unsigned any_nan = __ballot_sync(0xffffffffu, has_nan);
-    if (lane == 0) {
-      atomicMax(max_enc, float_order_enc(vmax));
-      if (any_nan) atomicOr(nan_flag, 1);
-    }
-  }
   // sample (q, k) of the thread is tile element 4 * (q * P_THREADS + tid) + k
 #pragma unroll
   for (int q = 0; q < P_ITEMS / 4; ++q) {
@@ -373,14 +364,46 @@ __device__ __forceinline__ void partition_tile(const float* __restrict__ times, 
     }
   }
   __syncthreads();
+  // stage the tile in bucket order; the scores ride along (second read of the tile's scores: this pass also owns
+  // max(scores) / the NaN flag when the histogram only sampled)
+  {
+    const uint64_t pol = make_evict_last_policy();
+    float vmax = -INFINITY;
+    bool has_nan = false;
 #pragma unroll
-  for (int j = 0; j < P_ITEMS; ++j) {
-    if (FULL || br[j] != 0xffffffffu) {
-      const int e = 4 * ((j >> 2) * P_THREADS + tid) + (j & 3);
-      const uint32_t b = br[j] >> 16;
-      const uint32_t pos = s_start[b] + (br[j] & 0xffffu);
-      s_pairs[pos] = make_uint2(key[j], uint32_t(tile_base + e) | (((ev >> j) & 1u) << 31));
-      s_bid[pos] = uint16_t(b);
+    for (int q = 0; q < P_ITEMS / 4; ++q) {
+      const int e0 = 4 * (q * P_THREADS + tid);
+      float s4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (scores != nullptr) {
+        if (FULL) {
+          const float4 v = ld_f32x4_hint(scores + tile_base + e0, pol);
+          s4[0] = v.x; s4[1] = v.y; s4[2] = v.z; s4[3] = v.w;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (e0 + k < n_valid) s4[k] = ld_f32_hint(scores + tile_base + e0 + k, pol);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = q * 4 + k;
+        has_nan |= (s4[k] != s4[k]);
+        vmax = fmaxf(vmax, s4[k]);
+        if (FULL || br[j] != 0xffffffffu) {
+          const uint32_t b = br[j] >> 16;
+          const uint32_t pos = s_start[b] + (br[j] & 0xffffu);
+          s_pairs[pos] = make_uint2(key[j], uint32_t(e0 + k) | (((ev >> j) & 1u) << 13) | (b << 14));
+          s_sc[pos] = s4[k];
+        }
+      }
+    }
+    if (do_max) {
+      vmax = warp_max(vmax);
+      const unsigned any_nan = __ballot_sync(0xffffffffu, has_nan);
+      if (lane == 0) {
+        atomicMax(max_enc, float_order_enc(vmax));
+        if (any_nan) atomicOr(nan_flag, 1);
+      }
     }
   }
   __syncthreads();
@@ -390,21 +413,26 @@ __device__ __forceinline__ void partition_tile(const float* __restrict__ times, 
     const int i = j * P_THREADS + tid;
     if (FULL || i < n_valid) {
       const uint2 pr = s_pairs[i];
-      const uint32_t b = s_bid[i];
+      const uint32_t b = pr.y >> 14;
       const uint32_t dst = uint32_t(i) + s_delta[b];
       // (3 slots stay free: the blocked 16-byte loads of the loss / backward kernels start at base & ~3)
-      if (dst < uint32_t(FS_CAP - 3)) pairs_out[size_t(b) * FS_CAP + dst] = pr;
-      else overflow = true;
+      if (dst < uint32_t(FS_CAP - 3)) {
+        const size_t o = size_t(b) * FS_CAP + dst;
+        pairs_out[o] = make_uint2(pr.x, uint32_t(tile_base + (pr.y & P_E_MASK)) | (((pr.y >> 13) & 1u) << 31));
+        if (scores != nullptr) sc_out[o] = s_sc[i];
+      } else {
+        overflow = true;
+      }
     }
   }
-  if (overflow) atomicExch(fallback, 1);
+  if (overflow) atomicOr(fallback, 1);
 }
 
 __global__ void __launch_bounds__(P_THREADS, 2) fs_partition_kernel(
-    const float* __restrict__ times, const float* __restrict__ status, const float* __restrict__ scores,
+    const float* __restrict__ times, const float* __restrict__ status, const float* __restrict__ scores, int do_max,
     uint32_t* __restrict__ max_enc, int32_t* __restrict__ nan_flag, int64_t n, const uint2* __restrict__ lut,
     const FsEdge* __restrict__ edge, int nb, uint32_t* __restrict__ cursor, uint2* __restrict__ pairs_out,
-    int32_t* __restrict__ nonbinary_flag, int32_t* __restrict__ fallback) {
+    float* __restrict__ sc_out, int32_t* __restrict__ nonbinary_flag, int32_t* __restrict__ fallback) {
   extern __shared__ __align__(16) uint32_t s_dyn[];
   __shared__ uint32_t s_w[P_THREADS / 32];
   __shared__ FsEdge s_E;
@@ -413,9 +441,8 @@ __global__ void __launch_bounds__(P_THREADS, 2) fs_partition_kernel(
   const int nbp = per * P_THREADS;
   uint32_t* s_cnt = s_dyn;
   uint32_t* s_start = s_dyn + nbp;
-  uint32_t* s_delta = s_dyn + 2 * nbp;
-  uint2* s_pairs = reinterpret_cast<uint2*>(s_dyn + 3 * nbp);
-  uint16_t* s_bid = reinterpret_cast<uint16_t*>(s_dyn + 3 * nbp + 2 * P_TILE);
+  uint2* s_pairs = reinterpret_cast<uint2*>(s_dyn + 2 * nbp);
+  float* s_sc = reinterpret_cast<float*>(s_dyn + 2 * nbp + 2 * P_TILE);
   if (tid < 8) reinterpret_cast<uint32_t*>(&s_E)[tid] = reinterpret_cast<const uint32_t*>(edge)[tid];
   for (int i = tid; i < nbp; i += P_THREADS) s_cnt[i] = 0;
   __syncthreads();
@@ -425,14 +452,14 @@ __global__ void __launch_bounds__(P_THREADS, 2) fs_partition_kernel(
                     (status == nullptr || (reinterpret_cast<uintptr_t>(status) & 15) == 0) &&
                     (scores == nullptr || (reinterpret_cast<uintptr_t>(scores) & 15) == 0);
   if (full)
-    partition_tile<true>(times, status, scores, max_enc, nan_flag, tile_base, n_valid, lut, nb, per, cursor, pairs_out,
-                         nonbinary_flag, fallback, s_cnt, s_start, s_delta, s_pairs, s_bid, &s_E, s_w);
+    partition_tile<true>(times, status, scores, do_max != 0, max_enc, nan_flag, tile_base, n_valid, lut, nb, per, cursor,
+                         pairs_out, sc_out, nonbinary_flag, fallback, s_cnt, s_start, s_pairs, s_sc, &s_E, s_w);
   else
-    partition_tile<false>(times, status, scores, max_enc, nan_flag, tile_base, n_valid, lut, nb, per, cursor, pairs_out,
-                          nonbinary_flag, fallback, s_cnt, s_start, s_delta, s_pairs, s_bid, &s_E, s_w);
+    partition_tile<false>(times, status, scores, do_max != 0, max_enc, nan_flag, tile_base, n_valid, lut, nb, per, cursor,
+                          pairs_out, sc_out, nonbinary_flag, fallback, s_cnt, s_start, s_pairs, s_sc, &s_E, s_w);
 }
 
-// ------------------------------------------------------------------------------------------ per-bucket sort + gather
+// ------------------------------------------------------------------------------------------ per-bucket sort
 // Row j of a block holds the samples j * B_THREADS + tid.  f(j, ok) runs for every row of the 4-row groups that hold
 // samples: groups of full rows with ok == true as a compile-time constant (no per-sample predicate), the one partial
 // group with ok = (sample exists); empty groups are skipped by a block-uniform branch.
@@ -451,38 +478,30 @@ __device__ __forceinline__ void for_rows(int cnt, int tid, F&& f) {
   }
 }
 
-// One block per bucket.  dynamic shared memory: s_a[FS_CAP + S_PAD] | s_b[FS_CAP + S_PAD] | s_cnt[S_SUB + 1]
+// One block per bucket.  dynamic shared memory: s_c[FS_CAP + S_PAD] (64-bit composites; after the finish its words hold
+// the sorted payloads [FS_CAP] | sorted s~ words [FS_CAP]) | s_cnt[S_SUB + 1]
 constexpr int S_SUB = 1 << FS_LOG_S;   // sub-buckets of the counting sort
-constexpr int S_PAD = 160;             // >= FS_CMAX sentinel keys behind the bucket (the finish reads past sub-bucket ends)
-constexpr int S_KU = 8;                // unrolled trip count of the finish (largest sub-bucket of a typical block)
+constexpr int S_PAD = 160;             // >= S_KU sentinels behind the bucket (the finish reads S_KU slots from a sub-bucket's start)
+constexpr int S_KU = 8;                // slots every sample compares unconditionally (largest sub-bucket of a typical block)
 constexpr int S_DYN_SMEM = (2 * (FS_CAP + S_PAD) + S_SUB + 8) * 4;
-static_assert(S_PAD >= FS_CMAX + 8, "sentinel padding must cover the largest accepted sub-bucket");
-
-// rank of (key, me) among the members [lo, hi) of its sub-bucket, in the total order (key, original index); kept out of
-// line: taken only for sub-buckets over S_KU samples and for tied survival times
-__device__ __noinline__ uint32_t finish_slow(const uint32_t* s_a, const uint32_t* s_b, uint32_t lo, uint32_t hi, uint32_t key,
-                                             uint32_t me) {
-  uint32_t rank = lo;
-  for (uint32_t q = lo; q < hi; ++q) {
-    const uint32_t k2 = s_a[q];
-    if (k2 < key || (k2 == key && (s_b[q] & 0x7fffffffu) < me)) ++rank;
-  }
-  return rank;
-}
+static_assert(S_PAD >= S_KU, "sentinel padding must cover the unconditional compares");
 
 __global__ void __launch_bounds__(B_THREADS, 2) fs_bucket_sort_kernel(
-    const uint2* __restrict__ pairs, const uint32_t* __restrict__ cursor, int nb, const float* __restrict__ scores,
-    const uint32_t* __restrict__ max_enc, int32_t* __restrict__ perm_out, float* __restrict__ saved_s, int32_t* max_count,
-    int32_t* __restrict__ max_list, double* __restrict__ agg_val, uint32_t* __restrict__ bucket_base,
-    uint32_t* __restrict__ bucket_cnt, int32_t* fallback) {
+    const uint2* __restrict__ pairs, const float* __restrict__ sc_part, const uint32_t* __restrict__ cursor, int nb,
+    int has_scores, const uint32_t* __restrict__ max_enc, int32_t* __restrict__ perm_out, float* __restrict__ saved_s,
+    int32_t* max_count, int32_t* __restrict__ max_list, double* __restrict__ agg_val, float* __restrict__ part32,
+    uint32_t* __restrict__ bucket_base, uint32_t* __restrict__ bucket_cnt, int32_t* fallback) {
   extern __shared__ __align__(16) uint32_t s_dyn[];
   __shared__ double s_red[B_THREADS / 32];
   __shared__ uint32_t s_w[B_THREADS / 32];
   __shared__ uint32_t s_w2[B_THREADS / 32];
+  __shared__ uint32_t s_w3[B_THREADS / 32];
   __shared__ uint32_t s_misc[4];   // 0: stop flag, 1: smallest key, 2: largest key
-  uint32_t* s_a = s_dyn;                          // keys in sub-bucket order, then the sorted payloads
-  uint32_t* s_b = s_dyn + (FS_CAP + S_PAD);       // payloads in sub-bucket order
-  uint32_t* s_cnt = s_dyn + 2 * (FS_CAP + S_PAD); // sub-bucket counters / starts, one sentinel
+  // (key << 32 | index << 1 | event) in sub-bucket order: one 64-bit compare orders by (key, original index)
+  unsigned long long* s_c = reinterpret_cast<unsigned long long*>(s_dyn);
+  uint32_t* s_p = s_dyn;                           // after the finish: payloads in sorted order
+  uint32_t* s_q = s_dyn + FS_CAP;                  // after the finish: |s~| | event << 31 in sorted order
+  uint32_t* s_cnt = s_dyn + 2 * (FS_CAP + S_PAD);  // sub-bucket counters / starts, one sentinel
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = B_THREADS / 32;
   const int b = blockIdx.x;
@@ -534,20 +553,25 @@ __global__ void __launch_bounds__(B_THREADS, 2) fs_bucket_sort_kernel(
       dr[j] = (d << 16) | atomicAdd(&s_cnt[d], 1u);
     }
   });
-  if (tid < S_PAD) s_a[cnt + tid] = 0xffffffffu;   // sentinels: larger than every key of the bucket
+  if (tid < S_PAD) s_c[cnt + tid] = ~0ull;   // sentinels: larger than every composite of the bucket
   __syncthreads();
   uint32_t cmax;   // largest sub-bucket of the block
   {
     constexpr int PER = S_SUB / B_THREADS;
-    uint32_t c[PER], sum = 0, big = 0;
+    uint32_t c[PER], sum = 0, big = 0, sq = 0;
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
       c[k] = s_cnt[tid * PER + k];
       sum += c[k];
       big = max(big, c[k]);
+      sq += c[k] > uint32_t(S_KU) ? c[k] * c[k] : 0u;   // (sizes add up to <= FS_CAP: the squares to < 2^27)
     }
     big = __reduce_max_sync(0xffffffffu, big);
-    if (lane == 0) s_w2[warp] = big;
+    sq = __reduce_add_sync(0xffffffffu, sq);
+    if (lane == 0) {
+      s_w2[warp] = big;
+      s_w3[warp] = sq;
+    }
     const uint2 sc = block_scan_u32<NW>(sum, s_w, lane, warp);   // (its barriers also publish s_w2)
     uint32_t run = sc.x - sum;
 #pragma unroll
@@ -557,12 +581,16 @@ __global__ void __launch_bounds__(B_THREADS, 2) fs_bucket_sort_kernel(
     }
     if (tid == 0) s_cnt[S_SUB] = uint32_t(cnt);
     cmax = 0;
+    uint32_t sqsum = 0;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) cmax = max(cmax, s_w2[w]);
-    // heavy ties / a density jump inside the bucket: the finish below would be quadratic.  Give the whole input up:
-    // the LSD pipeline redoes it.
-    if (cmax > uint32_t(FS_CMAX)) {
-      if (tid == 0) atomicExch(fallback, 1);
+    for (int w = 0; w < NW; ++w) {
+      cmax = max(cmax, s_w2[w]);
+      sqsum += s_w3[w];
+    }
+    // heavy ties / a density jump inside the bucket: the finish below is quadratic in the size of a sub-bucket.  Past the
+    // budget give the whole input up: the LSD pipeline redoes it.
+    if (sqsum > uint32_t(FS_SQ_BUDGET)) {
+      if (tid == 0) atomicOr(fallback, 2);
       return;
     }
   }
@@ -571,74 +599,88 @@ __global__ void __launch_bounds__(B_THREADS, 2) fs_bucket_sort_kernel(
     if (ok) {
       const uint32_t lo = s_cnt[dr[j] >> 16];
       const uint32_t pos = lo + (dr[j] & 0xffffu);
-      s_a[pos] = key[j];
-      s_b[pos] = val[j];
+      s_c[pos] = (static_cast<unsigned long long>(key[j]) << 32) | __funnelshift_l(val[j], val[j], 1);
       dr[j] = lo | (dr[j] & 0xffff0000u);   // sub-bucket << 16 | its first slot (< 8192)
     }
   });
   __syncthreads();
   // ---- final rank = first slot of the sub-bucket + members that precede in the total order (key, index).  Slots behind
-  // the sub-bucket hold larger keys (sub-buckets are ordered, the bucket ends in sentinels), so S_KU slots are compared
-  // unconditionally; equal keys (counted on the way: the sample itself is one) order by original index - the stable
+  // the sub-bucket hold larger composites (sub-buckets are ordered, the bucket ends in sentinels), so S_KU slots are
+  // compared unconditionally; tied survival times order by original index inside the same 64-bit compare - the stable
   // order, whatever order the atomics produced.
   for_rows(cnt, tid, [&](int j, bool ok) {
     if (ok) {
       const uint32_t lo = dr[j] & 0xffffu;
-      const uint32_t* row = s_a + lo;
-      uint32_t k2[S_KU];
+      const unsigned long long me = (static_cast<unsigned long long>(key[j]) << 32) | __funnelshift_l(val[j], val[j], 1);
+      const unsigned long long* row = s_c + lo;
+      unsigned long long c2[S_KU];
 #pragma unroll
-      for (int k = 0; k < S_KU; ++k) k2[k] = row[k];
-      uint32_t rank = lo, same = 0;
+      for (int k = 0; k < S_KU; ++k) c2[k] = row[k];
+      uint32_t rank = lo;
 #pragma unroll
-      for (int k = 0; k < S_KU; ++k) {
-        rank += (k2[k] < key[j]) ? 1u : 0u;
-        same += (k2[k] == key[j]) ? 1u : 0u;
-      }
-      // a sub-bucket over S_KU samples, or tied survival times (rare): compare (key, index) with every member
-      if (cmax > uint32_t(S_KU) || same > 1u) {
+      for (int k = 0; k < S_KU; ++k) rank += (c2[k] < me) ? 1u : 0u;
+      if (cmax > uint32_t(S_KU)) {   // (block-uniform, rare) a sub-bucket over S_KU samples: the rest of its members
         const uint32_t hi = s_cnt[(dr[j] >> 16) + 1];
-        if (hi - lo > uint32_t(S_KU) || same > 1u) rank = finish_slow(s_a, s_b, lo, hi, key[j], val[j] & 0x7fffffffu);
+#pragma unroll 4
+        for (uint32_t q = lo + S_KU; q < hi; ++q) rank += (s_c[q] < me) ? 1u : 0u;
       }
       dr[j] = rank;
     }
   });
-  __syncthreads();
-  for_rows(cnt, tid, [&](int j, bool ok) {
-    if (ok) s_a[dr[j]] = val[j];
-  });
-  __syncthreads();
-
-  if (scores == nullptr) {   // mmbs_risk_order: the permutation only
+  uint32_t* po = reinterpret_cast<uint32_t*>(perm_out) + base + tid;
+  if (!has_scores) {   // mmbs_risk_order: the permutation only
+    __syncthreads();
     for_rows(cnt, tid, [&](int j, bool ok) {
-      if (ok) perm_out[base + j * B_THREADS + tid] = int32_t(s_a[j * B_THREADS + tid]);
+      if (ok) s_p[dr[j]] = val[j];
+    });
+    __syncthreads();
+    for_rows(cnt, tid, [&](int j, bool ok) {
+      if (ok) po[j * B_THREADS] = s_p[j * B_THREADS + tid];
     });
     return;
   }
-  // ---- gather s~ = scores[index] - max through the sorted payloads (scores L2-resident: evict_last since the histogram);
-  // saved_s keeps |s~| with the event bit in the sign position (s~ <= 0 always)
+  // ---- the scores came along with the partition (same slot as the pair): s~ = score - max, kept as |s~| with the event
+  // bit in the sign position (s~ <= 0 always); both words move to their sorted slot
+  const float* scp = sc_part + size_t(b) * FS_CAP + tid;
+  for_rows(cnt, tid, [&](int j, bool ok) {   // (key is dead: its registers carry the scores)
+    key[j] = ok ? __float_as_uint(__ldg(scp + j * B_THREADS)) : 0u;
+  });
   const float smax = float_order_dec(__ldg(max_enc));
-  const uint64_t pol = make_evict_last_policy();
-  float esum = 0.f;
-  int32_t* po = perm_out + base + tid;
-  uint32_t* so = reinterpret_cast<uint32_t*>(saved_s) + base + tid;
-  for_rows(cnt, tid, [&](int j, bool ok) {   // (val / key are dead: their registers carry the gather)
-    val[j] = ok ? s_a[j * B_THREADS + tid] : 0u;
-  });
-  for_rows(cnt, tid, [&](int j, bool ok) {
-    key[j] = ok ? __float_as_uint(ld_f32_hint(scores + (val[j] & 0x7fffffffu), pol)) : 0u;
-  });
+  __syncthreads();   // every thread is done with the composites (and with the sub-bucket starts)
   for_rows(cnt, tid, [&](int j, bool ok) {
     if (ok) {
       const float sv = __uint_as_float(key[j]) - smax;
-      po[j * B_THREADS] = int32_t(val[j]);
-      so[j * B_THREADS] = (__float_as_uint(sv) & 0x7fffffffu) | (val[j] & 0x80000000u);
-      esum += fs_exp(sv);
+      s_p[dr[j]] = val[j];
+      s_q[dr[j]] = (__float_as_uint(sv) & 0x7fffffffu) | (val[j] & 0x80000000u);
       if (sv == 0.f) {   // an argmax position (gradient through max(scores) in the backward pass)
         const int pos = atomicAdd(max_count, 1);
         if (pos < FS_MAX_LIST) max_list[pos] = int32_t(val[j] & 0x7fffffffu);
       }
     }
   });
+  __syncthreads();
+  uint32_t* so = reinterpret_cast<uint32_t*>(saved_s) + base + tid;
+  for_rows(cnt, tid, [&](int j, bool ok) {
+    if (ok) {
+      po[j * B_THREADS] = s_p[j * B_THREADS + tid];
+      so[j * B_THREADS] = s_q[j * B_THREADS + tid];
+    }
+  });
+  // sums of exp(s~): thread t adds up the 16 consecutive sorted positions 16 t .. 16 t + 15 of the bucket, two adjacent
+  // threads make one of the 32-position partial sums the row kernels build their offsets from
+  float esum = 0.f;
+  if (16 * tid < cnt) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 x = *reinterpret_cast<const uint4*>(s_q + 16 * tid + 4 * q);
+      const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        esum += (16 * tid + 4 * q + k < cnt) ? fs_exp(__uint_as_float(xs[k] | 0x80000000u)) : 0.f;   // s~ = -|s~|
+    }
+  }
+  const float pair = esum + __shfl_xor_sync(0xffffffffu, esum, 1);
+  if ((tid & 1) == 0) part32[size_t(b) * FS_PART + (tid >> 1)] = pair;
   const double tot = block_sum_f64<NW>(double(esum), s_red, lane, warp);
   if (tid == 0) {
     agg_val[b] = tot;
@@ -647,18 +689,24 @@ __global__ void __launch_bounds__(B_THREADS, 2) fs_bucket_sort_kernel(
   }
 }
 
-// ------------------------------------------------------------------------------------------ per-bucket loss / gradient
-// Both kernels read their bucket in the BLOCKED arrangement straight from global memory: thread t owns 16 consecutive
-// sorted positions, fetched as four 16-byte loads from the 16-byte aligned address below the bucket's first position
-// (positions in front of the bucket / behind it are masked).  No shared-memory staging.  (1024 threads x 8 samples,
-// one block per SM, measured slower: 97 / 186 us against 55 / 141 us - a lone block stalls the SM at every barrier.)
-constexpr int L_THREADS = 512;
-constexpr int L_ITEMS = FS_CAP / L_THREADS;   // 16
-static_assert(L_ITEMS % 4 == 0, "blocked 16-byte loads");
+// ------------------------------------------------------------------------------------------ per-row loss / gradient
+// Both kernels work in WARP ROWS: warp `wg` (0..15) of bucket b owns the 512 sorted positions a0 + 512 wg .. +512, with
+// a0 = the bucket's first position rounded down to a multiple of 4; lane l owns 16 consecutive positions, fetched as four
+// 16-byte loads (positions in front of the bucket / behind it are masked).  A warp finds the sum of exp(s~) in front of its
+// row from the bucket prefix and the 32-position partial sums the sort kernel left (part32), scans inside the warp with
+// shuffles, and leaves per-row partial sums: no block-wide scan, no barrier between the phases of different warps.  (One
+// block per bucket with block-wide scans spent most of its time in barriers: 50 / 134 us against ... for this layout.)
+constexpr int R_THREADS = 128;
+constexpr int R_WARPS = R_THREADS / 32;
+constexpr int R_SPAN = 512;                    // positions per warp row
+constexpr int R_ROWS = FS_CAP / R_SPAN;        // 16 warp rows per bucket
+constexpr int R_BLOCKS = R_ROWS / R_WARPS;     // 4 blocks per bucket
+constexpr int L_ITEMS = R_SPAN / 32;           // 16
+static_assert(L_ITEMS % 4 == 0 && R_ROWS == 16 && FS_PART == FS_CAP / 32, "row geometry");
 struct BucketSlice {
-  uint32_t a0;     // first position covered by the block: bucket base rounded down to a multiple of 4
+  uint32_t a0;     // first position covered by the bucket's rows: bucket base rounded down to a multiple of 4
   int lead;        // masked positions in front of the bucket (0..3)
-  int end;         // lead + samples of the bucket: thread-local positions [lead, end) are real
+  int end;         // lead + samples of the bucket: row-local positions [lead, end) are real
 };
 __device__ __forceinline__ BucketSlice bucket_slice(const uint32_t* __restrict__ bucket_base,
                                                     const uint32_t* __restrict__ bucket_cnt, int b) {
@@ -669,7 +717,7 @@ __device__ __forceinline__ BucketSlice bucket_slice(const uint32_t* __restrict__
   s.end = s.lead + int(__ldg(bucket_cnt + b));
   return s;
 }
-// L_ITEMS consecutive words of the thread (zeros where no 16-byte group of the bucket lies)
+// L_ITEMS consecutive words of the lane (zeros where no 16-byte group of the bucket lies)
 __device__ __forceinline__ void load_items(const uint32_t* __restrict__ p, int first, int end, uint32_t (&v)[L_ITEMS]) {
 #pragma unroll
   for (int q = 0; q < L_ITEMS / 4; ++q) {
@@ -679,9 +727,9 @@ __device__ __forceinline__ void load_items(const uint32_t* __restrict__ p, int f
   }
 }
 
-// A thread is INTERIOR when all L_ITEMS of its positions are samples of the bucket (every thread but the one or two at the
-// bucket's ends and the idle ones behind it): its loops carry no per-sample predicate.  `sel(ok_true_type, f)` style:
-// f(j, ok) is instantiated once with ok == true as a constant and once with the real test.
+// A lane is INTERIOR when all L_ITEMS of its positions are samples of the bucket (every lane but the one or two at the
+// bucket's ends and the idle ones behind it): its loops carry no per-sample predicate.  f(j, ok) is instantiated once with
+// ok == true as a constant and once with the real test.
 template <typename F>
 __device__ __forceinline__ void for_items(bool interior, int first, int lead, int end, F&& f) {
   if (interior) {
@@ -702,85 +750,142 @@ __device__ __forceinline__ void for_items_rev(bool interior, int first, int lead
     for (int j = L_ITEMS - 1; j >= 0; --j) f(j, first + j >= lead && first + j < end);
   }
 }
+// exclusive scans of one double per lane: sum over the lower lanes / over the higher lanes
+__device__ __forceinline__ double warp_excl_fwd(double v, int lane) {
+  double incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  return incl - v;
+}
+__device__ __forceinline__ double warp_excl_rev(double v, int lane) {
+  double incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_down_sync(0xffffffffu, incl, o);
+    if (lane + o < 32) incl += t;
+  }
+  return incl - v;
+}
+// sum of a per-thread double over the block's R_WARPS warps (one barrier; every thread of the block must call)
+// sum of the lane's first `lead` running values = c[lead - 1] (lane 0 of a row: the samples in front of position 512 wg)
+__device__ __forceinline__ float lead_sum(const float (&c)[L_ITEMS], int lead) {
+  return lead == 1 ? c[0] : (lead == 2 ? c[1] : (lead == 3 ? c[2] : 0.f));
+}
+__device__ __forceinline__ double row_block_sum(double v, double* s_red, int lane, int warp) {
+  v = warp_sum(v);
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < R_WARPS; ++w) t += s_red[w];
+  return t;
+}
+// sum of exp(s~) over the first 512 wg positions of the bucket: 16 wg partial sums of 32 positions each.  (The row itself
+// starts `lead` positions earlier, at the 16-byte aligned address: the caller takes those samples' terms off again.)
+__device__ __forceinline__ double row_exp_offset(const float* __restrict__ part32, int b, int wg, int lane) {
+  const float* p = part32 + size_t(b) * FS_PART;
+  double s = 0.0;
+  for (int c = lane; c < wg * (R_SPAN / 32); c += 32) s += double(__ldg(p + c));
+  return warp_sum(s);
+}
 
-__global__ void __launch_bounds__(L_THREADS, 2) fs_bucket_loss_kernel(
+__global__ void __launch_bounds__(R_THREADS, 8) fs_row_loss_kernel(
     const float* __restrict__ saved_s, const int32_t* __restrict__ perm, const float* __restrict__ status, int nb, int64_t n,
     const uint32_t* __restrict__ bucket_base, const uint32_t* __restrict__ bucket_cnt, const double* __restrict__ agg_val,
-    double* __restrict__ exp_prefix, double* __restrict__ wsum, double* loss_part, uint32_t* counters, int32_t* nan_flag,
-    const int32_t* __restrict__ nonbinary_flag, float* __restrict__ loss_out, int32_t* __restrict__ flags_out,
-    const int32_t* __restrict__ fallback) {
-  __shared__ double s_red[L_THREADS / 32];
-  __shared__ uint32_t s_last;
-  constexpr int NW = L_THREADS / 32;
+    const float* __restrict__ part32, double* __restrict__ exp_prefix, double* row_loss, double* row_w, uint32_t* row_done,
+    double* wsum, double* loss_part, uint32_t* counters, int32_t* nan_flag, const int32_t* __restrict__ nonbinary_flag,
+    float* __restrict__ loss_out, int32_t* __restrict__ flags_out, const int32_t* __restrict__ fallback) {
+  __shared__ double s_red[R_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (*fallback != 0) return;   // final by now: the kernels that raise it have finished
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / R_BLOCKS, wg = (blockIdx.x % R_BLOCKS) * R_WARPS + warp;
   const BucketSlice sl = bucket_slice(bucket_base, bucket_cnt, b);
-  double pre = 0.0;
-  for (int q = tid; q < b; q += L_THREADS) pre += __ldg(agg_val + q);
-  const int first = tid * L_ITEMS;
-  const bool interior = first >= sl.lead && first + L_ITEMS <= sl.end;
+  const int first = wg * R_SPAN + lane * L_ITEMS;
+  const bool active = wg * R_SPAN < sl.end;   // warp-uniform: the row holds samples
   uint32_t enc[L_ITEMS];
-  load_items(reinterpret_cast<const uint32_t*>(saved_s) + sl.a0, first, sl.end, enc);
-  const double P = block_sum_f64<NW>(pre, s_red, lane, warp);   // sum of exp(s~) over all earlier buckets
-  float c[L_ITEMS];
-  float run = 0.f;
-  for_items(interior, first, sl.lead, sl.end, [&](int j, bool ok) {
-    run += ok ? fs_exp(__uint_as_float(enc[j] | 0x80000000u)) : 0.f;   // s~ = -|s~|
-    c[j] = run;
-  });
-  double total;
-  const double incl = block_scan_f64<NW, false>(double(run), s_red, lane, warp, &total);
-  const double off = P + (incl - double(run));
-  // C = off + c[j], rounded to fp32 once: off as a (hi, lo) float pair (2 FADD per sample instead of fp64 converts)
-  const float off_hi = float(off), off_lo = float(off - double(off_hi));
-  float lsum = 0.f, ws = 0.f;
-  bool bad = false;
-  if (*nonbinary_flag == 0) {
-    for_items(interior, first, sl.lead, sl.end, [&](int j, bool ok) {
-      if (ok && (enc[j] >> 31)) {
-        const float den = ((off_hi + c[j]) + off_lo) + FS_EPS;                        // cumsum + eps (models.py:104)
-        const float term = fs_log(den) - __uint_as_float(enc[j] | 0x80000000u);       // -(s~ - log(.)) (models.py:104-105)
-        lsum += term;
-        ws += __fdividef(1.f, den);
-        bad |= (term != term);
-      }
-    });
-  } else if (first < sl.end) {   // general status weights: gathered through the permutation
-    uint32_t pv[L_ITEMS];
-    load_items(reinterpret_cast<const uint32_t*>(perm) + sl.a0, first, sl.end, pv);
+  if (active) load_items(reinterpret_cast<const uint32_t*>(saved_s) + sl.a0, first, sl.end, enc);
+  double pre = 0.0;
+#pragma unroll 4
+  for (int q = tid; q < b; q += R_THREADS) pre += __ldg(agg_val + q);
+  const double P = row_block_sum(pre, s_red, lane, warp);   // sum of exp(s~) over all earlier buckets
+  if (blockIdx.x % R_BLOCKS == 0 && tid == 0) exp_prefix[b] = P;
+  double tl = 0.0, tw = 0.0;
+  if (active) {
+    const bool interior = first >= sl.lead && first + L_ITEMS <= sl.end;
+    const double rowoff = P + row_exp_offset(part32, b, wg, lane);
+    float c[L_ITEMS];
+    float run = 0.f;
 #pragma unroll
-    for (int j = 0; j < L_ITEMS; ++j) {
-      const bool ok = first + j >= sl.lead && first + j < sl.end;
-      if (ok) {
-        const float dl = __ldg(status + (pv[j] & 0x7fffffffu));
-        const float den = ((off_hi + c[j]) + off_lo) + FS_EPS;
-        const float term = -(__uint_as_float(enc[j] | 0x80000000u) - fs_log(den)) * dl;
-        lsum += term;
-        ws += __fdividef(dl, den);
-        bad |= (term != term);
+    for (int j = 0; j < L_ITEMS; ++j) c[j] = 0.f;
+    for_items(interior, first, sl.lead, sl.end, [&](int j, bool ok) {
+      run += ok ? fs_exp(__uint_as_float(enc[j] | 0x80000000u)) : 0.f;   // s~ = -|s~|
+      c[j] = run;
+    });
+    const float head = __shfl_sync(0xffffffffu, lead_sum(c, sl.lead), 0);
+    const double off = (rowoff - double(head)) + warp_excl_fwd(double(run), lane);
+    // C + eps = off + c[j] + eps, rounded to fp32 once: off as a (hi, lo) float pair, eps folded into lo (2 FADD per sample
+    // instead of fp64 converts)
+    const float off_hi = float(off), off_lo = float(off - double(off_hi)) + FS_EPS;
+    float lsum = 0.f, ws = 0.f;
+    if (*nonbinary_flag == 0) {
+      for_items(interior, first, sl.lead, sl.end, [&](int j, bool ok) {
+        const bool event = ok && (enc[j] >> 31);
+        const float den = (off_hi + c[j]) + off_lo;                                             // cumsum + eps (models.py:104)
+        const float term = fmaf(fs_lg2(den), 0.6931471805599453f, __uint_as_float(enc[j] & 0x7fffffffu));   // log(.) - s~
+        lsum += event ? term : 0.f;                                                             // (models.py:104-105)
+        ws += event ? fs_rcp(den) : 0.f;
+      });
+    } else if (first < sl.end) {   // general status weights: gathered through the permutation
+      uint32_t pv[L_ITEMS];
+      load_items(reinterpret_cast<const uint32_t*>(perm) + sl.a0, first, sl.end, pv);
+#pragma unroll
+      for (int j = 0; j < L_ITEMS; ++j) {
+        const bool ok = first + j >= sl.lead && first + j < sl.end;
+        if (ok) {
+          const float dl = __ldg(status + (pv[j] & 0x7fffffffu));
+          const float den = (off_hi + c[j]) + off_lo;
+          const float term = -(__uint_as_float(enc[j] | 0x80000000u) - fs_log(den)) * dl;
+          lsum += term;
+          ws += dl * fs_rcp(den);
+        }
       }
     }
+    const unsigned any_bad = __ballot_sync(0xffffffffu, lsum != lsum);   // a NaN term makes the lane's sum NaN
+    if (lane == 0 && any_bad) atomicOr(nan_flag, 1);
+    tl = warp_sum(double(lsum));
+    tw = warp_sum(double(ws));
   }
-  const unsigned any_bad = __ballot_sync(0xffffffffu, bad);
-  if (lane == 0 && any_bad) atomicOr(nan_flag, 1);
-  const double tl = block_sum_f64<NW>(double(lsum), s_red, lane, warp);
-  const double tw = block_sum_f64<NW>(double(ws), s_red, lane, warp);
-  if (tid == 0) {
-    exp_prefix[b] = P;
-    wsum[b] = tw;
-    loss_part[b] = tl;
+  // the last row of a bucket to finish adds the bucket's rows up (fixed order); the last bucket adds the buckets up
+  uint32_t last = 0;
+  if (lane == 0) {
+    row_loss[b * R_ROWS + wg] = tl;
+    row_w[b * R_ROWS + wg] = tw;
     __threadfence();
-    s_last = (atomicAdd(counters + 2, 1u) == uint32_t(nb) - 1u) ? 1u : 0u;
+    last = (atomicAdd(row_done + b, 1u) == uint32_t(R_ROWS) - 1u) ? 1u : 0u;
   }
-  __syncthreads();
-  if (s_last == 0u) return;
-  // the last block: loss = sum of the bucket partials / n   (.mean() over N, models.py:111)
+  if (__shfl_sync(0xffffffffu, last, 0) == 0u) return;
+  __threadfence();
+  tl = warp_sum(lane < R_ROWS ? __ldcg(row_loss + b * R_ROWS + lane) : 0.0);
+  tw = warp_sum(lane < R_ROWS ? __ldcg(row_w + b * R_ROWS + lane) : 0.0);
+  last = 0;
+  if (lane == 0) {
+    loss_part[b] = tl;
+    wsum[b] = tw;
+    row_done[b] = 0u;   // the backward pass counts its rows on the same words
+    __threadfence();
+    last = (atomicAdd(counters + 2, 1u) == uint32_t(nb) - 1u) ? 1u : 0u;
+  }
+  if (__shfl_sync(0xffffffffu, last, 0) == 0u) return;
+  // the last warp: loss = sum of the bucket partials / n   (.mean() over N, models.py:111)
   __threadfence();
   double t = 0.0;
-  for (int q = tid; q < nb; q += L_THREADS) t += ld_volatile_f64(loss_part + q);
-  t = block_sum_f64<NW>(t, s_red, lane, warp);
-  if (tid == 0) {
+#pragma unroll 8
+  for (int q = lane; q < nb; q += 32) t += __ldcg(loss_part + q);
+  t = warp_sum(t);
+  if (lane == 0) {
     const int f = *reinterpret_cast<const volatile int32_t*>(nan_flag);
     loss_out[0] = f ? __int_as_float(0x7fc00000) : float(t / double(n));
     if (flags_out) flags_out[0] = f;
@@ -789,12 +894,10 @@ __global__ void __launch_bounds__(L_THREADS, 2) fs_bucket_loss_kernel(
 
 // the per-sample part of the backward pass; GATHER: general (non-binary) status weights, read through the permutation
 template <bool GATHER>
-__device__ __forceinline__ double bucket_backward_body(const BucketSlice sl, const int32_t* __restrict__ perm,
-                                                       const float* __restrict__ saved_s, const float* __restrict__ status,
-                                                       double P, double S_later, float scale, float* grad_scores,
-                                                       double* s_red, int tid, int lane, int warp) {
-  constexpr int NW = L_THREADS / 32;
-  const int first = tid * L_ITEMS;
+__device__ __forceinline__ double row_backward_body(const BucketSlice sl, int first, const int32_t* __restrict__ perm,
+                                                    const float* __restrict__ saved_s, const float* __restrict__ status,
+                                                    double rowoff, double S_later, float scale, float* grad_scores,
+                                                    int lane) {
   const bool interior = first >= sl.lead && first + L_ITEMS <= sl.end;
   float e[L_ITEMS], cw[L_ITEMS], dl[GATHER ? L_ITEMS : 1];
   uint32_t evm = 0;
@@ -820,21 +923,19 @@ __device__ __forceinline__ double bucket_backward_body(const BucketSlice sl, con
       dl[GATHER ? j : 0] = ok ? __ldg(status + (pv[j] & 0x7fffffffu)) : 0.f;
     }
   }
-  double total;
-  const double incl = block_scan_f64<NW, false>(double(run), s_red, lane, warp, &total);
-  const double off = P + (incl - double(run));
-  const float off_hi = float(off), off_lo = float(off - double(off_hi));   // the same C as the forward pass
+  const float head = __shfl_sync(0xffffffffu, lead_sum(cw, sl.lead), 0);
+  const double off = (rowoff - double(head)) + warp_excl_fwd(double(run), lane);
+  const float off_hi = float(off), off_lo = float(off - double(off_hi)) + FS_EPS;   // the same C + eps as the forward pass
   float wrun = 0.f;
   for_items_rev(interior, first, sl.lead, sl.end, [&](int j, bool ok) {
-    const float den = ((off_hi + cw[j]) + off_lo) + FS_EPS;
+    const float den = (off_hi + cw[j]) + off_lo;
     float w;
-    if (GATHER) w = __fdividef(dl[GATHER ? j : 0], den);            // 0 where there is no sample
-    else w = ((evm >> j) & 1u) ? __fdividef(1.f, den) : 0.f;
+    if (GATHER) w = dl[GATHER ? j : 0] * fs_rcp(den);               // 0 where there is no sample
+    else w = ((evm >> j) & 1u) ? fs_rcp(den) : 0.f;
     wrun += w;
-    cw[j] = wrun;   // inclusive suffix of w inside the thread
+    cw[j] = wrun;   // inclusive suffix of w inside the lane
   });
-  const double sincl = block_scan_f64<NW, true>(double(wrun), s_red, lane, warp, &total);
-  const double soff = S_later + (sincl - double(wrun));
+  const double soff = S_later + warp_excl_rev(double(wrun), lane);
   const float soff_hi = float(soff), soff_lo = float(soff - double(soff_hi));
   uint32_t pv[L_ITEMS];
   load_items(reinterpret_cast<const uint32_t*>(perm) + sl.a0, first, sl.end, pv);
@@ -848,62 +949,77 @@ __device__ __forceinline__ double bucket_backward_body(const BucketSlice sl, con
       gs += g;
     }
   });
-  return block_sum_f64<NW>(double(gs), s_red, lane, warp);
+  return warp_sum(double(gs));
 }
 
-__device__ __noinline__ double bucket_backward_gather(const BucketSlice sl, const int32_t* __restrict__ perm,
-                                                      const float* __restrict__ saved_s, const float* __restrict__ status,
-                                                      double P, double S_later, float scale, float* grad_scores,
-                                                      double* s_red, int tid, int lane, int warp) {
-  return bucket_backward_body<true>(sl, perm, saved_s, status, P, S_later, scale, grad_scores, s_red, tid, lane, warp);
+__device__ __noinline__ double row_backward_gather(const BucketSlice sl, int first, const int32_t* __restrict__ perm,
+                                                   const float* __restrict__ saved_s, const float* __restrict__ status,
+                                                   double rowoff, double S_later, float scale, float* grad_scores, int lane) {
+  return row_backward_body<true>(sl, first, perm, saved_s, status, rowoff, S_later, scale, grad_scores, lane);
 }
 
-__global__ void __launch_bounds__(L_THREADS, 2) fs_bucket_backward_kernel(
+__global__ void __launch_bounds__(R_THREADS, 8) fs_row_backward_kernel(
     const int32_t* __restrict__ perm, const float* __restrict__ saved_s, const float* __restrict__ status,
     const float* __restrict__ grad_loss, int64_t n, int nb, const uint32_t* __restrict__ bucket_base,
-    const uint32_t* __restrict__ bucket_cnt, const double* __restrict__ exp_prefix, const double* __restrict__ wsum,
-    double* gsum_part, uint32_t* counters, const int32_t* __restrict__ nonbinary_flag, const int32_t* __restrict__ max_count,
+    const uint32_t* __restrict__ bucket_cnt, const double* __restrict__ exp_prefix, const float* __restrict__ part32,
+    const double* __restrict__ wsum, const double* __restrict__ row_w, double* row_g, uint32_t* row_done, double* gsum_part,
+    uint32_t* counters, const int32_t* __restrict__ nonbinary_flag, const int32_t* __restrict__ max_count,
     const int32_t* __restrict__ max_list, double* __restrict__ gsum_total, float* grad_scores,
     const int32_t* __restrict__ fallback) {
-  __shared__ double s_red[L_THREADS / 32];
-  __shared__ uint32_t s_last;
-  constexpr int NW = L_THREADS / 32;
+  __shared__ double s_red[R_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (*fallback != 0) return;
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / R_BLOCKS, wg = (blockIdx.x % R_BLOCKS) * R_WARPS + warp;
   const BucketSlice sl = bucket_slice(bucket_base, bucket_cnt, b);
-  const double P = __ldg(exp_prefix + b);
+  const int first = wg * R_SPAN + lane * L_ITEMS;
+  const bool active = wg * R_SPAN < sl.end;
   double later = 0.0;
-  for (int q = b + 1 + tid; q < nb; q += L_THREADS) later += __ldg(wsum + q);
-  const double S_later = block_sum_f64<NW>(later, s_red, lane, warp);   // sum of w over all later buckets
-  const float scale = float(double(grad_loss[0]) / double(n));
-  double tg;
-  if (*nonbinary_flag != 0)   // (rare, and out of line: its extra live array must not cost the common path registers)
-    tg = bucket_backward_gather(sl, perm, saved_s, status, P, S_later, scale, grad_scores, s_red, tid, lane, warp);
-  else
-    tg = bucket_backward_body<false>(sl, perm, saved_s, status, P, S_later, scale, grad_scores, s_red, tid, lane, warp);
-  if (tid == 0) {
-    gsum_part[b] = tg;
-    __threadfence();
-    s_last = (atomicAdd(counters + 3, 1u) == uint32_t(nb) - 1u) ? 1u : 0u;
+#pragma unroll 4
+  for (int q = b + 1 + tid; q < nb; q += R_THREADS) later += __ldg(wsum + q);
+  double S_later = row_block_sum(later, s_red, lane, warp);   // sum of w over all later buckets
+  double tg = 0.0;
+  if (active) {
+    S_later += warp_sum((lane > wg && lane < R_ROWS) ? __ldg(row_w + b * R_ROWS + lane) : 0.0);   // .. and later rows
+    const double rowoff = __ldg(exp_prefix + b) + row_exp_offset(part32, b, wg, lane);
+    const float scale = float(double(grad_loss[0]) / double(n));
+    if (*nonbinary_flag != 0)   // (rare, and out of line: its extra live array must not cost the common path registers)
+      tg = row_backward_gather(sl, first, perm, saved_s, status, rowoff, S_later, scale, grad_scores, lane);
+    else
+      tg = row_backward_body<false>(sl, first, perm, saved_s, status, rowoff, S_later, scale, grad_scores, lane);
   }
-  __syncthreads();
-  if (s_last == 0u) return;
-  // the last block: gradient through "- max(scores)": every argmax position receives -(sum_k g~_k) / count
+  uint32_t last = 0;
+  if (lane == 0) {
+    row_g[b * R_ROWS + wg] = tg;
+    __threadfence();
+    last = (atomicAdd(row_done + b, 1u) == uint32_t(R_ROWS) - 1u) ? 1u : 0u;
+  }
+  if (__shfl_sync(0xffffffffu, last, 0) == 0u) return;
+  __threadfence();
+  tg = warp_sum(lane < R_ROWS ? __ldcg(row_g + b * R_ROWS + lane) : 0.0);
+  last = 0;
+  if (lane == 0) {
+    gsum_part[b] = tg;
+    row_done[b] = 0u;   // a second backward over the same forward (retain_graph) counts from zero again
+    __threadfence();
+    last = (atomicAdd(counters + 3, 1u) == uint32_t(nb) - 1u) ? 1u : 0u;
+  }
+  if (__shfl_sync(0xffffffffu, last, 0) == 0u) return;
+  // the last warp: gradient through "- max(scores)": every argmax position receives -(sum_k g~_k) / count
   __threadfence();
   double t = 0.0;
-  for (int q = tid; q < nb; q += L_THREADS) t += ld_volatile_f64(gsum_part + q);
-  t = block_sum_f64<NW>(t, s_red, lane, warp);
-  if (tid == 0) gsum_total[0] = t;
+#pragma unroll 8
+  for (int q = lane; q < nb; q += 32) t += __ldcg(gsum_part + q);
+  t = warp_sum(t);
+  if (lane == 0) gsum_total[0] = t;
   const int mc = *max_count;
   if (mc <= FS_MAX_LIST) {
     const float fix = float(t / double(mc));
-    for (int i = tid; i < mc; i += L_THREADS) {
+    for (int i = lane; i < mc; i += 32) {
       float* p = grad_scores + max_list[i];
       *reinterpret_cast<volatile float*>(p) = *reinterpret_cast<volatile float*>(p) - fix;
     }
   }
-  if (tid == 0) counters[3] = 0u;   // a second backward over the same forward (retain_graph) counts from zero again
+  if (lane == 0) counters[3] = 0u;
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -929,7 +1045,7 @@ static int fs_configure() {
   static PerDeviceOnce configured;
   if (configured.first()) {
     MMBS_CUDA_TRY(cudaFuncSetAttribute(fs_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (3 * FS_MAX_BUCKETS + 2 * P_TILE) * 4 + P_TILE * 2));
+                                       (2 * FS_MAX_BUCKETS + 3 * P_TILE) * 4));
     MMBS_CUDA_TRY(cudaFuncSetAttribute(fs_bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_DYN_SMEM));
   }
   return MMBS_OK;
@@ -952,19 +1068,19 @@ int fs_forward_enqueue(const float* times, const float* status, const float* sco
   MMBS_LAUNCH_CHECK();
   const int64_t tiles = ceil_div(n, P_TILE);
   const int nbp = int(ceil_div(p.nb, P_THREADS)) * P_THREADS;
-  const int p_smem = (3 * nbp + 2 * P_TILE) * 4 + P_TILE * 2;
-  fs_partition_kernel<<<unsigned(tiles), P_THREADS, p_smem, stream>>>(times, status, sampled ? scores : nullptr, max_enc,
+  const int p_smem = (2 * nbp + 3 * P_TILE) * 4;
+  fs_partition_kernel<<<unsigned(tiles), P_THREADS, p_smem, stream>>>(times, status, scores, sampled ? 1 : 0, max_enc,
                                                                      nan_flag, n, w.lut, w.edge, p.nb, w.cursor, w.pairs,
-                                                                     nonbinary_flag, w.fallback);
+                                                                     w.sc_part, nonbinary_flag, w.fallback);
   MMBS_LAUNCH_CHECK();
-  fs_bucket_sort_kernel<<<p.nb, B_THREADS, S_DYN_SMEM, stream>>>(w.pairs, w.cursor, p.nb, scores, max_enc, perm_out,
-                                                                saved_s, max_count, max_list, w.agg_val, w.bucket_base,
-                                                                w.bucket_cnt, w.fallback);
+  fs_bucket_sort_kernel<<<p.nb, B_THREADS, S_DYN_SMEM, stream>>>(w.pairs, w.sc_part, w.cursor, p.nb, scores != nullptr,
+                                                                max_enc, perm_out, saved_s, max_count, max_list, w.agg_val,
+                                                                w.part32, w.bucket_base, w.bucket_cnt, w.fallback);
   MMBS_LAUNCH_CHECK();
   if (scores == nullptr) return MMBS_OK;   // mmbs_risk_order
-  fs_bucket_loss_kernel<<<p.nb, L_THREADS, 0, stream>>>(saved_s, perm_out, status, p.nb, n, w.bucket_base, w.bucket_cnt,
-                                                       w.agg_val, w.exp_prefix, w.wsum, w.loss_part, w.counters, nan_flag,
-                                                       nonbinary_flag, loss_out, flags_out, w.fallback);
+  fs_row_loss_kernel<<<p.nb * R_BLOCKS, R_THREADS, 0, stream>>>(
+      saved_s, perm_out, status, p.nb, n, w.bucket_base, w.bucket_cnt, w.agg_val, w.part32, w.exp_prefix, w.row_loss, w.row_w,
+      w.row_done, w.wsum, w.loss_part, w.counters, nan_flag, nonbinary_flag, loss_out, flags_out, w.fallback);
   MMBS_LAUNCH_CHECK();
   return MMBS_OK;
 }
@@ -973,9 +1089,9 @@ int fs_backward_enqueue(const float* status, const int32_t* perm, const float* s
                         const FastSortWs& w, const int32_t* nonbinary_flag, const int32_t* max_count,
                         const int32_t* max_list, double* gsum_total, float* grad_scores, cudaStream_t stream) {
   const FsPlan p = fs_plan(n);
-  fs_bucket_backward_kernel<<<p.nb, L_THREADS, 0, stream>>>(
-      perm, saved_s, status, grad_loss, n, p.nb, w.bucket_base, w.bucket_cnt, w.exp_prefix, w.wsum, w.gsum_part, w.counters,
-      nonbinary_flag, max_count, max_list, gsum_total, grad_scores, w.fallback);
+  fs_row_backward_kernel<<<p.nb * R_BLOCKS, R_THREADS, 0, stream>>>(
+      perm, saved_s, status, grad_loss, n, p.nb, w.bucket_base, w.bucket_cnt, w.exp_prefix, w.part32, w.wsum, w.row_w, w.row_g,
+      w.row_done, w.gsum_part, w.counters, nonbinary_flag, max_count, max_list, gsum_total, grad_scores, w.fallback);
   MMBS_LAUNCH_CHECK();
   return MMBS_OK;
 }

@@ -12,7 +12,10 @@ constexpr int FS_MAX_BUCKETS = 4096;
 constexpr int FS_CAP = 8192;               // samples one block sorts in shared memory (= slots per bucket region)
 constexpr int FS_TARGET = 6144;            // aimed bucket size (12 of the 16 rows of a block): 1.33x head-room below FS_CAP
 constexpr int FS_LOG_S = 12;               // 4096 sub-buckets per bucket (~1.25 samples each)
-constexpr int FS_CMAX = 128;               // largest sub-bucket the rank-by-comparison finish accepts
+constexpr int FS_SQ_BUDGET = 1 << 20;      // rank-by-comparison finish: accepted sum of (sub-bucket size)^2 over the sub-buckets
+                                           // of more than 8 samples (one run of ~1000 tied times, or the bucket that ends at
+                                           // t -> 0 and spans a hundred binades); beyond: the LSD pipeline
+constexpr int FS_PART = FS_CAP / 32;        // partial sums of exp(s~) per bucket: one per 32 sorted positions
 constexpr int FS_MAX_LIST = 1024;          // argmax positions remembered for the gradient through max(scores)
 constexpr int64_t FS_MAX_N = int64_t(FS_MAX_BUCKETS) * FS_TARGET;   // 25.2 M; beyond: LSD sort
 
@@ -53,6 +56,7 @@ struct FastSortWs {
   uint32_t* counters;      // [8]: 0 histogram blocks done, 2 loss blocks done, 3 backward blocks done
   uint32_t* cursor;        // [FS_MAX_BUCKETS] samples written to every bucket region
   int32_t* fallback;       // [1] set when this pipeline gave up: the LSD-sort pipeline must (re)do the work
+  uint32_t* row_done;      // [FS_MAX_BUCKETS] warp rows of the bucket that finished (loss pass, then backward pass)
   // not zeroed
   uint2* lut;              // [FS_BINS] (exclusive prefix, count) of every 12-bit bin
   FsEdge* edge;            // [1]
@@ -64,6 +68,11 @@ struct FastSortWs {
   uint32_t* bucket_base;   // [FS_MAX_BUCKETS] first sorted position of the bucket               (kept for backward)
   uint32_t* bucket_cnt;    // [FS_MAX_BUCKETS]                                                    (kept for backward)
   uint2* pairs;            // [nb * FS_CAP] partitioned (key, index | event << 31)
+  float* part32;           // [FS_MAX_BUCKETS * FS_PART] sums of exp(s~) over 32 sorted positions       (kept for backward)
+  double* row_loss;        // [FS_MAX_BUCKETS * 16] per warp row: loss terms, w, gradient sums
+  double* row_w;           //                                                                    (kept for backward)
+  double* row_g;
+  float* sc_part;          // [nb * FS_CAP] the samples' scores in the same slots (the bucket sort never gathers)
 };
 
 // Forward: histogram (+ max / NaN flag over `scores`) -> partition -> per-bucket sort + gather + scan + loss.

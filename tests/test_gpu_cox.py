@@ -114,10 +114,47 @@ def test_integer_month_ties_at_300k():
     _check(s, t, e, "integer months")
 
 
-def test_lsd_path_above_fast_sort_limit():
-    """n > FS_MAX_N (12 M) takes the 4-pass LSD sort: order checked against torch.sort(stable)."""
+@pytest.mark.parametrize("dist", ["uniform200", "exponential"])
+@pytest.mark.parametrize("n", [3_000_000, 10_000_000])
+def test_smooth_distributions_stay_on_the_bucketed_pipeline(n, dist):
+    """Smooth survival-time distributions must not raise the device-side fallback (a fallback is correct but 3x
+    slower).  The bucket that ends at t -> 0 spans a hundred binades and crowds a few sub-buckets: inside the
+    squared-size budget of the rank-by-comparison finish (FS_SQ_BUDGET)."""
     from multimodalbrainsurvival_b200 import cox
-    n = 12_500_000
+    dev = "cuda:0"
+    for seed in (0, 1, 5, 7, 8):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        u = torch.rand(n, device=dev, generator=g)
+        t = u * 200 if dist == "uniform200" else -torch.log1p(-u) * 30
+        st = cox.pipeline_state(t)
+        assert st["state"] == 0 and st["largest_bucket"] <= st["capacity"] - 3, (seed, st)
+
+
+def test_heavy_ties_hand_over_to_the_lsd_pipeline():
+    """150 k copies of two values: a bucket overflows (or a sub-bucket exceeds the finish budget) -> state != 0."""
+    from multimodalbrainsurvival_b200 import cox
+    t = torch.where(torch.rand(150_000, device="cuda:0") < 0.5, 7.0, 7.5)
+    assert cox.pipeline_state(t)["state"] > 0
+
+
+def test_bucketed_pipeline_with_the_4096_bucket_table():
+    """n = 14 M: more than 2048 buckets (the partition kernel's larger shared-memory layout, one block per SM)."""
+    from multimodalbrainsurvival_b200 import cox
+    n = 14_000_000
+    dev = "cuda:0"
+    g = torch.Generator(device=dev).manual_seed(4)
+    t = torch.rand(n, device=dev, generator=g) * 200
+    st = cox.pipeline_state(t)
+    assert st["state"] == 0 and st["buckets"] > 2048, st
+    perm = cox.risk_order(t).long()
+    _, idx = torch.sort(-t, stable=True)
+    assert bool((idx == perm).all())
+
+
+def test_lsd_path_above_fast_sort_limit():
+    """n > FS_MAX_N (25.2 M) takes the 4-pass LSD sort: order checked against torch.sort(stable)."""
+    from multimodalbrainsurvival_b200 import cox
+    n = 26_000_000
     dev = "cuda:0"
     g = torch.Generator(device=dev).manual_seed(3)
     t = torch.rand(n, device=dev, generator=g) * 200
@@ -130,7 +167,8 @@ def test_lsd_path_above_fast_sort_limit():
     loss.backward()
     cs = s.detach()[idx] - s.detach().max()
     ref = (-(cs - torch.log(torch.cumsum(torch.exp(cs).double(), 0).float() + 1e-5)) * e[idx]).double().mean()
-    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert cox.pipeline_state(t)["state"] == -1
+    assert abs(float(loss.detach()) - float(ref)) <= 1e-5 * abs(float(ref))
     assert abs(float(s.grad.double().sum())) < 1e-6
 
 

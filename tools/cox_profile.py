@@ -29,5 +29,15 @@ for i in range(reps):
     if i >= 2:
         fw.append(a.elapsed_time(b))
         tot.append(a.elapsed_time(c))
+# back to back (no host synchronisation between calls): what a training loop sees
+a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize()
+a.record()
+for i in range(reps):
+    s.grad = None
+    cox.cox_loss(s, t, e).backward()
+c.record()
+torch.cuda.synchronize()
+print(f"n={n} back-to-back fwd+bwd {a.elapsed_time(c) / reps:.4f} ms per call")
 print(f"n={n} fwd {statistics.median(fw):.4f} ms  fwd+bwd {statistics.median(tot):.4f} ms  "
-      f"-> {n * 112 / statistics.median(tot) / 1e6:.1f} GB/s  loss {float(loss):.6f}")
+      f"-> {n * 112 / statistics.median(tot) / 1e6:.1f} GB/s  loss {float(loss.detach()):.6f}")
