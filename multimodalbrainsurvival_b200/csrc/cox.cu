@@ -525,7 +525,6 @@ struct CoxWorkspace {
   uint32_t* fs_counters;   // [8]
   uint32_t* fs_cursor;     // [FS_MAX_BUCKETS]
   double* fs_agg_val;      // [FS_MAX_BUCKETS]
-  uint32_t* fs_row_done;   // [FS_MAX_BUCKETS]
   size_t zero_bytes;
   // zeroed by the LSD pipeline itself, only when it runs
   uint32_t* lookback;      // [4][rs_tiles][256]
@@ -536,8 +535,6 @@ struct CoxWorkspace {
   FsEdge* fs_edge;         // [1]
   double* fs_exp_prefix;   // [FS_MAX_BUCKETS] each
   double* fs_wsum;
-  double* fs_loss_part;
-  double* fs_gsum_part;
   uint32_t* fs_bucket_base;
   uint32_t* fs_bucket_cnt;
   float* fs_part32;        // [FS_MAX_BUCKETS * FS_PART]
@@ -575,7 +572,6 @@ static CoxWorkspace carve_cox(void* base, int64_t n) {
   w.fs_counters = c.take<uint32_t>(8);
   w.fs_cursor = c.take<uint32_t>(FS_MAX_BUCKETS);
   w.fs_agg_val = c.take<double>(FS_MAX_BUCKETS);
-  w.fs_row_done = c.take<uint32_t>(FS_MAX_BUCKETS);
   w.zero_bytes = align_up(c.off, 256);
   w.lookback_words = size_t(4) * rt * RS_RADIX;
   w.lookback = c.take<uint32_t>(w.lookback_words);
@@ -584,8 +580,6 @@ static CoxWorkspace carve_cox(void* base, int64_t n) {
   w.fs_edge = c.take<FsEdge>(1);
   w.fs_exp_prefix = c.take<double>(FS_MAX_BUCKETS);
   w.fs_wsum = c.take<double>(FS_MAX_BUCKETS);
-  w.fs_loss_part = c.take<double>(FS_MAX_BUCKETS);
-  w.fs_gsum_part = c.take<double>(FS_MAX_BUCKETS);
   w.fs_bucket_base = c.take<uint32_t>(FS_MAX_BUCKETS);
   w.fs_bucket_cnt = c.take<uint32_t>(FS_MAX_BUCKETS);
   w.fs_part32 = c.take<float>(size_t(FS_MAX_BUCKETS) * FS_PART);
@@ -623,9 +617,9 @@ static FastSortWs fast_ws(const CoxWorkspace& w) {
   FastSortWs f;
   f.hist12 = w.fs_hist12; f.kext = w.fs_kext; f.counters = w.fs_counters; f.cursor = w.fs_cursor;
   f.agg_val = w.fs_agg_val; f.fallback = w.fallback; f.lut = w.fs_lut; f.edge = w.fs_edge;
-  f.exp_prefix = w.fs_exp_prefix; f.wsum = w.fs_wsum; f.loss_part = w.fs_loss_part; f.gsum_part = w.fs_gsum_part;
+  f.exp_prefix = w.fs_exp_prefix; f.wsum = w.fs_wsum;
   f.bucket_base = w.fs_bucket_base; f.bucket_cnt = w.fs_bucket_cnt; f.pairs = w.fs_pairs;
-  f.sc_part = w.fs_sc_part; f.row_done = w.fs_row_done; f.part32 = w.fs_part32;
+  f.sc_part = w.fs_sc_part; f.part32 = w.fs_part32;
   f.row_loss = w.fs_row_loss; f.row_w = w.fs_row_w; f.row_g = w.fs_row_g;
   return f;
 }

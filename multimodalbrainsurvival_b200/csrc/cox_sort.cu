@@ -793,12 +793,10 @@ __device__ __forceinline__ double row_exp_offset(const float* __restrict__ part3
 }
 
 __global__ void __launch_bounds__(R_THREADS, 8) fs_row_loss_kernel(
-    const float* __restrict__ saved_s, const int32_t* __restrict__ perm, const float* __restrict__ status, int nb, int64_t n,
-    const uint32_t* __restrict__ bucket_base, const uint32_t* __restrict__ bucket_cnt, const double* __restrict__ agg_val,
-    const float* __restrict__ part32, double* __restrict__ exp_prefix, double* row_loss, double* row_w, uint32_t* row_done,
-    double* wsum, double* loss_part, uint32_t* counters, int32_t* nan_flag, const int32_t* __restrict__ nonbinary_flag,
-    float* __restrict__ loss_out, int32_t* __restrict__ flags_out, const int32_t* __restrict__ fallback) {
-  __shared__ double s_red[R_WARPS];
+    const float* __restrict__ saved_s, const int32_t* __restrict__ perm, const float* __restrict__ status,
+    const uint32_t* __restrict__ bucket_base, const uint32_t* __restrict__ bucket_cnt, const double* __restrict__ exp_prefix,
+    const float* __restrict__ part32, double* __restrict__ row_loss, double* __restrict__ row_w, int32_t* nan_flag,
+    const int32_t* __restrict__ nonbinary_flag, const int32_t* __restrict__ fallback) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (*fallback != 0) return;   // final by now: the kernels that raise it have finished
   const int b = blockIdx.x / R_BLOCKS, wg = (blockIdx.x % R_BLOCKS) * R_WARPS + warp;
@@ -807,11 +805,7 @@ __global__ void __launch_bounds__(R_THREADS, 8) fs_row_loss_kernel(
   const bool active = wg * R_SPAN < sl.end;   // warp-uniform: the row holds samples
   uint32_t enc[L_ITEMS];
   if (active) load_items(reinterpret_cast<const uint32_t*>(saved_s) + sl.a0, first, sl.end, enc);
-  double pre = 0.0;
-#pragma unroll 4
-  for (int q = tid; q < b; q += R_THREADS) pre += __ldg(agg_val + q);
-  const double P = row_block_sum(pre, s_red, lane, warp);   // sum of exp(s~) over all earlier buckets
-  if (blockIdx.x % R_BLOCKS == 0 && tid == 0) exp_prefix[b] = P;
+  const double P = __ldg(exp_prefix + b);   // sum of exp(s~) over all earlier buckets (fs_prefix_kernel)
   double tl = 0.0, tw = 0.0;
   if (active) {
     const bool interior = first >= sl.lead && first + L_ITEMS <= sl.end;
@@ -858,37 +852,9 @@ __global__ void __launch_bounds__(R_THREADS, 8) fs_row_loss_kernel(
     tl = warp_sum(double(lsum));
     tw = warp_sum(double(ws));
   }
-  // the last row of a bucket to finish adds the bucket's rows up (fixed order); the last bucket adds the buckets up
-  uint32_t last = 0;
-  if (lane == 0) {
+  if (lane == 0) {   // fs_loss_finalize_kernel adds the rows up
     row_loss[b * R_ROWS + wg] = tl;
     row_w[b * R_ROWS + wg] = tw;
-    __threadfence();
-    last = (atomicAdd(row_done + b, 1u) == uint32_t(R_ROWS) - 1u) ? 1u : 0u;
-  }
-  if (__shfl_sync(0xffffffffu, last, 0) == 0u) return;
-  __threadfence();
-  tl = warp_sum(lane < R_ROWS ? __ldcg(row_loss + b * R_ROWS + lane) : 0.0);
-  tw = warp_sum(lane < R_ROWS ? __ldcg(row_w + b * R_ROWS + lane) : 0.0);
-  last = 0;
-  if (lane == 0) {
-    loss_part[b] = tl;
-    wsum[b] = tw;
-    row_done[b] = 0u;   // the backward pass counts its rows on the same words
-    __threadfence();
-    last = (atomicAdd(counters + 2, 1u) == uint32_t(nb) - 1u) ? 1u : 0u;
-  }
-  if (__shfl_sync(0xffffffffu, last, 0) == 0u) return;
-  // the last warp: loss = sum of the bucket partials / n   (.mean() over N, models.py:111)
-  __threadfence();
-  double t = 0.0;
-#pragma unroll 8
-  for (int q = lane; q < nb; q += 32) t += __ldcg(loss_part + q);
-  t = warp_sum(t);
-  if (lane == 0) {
-    const int f = *reinterpret_cast<const volatile int32_t*>(nan_flag);
-    loss_out[0] = f ? __int_as_float(0x7fc00000) : float(t / double(n));
-    if (flags_out) flags_out[0] = f;
   }
 }
 
@@ -960,26 +926,20 @@ __device__ __noinline__ double row_backward_gather(const BucketSlice sl, int fir
 
 __global__ void __launch_bounds__(R_THREADS, 8) fs_row_backward_kernel(
     const int32_t* __restrict__ perm, const float* __restrict__ saved_s, const float* __restrict__ status,
-    const float* __restrict__ grad_loss, int64_t n, int nb, const uint32_t* __restrict__ bucket_base,
+    const float* __restrict__ grad_loss, int64_t n, const uint32_t* __restrict__ bucket_base,
     const uint32_t* __restrict__ bucket_cnt, const double* __restrict__ exp_prefix, const float* __restrict__ part32,
-    const double* __restrict__ wsum, const double* __restrict__ row_w, double* row_g, uint32_t* row_done, double* gsum_part,
-    uint32_t* counters, const int32_t* __restrict__ nonbinary_flag, const int32_t* __restrict__ max_count,
-    const int32_t* __restrict__ max_list, double* __restrict__ gsum_total, float* grad_scores,
-    const int32_t* __restrict__ fallback) {
-  __shared__ double s_red[R_WARPS];
+    const double* __restrict__ wsuffix, const double* __restrict__ row_w, double* __restrict__ row_g,
+    const int32_t* __restrict__ nonbinary_flag, float* grad_scores, const int32_t* __restrict__ fallback) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (*fallback != 0) return;
   const int b = blockIdx.x / R_BLOCKS, wg = (blockIdx.x % R_BLOCKS) * R_WARPS + warp;
   const BucketSlice sl = bucket_slice(bucket_base, bucket_cnt, b);
   const int first = wg * R_SPAN + lane * L_ITEMS;
-  const bool active = wg * R_SPAN < sl.end;
-  double later = 0.0;
-#pragma unroll 4
-  for (int q = b + 1 + tid; q < nb; q += R_THREADS) later += __ldg(wsum + q);
-  double S_later = row_block_sum(later, s_red, lane, warp);   // sum of w over all later buckets
   double tg = 0.0;
-  if (active) {
-    S_later += warp_sum((lane > wg && lane < R_ROWS) ? __ldg(row_w + b * R_ROWS + lane) : 0.0);   // .. and later rows
+  if (wg * R_SPAN < sl.end) {   // warp-uniform: the row holds samples
+    // sum of w over all later buckets (fs_loss_finalize_kernel) and over the later rows of this bucket
+    const double S_later = __ldg(wsuffix + b) +
+                           warp_sum((lane > wg && lane < R_ROWS) ? __ldg(row_w + b * R_ROWS + lane) : 0.0);
     const double rowoff = __ldg(exp_prefix + b) + row_exp_offset(part32, b, wg, lane);
     const float scale = float(double(grad_loss[0]) / double(n));
     if (*nonbinary_flag != 0)   // (rare, and out of line: its extra live array must not cost the common path registers)
@@ -987,39 +947,121 @@ __global__ void __launch_bounds__(R_THREADS, 8) fs_row_backward_kernel(
     else
       tg = row_backward_body<false>(sl, first, perm, saved_s, status, rowoff, S_later, scale, grad_scores, lane);
   }
-  uint32_t last = 0;
-  if (lane == 0) {
-    row_g[b * R_ROWS + wg] = tg;
-    __threadfence();
-    last = (atomicAdd(row_done + b, 1u) == uint32_t(R_ROWS) - 1u) ? 1u : 0u;
+  if (lane == 0) row_g[b * R_ROWS + wg] = tg;   // fs_backward_finalize_kernel adds the rows up
+}
+
+// ------------------------------------------------------------------------------------------ one-block scans between the passes
+// (A grid-wide "last block finishes the job" needs a fence + counter atomic in every warp row; with sixteen scattered
+// stores in flight per lane those fences were a quarter of the backward kernel's stall samples.  Kernel boundaries order
+// the passes instead: three launches of one block each.)
+constexpr int F_THREADS = 1024;
+constexpr int F_PER = FS_MAX_BUCKETS / F_THREADS;   // 4 consecutive buckets per thread
+
+// exclusive prefix of the buckets' sums of exp(s~)
+__global__ void __launch_bounds__(F_THREADS, 1) fs_prefix_kernel(const double* __restrict__ agg_val, int nb,
+                                                                 double* __restrict__ exp_prefix,
+                                                                 const int32_t* __restrict__ fallback) {
+  __shared__ double s_red[F_THREADS / 32];
+  if (*fallback != 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double v[F_PER], sum = 0.0;
+#pragma unroll
+  for (int k = 0; k < F_PER; ++k) {
+    const int q = tid * F_PER + k;
+    v[k] = q < nb ? __ldg(agg_val + q) : 0.0;
+    sum += v[k];
   }
-  if (__shfl_sync(0xffffffffu, last, 0) == 0u) return;
-  __threadfence();
-  tg = warp_sum(lane < R_ROWS ? __ldcg(row_g + b * R_ROWS + lane) : 0.0);
-  last = 0;
-  if (lane == 0) {
-    gsum_part[b] = tg;
-    row_done[b] = 0u;   // a second backward over the same forward (retain_graph) counts from zero again
-    __threadfence();
-    last = (atomicAdd(counters + 3, 1u) == uint32_t(nb) - 1u) ? 1u : 0u;
+  double total;
+  double run = block_scan_f64<F_THREADS / 32, false>(sum, s_red, lane, warp, &total) - sum;
+#pragma unroll
+  for (int k = 0; k < F_PER; ++k) {
+    const int q = tid * F_PER + k;
+    if (q < nb) exp_prefix[q] = run;
+    run += v[k];
   }
-  if (__shfl_sync(0xffffffffu, last, 0) == 0u) return;
-  // the last warp: gradient through "- max(scores)": every argmax position receives -(sum_k g~_k) / count
-  __threadfence();
-  double t = 0.0;
-#pragma unroll 8
-  for (int q = lane; q < nb; q += 32) t += __ldcg(gsum_part + q);
-  t = warp_sum(t);
-  if (lane == 0) gsum_total[0] = t;
+}
+
+// loss = sum of the row partials / n (.mean() over N, models.py:111); wsuffix[b] = sum of w over all LATER buckets.
+// Element e = 16 b + r of the row arrays goes to thread e mod 1024: coalesced, every load independent; a bucket's 16 rows
+// sit in one half-warp.
+__global__ void __launch_bounds__(F_THREADS, 1) fs_loss_finalize_kernel(
+    const double* __restrict__ row_loss, const double* __restrict__ row_w, int nb, int64_t n, double* __restrict__ wsuffix,
+    const int32_t* __restrict__ nan_flag, float* __restrict__ loss_out, int32_t* __restrict__ flags_out,
+    const int32_t* __restrict__ fallback) {
+  __shared__ double s_red[F_THREADS / 32];
+  __shared__ double s_wb[FS_MAX_BUCKETS];
+  if (*fallback != 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int total = nb * R_ROWS;
+  constexpr int BATCH = 8;
+  double lsum = 0.0;
+  for (int e0 = 0; e0 < total; e0 += BATCH * F_THREADS) {   // block-uniform trip count (shuffles inside)
+    double l[BATCH], w[BATCH];
+#pragma unroll
+    for (int k = 0; k < BATCH; ++k) {
+      const int e = e0 + k * F_THREADS + tid;
+      l[k] = e < total ? __ldg(row_loss + e) : 0.0;
+      w[k] = e < total ? __ldg(row_w + e) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < BATCH; ++k) {
+      lsum += l[k];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) w[k] += __shfl_xor_sync(0xffffffffu, w[k], o);   // over the 16 rows of the bucket
+      const int e = e0 + k * F_THREADS + tid;
+      if ((lane & 15) == 0 && e < FS_MAX_BUCKETS * R_ROWS) s_wb[e >> 4] = w[k];
+    }
+  }
+  __syncthreads();
+  double w[F_PER], wsum = 0.0;
+#pragma unroll
+  for (int k = 0; k < F_PER; ++k) {
+    const int q = tid * F_PER + k;
+    w[k] = q < nb ? s_wb[q] : 0.0;
+    wsum += w[k];
+  }
+  double tot;
+  double later = block_scan_f64<F_THREADS / 32, true>(wsum, s_red, lane, warp, &tot) - wsum;   // higher threads only
+#pragma unroll
+  for (int k = F_PER - 1; k >= 0; --k) {
+    const int q = tid * F_PER + k;
+    if (q < nb) wsuffix[q] = later;
+    later += w[k];
+  }
+  const double t = block_sum_f64<F_THREADS / 32>(lsum, s_red, lane, warp);
+  if (tid == 0) {
+    const int f = *nan_flag;
+    loss_out[0] = f ? __int_as_float(0x7fc00000) : float(t / double(n));
+    if (flags_out) flags_out[0] = f;
+  }
+}
+
+// gradient through "- max(scores)": every argmax position receives -(sum_k g~_k) / count
+__global__ void __launch_bounds__(F_THREADS, 1) fs_backward_finalize_kernel(
+    const double* __restrict__ row_g, int nb, const int32_t* __restrict__ max_count, const int32_t* __restrict__ max_list,
+    double* __restrict__ gsum_total, float* grad_scores, const int32_t* __restrict__ fallback) {
+  __shared__ double s_red[F_THREADS / 32];
+  if (*fallback != 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double g = 0.0;
+  const double2* pg = reinterpret_cast<const double2*>(row_g);
+  for (int i0 = 0; i0 < nb * (R_ROWS / 2); i0 += 8 * F_THREADS) {
+    double2 a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = i0 + k * F_THREADS + tid;
+      a[k] = i < nb * (R_ROWS / 2) ? __ldg(pg + i) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g += a[k].x + a[k].y;
+  }
+  const double t = block_sum_f64<F_THREADS / 32>(g, s_red, lane, warp);
+  if (tid == 0) gsum_total[0] = t;
   const int mc = *max_count;
   if (mc <= FS_MAX_LIST) {
     const float fix = float(t / double(mc));
-    for (int i = lane; i < mc; i += 32) {
-      float* p = grad_scores + max_list[i];
-      *reinterpret_cast<volatile float*>(p) = *reinterpret_cast<volatile float*>(p) - fix;
-    }
+    for (int i = tid; i < mc; i += F_THREADS) grad_scores[max_list[i]] -= fix;
   }
-  if (lane == 0) counters[3] = 0u;
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -1078,9 +1120,14 @@ int fs_forward_enqueue(const float* times, const float* status, const float* sco
                                                                 w.part32, w.bucket_base, w.bucket_cnt, w.fallback);
   MMBS_LAUNCH_CHECK();
   if (scores == nullptr) return MMBS_OK;   // mmbs_risk_order
-  fs_row_loss_kernel<<<p.nb * R_BLOCKS, R_THREADS, 0, stream>>>(
-      saved_s, perm_out, status, p.nb, n, w.bucket_base, w.bucket_cnt, w.agg_val, w.part32, w.exp_prefix, w.row_loss, w.row_w,
-      w.row_done, w.wsum, w.loss_part, w.counters, nan_flag, nonbinary_flag, loss_out, flags_out, w.fallback);
+  fs_prefix_kernel<<<1, F_THREADS, 0, stream>>>(w.agg_val, p.nb, w.exp_prefix, w.fallback);
+  MMBS_LAUNCH_CHECK();
+  fs_row_loss_kernel<<<p.nb * R_BLOCKS, R_THREADS, 0, stream>>>(saved_s, perm_out, status, w.bucket_base, w.bucket_cnt,
+                                                               w.exp_prefix, w.part32, w.row_loss, w.row_w, nan_flag,
+                                                               nonbinary_flag, w.fallback);
+  MMBS_LAUNCH_CHECK();
+  fs_loss_finalize_kernel<<<1, F_THREADS, 0, stream>>>(w.row_loss, w.row_w, p.nb, n, w.wsum, nan_flag, loss_out, flags_out,
+                                                      w.fallback);
   MMBS_LAUNCH_CHECK();
   return MMBS_OK;
 }
@@ -1089,9 +1136,12 @@ int fs_backward_enqueue(const float* status, const int32_t* perm, const float* s
                         const FastSortWs& w, const int32_t* nonbinary_flag, const int32_t* max_count,
                         const int32_t* max_list, double* gsum_total, float* grad_scores, cudaStream_t stream) {
   const FsPlan p = fs_plan(n);
-  fs_row_backward_kernel<<<p.nb * R_BLOCKS, R_THREADS, 0, stream>>>(
-      perm, saved_s, status, grad_loss, n, p.nb, w.bucket_base, w.bucket_cnt, w.exp_prefix, w.part32, w.wsum, w.row_w, w.row_g,
-      w.row_done, w.gsum_part, w.counters, nonbinary_flag, max_count, max_list, gsum_total, grad_scores, w.fallback);
+  fs_row_backward_kernel<<<p.nb * R_BLOCKS, R_THREADS, 0, stream>>>(perm, saved_s, status, grad_loss, n, w.bucket_base,
+                                                                   w.bucket_cnt, w.exp_prefix, w.part32, w.wsum, w.row_w,
+                                                                   w.row_g, nonbinary_flag, grad_scores, w.fallback);
+  MMBS_LAUNCH_CHECK();
+  fs_backward_finalize_kernel<<<1, F_THREADS, 0, stream>>>(w.row_g, p.nb, max_count, max_list, gsum_total, grad_scores,
+                                                          w.fallback);
   MMBS_LAUNCH_CHECK();
   return MMBS_OK;
 }

@@ -53,18 +53,15 @@ struct FastSortWs {
   // zeroed by the caller before every forward pass
   uint32_t* hist12;        // [FS_BINS]
   uint32_t* kext;          // [2]: max(~key), max(key)
-  uint32_t* counters;      // [8]: 0 histogram blocks done, 2 loss blocks done, 3 backward blocks done
+  uint32_t* counters;      // [8]: 0 histogram blocks done, 1 bucket-sort blocks done
   uint32_t* cursor;        // [FS_MAX_BUCKETS] samples written to every bucket region
   int32_t* fallback;       // [1] set when this pipeline gave up: the LSD-sort pipeline must (re)do the work
-  uint32_t* row_done;      // [FS_MAX_BUCKETS] warp rows of the bucket that finished (loss pass, then backward pass)
   // not zeroed
   uint2* lut;              // [FS_BINS] (exclusive prefix, count) of every 12-bit bin
   FsEdge* edge;            // [1]
   double* agg_val;         // [FS_MAX_BUCKETS] sum of exp(s~) over the bucket
   double* exp_prefix;      // [FS_MAX_BUCKETS] sum of exp(s~) over all earlier buckets           (kept for backward)
-  double* wsum;            // [FS_MAX_BUCKETS] sum of w = status / (C + eps) over the bucket     (kept for backward)
-  double* loss_part;       // [FS_MAX_BUCKETS]
-  double* gsum_part;       // [FS_MAX_BUCKETS]
+  double* wsum;            // [FS_MAX_BUCKETS] sum of w = status / (C + eps) over all LATER buckets (kept for backward)
   uint32_t* bucket_base;   // [FS_MAX_BUCKETS] first sorted position of the bucket               (kept for backward)
   uint32_t* bucket_cnt;    // [FS_MAX_BUCKETS]                                                    (kept for backward)
   uint2* pairs;            // [nb * FS_CAP] partitioned (key, index | event << 31)
