@@ -185,6 +185,11 @@ int mmbs_stem_pack_input_u8(const uint8_t* x_nchw, void* out_s2d_bf16, int64_t b
                             const float* std_host, void* stream);
 /* stem weight: [64,3,7,7] fp32 -> bf16 [64, 4*64] in the matching (a, b, p, q, c) order */
 int mmbs_stem_pack_weight(const float* w_oihw, void* out_bf16, void* stream);
+/* 1- / 3- / 4-channel stems (RNone / ResNet / RNfour of /root/reference/5_JointFusion/resnet.py:94-337): fp32
+ * [B,C,224,224] -> the same space-to-depth buffer (element (p*2+q)*C + c of every 16-slot pixel), and the matching
+ * [64,C,7,7] weight pack. */
+int mmbs_stem_pack_input_c(const float* x_nchw, void* out_s2d_bf16, int64_t batch, int channels, void* stream);
+int mmbs_stem_pack_weight_c(const float* w_oihw, void* out_bf16, int channels, void* stream);
 /* conv weight OIHW fp32 -> [O][kh][kw][I] bf16 */
 int mmbs_pack_conv_weight(const float* w_oihw, void* out_bf16, int64_t c_out, int64_t c_in,
                           int64_t ksize, void* stream);
@@ -354,6 +359,16 @@ int mmbs_nll_surv_backward(const float* grad_unit, const float* grad_loss, int64
  * byte for byte ('%.18e', ',' between columns, '\n' per row).  data: rows x cols float64, row-major, HOST memory.
  * threads <= 0: one per hardware thread (at most 64). */
 int mmbs_write_matrix_csv(const double* data, int64_t rows, int64_t cols, const char* path, int32_t threads);
+
+/* ------------------------------------------------------- attention aggregation
+ * Tail of TanhAttention.forward (/root/reference/1_HistoPathology/models.py:22-33; 5_JointFusion/models.py, same text):
+ *   attn[b, p] = softmax_p( tanh(h[b, p, :]) . vector ),  h = x W^T (fp32, from a linear plan)
+ *   out[b, p, :] = x[b, p, :] * attn[b, p] * bag          (optional)
+ *   pooled[b, :] = sum_p x[b, p, :] * attn[b, p]          (optional; = out.mean(dim = 1))
+ * x, h: [batch, bag, dim] fp32; bag <= 8192.  mmbs_tanh_inplace_f32: the F.tanh of AggregationProjectModel.extract. */
+int mmbs_attention_pool(const float* x, const float* h, const float* vector, int64_t batch, int bag, int dim,
+                        float* attn, float* out, float* pooled, void* stream);
+int mmbs_tanh_inplace_f32(float* x, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -88,6 +88,11 @@ SIGNATURES = {
     "mmbs_stem_pack_input_u8": (ctypes.c_int, [c_void_p, c_void_p, c_i64, ctypes.POINTER(c_float),
                                                ctypes.POINTER(c_float), c_void_p]),
     "mmbs_stem_pack_weight": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
+    "mmbs_stem_pack_input_c": (ctypes.c_int, [c_void_p, c_void_p, c_i64, ctypes.c_int, c_void_p]),
+    "mmbs_stem_pack_weight_c": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, c_void_p]),
+    "mmbs_attention_pool": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, ctypes.c_int, ctypes.c_int, c_void_p,
+                                           c_void_p, c_void_p, c_void_p]),
+    "mmbs_tanh_inplace_f32": (ctypes.c_int, [c_void_p, c_i64, c_void_p]),
     "mmbs_pack_conv_weight": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
     "mmbs_bn_fold": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_i64, c_void_p,
                                     c_void_p, c_void_p]),

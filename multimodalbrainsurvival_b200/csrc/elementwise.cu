@@ -94,6 +94,58 @@ __global__ void __launch_bounds__(128) stem_pack_input_u8_kernel(const uint8_t* 
   out[pix * 2 + 1] = o1;
 }
 
+// ---- 1- and 4-channel stems (RNone / RNfour, /root/reference/5_JointFusion/resnet.py:167-337): the same space-to-depth
+// buffer with C channels per (row parity, column parity) slot: element (p * 2 + q) * C + c, the rest of the 16 zero.
+template <int C>
+__global__ void __launch_bounds__(128) stem_pack_input_c_kernel(const float* __restrict__ x, uint4* __restrict__ out,
+                                                                int64_t batch) {
+  static_assert(C >= 1 && C <= 4, "16 slots hold 4 pixel positions of up to 4 channels");
+  const int64_t pix = int64_t(blockIdx.x) * 128 + threadIdx.x;
+  const int64_t total = batch * 116 * 116;
+  if (pix >= total) return;
+  const int s = int(pix % 116), r = int((pix / 116) % 116);
+  const int64_t n = pix / (116 * 116);
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = 0.f;
+  const int col = 2 * (s - 2);
+  if (col >= 0 && col < 224) {
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const int row = 2 * (r - 2) + p;
+      if (row >= 0 && row < 224) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float2 t = __ldg(reinterpret_cast<const float2*>(x + ((n * C + c) * 224 + row) * 224 + col));
+          v[(p * 2 + 0) * C + c] = t.x;
+          v[(p * 2 + 1) * C + c] = t.y;
+        }
+      }
+    }
+  }
+  uint4 o0, o1;
+  o0.x = pack_bf16x2(v[0], v[1]);   o0.y = pack_bf16x2(v[2], v[3]);
+  o0.z = pack_bf16x2(v[4], v[5]);   o0.w = pack_bf16x2(v[6], v[7]);
+  o1.x = pack_bf16x2(v[8], v[9]);   o1.y = pack_bf16x2(v[10], v[11]);
+  o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+  out[pix * 2] = o0;
+  out[pix * 2 + 1] = o1;
+}
+
+// stem weight [64,C,7,7] fp32 -> [64][a(4)][b(4)][(p*2+q)*C+c (16)] bf16 (same tap order as stem_pack_weight_kernel)
+__global__ void stem_pack_weight_c_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 256) return;
+  const int ch = i & 15, b = (i >> 4) & 3, a = (i >> 6) & 3, o = i >> 8;
+  float v = 0.f;
+  if (ch < 4 * C) {
+    const int c = ch % C, pq = ch / C, p = pq >> 1, q = pq & 1;
+    const int kh = 2 * a + p - 1, kw = 2 * b + q - 1;
+    if (kh >= 0 && kw >= 0) v = w[((o * C + c) * 7 + kh) * 7 + kw];
+  }
+  out[i] = __float2bfloat16_rn(v);
+}
+
 // ---- stem weight: [64,3,7,7] fp32 -> [64][a(4)][b(4)][(p*2+q)*3+c (16)] bf16,
 // kh = 2a+p-1, kw = 2b+q-1 (the 7x7 kernel zero-extended to 8x8 at the top/left).
 __global__ void stem_pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
@@ -280,6 +332,30 @@ extern "C" int mmbs_stem_pack_input_u8(const uint8_t* x_nchw, void* out, int64_t
   stem_pack_input_u8_kernel<<<blocks_for(batch * 116 * 116, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       x_nchw, static_cast<uint4*>(out), batch, mean_host[0], mean_host[1], mean_host[2], 1.0f / std_host[0],
       1.0f / std_host[1], 1.0f / std_host[2]);
+  MMBS_LAUNCH_CHECK();
+  return MMBS_OK;
+}
+
+extern "C" int mmbs_stem_pack_input_c(const float* x_nchw, void* out, int64_t batch, int channels, void* stream) {
+  if (int rc = mmbs_device_check()) return rc;
+  MMBS_REQUIRE(x_nchw && out && batch > 0, "mmbs_stem_pack_input_c: bad argument");
+  MMBS_REQUIRE(channels == 1 || channels == 3 || channels == 4, "mmbs_stem_pack_input_c: channels=%d (1, 3 or 4)", channels);
+  MMBS_REQUIRE(reinterpret_cast<uintptr_t>(x_nchw) % 8 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0,
+               "mmbs_stem_pack_input_c: misaligned pointer");
+  const unsigned grid = blocks_for(batch * 116 * 116, 128);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (channels == 1) stem_pack_input_c_kernel<1><<<grid, 128, 0, st>>>(x_nchw, static_cast<uint4*>(out), batch);
+  else if (channels == 3) stem_pack_input_c_kernel<3><<<grid, 128, 0, st>>>(x_nchw, static_cast<uint4*>(out), batch);
+  else stem_pack_input_c_kernel<4><<<grid, 128, 0, st>>>(x_nchw, static_cast<uint4*>(out), batch);
+  MMBS_LAUNCH_CHECK();
+  return MMBS_OK;
+}
+
+extern "C" int mmbs_stem_pack_weight_c(const float* w, void* out, int channels, void* stream) {
+  if (int rc = mmbs_device_check()) return rc;
+  MMBS_REQUIRE(w && out, "mmbs_stem_pack_weight_c: null pointer");
+  MMBS_REQUIRE(channels == 1 || channels == 3 || channels == 4, "mmbs_stem_pack_weight_c: channels=%d (1, 3 or 4)", channels);
+  stem_pack_weight_c_kernel<<<64, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, static_cast<__nv_bfloat16*>(out), channels);
   MMBS_LAUNCH_CHECK();
   return MMBS_OK;
 }

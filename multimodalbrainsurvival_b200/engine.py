@@ -138,11 +138,16 @@ def pack_conv_weight_halo(w_oihw: torch.Tensor) -> torch.Tensor:
 
 
 def pack_stem_weight(w_oihw: torch.Tensor) -> torch.Tensor:
-    assert tuple(w_oihw.shape) == (64, 3, 7, 7), "stem conv must be Conv2d(3, 64, 7, stride 2, pad 3)"
+    c = int(w_oihw.shape[1])
+    assert tuple(w_oihw.shape) == (64, c, 7, 7) and c in (1, 3, 4), "stem conv must be Conv2d(1|3|4, 64, 7, stride 2, pad 3)"
     w = w_oihw.detach().float().contiguous()
     out = torch.empty((64, 256), dtype=torch.bfloat16, device=w.device)
-    _lib.check(_lib.lib().mmbs_stem_pack_weight(_lib.ptr(w), _lib.ptr(out), _lib.stream_ptr()),
-               "mmbs_stem_pack_weight")
+    if c == 3:
+        _lib.check(_lib.lib().mmbs_stem_pack_weight(_lib.ptr(w), _lib.ptr(out), _lib.stream_ptr()),
+                   "mmbs_stem_pack_weight")
+    else:   # RNone / RNfour
+        _lib.check(_lib.lib().mmbs_stem_pack_weight_c(_lib.ptr(w), _lib.ptr(out), c, _lib.stream_ptr()),
+                   "mmbs_stem_pack_weight_c")
     return out
 
 
@@ -346,6 +351,9 @@ class ResNetEngine:
             sd = (ctypes.c_float * 3)(*norm[1])
             _lib.check(L.mmbs_stem_pack_input_u8(_lib.ptr(x_nchw), _lib.ptr(self.x_s2d), B, m, sd, _lib.stream_ptr()),
                        "mmbs_stem_pack_input_u8")
+        elif x_nchw.shape[1] != 3:   # RNone / RNfour stems
+            _lib.check(L.mmbs_stem_pack_input_c(_lib.ptr(x_nchw), _lib.ptr(self.x_s2d), B, int(x_nchw.shape[1]),
+                                                _lib.stream_ptr()), "mmbs_stem_pack_input_c")
         else:
             _lib.check(L.mmbs_stem_pack_input(_lib.ptr(x_nchw), _lib.ptr(self.x_s2d), B, _lib.stream_ptr()),
                        "mmbs_stem_pack_input")

@@ -33,6 +33,31 @@ class Identity(nn.Module):
         return x, torch.ones(x.shape[0], x.shape[1], device=x.device)
 
 
+def _inference(module, *tensors):
+    """CUDA fp32 tensors and nothing to differentiate: the fused kernels may run (they have no backward)."""
+    import os
+    if os.environ.get("MMBS_DISABLE_KERNELS", "0") == "1":
+        return False
+    if not all(isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 for t in tensors):
+        return False
+    if torch.is_grad_enabled() and (any(t.requires_grad for t in tensors) or
+                                    any(p.requires_grad for p in module.parameters())):
+        return False
+    return True
+
+
+def _linear(owner, name, x2d):
+    """``getattr(owner, name)(x2d)`` for an nn.Linear child through the tcgen05 linear plan (mlp._MLPEngine reads the
+    stock parameters in place).  The one-layer Sequential lives in __dict__ only: it must not appear in state_dict."""
+    key = "_mmbs_seq_" + name
+    seq = owner.__dict__.get(key)
+    if seq is None or seq[0] is not getattr(owner, name):
+        seq = nn.Sequential(getattr(owner, name))
+        owner.__dict__[key] = seq
+    seq.train(False)
+    return _mlp.run_mlp(seq, x2d)
+
+
 class TanhAttention(nn.Module):
     def __init__(self, dim=2048):
         super().__init__()
@@ -40,10 +65,56 @@ class TanhAttention(nn.Module):
         self.vector = torch.nn.Parameter(torch.zeros(dim))
         self.linear = nn.Linear(dim, dim, bias=False)
 
+    def _fused(self, x, want_out):
+        """csrc/attention.cu behind the linear layer's GEMM: -> (out | None, pooled, attention_weights)."""
+        from . import _lib
+        b, bag, dim = x.shape
+        x = x.contiguous()
+        h = _linear(self, "linear", x.view(b * bag, dim))
+        attn = torch.empty((b, bag, 1), dtype=torch.float32, device=x.device)
+        out = torch.empty_like(x) if want_out else None
+        pooled = torch.empty((b, dim), dtype=torch.float32, device=x.device)
+        vec = self.vector.detach().float().contiguous()
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().mmbs_attention_pool(_lib.ptr(x), _lib.ptr(h), _lib.ptr(vec), b, bag, dim, _lib.ptr(attn),
+                                                      _lib.ptr(out), _lib.ptr(pooled), _lib.stream_ptr()),
+                       "mmbs_attention_pool")
+        return out, pooled, attn
+
+    def _fusable(self, x):
+        return (x.dim() == 3 and x.shape[2] == self.dim and 1 <= x.shape[1] <= 8192 and x.shape[0] >= 1
+                and _inference(self, x))
+
     def forward(self, x):
+        if self._fusable(x):
+            out, _, attention_weights = self._fused(x, True)
+            return out, attention_weights
         logits = torch.tanh(self.linear(x)).matmul(self.vector.unsqueeze(-1))
         attention_weights = F.softmax(logits, dim=1)
         return x * attention_weights * x.shape[1], attention_weights
+
+    def pooled(self, x):
+        """(mean over the bag of forward(x)[0], attention_weights) without the per-patch intermediate."""
+        if self._fusable(x):
+            _, pooled, attention_weights = self._fused(x, False)
+            return pooled, attention_weights
+        out, attention_weights = self.forward(x)
+        return out.mean(dim=1), attention_weights
+
+
+def _aggregate(aggregator, features):
+    """aggregator(features) followed by the mean over the bag (reference AggregationModel.extract :53-56)."""
+    if isinstance(aggregator, TanhAttention):
+        return aggregator.pooled(features)
+    features, attention_weights = aggregator(features)
+    return features.mean(dim=1), attention_weights
+
+
+def _head(owner, name, x):
+    """An nn.Linear head on (B, features): the linear plan when nothing is differentiated, the module otherwise."""
+    if x.dim() == 2 and _inference(owner, x):
+        return _linear(owner, name, x)
+    return getattr(owner, name)(x)
 
 
 def _bag_features(resnet, x, resnet_dim):
@@ -63,13 +134,11 @@ class AggregationModel(nn.Module):
         self.resnet_dim = resnet_dim
 
     def extract(self, x):
-        features = _bag_features(self.resnet, x, self.resnet_dim)
-        features, attention_weights = self.aggregator(features)
-        return features.mean(dim=1), attention_weights
+        return _aggregate(self.aggregator, _bag_features(self.resnet, x, self.resnet_dim))
 
     def forward(self, x):
         features, attention_weights = self.extract(x)
-        return self.fc(features), attention_weights
+        return _head(self, "fc", features), attention_weights
 
 
 class AggregationProjectModel(nn.Module):
@@ -85,14 +154,20 @@ class AggregationProjectModel(nn.Module):
         self.fc = nn.Linear(hdim, out_features)
 
     def extract(self, x):
-        features = _bag_features(self.resnet, x, self.resnet_dim)
-        features, attention_weights = self.aggregator(features)
-        features = self.dropout(torch.tanh(self.project(features.mean(dim=1))))
+        features, attention_weights = _aggregate(self.aggregator, _bag_features(self.resnet, x, self.resnet_dim))
+        if features.dim() == 2 and not self.training and _inference(self, features):
+            from . import _lib
+            features = _linear(self, "project", features)   # tcgen05 GEMM + bias; F.tanh in place; eval dropout = identity
+            with torch.cuda.device(features.device):
+                _lib.check(_lib.lib().mmbs_tanh_inplace_f32(_lib.ptr(features), features.numel(), _lib.stream_ptr()),
+                           "mmbs_tanh_inplace_f32")
+            return features, attention_weights
+        features = self.dropout(torch.tanh(self.project(features)))
         return features, attention_weights
 
     def forward(self, x):
         features, attention_weights = self.extract(x)
-        return self.fc(features), attention_weights
+        return _head(self, "fc", features), attention_weights
 
 
 class BagHistopathologyRNAModel(nn.Module):

@@ -127,21 +127,10 @@ class _Trunk(nn.Module):
         x = self.avgpool(x)
         return x.view(x.size(0), -1)
 
-    def _can_accelerate(self, x):
-        return False
-
-    def forward_extract(self, x):
-        if self._can_accelerate(x):
-            return self._features_b200(x)
-        return self._features_torch(x)
-
     def forward(self, x):
         return self.fc(self.forward_extract(x))
 
-
-class ResNet(_Trunk):
-    _in_channels = 3
-    # uint8 inputs (raw pixels) are normalised on the device with the reference's transform constants
+    # uint8 inputs (raw pixels, 3-channel stems only) are normalised on the device with the reference's transform constants
     # (Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225]), 4_HistoPath_extractfeatures.py:133-137)
     input_mean = (0.485, 0.456, 0.406)
     input_std = (0.229, 0.224, 0.225)
@@ -156,24 +145,30 @@ class ResNet(_Trunk):
             # host-side tooling: checkpoint round-trips, oracle pinning.)
             raise RuntimeError("ResNet.forward_extract: input must be a CUDA tensor (this build has no CPU path; "
                                "move the model and the batch to the GPU)")
+        if x.dtype == torch.uint8 and self._in_channels != 3:
+            raise RuntimeError("uint8 pixels are only defined for the 3-channel stem (the reference normalises RGB patches)")
         if x.dtype == torch.uint8 and not self._can_accelerate(x):
             mean = torch.tensor(self.input_mean, device=x.device).view(1, 3, 1, 1)
             std = torch.tensor(self.input_std, device=x.device).view(1, 3, 1, 1)
             x = (x.float() / 255.0 - mean) / std
-        return super().forward_extract(x)
+        if self._can_accelerate(x):
+            return self._features_b200(x)
+        return self._features_torch(x)
 
     def _can_accelerate(self, x):
         if os.environ.get("MMBS_DISABLE_KERNELS", "0") == "1":
             return False
         # every depth of the reference's resnet.py (18/34: BasicBlock, 50/101/152: Bottleneck; resnet.py:167-337)
         return (x.is_cuda and not self.training and not torch.is_grad_enabled()
-                and x.dim() == 4 and tuple(x.shape[1:]) == (3, 224, 224)
+                and x.dim() == 4 and tuple(x.shape[1:]) == (self._in_channels, 224, 224)
                 and isinstance(self.layer1[0], (Bottleneck, BasicBlock))
                 and self.fc.in_features == 512 * type(self.layer1[0]).expansion)
 
     def _can_accelerate_train(self, x):
         """model.train() on CUDA, fp32 224x224 patches, ResNet-50, gradients (if any) confined to layer4."""
         if os.environ.get("MMBS_DISABLE_KERNELS", "0") == "1" or os.environ.get("MMBS_RESNET_TRAIN", "1") != "1":
+            return False
+        if self._in_channels != 3:   # the training engine is built for the RGB stem
             return False
         if not (self.training and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
                 and tuple(x.shape[1:]) == (3, 224, 224) and isinstance(self.layer1[0], Bottleneck)
@@ -226,12 +221,37 @@ class ResNet(_Trunk):
         return d
 
 
+class ResNet(_Trunk):
+    _in_channels = 3
+
+
 class RNfour(_Trunk):
+    """4-channel stem (reference resnet.py:167-250); eval-mode extraction runs the same kernels."""
     _in_channels = 4
 
 
 class RNone(_Trunk):
+    """1-channel stem (reference resnet.py:253-337)."""
     _in_channels = 1
+
+
+def adapt_pretrained_stem(model, pretrained_dict):
+    """Load 3-channel ImageNet weights into a 1- / 4-channel trunk the way the reference does
+    (resnet50_4channel / resnet50_1channel, resnet.py:375-428): everything but conv1 as is; 4 channels: conv1 ~
+    N(0, 0.001) with the RGB filters copied into the first three input channels; 1 channel: the mean of the RGB filters."""
+    own = model.state_dict()
+    own.update({k: v for k, v in pretrained_dict.items() if k != 'conv1.weight'})
+    model.load_state_dict(own)
+    w = pretrained_dict['conv1.weight']
+    with torch.no_grad():
+        if model._in_channels == 4:
+            model.conv1.weight.normal_(0, 0.001)
+            model.conv1.weight[:, :3] = w
+        elif model._in_channels == 1:
+            model.conv1.weight.copy_(w.mean(dim=1, keepdim=True))
+        else:
+            model.conv1.weight.copy_(w)
+    return model
 
 
 class ResNetProject(nn.Module):
@@ -263,9 +283,8 @@ def _build(name, pretrained, cls=ResNet, **kwargs):
     if pretrained:
         import torch.utils.model_zoo as model_zoo
         state = model_zoo.load_url(model_urls[name])
-        if cls is not ResNet:  # 1-/4-channel stems keep their own random conv1
-            state = {k: v for k, v in state.items() if not k.startswith('conv1.')}
-            model.load_state_dict(state, strict=False)
+        if cls is not ResNet:
+            adapt_pretrained_stem(model, state)
         else:
             model.load_state_dict(state)
     return model

@@ -344,8 +344,61 @@ def gen_nll():
     print("nll: 4 cases")
 
 
+# ------------------------------------------------------------------------- attention / project / stems
+def gen_variants():
+    """TanhAttention, AggregationModel / AggregationProjectModel around it, and the 1- / 4-channel stems, all run through the
+    reference's own classes (5_JointFusion/models.py, resnet.py) with seeded parameters that the test rebuilds."""
+    import torch.nn as nn
+    joint_models = load_ref("5_JointFusion/models.py", "ref_joint_models3")
+    ref_resnet = load_ref("5_JointFusion/resnet.py", "ref_resnet3")
+
+    class FakeResnet(nn.Module):
+        def forward_extract(self, p):
+            return p.flatten(1)
+
+    out = {}
+    torch.manual_seed(4444)
+    dim, hdim = 256, 64
+    att = joint_models.TanhAttention(dim)
+    with torch.no_grad():
+        att.vector.normal_(0, 0.5)
+    x = torch.tensor(det_input((3, 5, dim), a=0.31))
+    with torch.no_grad():
+        o, a = att(x)
+    out.update(att_x=x.numpy(), att_vector=att.vector.detach().numpy(), att_linear=att.linear.weight.detach().numpy(),
+               att_out=o.numpy(), att_weights=a.numpy())
+    agg = joint_models.AggregationModel(FakeResnet(), att, dim, resnet_dim=dim).eval()
+    proj = joint_models.AggregationProjectModel(FakeResnet(), att, dim, resnet_dim=dim, hdim=hdim).eval()
+    bag = x.view(3, 5, 1, 16, 16)
+    with torch.no_grad():
+        y_agg, _ = agg(bag)
+        f_agg, _ = agg.extract(bag)
+        y_proj, _ = proj(bag)
+        f_proj, _ = proj.extract(bag)
+    out.update(agg_fc_w=agg.fc.weight.detach().numpy(), agg_fc_b=agg.fc.bias.detach().numpy(), agg_out=y_agg.numpy(),
+               agg_feat=f_agg.numpy(), proj_w=proj.project.weight.detach().numpy(), proj_b=proj.project.bias.detach().numpy(),
+               proj_fc_w=proj.fc.weight.detach().numpy(), proj_fc_b=proj.fc.bias.detach().numpy(), proj_out=y_proj.numpy(),
+               proj_feat=f_proj.numpy())
+    # 1- / 4-channel stems: seeded trunk = the 3-channel seeded state_dict of the resnet oracle + a seeded conv1
+    from oracle import resnet_oracle
+    sd = resnet_oracle.init_state_dict(seed=77)
+    for c, ctor in ((4, ref_resnet.resnet50_4channel), (1, ref_resnet.resnet50_1channel)):
+        net = ctor(pretrained=False).eval()
+        own = net.state_dict()
+        own.update({k: v for k, v in sd.items() if k != "conv1.weight"})
+        g = torch.Generator().manual_seed(100 + c)
+        own["conv1.weight"] = torch.randn(64, c, 7, 7, generator=g) * (2.0 / (49 * 64)) ** 0.5
+        net.load_state_dict(own)
+        xi = torch.tensor(det_input((2, c, 224, 224), a=0.013 * c))
+        with torch.no_grad():
+            f = net.forward_extract(xi)
+        out["stem%d_feat" % c] = f.numpy()
+    np.savez_compressed(os.path.join(OUT, "variants_reference.npz"), **out)
+    print("variants:", {k: v.shape for k, v in out.items() if k.endswith(("out", "feat"))})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["cox", "aggregate", "resnet", "resnet_train", "mlp", "nll", "rna_script"]
+    which = sys.argv[1:] or ["cox", "aggregate", "resnet", "resnet_train", "mlp", "nll", "rna_script", "variants"]
     for w in which:
         globals()["gen_" + w]()
