@@ -370,6 +370,30 @@ int mmbs_attention_pool(const float* x, const float* h, const float* vector, int
                         float* attn, float* out, float* pooled, void* stream);
 int mmbs_tanh_inplace_f32(float* x, int64_t n, void* stream);
 
+/* ------------------------------------------------------- input pipeline
+ * Replaces, for the histopathology loaders, PatchBagDataset.__getitem__'s decode
+ *   (/root/reference/1_HistoPathology/models.py:280-286: Image.open(f).convert('RGB'))
+ * and the training transforms RandomHorizontalFlip / RandomVerticalFlip / ColorJitter
+ *   (/root/reference/1_HistoPathology/2_HistoPath_train.py:474-488);
+ * ToTensor + Normalize are fused into mmbs_stem_pack_input_u8.
+ *
+ * mmbs_png_decode / mmbs_png_decode_files: HOST code (no device needed).  8-bit non-interlaced PNG (grey, RGB, palette,
+ * with or without alpha - alpha is dropped) -> uint8 [h, w, 3]; the file list is decoded by `threads` host threads
+ * (0 = all cores) into out_hwc[count, h, w, 3] (pinned memory recommended).
+ *
+ * mmbs_augment_u8: uint8 [batch, h, w, 3] -> uint8 [batch, 3, h, w] on the device, bit-exact with torchvision 0.26 on PIL
+ * images (Pillow 12.2): one mmbs_aug_params per image, lsum_ws = batch uint32 words of scratch. */
+typedef struct mmbs_aug_params {
+  int32_t hflip, vflip;
+  int32_t order[4];   /* operations in application order: 0 brightness, 1 contrast, 2 saturation, 3 hue, -1 none */
+  float factor[3];    /* brightness, contrast, saturation factors */
+  int32_t hue_shift;  /* int(np.int32(hue_factor * 255).astype(np.uint8)) */
+} mmbs_aug_params;
+int mmbs_png_decode(const uint8_t* file_bytes, size_t nbytes, uint8_t* out_hwc, int h, int w);
+int mmbs_png_decode_files(const char* const* paths, int64_t count, uint8_t* out_hwc, int h, int w, int threads);
+int mmbs_augment_u8(const uint8_t* in_hwc, uint8_t* out_chw, int64_t batch, int h, int w, const void* params_dev,
+                    uint32_t* lsum_ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,3 +79,65 @@ class HostWriter:
 
     def wait(self) -> None:
         self.stream.synchronize()
+
+
+# ----------------------------------------------------------------------------- patch decode + augmentation
+AUG_PARAM_WORDS = 10   # include/mmbs.h mmbs_aug_params: hflip, vflip, order[4], factor[3] (fp32 bits), hue_shift
+
+
+def decode_png_files(paths, size: int = 224, out: torch.Tensor | None = None, threads: int = 0) -> torch.Tensor:
+    """Decode patch files the way ``Image.open(f).convert('RGB')`` does (reference PatchBagDataset.__getitem__,
+    1_HistoPathology/models.py:280-284) with the library's multi-threaded host decoder (csrc/png.cu):
+    -> uint8 [len(paths), size, size, 3], pinned when CUDA is available so that it can be copied asynchronously."""
+    import ctypes
+    from . import _lib
+    n = len(paths)
+    if out is None:
+        out = torch.empty((n, size, size, 3), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    if tuple(out.shape) != (n, size, size, 3) or out.dtype != torch.uint8 or not out.is_contiguous() or out.is_cuda:
+        raise ValueError("decode_png_files: `out` must be a contiguous host uint8 tensor [n, size, size, 3]")
+    arr = (ctypes.c_char_p * max(n, 1))(*[str(p).encode() for p in paths])
+    _lib.check(_lib.lib().mmbs_png_decode_files(arr, n, ctypes.c_void_p(out.data_ptr()), size, size, int(threads)),
+               "mmbs_png_decode_files")
+    return out
+
+
+def sample_augment_params(batch: int, brightness: float = 64.0 / 255, contrast: float = 0.75, saturation: float = 0.25,
+                          hue: float = 0.04, p_flip: float = 0.5, generator: torch.Generator | None = None) -> torch.Tensor:
+    """Per-image parameters of RandomHorizontalFlip -> RandomVerticalFlip -> ColorJitter(brightness, contrast, saturation,
+    hue) (reference 2_HistoPath_train.py:474-488), drawn from the torch CPU generator in torchvision's own order: one
+    ``rand(1)`` per flip, ``randperm(4)``, then one ``uniform_`` per factor.  -> int32 [batch, 10] (mmbs_aug_params rows)."""
+    import numpy as np
+    rows = np.zeros((batch, AUG_PARAM_WORDS), dtype=np.int32)
+    fview = rows.view(np.float32)
+    ranges = ((max(0.0, 1.0 - brightness), 1.0 + brightness), (max(0.0, 1.0 - contrast), 1.0 + contrast),
+              (max(0.0, 1.0 - saturation), 1.0 + saturation), (-hue, hue))
+    for i in range(batch):
+        rows[i, 0] = int(torch.rand(1, generator=generator) < p_flip)
+        rows[i, 1] = int(torch.rand(1, generator=generator) < p_flip)
+        rows[i, 2:6] = torch.randperm(4, generator=generator).numpy()
+        f = [float(torch.empty(1).uniform_(lo, hi, generator=generator)) for lo, hi in ranges]
+        fview[i, 6:9] = f[:3]
+        rows[i, 9] = int(np.int32(f[3] * 255).astype(np.uint8))   # torchvision adjust_hue's wrap-around shift
+    return torch.from_numpy(rows)
+
+
+def augment(patches_u8_hwc: torch.Tensor, params: torch.Tensor) -> torch.Tensor:
+    """Flips + ColorJitter on the device (csrc/augment.cu), bit-exact with torchvision on PIL images:
+    uint8 [B, H, W, 3] (CUDA) + int32 [B, 10] parameter rows -> uint8 [B, 3, H, W], what ``forward_extract`` takes as raw
+    pixels (ToTensor + Normalize happen in its stem pack kernel)."""
+    from . import _lib
+    x = patches_u8_hwc
+    if not (x.is_cuda and x.dtype == torch.uint8 and x.dim() == 4 and x.shape[3] == 3):
+        raise RuntimeError("augment: patches must be a CUDA uint8 tensor [B, H, W, 3] (no CPU path in this build)")
+    b, h, w, _ = x.shape
+    if tuple(params.shape) != (b, AUG_PARAM_WORDS) or params.dtype != torch.int32:
+        raise ValueError("augment: params must be int32 [B, 10] (sample_augment_params)")
+    x = x.contiguous()
+    p = params.to(x.device, non_blocking=True).contiguous()
+    out = torch.empty((b, 3, h, w), dtype=torch.uint8, device=x.device)
+    ws = torch.empty(b, dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().mmbs_augment_u8(_lib.ptr(x), _lib.ptr(out), b, h, w, _lib.ptr(p), _lib.ptr(ws),
+                                              _lib.stream_ptr()), "mmbs_augment_u8")
+    return out

@@ -397,8 +397,33 @@ def gen_variants():
     print("variants:", {k: v.shape for k, v in out.items() if k.endswith(("out", "feat"))})
 
 
+# ------------------------------------------------------------------------- augmentation
+def gen_augment():
+    """Patches through the reference's training transforms (2_HistoPath_train.py:474-488) run by torchvision on PIL
+    images, with the per-image parameters torchvision drew (replayed by pipeline.sample_augment_params under the same
+    seed): inputs, parameter rows and outputs for the device kernel's parity test."""
+    from PIL import Image
+    import torchvision.transforms as T
+    from multimodalbrainsurvival_b200 import pipeline
+    size, n = 48, 8
+    tf = T.Compose([T.Resize(size), T.RandomHorizontalFlip(), T.RandomVerticalFlip(),
+                    T.ColorJitter(64.0 / 255, 0.75, 0.25, 0.04)])
+    rng = np.random.default_rng(20261018)
+    imgs = rng.integers(0, 256, (n, size, size, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[0:size, 0:size]
+    imgs[1] = np.stack([(yy * 5) % 256, (xx * 5) % 256, (yy + xx) * 2 % 256], -1)           # smooth ramps
+    imgs[2] = (np.array([200, 180, 190]) + rng.integers(-6, 6, (size, size, 3))).clip(0, 255)  # pale H&E-like patch
+    imgs[3] = 128                                                                            # flat grey
+    torch.manual_seed(4242)
+    outs = np.stack([np.asarray(tf(Image.fromarray(im, "RGB"))) for im in imgs])
+    torch.manual_seed(4242)
+    rows = pipeline.sample_augment_params(n).numpy()
+    np.savez_compressed(os.path.join(OUT, "augment_reference.npz"), imgs=imgs, params=rows, outs=outs)
+    print("augment:", imgs.shape, rows.shape, outs.shape)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["cox", "aggregate", "resnet", "resnet_train", "mlp", "nll", "rna_script", "variants"]
+    which = sys.argv[1:] or ["cox", "aggregate", "resnet", "resnet_train", "mlp", "nll", "rna_script", "variants", "augment"]
     for w in which:
         globals()["gen_" + w]()
