@@ -165,12 +165,13 @@ class _Trunk(nn.Module):
                 and self.fc.in_features == 512 * type(self.layer1[0]).expansion)
 
     def _can_accelerate_train(self, x):
-        """model.train() on CUDA, fp32 224x224 patches, ResNet-50, gradients (if any) confined to layer4."""
+        """model.train() on CUDA, fp32 (normalised) or uint8 (raw) 224x224 patches, ResNet-50, gradients (if any) confined
+        to layer4."""
         if os.environ.get("MMBS_DISABLE_KERNELS", "0") == "1" or os.environ.get("MMBS_RESNET_TRAIN", "1") != "1":
             return False
         if self._in_channels != 3:   # the training engine is built for the RGB stem
             return False
-        if not (self.training and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+        if not (self.training and x.is_cuda and x.dtype in (torch.float32, torch.uint8) and x.dim() == 4
                 and tuple(x.shape[1:]) == (3, 224, 224) and isinstance(self.layer1[0], Bottleneck)
                 and self.fc.in_features == 2048 and [len(l) for l in (self.layer1, self.layer2, self.layer3,
                                                                       self.layer4)] == [3, 4, 6, 3]):

@@ -335,8 +335,15 @@ class ResNetTrainEngine:
         net = self._net_ref()
         if net is not None:
             net._mmbs_train_steps = getattr(net, "_mmbs_train_steps", 0) + 1
-        _ck(L.mmbs_stem_pack_input(_lib.ptr(x_nchw), _lib.ptr(self.x_s2d), self.B, _lib.stream_ptr()),
-            "mmbs_stem_pack_input")
+        if x_nchw.dtype == torch.uint8:   # raw pixels (e.g. pipeline.augment output): ToTensor + Normalize in the pack kernel
+            import ctypes
+            mean = (ctypes.c_float * 3)(*(net.input_mean if net is not None else (0.485, 0.456, 0.406)))
+            std = (ctypes.c_float * 3)(*(net.input_std if net is not None else (0.229, 0.224, 0.225)))
+            _ck(L.mmbs_stem_pack_input_u8(_lib.ptr(x_nchw), _lib.ptr(self.x_s2d), self.B, mean, std, _lib.stream_ptr()),
+                "mmbs_stem_pack_input_u8")
+        else:
+            _ck(L.mmbs_stem_pack_input(_lib.ptr(x_nchw), _lib.ptr(self.x_s2d), self.B, _lib.stream_ptr()),
+                "mmbs_stem_pack_input")
         self._run("fwd", self._fwd_body)
         return self.feats.clone()
 
@@ -430,7 +437,8 @@ def trainable_outside_layer4(net) -> bool:
 
 
 def run_train(net, x: torch.Tensor, engines: dict) -> torch.Tensor:
-    """Training-mode ``forward_extract`` of ``net`` on fp32 NCHW ``x`` (no gradient into x)."""
+    """Training-mode ``forward_extract`` of ``net`` on fp32 (normalised) or uint8 (raw pixels) NCHW ``x`` (no gradient
+    into x)."""
     B = x.shape[0]
     key = ("train", x.device.index, B)
     eng = engines.get(key)
@@ -444,6 +452,7 @@ def run_train(net, x: torch.Tensor, engines: dict) -> torch.Tensor:
         engines.pop(key)                   # re-insert: most recently used last
     engines[key] = eng
     params = [p for p in net.layer4.parameters()]
+    x = x.detach().contiguous() if x.dtype == torch.uint8 else x.detach().float().contiguous()
     if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-        return _TrunkTrainFn.apply(x.detach().float().contiguous(), eng, *params)
-    return eng.forward(x.detach().float().contiguous())
+        return _TrunkTrainFn.apply(x, eng, *params)
+    return eng.forward(x)

@@ -76,3 +76,30 @@ def test_decode_augment_extract_pipeline(tmp_path):
     with torch.no_grad():
         f = net.forward_extract(pipeline.augment(host.to(DEV), pipeline.sample_augment_params(4)))
     assert tuple(f.shape) == (4, 2048) and bool(torch.isfinite(f).all())
+
+
+def test_training_engine_takes_raw_pixels():
+    """model.train(): uint8 pixels (the augmentation kernel's output) normalised by the stem pack kernel give the
+    features of the fp32 tensor ToTensor + Normalize would have produced.  The two inputs differ by fp32 rounding of the
+    normalisation before the bf16 cast; batch-statistics BatchNorm over 8 patches amplifies that like any other bf16
+    rounding (training-mode features are within 5e-3 of the fp32 reference) - same bound here."""
+    from multimodalbrainsurvival_b200 import resnet
+    from oracle import resnet_oracle
+    net = resnet.resnet50()
+    net.load_state_dict(resnet_oracle.init_state_dict(seed=9, bn3_gamma_scale=0.1))
+    net = net.to(DEV).train()
+    for p in net.parameters():
+        p.requires_grad = False
+    for p in net.layer4.parameters():
+        p.requires_grad = True
+    g = torch.Generator().manual_seed(0)
+    u8 = torch.randint(0, 256, (8, 3, 224, 224), dtype=torch.uint8, generator=g).to(DEV)
+    mean = torch.tensor(net.input_mean, device=DEV).view(1, 3, 1, 1)
+    std = torch.tensor(net.input_std, device=DEV).view(1, 3, 1, 1)
+    f_u8 = net.forward_extract(u8)
+    assert net._engines and f_u8.requires_grad
+    f_u8.sum().backward()
+    assert net.layer4[2].conv3.weight.grad is not None
+    f_fp = net.forward_extract((u8.float() / 255.0 - mean) / std)
+    rel = float((f_u8.detach() - f_fp.detach()).norm() / f_fp.detach().norm())
+    assert rel < 5e-3, rel
