@@ -79,12 +79,33 @@ def pipeline_state(times: torch.Tensor) -> dict:
     return {"state": int(out[0]), "largest_bucket": int(out[1]), "buckets": int(out[2]), "capacity": int(out[3])}
 
 
+_WS_BYTES = {}   # n -> mmbs_cox_workspace_bytes(n): a pure function of n, one ctypes round trip saved per call
+
+
+def _ws_bytes(L, n: int) -> int:
+    v = _WS_BYTES.get(n)
+    if v is None:
+        if len(_WS_BYTES) > 256:
+            _WS_BYTES.clear()
+        v = _WS_BYTES[n] = int(L.mmbs_cox_workspace_bytes(n))
+    return v
+
+
+def _flat_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    """_prep without tensor operations for the common case (a contiguous 1-D fp32 CUDA tensor)."""
+    if t.is_cuda and t.dtype == torch.float32 and t.dim() == 1 and t.is_contiguous():
+        return t.detach() if t.requires_grad else t
+    return _prep(t, name)
+
+
 class _CoxLossFn(torch.autograd.Function):
+    # The host side of a call is on the critical path when the caller synchronises between steps (the GPU idles until
+    # the first launch): no tensor views, the output pointers are computed from ONE allocation's base address.
     @staticmethod
     def forward(ctx, cox_scores, times, status):
-        s = _prep(cox_scores, "cox_scores")
-        t = _prep(times, "times")
-        d = _prep(status, "status")
+        s = _flat_f32(cox_scores, "cox_scores")
+        t = _flat_f32(times, "times")
+        d = _flat_f32(status, "status")
         n = s.numel()
         if t.numel() != n or d.numel() != n:
             raise ValueError(f"cox_loss: size mismatch scores={tuple(cox_scores.shape)} "
@@ -97,23 +118,28 @@ class _CoxLossFn(torch.autograd.Function):
             return torch.full((), float("nan"), device=dev)
         L = _lib.lib()
         npad = _pad64(n)
-        with torch.cuda.device(dev):
+        switch = torch.cuda.current_device() != dev.index
+        if switch:
+            prev = torch.cuda.current_device()
+            torch.cuda.set_device(dev)
+        try:
             # one allocation: [perm | saved s~ | saved w | loss, flags]  (all 4-byte words)
             buf = torch.empty(3 * npad + 64, dtype=torch.float32, device=dev)
-            perm = buf[:npad].view(torch.int32)[:n]
-            saved = buf[npad:3 * npad].view(2, npad)
-            out = buf[3 * npad:3 * npad + 2]
-            flags = out[1:].view(torch.int32)
+            base = buf.data_ptr()
             if n <= SMALL_N:
-                ws, nbytes = None, 0
+                ws, nbytes, ws_ptr = None, 0, 0
             else:
-                nbytes = L.mmbs_cox_workspace_bytes(n)
+                nbytes = _ws_bytes(L, n)
                 ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            _lib.check(L.mmbs_cox_forward(_lib.ptr(s), _lib.ptr(t), _lib.ptr(d), n, _lib.ptr(perm),
-                                          _lib.ptr(saved[0]), _lib.ptr(saved[1]), _lib.ptr(out),
-                                          _lib.ptr(flags), _lib.ptr(ws), nbytes, _lib.stream_ptr()),
-                       "mmbs_cox_forward")
-        if os.environ.get("MMBS_COX_CHECK_NAN", "0") == "1" and int(flags.item()) != 0:
+                ws_ptr = ws.data_ptr()
+            out_ptr = base + 12 * npad
+            _lib.check(L.mmbs_cox_forward(s.data_ptr(), t.data_ptr(), d.data_ptr(), n, base, base + 4 * npad,
+                                          base + 8 * npad, out_ptr, out_ptr + 4, ws_ptr, nbytes,
+                                          torch.cuda.current_stream().cuda_stream), "mmbs_cox_forward")
+        finally:
+            if switch:
+                torch.cuda.set_device(prev)
+        if os.environ.get("MMBS_COX_CHECK_NAN", "0") == "1" and int(buf[3 * npad + 1:3 * npad + 2].view(torch.int32).item()) != 0:
             raise FloatingPointError(f"cox_loss: NaN in the loss terms (n={n})")
         ctx.n = n
         ctx.in_shape = cox_scores.shape
@@ -121,7 +147,7 @@ class _CoxLossFn(torch.autograd.Function):
         ctx.ws_bytes = nbytes
         ctx.save_for_backward(s, d, buf, *([ws] if ws is not None else []))
         ctx.npad = npad
-        return out[0].clone().reshape(())
+        return buf[3 * npad].clone()
 
     @staticmethod
     def backward(ctx, grad_loss):
@@ -130,17 +156,26 @@ class _CoxLossFn(torch.autograd.Function):
         s, d, buf = ctx.saved_tensors[:3]
         ws = ctx.saved_tensors[3] if len(ctx.saved_tensors) > 3 else None
         n, npad = ctx.n, ctx.npad
-        perm = buf[:npad].view(torch.int32)
-        saved = buf[npad:3 * npad].view(2, npad)
-        g = grad_loss.detach().reshape(1).float().contiguous()
+        g = grad_loss
+        if not (g.dtype == torch.float32 and g.is_contiguous() and g.device == s.device):
+            g = g.detach().reshape(1).to(s.device).float().contiguous()
         grad = torch.empty(n, dtype=torch.float32, device=s.device)
         L = _lib.lib()
-        with torch.cuda.device(s.device):
-            _lib.check(L.mmbs_cox_backward(_lib.ptr(s), _lib.ptr(d), _lib.ptr(perm), _lib.ptr(saved[0]),
-                                           _lib.ptr(saved[1]), _lib.ptr(g), n, _lib.ptr(grad), _lib.ptr(ws),
-                                           ctx.ws_bytes, _lib.stream_ptr()),
-                       "mmbs_cox_backward")
-        return grad.reshape(ctx.in_shape).to(ctx.in_dtype), None, None
+        base = buf.data_ptr()
+        switch = torch.cuda.current_device() != s.device.index
+        if switch:
+            prev = torch.cuda.current_device()
+            torch.cuda.set_device(s.device)
+        try:
+            _lib.check(L.mmbs_cox_backward(s.data_ptr(), d.data_ptr(), base, base + 4 * npad, base + 8 * npad,
+                                           g.data_ptr(), n, grad.data_ptr(), ws.data_ptr() if ws is not None else 0,
+                                           ctx.ws_bytes, torch.cuda.current_stream().cuda_stream), "mmbs_cox_backward")
+        finally:
+            if switch:
+                torch.cuda.set_device(prev)
+        if grad.shape != ctx.in_shape:
+            grad = grad.reshape(ctx.in_shape)
+        return (grad if ctx.in_dtype == torch.float32 else grad.to(ctx.in_dtype)), None, None
 
 
 def cox_loss(cox_scores, times, status):
