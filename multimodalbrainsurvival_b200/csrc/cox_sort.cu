@@ -293,32 +293,6 @@ __global__ void __launch_bounds__(FS_HIST_THREADS, 6) fs_hist_kernel(
 constexpr uint32_t P_E_MASK = P_TILE - 1;
 static_assert(P_TILE == 8192 && FS_MAX_BUCKETS <= 4096, "staged payload packs 13 + 1 + 12 bits");
 
-// thread tid owns buckets tid*per .. +per: tile-local starts, and the tile's slots in every bucket region.  All of the
-// thread's global atomics are in flight together (one after the other they cost a round trip to the L2 each: a fifth of
-// the kernel's stall samples).  s_cnt is overwritten with the slot deltas (a count is dead once its start is known).
-template <int PER_MAX>
-__device__ __forceinline__ void partition_claim_slots(int per, uint32_t* __restrict__ cursor, uint32_t* s_cnt,
-                                                      uint32_t* s_start, uint32_t* s_w, int tid, int lane, int warp) {
-  uint32_t c[PER_MAX], g[PER_MAX], sum = 0;
-#pragma unroll
-  for (int k = 0; k < PER_MAX; ++k) {
-    c[k] = (k < per) ? s_cnt[tid * per + k] : 0u;
-    g[k] = (c[k] != 0u) ? atomicAdd(cursor + tid * per + k, c[k]) : 0u;
-    sum += c[k];
-  }
-  const uint2 sc = block_scan_u32<P_THREADS / 32>(sum, s_w, lane, warp);
-  uint32_t run = sc.x - sum;
-#pragma unroll
-  for (int k = 0; k < PER_MAX; ++k) {
-    if (k < per) {
-      const int b = tid * per + k;
-      s_start[b] = run;
-      s_cnt[b] = g[k] - run;   // slot in the bucket region = tile position + delta (unused when the count is zero)
-      run += c[k];
-    }
-  }
-}
-
 template <bool FULL>   // FULL: the tile holds P_TILE samples and `times` / `status` / `scores` are 16-byte aligned
 __device__ __forceinline__ void partition_tile(const float* __restrict__ times, const float* __restrict__ status,
                                                const float* __restrict__ scores, bool do_max, uint32_t* __restrict__ max_enc,
@@ -375,8 +349,20 @@ __device__ __forceinline__ void partition_tile(const float* __restrict__ times, 
   if (nonbinary) atomicOr(nonbinary_flag, 1);
   __syncthreads();
 
-  if (per <= 4) partition_claim_slots<4>(per, cursor, s_cnt, s_start, s_w, tid, lane, warp);
-  else partition_claim_slots<FS_MAX_BUCKETS / P_THREADS>(per, cursor, s_cnt, s_start, s_w, tid, lane, warp);
+  // thread tid owns buckets tid*per .. +per: tile-local starts, and the tile's slots in every bucket region
+  {
+    uint32_t sum = 0;
+    for (int k = 0; k < per; ++k) sum += s_cnt[tid * per + k];
+    const uint2 sc = block_scan_u32<P_THREADS / 32>(sum, s_w, lane, warp);
+    uint32_t run = sc.x - sum;
+    for (int k = 0; k < per; ++k) {
+      const int b = tid * per + k;
+      const uint32_t c = s_cnt[b];
+      s_start[b] = run;
+      if (c != 0u) s_delta[b] = atomicAdd(cursor + b, c) - run;   // slot in the bucket region = tile position + delta
+      run += c;
+    }
+  }
   __syncthreads();
   // stage the tile in bucket order; the scores ride along (second read of the tile's scores: this pass also owns
   // max(scores) / the NaN flag when the histogram only sampled)
