@@ -90,6 +90,8 @@ struct ConvParams {
   // split-K (weight-gradient GEMMs: few output tiles, very long K): tile = ks * mn_tiles + (m, n) tile; split ks
   // covers K chunks [ks * chunks_per_split, ...) and adds its partial sums to the pre-zeroed fp32 output
   int32_t k_split, chunks_per_split, mn_tiles;
+  int32_t cluster2;   // CTA pairs: the two CTAs of a cluster work on adjacent pixel tiles of the same column tile and
+                      // each fetches half of every weight box for both (TMA multicast)
   int32_t mn_major;   // bit0: A is MN-major (row-major [K, M]); bit1: B is MN-major (row-major [K, N]).  3 = TN GEMM (weight
                       // gradients from NHWC tensors); 2 = data gradient reading the FORWARD conv's packed weights
   // implicit weight-gradient GEMM of a convolution (mn_major == 3, wg_conv): K chunk = 64 images at one output pixel
@@ -143,8 +145,14 @@ struct TileCoord {
 __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int tile, int n_tiles) {
   TileCoord c;
   // n-tile fastest: CTAs that share an A tile run back to back (L2 reuse)
-  const uint32_t mt = fdiv(uint32_t(tile), p.fd_ntiles);
+  uint32_t mt = fdiv(uint32_t(tile), p.fd_ntiles);
   c.nt = tile - int(mt) * n_tiles;
+  if (p.cluster2) {   // tiles 2j, 2j+1 (the two CTAs of a pair): pixel tiles 2i, 2i+1 of the same column tile
+    const uint32_t pair = uint32_t(tile) >> 1;
+    const uint32_t mtp = fdiv(pair, p.fd_ntiles);
+    c.nt = int(pair) - int(mtp) * n_tiles;
+    mt = 2u * mtp + (uint32_t(tile) & 1u);
+  }
   const uint32_t in_ = fdiv(mt, p.fd_twh);                 // image-box index
   const uint32_t rem = mt - in_ * p.fd_twh.d;
   const uint32_t ih = fdiv(rem, p.fd_tw);
@@ -363,9 +371,11 @@ __device__ __forceinline__ void staging_column_stats(StatsAcc& a, uint32_t stg, 
   a.s0 += s0; a.s1 += s1; a.q0 += q0; a.q1 += q1;
 }
 
-template <int N_TILE, int STAGES, int NSTG, int A_STAGE, int RES_BYTES>
+template <int N_TILE, int STAGES, int NSTG, int A_STAGE, int RES_BYTES, int CL = 1>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ ConvParams p) {
+  static_assert(CL == 1 || (CL == 2 && RES_BYTES == 0 && N_TILE == 256), "CTA pairs: streamed 256-wide tiles only");
+  const uint32_t cta_rank = (CL == 2) ? tc::cluster_ctarank() : 0u;
   using L = GemmSmem<N_TILE, STAGES, NSTG, A_STAGE, RES_BYTES>;
   constexpr bool kResident = RES_BYTES > 0;
   extern __shared__ uint8_t smem_raw[];
@@ -407,7 +417,7 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
     if (N_TILE >= 64 && !p.out_f32 && p.residual != nullptr) tc::tma_prefetch_desc(&p.res_map);
     for (int s = 0; s < STAGES; ++s) {
       tc::mbar_init(full_bar + 8 * s, 1);
-      tc::mbar_init(empty_bar + 8 * s, 1);
+      tc::mbar_init(empty_bar + 8 * s, CL);   // CTA pairs: both consumers release a stage (the peer refills half of it)
     }
     for (int a = 0; a < 2; ++a) {
       tc::mbar_init(tfull_bar + 8 * a, 1);
@@ -427,6 +437,7 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (CL == 2) tc::cluster_sync();   // the peer's barriers exist before anything is multicast onto them
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
@@ -489,7 +500,11 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
                                   c * GM_CHUNK_K);
             } else {
               tc::tma_load_4d(amap, full_bar + 8 * s, a_dst, c * GM_CHUNK_K, cw, ch, tcd.n0);
-              if (!kResident)
+              if (CL == 2)   // this CTA's half of the weight box, for both CTAs of the pair
+                tc::tma_load_2d_multicast(&p.b_map, full_bar + 8 * s, a_dst + GM_A_BYTES + cta_rank * (N_TILE / 2) * 128u,
+                                          (t * p.k_chunks + c) * GM_CHUNK_K, tcd.nt * N_TILE + int(cta_rank) * (N_TILE / 2),
+                                          uint16_t(3));
+              else if (!kResident)
                 tc::tma_load_2d(&p.b_map, full_bar + 8 * s, a_dst + GM_A_BYTES,
                                 (t * p.k_chunks + c) * GM_CHUNK_K, tcd.nt * N_TILE);
             }
@@ -548,7 +563,9 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
                             (ki | k) != 0 ? 1u : 0u);
             }
           }
-          tc::umma_commit(empty_bar + 8 * s);  // frees the smem stage when these MMAs retire
+          // frees the smem stage when these MMAs retire (CTA pairs: in both CTAs)
+          if (CL == 2) tc::umma_commit_multicast(empty_bar + 8 * s, uint16_t(3));
+          else tc::umma_commit(empty_bar + 8 * s);
           if (ki == k_iters - 1) tc::umma_commit(tfull_bar + 8 * acc);  // accumulator complete
         }
         __syncwarp();
@@ -786,6 +803,7 @@ conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (CL == 2) tc::cluster_sync();   // no CTA leaves while its peer may still signal its barriers
   if (warp == 1) tc::tmem_dealloc(tmem_base, L::TMEM_COLS);
 }
 
@@ -845,18 +863,19 @@ using namespace mmbs;
 struct mmbs_conv_plan {
   ConvParams p;
   int variant;   // 0 = streamed weights, 1 = weights resident in smem
+  int cluster;   // 1, or 2: CTA pairs sharing the weight boxes through TMA multicast
   int n_tile;
   int stages;
   unsigned grid;
   size_t zero_bytes;   // split-K: the fp32 output is cleared before every run (the splits accumulate into it)
 };
 
-template <int N_TILE, int STAGES, int NSTG, int A_STAGE = 0, int RES_BYTES = 0>
+template <int N_TILE, int STAGES, int NSTG, int A_STAGE = 0, int RES_BYTES = 0, int CL = 1>
 static int launch_conv(const mmbs_conv_plan* plan, cudaStream_t stream) {
   using L = GemmSmem<N_TILE, STAGES, NSTG, A_STAGE, RES_BYTES>;
   static PerDeviceOnce configured;
   if (configured.first())
-    MMBS_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE, STAGES, NSTG, A_STAGE, RES_BYTES>,
+    MMBS_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<N_TILE, STAGES, NSTG, A_STAGE, RES_BYTES, CL>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYNAMIC));
   static const bool use_pdl = []() {
     const char* e = getenv("MMBS_PDL");
@@ -868,12 +887,23 @@ static int launch_conv(const mmbs_conv_plan* plan, cudaStream_t stream) {
   cfg.blockDim = dim3(GM_THREADS);
   cfg.dynamicSmemBytes = L::DYNAMIC;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CL == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (use_pdl && plan->zero_bytes == 0) {   // a memset precedes split-K launches: plain ordering
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = (use_pdl && plan->zero_bytes == 0) ? 1 : 0;   // a memset precedes split-K launches: plain ordering
-  MMBS_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N_TILE, STAGES, NSTG, A_STAGE, RES_BYTES>, plan->p));
+  cfg.numAttrs = na;
+  MMBS_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<N_TILE, STAGES, NSTG, A_STAGE, RES_BYTES, CL>, plan->p));
   count_launch();
   return MMBS_OK;
 }
@@ -890,7 +920,9 @@ extern "C" int mmbs_conv_run(const mmbs_conv_plan* plan, void* stream_) {
     return MMBS_ERR_ARG;
   }
   switch (plan->n_tile) {
-    case 256: return launch_conv<256, 3, 1>(plan, stream);
+    case 256:
+      if (plan->cluster == 2) return launch_conv<256, 3, 1, 0, 0, 2>(plan, stream);
+      return launch_conv<256, 3, 1>(plan, stream);
     case 128: return launch_conv<128, 4, 2>(plan, stream);
     case 64: return launch_conv<64, 6, 2>(plan, stream);
     case 32: return launch_conv<32, 6, 1>(plan, stream);
@@ -1083,6 +1115,20 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
   p.fd_mn = make_fastdiv(uint32_t(p.mn_tiles));
   p.total_tiles = p.mn_tiles * p.k_split;
   plan->grid = unsigned(std::min<int64_t>(p.total_tiles, sm_count()));  // persistent: <= one CTA per SM
+  // CTA pairs (MMBS_CLUSTER=1): forward convs on the streamed 256-wide path with an even number of pixel tiles
+  plan->cluster = 1;
+  {
+    static const bool want = []() {
+      const char* e = getenv("MMBS_CLUSTER");
+      return e && e[0] == '1';
+    }();
+    if (want && !linear_mode && !stem_mode && plan->variant == 0 && plan->n_tile == 256 && p.k_split == 1 &&
+        !(d->flags & 2) && m_tiles % 2 == 0 && plan->grid >= 2) {
+      plan->cluster = 2;
+      p.cluster2 = 1;
+      plan->grid &= ~1u;
+    }
+  }
   const bool fwd_weights = linear_mode != 2 && !stem_mode && (d->flags & 2) != 0;   // dgrad on the forward weights
   p.mn_major = (linear_mode == 2) ? 3 : (fwd_weights ? 2 : 0);
   p.out_col_stride = 1;
@@ -1148,7 +1194,7 @@ static int build_plan(const mmbs_conv_desc* d, int stem_mode, int linear_mode, m
   } else if (!rc) {
     const uint64_t dims[2] = {uint64_t(k_total), uint64_t(d->c_out)};
     const uint64_t str[1] = {uint64_t(k_total) * 2};
-    const uint32_t box_b[2] = {64u, uint32_t(plan->n_tile)};
+    const uint32_t box_b[2] = {64u, uint32_t(plan->n_tile / plan->cluster)};   // (CTA pairs: each CTA fetches half a box)
     rc = encode_map(&p.b_map, d->weight, 2, dims, str, box_b);
   }
   if (!rc && !d->out_f32 && plan->n_tile >= 64) {

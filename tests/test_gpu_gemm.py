@@ -212,3 +212,17 @@ def test_conv_weight_gradient_implicit_gemm(B, H, W, Cin, Cout, k, s):
                                       stride=s, padding=k // 2)
     err = float((dw.double() - ref).abs().max())
     assert err <= 2e-5 * float(ref.abs().max()) + 1e-3, f"max err {err} (scale {float(ref.abs().max())})"
+
+
+def test_cta_pair_variant_matches_torch():
+    """MMBS_CLUSTER=1 (CTA pairs sharing the weight boxes through TMA multicast) is read once per process:
+    run the conv parity cases again in a child process with the variant switched on."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, MMBS_CLUSTER="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_gemm.py"), "-q", "-x", "-k",
+                        "conv and not cta_pair", "-p", "no:cacheprovider"], env=env, capture_output=True, text=True,
+                       timeout=600, cwd=os.path.dirname(here))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
