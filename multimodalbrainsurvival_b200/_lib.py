@@ -187,8 +187,38 @@ def launch_count() -> int:
 
 
 def stream_ptr():
+    """The current CUDA stream of the current device as an integer handle (every launch passes one: the raw C call is
+    ~20x cheaper than building a torch.cuda.Stream object - 19 launches per RNA training step made that 10 % of the step)."""
     import torch
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+    except AttributeError:   # private names moved: the public (slower) route
+        return torch.cuda.current_stream().cuda_stream
+
+
+class on_device:
+    """``with torch.cuda.device(dev)`` that costs nothing when `dev` is already current (the usual case)."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        import torch
+        idx = getattr(device, "index", device)
+        self.idx = torch._C._cuda_getDevice() if idx is None else int(idx)
+        self.prev = -1
+
+    def __enter__(self):
+        import torch
+        cur = torch._C._cuda_getDevice()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            import torch
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 def ptr(t):

@@ -135,7 +135,7 @@ class _CoxLossFn(torch.autograd.Function):
             out_ptr = base + 12 * npad
             _lib.check(L.mmbs_cox_forward(s.data_ptr(), t.data_ptr(), d.data_ptr(), n, base, base + 4 * npad,
                                           base + 8 * npad, out_ptr, out_ptr + 4, ws_ptr, nbytes,
-                                          torch.cuda.current_stream().cuda_stream), "mmbs_cox_forward")
+                                          _lib.stream_ptr()), "mmbs_cox_forward")
         finally:
             if switch:
                 torch.cuda.set_device(prev)
@@ -169,7 +169,7 @@ class _CoxLossFn(torch.autograd.Function):
         try:
             _lib.check(L.mmbs_cox_backward(s.data_ptr(), d.data_ptr(), base, base + 4 * npad, base + 8 * npad,
                                            g.data_ptr(), n, grad.data_ptr(), ws.data_ptr() if ws is not None else 0,
-                                           ctx.ws_bytes, torch.cuda.current_stream().cuda_stream), "mmbs_cox_backward")
+                                           ctx.ws_bytes, _lib.stream_ptr()), "mmbs_cox_backward")
         finally:
             if switch:
                 torch.cuda.set_device(prev)

@@ -98,7 +98,7 @@ def _fused_step(opt) -> bool:
         tensors[i].n, tensors[i].group = p.numel(), row_of[i]
     n_rows = len(rows)
     dev = next(iter(devices))
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         _lib.check(_lib.lib().mmbs_adam_step(tensors, len(work), hyper, n_rows, _lib.stream_ptr()),
                    "mmbs_adam_step")
     # the kernel wrote through raw pointers: bump the version counters like an in-place torch op would, so that
