@@ -391,6 +391,15 @@ typedef struct mmbs_aug_params {
 } mmbs_aug_params;
 int mmbs_png_decode(const uint8_t* file_bytes, size_t nbytes, uint8_t* out_hwc, int h, int w);
 int mmbs_png_decode_files(const char* const* paths, int64_t count, uint8_t* out_hwc, int h, int w, int threads);
+/* transforms.Resize(img_size) on PIL images = Image.resize(BILINEAR) (/root/reference/1_HistoPathology/
+ * 2_HistoPath_train.py:476,484): Pillow's antialiased triangle filter, bit-exact.  mmbs_resample_coeffs (HOST code) fills
+ * the 22-bit fixed-point coefficient rows of one axis (call with null pointers for the row length `ksize`); the caller
+ * uploads them; mmbs_resize_bilinear_u8 runs the horizontal then the vertical pass on uint8 [batch, h, w, 3]
+ * (tmp: batch * in_h * out_w * 3 bytes). */
+int mmbs_resample_coeffs(int in_size, int out_size, int32_t* bounds_host, int32_t* kk_host, int kk_capacity);
+int mmbs_resize_bilinear_u8(const uint8_t* in_hwc, uint8_t* out_hwc, uint8_t* tmp, int64_t batch, int in_h, int in_w,
+                            int out_h, int out_w, const int32_t* bounds_w, const int32_t* kk_w, int ksize_w,
+                            const int32_t* bounds_h, const int32_t* kk_h, int ksize_h, void* stream);
 int mmbs_augment_u8(const uint8_t* in_hwc, uint8_t* out_chw, int64_t batch, int h, int w, const void* params_dev,
                     uint32_t* lsum_ws, void* stream);
 

@@ -96,6 +96,10 @@ SIGNATURES = {
     "mmbs_png_decode": (ctypes.c_int, [c_void_p, c_size, c_void_p, ctypes.c_int, ctypes.c_int]),
     "mmbs_png_decode_files": (ctypes.c_int, [ctypes.POINTER(ctypes.c_char_p), c_i64, c_void_p, ctypes.c_int, ctypes.c_int,
                                              ctypes.c_int]),
+    "mmbs_resample_coeffs": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, ctypes.c_int]),
+    "mmbs_resize_bilinear_u8": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_int, c_void_p, c_void_p, ctypes.c_int, c_void_p, c_void_p,
+                                               ctypes.c_int, c_void_p]),
     "mmbs_augment_u8": (ctypes.c_int, [c_void_p, c_void_p, c_i64, ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p]),
     "mmbs_pack_conv_weight": (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
     "mmbs_bn_fold": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_i64, c_void_p,

@@ -10,6 +10,9 @@
 // ColorJitter's contrast blends with the mean luma of the image AS IT IS at that point of the (random) operation order:
 // pass 1 runs the operations in front of the contrast step and sums L per image (integer atomics: exact, order-free),
 // pass 2 runs the whole chain.  One thread per pixel.
+#include <cmath>
+#include <vector>
+
 #include "common.cuh"
 
 namespace mmbs {
@@ -149,9 +152,96 @@ __global__ void __launch_bounds__(AUG_THREADS) augment_kernel(const uint8_t* __r
   dst[2 * int64_t(h) * w] = uint8_t(b);
 }
 
+// ---- transforms.Resize on PIL images = Image.resize(BILINEAR): Pillow's antialiased triangle filter (Resample.c), a
+// horizontal pass then a vertical pass over 22-bit fixed-point coefficient rows, each pass rounded to uint8.
+constexpr int RS_PRECISION_BITS = 32 - 8 - 2;
+
+// one thread per output pixel of the pass; AXIS 0: along rows (vertical pass), 1: along columns (horizontal pass)
+template <int AXIS>
+__global__ void __launch_bounds__(256) resample_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int64_t batch,
+                                                       int in_h, int in_w, int out_h, int out_w,
+                                                       const int32_t* __restrict__ bounds, const int32_t* __restrict__ kk,
+                                                       int ksize) {
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= batch * out_h * out_w) return;
+  const int ox = int(i % out_w), oy = int((i / out_w) % out_h);
+  const int64_t n = i / (int64_t(out_w) * out_h);
+  const int o = AXIS ? ox : oy;
+  const int first = __ldg(bounds + 2 * o), cnt = __ldg(bounds + 2 * o + 1);
+  const int32_t* k = kk + int64_t(o) * ksize;
+  int32_t a0 = 1 << (RS_PRECISION_BITS - 1), a1 = a0, a2 = a0;
+  const int64_t step = AXIS ? 3 : int64_t(in_w) * 3;
+  const uint8_t* src = in + ((n * in_h + (AXIS ? oy : first)) * int64_t(in_w) + (AXIS ? first : ox)) * 3;
+  for (int x = 0; x < cnt; ++x, src += step) {
+    const int32_t c = __ldg(k + x);
+    a0 += int32_t(src[0]) * c;
+    a1 += int32_t(src[1]) * c;
+    a2 += int32_t(src[2]) * c;
+  }
+  uint8_t* dst = out + i * 3;
+  dst[0] = uint8_t(clip8(a0 >> RS_PRECISION_BITS));
+  dst[1] = uint8_t(clip8(a1 >> RS_PRECISION_BITS));
+  dst[2] = uint8_t(clip8(a2 >> RS_PRECISION_BITS));
+}
+
 }  // namespace mmbs
 
 using namespace mmbs;
+
+// Pillow precompute_coeffs + normalize_coeffs_8bpc (bilinear filter, the whole axis): host code, double arithmetic in the
+// order of the C source.  bounds[2 * out_size] = (first input index, count); kk[out_size * ksize]; returns ksize.
+extern "C" int mmbs_resample_coeffs(int in_size, int out_size, int32_t* bounds, int32_t* kk, int kk_capacity) {
+  if (in_size < 1 || out_size < 1) return -1;
+  const double scale = double(in_size) / double(out_size);
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 1.0 * filterscale;
+  const int ksize = int(ceil(support)) * 2 + 1;
+  if (bounds == nullptr || kk == nullptr) return ksize;   // size query
+  if (int64_t(out_size) * ksize > int64_t(kk_capacity)) return -1;
+  const double ss = 1.0 / filterscale;
+  std::vector<double> w(size_t(ksize), 0.0);
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    int xmin = int(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = int(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      double t = (x + xmin - center + 0.5) * ss;
+      if (t < 0.0) t = -t;
+      w[size_t(x)] = t < 1.0 ? 1.0 - t : 0.0;
+      ww += w[size_t(x)];
+    }
+    for (int x = 0; x < ksize; ++x) {
+      double v = 0.0;
+      if (x < xmax) v = (ww != 0.0) ? w[size_t(x)] / ww : w[size_t(x)];
+      kk[int64_t(xx) * ksize + x] = v < 0 ? int32_t(-0.5 + v * (1 << RS_PRECISION_BITS)) : int32_t(0.5 + v * (1 << RS_PRECISION_BITS));
+    }
+    bounds[2 * xx] = xmin;
+    bounds[2 * xx + 1] = xmax;
+  }
+  return ksize;
+}
+
+extern "C" int mmbs_resize_bilinear_u8(const uint8_t* in_hwc, uint8_t* out_hwc, uint8_t* tmp, int64_t batch, int in_h, int in_w,
+                                       int out_h, int out_w, const int32_t* bounds_w, const int32_t* kk_w, int ksize_w,
+                                       const int32_t* bounds_h, const int32_t* kk_h, int ksize_h, void* stream_) {
+  if (int rc = mmbs_device_check()) return rc;
+  MMBS_REQUIRE(in_hwc && out_hwc && tmp && bounds_w && kk_w && bounds_h && kk_h, "mmbs_resize_bilinear_u8: null pointer");
+  MMBS_REQUIRE(batch >= 1 && in_h >= 1 && in_w >= 1 && out_h >= 1 && out_w >= 1 && ksize_w >= 1 && ksize_h >= 1,
+               "mmbs_resize_bilinear_u8: bad shape");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  // horizontal pass: [B, in_h, in_w] -> tmp [B, in_h, out_w]; vertical pass: tmp -> [B, out_h, out_w]
+  resample_kernel<1><<<unsigned(ceil_div(batch * in_h * out_w, 256)), 256, 0, stream>>>(in_hwc, tmp, batch, in_h, in_w, in_h,
+                                                                                        out_w, bounds_w, kk_w, ksize_w);
+  MMBS_LAUNCH_CHECK();
+  resample_kernel<0><<<unsigned(ceil_div(batch * out_h * out_w, 256)), 256, 0, stream>>>(tmp, out_hwc, batch, in_h, out_w, out_h,
+                                                                                         out_w, bounds_h, kk_h, ksize_h);
+  MMBS_LAUNCH_CHECK();
+  return MMBS_OK;
+}
 
 extern "C" int mmbs_augment_u8(const uint8_t* in_hwc, uint8_t* out_chw, int64_t batch, int h, int w, const void* params_dev,
                                uint32_t* lsum_ws, void* stream_) {

@@ -141,3 +141,64 @@ def augment(patches_u8_hwc: torch.Tensor, params: torch.Tensor) -> torch.Tensor:
         _lib.check(_lib.lib().mmbs_augment_u8(_lib.ptr(x), _lib.ptr(out), b, h, w, _lib.ptr(p), _lib.ptr(ws),
                                               _lib.stream_ptr()), "mmbs_augment_u8")
     return out
+
+
+_RESAMPLE_TABLES = {}   # (in_size, out_size, device index) -> (bounds, coefficients, ksize) on the device
+
+
+def resample_coeffs(in_size: int, out_size: int):
+    """Pillow's bilinear coefficient rows for one axis (host code in the library, csrc/augment.cu):
+    -> (bounds int32 [out, 2], coefficients int32 [out, ksize])."""
+    import ctypes
+    import numpy as np
+    from . import _lib
+    L = _lib.lib()
+    ksize = L.mmbs_resample_coeffs(in_size, out_size, None, None, 0)
+    if ksize < 1:
+        raise ValueError(f"resample_coeffs: bad sizes {in_size} -> {out_size}")
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ksize), np.int32)
+    rc = L.mmbs_resample_coeffs(in_size, out_size, ctypes.c_void_p(bounds.ctypes.data), ctypes.c_void_p(kk.ctypes.data), kk.size)
+    if rc != ksize:
+        raise RuntimeError("mmbs_resample_coeffs failed")
+    return bounds, kk
+
+
+def resize(patches_u8_hwc: torch.Tensor, size) -> torch.Tensor:
+    """``transforms.Resize(size)`` of the reference's transform chains (2_HistoPath_train.py:476,484) on a batch of decoded
+    patches: uint8 [B, H, W, 3] (CUDA) -> uint8 [B, h, w, 3], bit-exact with PIL's antialiased bilinear resize.  An int
+    `size` scales the smaller edge to it (torchvision's rule); patches already of that size are returned as they are."""
+    from . import _lib
+    x = patches_u8_hwc
+    if not (x.is_cuda and x.dtype == torch.uint8 and x.dim() == 4 and x.shape[3] == 3):
+        raise RuntimeError("resize: patches must be a CUDA uint8 tensor [B, H, W, 3] (no CPU path in this build)")
+    b, h, w, _ = x.shape
+    if isinstance(size, int):
+        if h <= w:
+            oh, ow = size, int(size * w / h)
+        else:
+            oh, ow = int(size * h / w), size
+    else:
+        oh, ow = int(size[0]), int(size[1])
+    if (oh, ow) == (h, w):
+        return x
+    x = x.contiguous()
+    tabs = []
+    for n_in, n_out in ((w, ow), (h, oh)):
+        key = (n_in, n_out, x.device.index)
+        t = _RESAMPLE_TABLES.get(key)
+        if t is None:
+            bounds, kk = resample_coeffs(n_in, n_out)
+            t = (torch.from_numpy(bounds).to(x.device), torch.from_numpy(kk).to(x.device), kk.shape[1])
+            if len(_RESAMPLE_TABLES) > 64:
+                _RESAMPLE_TABLES.clear()
+            _RESAMPLE_TABLES[key] = t
+        tabs.append(t)
+    out = torch.empty((b, oh, ow, 3), dtype=torch.uint8, device=x.device)
+    tmp = torch.empty((b, h, ow, 3), dtype=torch.uint8, device=x.device)
+    (bw, kw, ksw), (bh, kh, ksh) = tabs
+    with _lib.on_device(x.device):
+        _lib.check(_lib.lib().mmbs_resize_bilinear_u8(_lib.ptr(x), _lib.ptr(out), _lib.ptr(tmp), b, h, w, oh, ow, _lib.ptr(bw),
+                                                      _lib.ptr(kw), ksw, _lib.ptr(bh), _lib.ptr(kh), ksh, _lib.stream_ptr()),
+                   "mmbs_resize_bilinear_u8")
+    return out

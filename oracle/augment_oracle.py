@@ -123,3 +123,59 @@ def augment(img_hwc: np.ndarray, hflip: bool, vflip: bool, order, factors) -> np
         if op >= 0:
             out = _OPS[op](out, float(factors[op]))
     return out
+
+
+# ----------------------------------------------------------------------------- Resize (Pillow libImaging/Resample.c)
+PRECISION_BITS = 32 - 8 - 2
+
+
+def resample_coeffs(in_size: int, out_size: int):
+    """Pillow precompute_coeffs + normalize_coeffs_8bpc for the bilinear (triangle) filter over the whole axis:
+    -> (bounds int32 [out, 2] = (first input index, count), coefficients int32 [out, ksize] in 22-bit fixed point)."""
+    scale = float(in_size) / out_size            # (double)(in1 - in0) / outSize
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale                  # bilinear support = 1
+    ksize = int(np.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ksize), np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = []
+        ww = 0.0
+        for x in range(xmax):
+            t = abs((x + xmin - center + 0.5) * ss)
+            v = 1.0 - t if t < 1.0 else 0.0
+            w.append(v)
+            ww += v
+        for x in range(xmax):
+            v = w[x] / ww if ww != 0.0 else w[x]
+            kk[xx, x] = int(-0.5 + v * (1 << PRECISION_BITS)) if v < 0 else int(0.5 + v * (1 << PRECISION_BITS))
+        bounds[xx] = (xmin, xmax)
+    return bounds, kk
+
+
+def _resample_axis(img: np.ndarray, bounds, kk, axis: int) -> np.ndarray:
+    src = np.moveaxis(img, axis, 0).astype(np.int64)
+    out = np.empty((bounds.shape[0],) + src.shape[1:], np.uint8)
+    for xx in range(bounds.shape[0]):
+        xmin, cnt = int(bounds[xx, 0]), int(bounds[xx, 1])
+        acc = np.full(src.shape[1:], 1 << (PRECISION_BITS - 1), np.int64)
+        for x in range(cnt):
+            acc += src[xmin + x] * int(kk[xx, x])
+        out[xx] = np.clip(acc >> PRECISION_BITS, 0, 255).astype(np.uint8)
+    return np.moveaxis(out, 0, axis)
+
+
+def resize_bilinear(img_hwc: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """`Image.resize((out_w, out_h), Image.BILINEAR)` = what transforms.Resize does to a PIL image (antialiased triangle
+    filter, horizontal pass then vertical pass, each rounded to uint8)."""
+    h, w = img_hwc.shape[:2]
+    out = img_hwc
+    if out_w != w:
+        out = _resample_axis(out, *resample_coeffs(w, out_w), axis=1)
+    if out_h != h:
+        out = _resample_axis(out, *resample_coeffs(h, out_h), axis=0)
+    return out

@@ -56,6 +56,21 @@ def test_every_operation_order_matches_the_oracle():
         assert np.array_equal(got[i], x), (i, rows[i].tolist(), int((got[i] != x).sum()))
 
 
+def test_resize_matches_torchvision_golden_and_oracle(golden):
+    from multimodalbrainsurvival_b200 import pipeline
+    g = golden("augment_reference.npz")
+    for key in ("resize", "upscale"):
+        got = pipeline.resize(torch.tensor(g[key + "_in"], device=DEV), 48).cpu().numpy()
+        assert got.shape == g[key + "_out"].shape and np.array_equal(got, g[key + "_out"]), key
+    rng = np.random.default_rng(4)
+    x = rng.integers(0, 256, (3, 256, 256, 3), dtype=np.uint8)
+    got = pipeline.resize(torch.tensor(x, device=DEV), 224).cpu().numpy()
+    for i in range(3):
+        assert np.array_equal(got[i], ao.resize_bilinear(x[i], 224, 224))
+    same = torch.tensor(x[:, :224, :224].copy(), device=DEV)
+    assert pipeline.resize(same, 224) is same   # the reference's 224 x 224 patches: Resize(224) is the identity
+
+
 def test_decode_augment_extract_pipeline(tmp_path):
     """PNG files -> host decoder -> device augmentation -> forward_extract on raw pixels: what a training loader feeds."""
     Image = pytest.importorskip("PIL.Image")

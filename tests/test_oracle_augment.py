@@ -81,6 +81,22 @@ def test_parameter_sampler_follows_torchvision_compose():
         assert np.array_equal(full, want)
 
 
+@pytest.mark.parametrize("shape", [(256, 256, 224, 224), (512, 512, 224, 224), (224, 224, 299, 299), (300, 200, 224, 149),
+                                   (97, 131, 224, 224), (1000, 1000, 224, 224)])
+def test_resize_matches_pillow(shape):
+    """Image.resize(BILINEAR) = transforms.Resize on PIL images (antialiased triangle filter, two uint8 passes); the
+    library's host coefficient routine (csrc/augment.cu mmbs_resample_coeffs) must produce the oracle's rows."""
+    from multimodalbrainsurvival_b200 import pipeline
+    h, w, oh, ow = shape
+    img = np.random.default_rng(h + ow).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    ref = np.asarray(Image.fromarray(img, "RGB").resize((ow, oh), Image.BILINEAR))
+    assert np.array_equal(ao.resize_bilinear(img, oh, ow), ref)
+    for n_in, n_out in ((w, ow), (h, oh)):
+        bo, ko = ao.resample_coeffs(n_in, n_out)
+        bl, kl = pipeline.resample_coeffs(n_in, n_out)
+        assert np.array_equal(bo, bl) and np.array_equal(ko, kl)
+
+
 @pytest.mark.parametrize("mode", ["RGB", "RGBA", "L", "P", "LA"])
 def test_png_decoder_matches_pillow(tmp_path, mode):
     from multimodalbrainsurvival_b200 import pipeline

@@ -418,8 +418,14 @@ def gen_augment():
     outs = np.stack([np.asarray(tf(Image.fromarray(im, "RGB"))) for im in imgs])
     torch.manual_seed(4242)
     rows = pipeline.sample_augment_params(n).numpy()
-    np.savez_compressed(os.path.join(OUT, "augment_reference.npz"), imgs=imgs, params=rows, outs=outs)
-    print("augment:", imgs.shape, rows.shape, outs.shape)
+    # transforms.Resize on non-square, non-224 patches (smaller edge -> 48; down- and up-scaling)
+    rs_in = rng.integers(0, 256, (2, 70, 90, 3), dtype=np.uint8)
+    rs_out = np.stack([np.asarray(T.Resize(48)(Image.fromarray(im, "RGB"))) for im in rs_in])
+    up_in = rng.integers(0, 256, (2, 20, 20, 3), dtype=np.uint8)
+    up_out = np.stack([np.asarray(T.Resize(48)(Image.fromarray(im, "RGB"))) for im in up_in])
+    np.savez_compressed(os.path.join(OUT, "augment_reference.npz"), imgs=imgs, params=rows, outs=outs,
+                        resize_in=rs_in, resize_out=rs_out, upscale_in=up_in, upscale_out=up_out)
+    print("augment:", imgs.shape, rows.shape, outs.shape, rs_out.shape, up_out.shape)
 
 
 if __name__ == "__main__":
