@@ -105,3 +105,30 @@ def test_uncovered_configurations_run_torchs_own_step():
     assert _lib.launch_count() == l0 and torch.equal(p, q)
     sgd = torch.optim.SGD([p], lr=0.1)
     assert optim.accelerate_optimizer(sgd) is sgd and not getattr(sgd, "_mmbs_accelerated", False)
+
+
+def test_cached_tables_follow_changing_gradient_sets_and_reloaded_state():
+    """The fused step caches its tensor table per optimizer: a parameter that skips steps (grad None), a changed set of
+    parameters with gradients, and a load_state_dict in the middle must all keep matching torch's own Adam."""
+    from multimodalbrainsurvival_b200 import optim
+    torch.manual_seed(3)
+    ref_p = [torch.randn(257, 33, device=DEV, requires_grad=True), torch.randn(1000, device=DEV, requires_grad=True),
+             torch.randn(64, 64, device=DEV, requires_grad=True)]
+    our_p = [p.detach().clone().requires_grad_(True) for p in ref_p]
+    ref = torch.optim.Adam(ref_p, lr=1e-2, weight_decay=1e-3)
+    ours = optim.accelerate_optimizer(torch.optim.Adam(our_p, lr=1e-2, weight_decay=1e-3))
+    g = torch.Generator(device=DEV).manual_seed(1)
+    for step in range(9):
+        active = [0, 1, 2] if step % 3 == 0 else ([0, 2] if step % 3 == 1 else [1])   # parameters that get a gradient
+        for i in range(3):
+            grad = torch.randn(ref_p[i].shape, device=DEV, generator=g) if i in active else None
+            ref_p[i].grad = grad
+            our_p[i].grad = None if grad is None else grad.clone()
+        if step == 5:   # reload the state (new state objects): the cache must notice
+            ours.load_state_dict(ours.state_dict())
+        ref.step()
+        ours.step()
+    for a, b in zip(ref_p, our_p):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-7), float((a - b).abs().max())
+    for a, b in zip(ref_p, our_p):
+        assert float(ref.state[a]["step"]) == float(ours.state[b]["step"])
