@@ -172,14 +172,24 @@ def run(kind, torch, dev, world=1, rank=0, steps=10, warmup=3, batch=128):
 
     from multimodalbrainsurvival_b200 import pipeline
 
+    loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_done = [torch.cuda.Event(), torch.cuda.Event()]
+
     def e2e_loop(n):
         """Pinned host batches staged by pipeline.prefetch_to_device (the H2D copy of batch i+1 overlaps the
-        kernels of batch i); the loss is read back to the host every step."""
+        kernels of batch i); the loss of EVERY step is copied to pinned host memory and read there one step later (what a
+        logging training loop does: a blocking .item() per step would idle the GPU between steps)."""
         last = None
-        for x in pipeline.prefetch_to_device((host_x[i % 2] for i in range(n)), dev, depth=2):
+        for i, x in enumerate(pipeline.prefetch_to_device((host_x[i % 2] for i in range(n)), dev, depth=2)):
             r = host_rna.to(dev, non_blocking=True) if kind == "joint" else None
-            last = float(step(x, r).detach())      # D2H of the loss
-        return last
+            loss = step(x, r).detach()
+            loss_host[i % 2].copy_(loss.reshape(1), non_blocking=True)      # D2H of this step's loss
+            loss_done[i % 2].record()
+            if i > 0:                                                        # .. read on the host one step later
+                loss_done[(i - 1) % 2].synchronize()
+                last = float(loss_host[(i - 1) % 2])
+        loss_done[(n - 1) % 2].synchronize()
+        return float(loss_host[(n - 1) % 2])
 
     e2e_loop(2)
     ms_e2e, _, _ = timed(lambda i: e2e_loop(steps) if i == 0 else None, 1)
