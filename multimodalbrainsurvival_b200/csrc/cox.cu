@@ -647,10 +647,18 @@ struct CoxLsdForward {
   double* tile_sum; double* tile_wsum; double* loss_partial;
   const int32_t* fallback;
   int zero_grid, hist_grid; unsigned sort_grid; int64_t sort_tiles, scan_tiles;
+  // the bucketed pipeline's one-block finish (cox_sort.cuh fs_loss_finalize_block)
+  const double* fs_row_loss; const double* fs_row_w; double* fs_wsuffix; int fs_nb;
 };
 
-__global__ void cox_lsd_forward_dispatch_kernel(CoxLsdForward a) {
-  if (*a.fallback == 0) return;
+// One block behind the bucketed forward pass: finishes it (loss, suffix sums of w) - or, when the pipeline gave the input
+// up, enqueues the LSD pipeline instead.
+__global__ void __launch_bounds__(FS_FINAL_THREADS, 1) cox_lsd_forward_dispatch_kernel(CoxLsdForward a) {
+  if (*a.fallback == 0) {   // (block-uniform)
+    fs_loss_finalize_block(a.fs_row_loss, a.fs_row_w, a.fs_nb, a.n, a.fs_wsuffix, a.nan_flag, a.loss_out, a.flags_out);
+    return;
+  }
+  if (threadIdx.x != 0) return;
   const unsigned tiles = unsigned(a.scan_tiles);
   cox_zero_words_kernel<<<a.zero_grid, 256, 0, cudaStreamTailLaunch>>>(a.sw.lookback, a.lookback_words, a.fallback);
   rs_sort_tail_launch(a.times, int(KEY_NEG_TIME_F32), a.n, 4, a.sw, a.perm_out, a.status, a.nonbinary, a.hist_grid,
@@ -672,10 +680,13 @@ struct CoxLsdBackward {
   uint32_t* max_enc; int32_t* max_count; int32_t* max_list; int32_t* nonbinary; const int32_t* fallback;
   double* tile_wsum; double* tile_suffix; double* gsum_partial; double* gsum_total;
   int64_t scan_tiles; int full_grid;
+  const double* fs_row_g; int fs_nb;   // the bucketed pipeline's one-block finish (fs_backward_finalize_block)
 };
 
-__global__ void cox_lsd_backward_dispatch_kernel(CoxLsdBackward a) {
+__global__ void __launch_bounds__(FS_FINAL_THREADS, 1) cox_lsd_backward_dispatch_kernel(CoxLsdBackward a) {
   const bool fb = *a.fallback != 0;
+  if (!fb) fs_backward_finalize_block(a.fs_row_g, a.fs_nb, a.max_count, a.max_list, a.gsum_total, a.grad_scores);
+  if (threadIdx.x != 0) return;
   if (fb) {
     const unsigned tiles = unsigned(a.scan_tiles);
     cox_tile_scan_kernel<<<1, 1024, 0, cudaStreamTailLaunch>>>(a.tile_wsum, a.tile_suffix, a.scan_tiles, 1, nullptr);
@@ -827,7 +838,8 @@ extern "C" int mmbs_cox_forward(const float* scores, const float* times, const f
     a.fallback = w.fallback;
     a.zero_grid = lsd_zero_grid(w); a.hist_grid = rs_hist_grid(n); a.sort_grid = rs_sort_grid(n);
     a.sort_tiles = rs_tiles(n); a.scan_tiles = tiles;
-    cox_lsd_forward_dispatch_kernel<<<1, 1, 0, stream>>>(a);
+    a.fs_row_loss = w.fs_row_loss; a.fs_row_w = w.fs_row_w; a.fs_wsuffix = w.fs_wsum; a.fs_nb = fs_plan(n).nb;
+    cox_lsd_forward_dispatch_kernel<<<1, FS_FINAL_THREADS, 0, stream>>>(a);
     MMBS_LAUNCH_CHECK();
     return MMBS_OK;
   }
@@ -886,7 +898,8 @@ extern "C" int mmbs_cox_backward(const float* scores, const float* status, const
     a.max_enc = w.max_enc; a.max_count = w.max_count; a.max_list = w.max_list; a.nonbinary = w.nonbinary;
     a.fallback = w.fallback; a.tile_wsum = w.tile_wsum; a.tile_suffix = w.tile_suffix;
     a.gsum_partial = w.gsum_partial; a.gsum_total = w.gsum_total; a.scan_tiles = tiles; a.full_grid = full_grid;
-    cox_lsd_backward_dispatch_kernel<<<1, 1, 0, stream>>>(a);
+    a.fs_row_g = w.fs_row_g; a.fs_nb = fs_plan(n).nb;
+    cox_lsd_backward_dispatch_kernel<<<1, FS_FINAL_THREADS, 0, stream>>>(a);
     MMBS_LAUNCH_CHECK();
     return MMBS_OK;
   }

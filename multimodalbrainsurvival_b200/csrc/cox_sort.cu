@@ -114,41 +114,6 @@ __device__ __forceinline__ uint2 block_scan_u32(uint32_t v, uint32_t* s_w, int l
   return make_uint2(incl + off, tot);
 }
 
-// inclusive scan of one double per thread over the block, forward (lower threads first) or reverse; *total = block sum
-template <int NW, bool REVERSE>
-__device__ __forceinline__ double block_scan_f64(double v, double* s_red, int lane, int warp, double* total) {
-  double incl = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const double t = REVERSE ? __shfl_down_sync(0xffffffffu, incl, o) : __shfl_up_sync(0xffffffffu, incl, o);
-    if (REVERSE ? (lane + o < 32) : (lane >= o)) incl += t;
-  }
-  __syncthreads();
-  if (lane == (REVERSE ? 0 : 31)) s_red[warp] = incl;
-  __syncthreads();
-  double off = 0.0, tot = 0.0;
-#pragma unroll
-  for (int w = 0; w < NW; ++w) {
-    const double c = s_red[w];
-    if (REVERSE ? (w > warp) : (w < warp)) off += c;
-    tot += c;
-  }
-  *total = tot;
-  return incl + off;
-}
-
-template <int NW>
-__device__ __forceinline__ double block_sum_f64(double v, double* s_red, int lane, int warp) {
-  v = warp_sum(v);
-  __syncthreads();
-  if (lane == 0) s_red[warp] = v;
-  __syncthreads();
-  double t = 0.0;
-#pragma unroll
-  for (int w = 0; w < NW; ++w) t += s_red[w];
-  return t;
-}
-
 // ------------------------------------------------------------------------------------------ histogram + CDF table
 __global__ void __launch_bounds__(FS_HIST_THREADS, 6) fs_hist_kernel(
     const float* __restrict__ times, int64_t n, int sample_shift, int nb, const float* __restrict__ scores,
@@ -953,8 +918,9 @@ __global__ void __launch_bounds__(R_THREADS, 8) fs_row_backward_kernel(
 // ------------------------------------------------------------------------------------------ one-block scans between the passes
 // (A grid-wide "last block finishes the job" needs a fence + counter atomic in every warp row; with sixteen scattered
 // stores in flight per lane those fences were a quarter of the backward kernel's stall samples.  Kernel boundaries order
-// the passes instead: three launches of one block each.)
-constexpr int F_THREADS = 1024;
+// the passes instead: the prefix kernel below, and fs_loss_finalize_block / fs_backward_finalize_block (cox_sort.cuh),
+// which run inside the one-block dispatch kernels of cox.cu that follow either pass anyway.)
+constexpr int F_THREADS = FS_FINAL_THREADS;
 constexpr int F_PER = FS_MAX_BUCKETS / F_THREADS;   // 4 consecutive buckets per thread
 
 // exclusive prefix of the buckets' sums of exp(s~)
@@ -978,89 +944,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) fs_prefix_kernel(const double* _
     const int q = tid * F_PER + k;
     if (q < nb) exp_prefix[q] = run;
     run += v[k];
-  }
-}
-
-// loss = sum of the row partials / n (.mean() over N, models.py:111); wsuffix[b] = sum of w over all LATER buckets.
-// Element e = 16 b + r of the row arrays goes to thread e mod 1024: coalesced, every load independent; a bucket's 16 rows
-// sit in one half-warp.
-__global__ void __launch_bounds__(F_THREADS, 1) fs_loss_finalize_kernel(
-    const double* __restrict__ row_loss, const double* __restrict__ row_w, int nb, int64_t n, double* __restrict__ wsuffix,
-    const int32_t* __restrict__ nan_flag, float* __restrict__ loss_out, int32_t* __restrict__ flags_out,
-    const int32_t* __restrict__ fallback) {
-  __shared__ double s_red[F_THREADS / 32];
-  __shared__ double s_wb[FS_MAX_BUCKETS];
-  if (*fallback != 0) return;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int total = nb * R_ROWS;
-  constexpr int BATCH = 8;
-  double lsum = 0.0;
-  for (int e0 = 0; e0 < total; e0 += BATCH * F_THREADS) {   // block-uniform trip count (shuffles inside)
-    double l[BATCH], w[BATCH];
-#pragma unroll
-    for (int k = 0; k < BATCH; ++k) {
-      const int e = e0 + k * F_THREADS + tid;
-      l[k] = e < total ? __ldg(row_loss + e) : 0.0;
-      w[k] = e < total ? __ldg(row_w + e) : 0.0;
-    }
-#pragma unroll
-    for (int k = 0; k < BATCH; ++k) {
-      lsum += l[k];
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) w[k] += __shfl_xor_sync(0xffffffffu, w[k], o);   // over the 16 rows of the bucket
-      const int e = e0 + k * F_THREADS + tid;
-      if ((lane & 15) == 0 && e < FS_MAX_BUCKETS * R_ROWS) s_wb[e >> 4] = w[k];
-    }
-  }
-  __syncthreads();
-  double w[F_PER], wsum = 0.0;
-#pragma unroll
-  for (int k = 0; k < F_PER; ++k) {
-    const int q = tid * F_PER + k;
-    w[k] = q < nb ? s_wb[q] : 0.0;
-    wsum += w[k];
-  }
-  double tot;
-  double later = block_scan_f64<F_THREADS / 32, true>(wsum, s_red, lane, warp, &tot) - wsum;   // higher threads only
-#pragma unroll
-  for (int k = F_PER - 1; k >= 0; --k) {
-    const int q = tid * F_PER + k;
-    if (q < nb) wsuffix[q] = later;
-    later += w[k];
-  }
-  const double t = block_sum_f64<F_THREADS / 32>(lsum, s_red, lane, warp);
-  if (tid == 0) {
-    const int f = *nan_flag;
-    loss_out[0] = f ? __int_as_float(0x7fc00000) : float(t / double(n));
-    if (flags_out) flags_out[0] = f;
-  }
-}
-
-// gradient through "- max(scores)": every argmax position receives -(sum_k g~_k) / count
-__global__ void __launch_bounds__(F_THREADS, 1) fs_backward_finalize_kernel(
-    const double* __restrict__ row_g, int nb, const int32_t* __restrict__ max_count, const int32_t* __restrict__ max_list,
-    double* __restrict__ gsum_total, float* grad_scores, const int32_t* __restrict__ fallback) {
-  __shared__ double s_red[F_THREADS / 32];
-  if (*fallback != 0) return;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double g = 0.0;
-  const double2* pg = reinterpret_cast<const double2*>(row_g);
-  for (int i0 = 0; i0 < nb * (R_ROWS / 2); i0 += 8 * F_THREADS) {
-    double2 a[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int i = i0 + k * F_THREADS + tid;
-      a[k] = i < nb * (R_ROWS / 2) ? __ldg(pg + i) : make_double2(0.0, 0.0);
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) g += a[k].x + a[k].y;
-  }
-  const double t = block_sum_f64<F_THREADS / 32>(g, s_red, lane, warp);
-  if (tid == 0) gsum_total[0] = t;
-  const int mc = *max_count;
-  if (mc <= FS_MAX_LIST) {
-    const float fix = float(t / double(mc));
-    for (int i = tid; i < mc; i += F_THREADS) grad_scores[max_list[i]] -= fix;
   }
 }
 
@@ -1126,10 +1009,7 @@ int fs_forward_enqueue(const float* times, const float* status, const float* sco
                                                                w.exp_prefix, w.part32, w.row_loss, w.row_w, nan_flag,
                                                                nonbinary_flag, w.fallback);
   MMBS_LAUNCH_CHECK();
-  fs_loss_finalize_kernel<<<1, F_THREADS, 0, stream>>>(w.row_loss, w.row_w, p.nb, n, w.wsum, nan_flag, loss_out, flags_out,
-                                                      w.fallback);
-  MMBS_LAUNCH_CHECK();
-  return MMBS_OK;
+  return MMBS_OK;   // the caller's dispatch kernel (cox.cu) finishes the pass: fs_loss_finalize_block
 }
 
 int fs_backward_enqueue(const float* status, const int32_t* perm, const float* saved_s, const float* grad_loss, int64_t n,
@@ -1140,10 +1020,7 @@ int fs_backward_enqueue(const float* status, const int32_t* perm, const float* s
                                                                    w.bucket_cnt, w.exp_prefix, w.part32, w.wsum, w.row_w,
                                                                    w.row_g, nonbinary_flag, grad_scores, w.fallback);
   MMBS_LAUNCH_CHECK();
-  fs_backward_finalize_kernel<<<1, F_THREADS, 0, stream>>>(w.row_g, p.nb, max_count, max_list, gsum_total, grad_scores,
-                                                          w.fallback);
-  MMBS_LAUNCH_CHECK();
-  return MMBS_OK;
+  return MMBS_OK;   // the caller's dispatch kernel (cox.cu) finishes the pass: fs_backward_finalize_block
 }
 
 }  // namespace mmbs

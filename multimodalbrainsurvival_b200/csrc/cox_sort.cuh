@@ -84,4 +84,130 @@ int fs_backward_enqueue(const float* status, const int32_t* perm, const float* s
                         const FastSortWs& w, const int32_t* nonbinary_flag, const int32_t* max_count,
                         const int32_t* max_list, double* gsum_total, float* grad_scores, cudaStream_t stream);
 
+#ifdef __CUDACC__
+constexpr int FS_FINAL_THREADS = 512;    // block size of the one-block finishing passes (<= 128 registers per thread: the
+                                         // dispatch kernels call the separately compiled rs_sort_tail_launch, 106 registers)
+constexpr int FS_ROWS = 16;              // warp rows per bucket (cox_sort.cu R_ROWS)
+
+// inclusive scan of one double per thread over the block, forward (lower threads first) or reverse; *total = block sum
+template <int NW, bool REVERSE>
+__device__ __forceinline__ double block_scan_f64(double v, double* s_red, int lane, int warp, double* total) {
+  double incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = REVERSE ? __shfl_down_sync(0xffffffffu, incl, o) : __shfl_up_sync(0xffffffffu, incl, o);
+    if (REVERSE ? (lane + o < 32) : (lane >= o)) incl += t;
+  }
+  __syncthreads();
+  if (lane == (REVERSE ? 0 : 31)) s_red[warp] = incl;
+  __syncthreads();
+  double off = 0.0, tot = 0.0;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    const double c = s_red[w];
+    if (REVERSE ? (w > warp) : (w < warp)) off += c;
+    tot += c;
+  }
+  *total = tot;
+  return incl + off;
+}
+
+template <int NW>
+__device__ __forceinline__ double block_sum_f64(double v, double* s_red, int lane, int warp) {
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) t += s_red[w];
+  return t;
+}
+
+
+// Finish of the forward pass, ONE block of FS_FINAL_THREADS threads: loss = sum of the row partials / n (.mean() over N,
+// models.py:111); wsuffix[b] = sum of w over all LATER buckets.  Element e = 16 b + r of the row arrays goes to thread
+// e mod 1024: coalesced, every load independent; a bucket's 16 rows sit in one half-warp.
+__device__ __forceinline__ void fs_loss_finalize_block(const double* __restrict__ row_loss, const double* __restrict__ row_w,
+                                                       int nb, int64_t n, double* __restrict__ wsuffix,
+                                                       const int32_t* __restrict__ nan_flag, float* __restrict__ loss_out,
+                                                       int32_t* __restrict__ flags_out) {
+  constexpr int PER = FS_MAX_BUCKETS / FS_FINAL_THREADS;
+  __shared__ double s_red[FS_FINAL_THREADS / 32];
+  __shared__ double s_wb[FS_MAX_BUCKETS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int total = nb * FS_ROWS;
+  constexpr int BATCH = 8;
+  double lsum = 0.0;
+  for (int e0 = 0; e0 < total; e0 += BATCH * FS_FINAL_THREADS) {   // block-uniform trip count (shuffles inside)
+    double l[BATCH], w[BATCH];
+#pragma unroll
+    for (int k = 0; k < BATCH; ++k) {
+      const int e = e0 + k * FS_FINAL_THREADS + tid;
+      l[k] = e < total ? __ldg(row_loss + e) : 0.0;
+      w[k] = e < total ? __ldg(row_w + e) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < BATCH; ++k) {
+      lsum += l[k];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) w[k] += __shfl_xor_sync(0xffffffffu, w[k], o);   // over the 16 rows of the bucket
+      const int e = e0 + k * FS_FINAL_THREADS + tid;
+      if ((lane & 15) == 0 && e < FS_MAX_BUCKETS * FS_ROWS) s_wb[e >> 4] = w[k];
+    }
+  }
+  __syncthreads();
+  double w[PER], wsum = 0.0;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int q = tid * PER + k;
+    w[k] = q < nb ? s_wb[q] : 0.0;
+    wsum += w[k];
+  }
+  double tot;
+  double later = block_scan_f64<FS_FINAL_THREADS / 32, true>(wsum, s_red, lane, warp, &tot) - wsum;   // higher threads only
+#pragma unroll
+  for (int k = PER - 1; k >= 0; --k) {
+    const int q = tid * PER + k;
+    if (q < nb) wsuffix[q] = later;
+    later += w[k];
+  }
+  const double t = block_sum_f64<FS_FINAL_THREADS / 32>(lsum, s_red, lane, warp);
+  if (tid == 0) {
+    const int f = *nan_flag;
+    loss_out[0] = f ? __int_as_float(0x7fc00000) : float(t / double(n));
+    if (flags_out) flags_out[0] = f;
+  }
+}
+
+// Finish of the backward pass, ONE block: gradient through "- max(scores)": every argmax position receives
+// -(sum_k g~_k) / count (when the positions fit the list; otherwise cox_maxfix_full_kernel reads gsum_total)
+__device__ __forceinline__ void fs_backward_finalize_block(const double* __restrict__ row_g, int nb,
+                                                           const int32_t* __restrict__ max_count,
+                                                           const int32_t* __restrict__ max_list,
+                                                           double* __restrict__ gsum_total, float* grad_scores) {
+  __shared__ double s_red[FS_FINAL_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double g = 0.0;
+  const double2* pg = reinterpret_cast<const double2*>(row_g);
+  for (int i0 = 0; i0 < nb * (FS_ROWS / 2); i0 += 8 * FS_FINAL_THREADS) {
+    double2 a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = i0 + k * FS_FINAL_THREADS + tid;
+      a[k] = i < nb * (FS_ROWS / 2) ? __ldg(pg + i) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g += a[k].x + a[k].y;
+  }
+  const double t = block_sum_f64<FS_FINAL_THREADS / 32>(g, s_red, lane, warp);
+  if (tid == 0) gsum_total[0] = t;
+  const int mc = *max_count;
+  if (mc <= FS_MAX_LIST) {
+    const float fix = float(t / double(mc));
+    for (int i = tid; i < mc; i += FS_FINAL_THREADS) grad_scores[max_list[i]] -= fix;
+  }
+}
+#endif
+
 }  // namespace mmbs
