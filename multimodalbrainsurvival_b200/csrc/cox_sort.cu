@@ -1,28 +1,34 @@
-// Bucketed Cox pipeline (sm_100a) for risk sets of 2049 .. FS_MAX_N samples: the whole forward pass is
-//   fs_hist_kernel            one read of `times` (+ `scores`): 4096-bin histogram of the top 12 key bits, smallest /
-//                             largest key, max(scores), NaN flag; its last block turns the histogram into a
-//                             piecewise-linear CDF table  lut[bin] = (P, c)  and the two edge-bin corrections.
+// Bucketed Cox pipeline (sm_100a) for risk sets of 2049 .. FS_MAX_N samples: the forward pass is
+//   fs_hist_kernel            one read of `times` (a 1-in-8 sample of it for n >= 2 M): 4096-bin histogram of the top 12 key
+//                             bits, smallest / largest key (+ max(scores), NaN flag when everything is read); its last block
+//                             turns the histogram into a piecewise-linear CDF table  lut[bin] = (P, c)  and the two edge-bin
+//                             corrections.
 //   fs_partition_kernel       every sample goes to bucket  floor(nb * R(key) / n),  R(key) = P[bin] + frac * c[bin]
-//                             (monotone in the key, so buckets are contiguous key ranges of ~5 K samples for any smooth
+//                             (monotone in the key, so buckets are contiguous key ranges of ~6 K samples for any smooth
 //                             distribution of survival times).  Ranking inside a tile is ONE shared-memory atomic per
 //                             sample and a tile claims its slots in a bucket region with one global atomic per bucket:
-//                             the partition is NOT stable and does not have to be (below).  8 B read + 8 B written.
-//   fs_bucket_forward_kernel  one block per bucket: counting sort over ~4096 sub-buckets of the same rank estimate
-//                             (~1.25 samples each, one shared-memory atomic per sample), then every sample finds its
-//                             final rank by comparing (key, index) with the few members of its sub-bucket - a total
-//                             order, so the result is the stable order whatever the atomics did.  The block then
-//                             gathers scores through the sorted indices, writes perm / s~, scans exp(s~), fetches the
-//                             sum over all earlier buckets by look-back (buckets are handed out by ticket, so every
-//                             predecessor is running), and accumulates the loss terms; the last block reduces the loss.
-// and the backward pass is fs_bucket_backward_kernel: per bucket, recompute C and w = status / (C + eps) from s~, suffix
-// sums, gradient scatter; the last block applies the gradient through max(scores).
+//                             the partition is NOT stable and does not have to be (below).  The sample's score travels to
+//                             the same slot of a parallel array.  12 B read + 12 B written per sample.
+//   fs_bucket_sort_kernel     one block per bucket: counting sort over 4096 sub-buckets (~1.5 samples each, one
+//                             shared-memory atomic per sample) of 64-bit (key, index, event) composites, then every sample
+//                             finds its final rank by comparing its composite with the few slots from its sub-bucket's
+//                             start - a total order, so the result is the stable order whatever the atomics did.  Scores
+//                             move to their sorted slot through shared memory; the block writes perm, |s~| | event << 31,
+//                             its sum of exp(s~) and one partial sum per 32 sorted positions.
+//   fs_prefix_kernel          exclusive prefix of the buckets' sums (one block).
+//   fs_row_loss_kernel        one WARP per 512 sorted positions: offset from the bucket prefix + the partial sums in front
+//                             of the row, scan with shuffles, per-row partials of the loss terms and of w.
+//   fs_loss_finalize_block    (cox_sort.cuh; runs inside cox.cu's one-block dispatch kernel) loss, suffix sums of w.
+// and the backward pass is fs_row_backward_kernel (same warp rows: recompute C and w = status / (C + eps) from s~, suffix
+// sums, gradient scatter) + fs_backward_finalize_block (the gradient through max(scores)).
 //
 // Replaces  _, idx = torch.sort(-times); scores[idx]; status[idx]; exp; cumsum; log; mask; mean  of cox_loss()
 //   /root/reference/1_HistoPathology/models.py:99-111 (and its three textual copies).
 //
-// Inputs this map cannot balance (a bucket over FS_CAP samples, sub-buckets whose squared sizes add up to more than FS_SQ_BUDGET: heavy ties, densities with
-// jumps inside a 12-bit bin) raise the device flag `fallback`; the LSD-sort pipeline of radix_sort.cu / cox.cu is
-// enqueued behind and only runs when the flag is set - the decision never costs a host synchronisation.
+// Inputs this map cannot balance (a bucket over FS_CAP samples, sub-buckets whose squared sizes add up to more than
+// FS_SQ_BUDGET: heavy ties, densities with jumps inside a 12-bit bin) raise the device flag `fallback`; the LSD-sort
+// pipeline of radix_sort.cu / cox.cu is enqueued behind and only runs when the flag is set - the decision never costs a
+// host synchronisation.
 #include <algorithm>
 #include <cstdlib>
 

@@ -1,6 +1,6 @@
 // Bucketed risk-set pipeline of the Cox loss for 2048 < n <= FS_MAX_N (see cox_sort.cu): equalised-CDF partition into
-// buckets of ~5 K samples, one block per bucket sorts it in shared memory and runs the forward pass on it, one block
-// per bucket runs the backward pass.
+// buckets of ~6 K samples, one block per bucket sorts it in shared memory, one warp per 512 sorted positions runs the
+// forward / backward scans, one-block passes in between carry the sums across buckets.
 #pragma once
 
 #include "radix_sort.cuh"
