@@ -1,7 +1,13 @@
 """GPU parity of the fused MLP paths (multimodalbrainsurvival_b200/mlp.py over the tcgen05 GEMM):
 inference vs the reference golden outputs / fp32 oracle, training (forward, dgrad, wgrad, Philox
 dropout) vs torch autograd on an emulation that reuses the kernel's own dropout masks.
-Tolerance: bf16 operands, fp32 accumulation -> 2e-2 relative to the tensor's max."""
+Tolerance: bf16 operands, fp32 accumulation -> 2e-2 relative (Frobenius) to the fp32 reference.  Why not the 1e-2 the
+north_star states for ResNet features: here the INPUTS are rounded to bf16 as well as the weights (a K = 12778 dot product
+of two bf16-rounded vectors carries ~2^-8 / sqrt(3) per product, ~4e-3 of the output norm, measured 3-6e-3 on these cases),
+two more layers compound it, and a hidden unit whose pre-activation sits within that error of zero takes the other ReLU
+branch than the reference, which moves single entries by a whole term.  The same cases against an oracle that rounds its
+operands to bf16 (oracle/mlp_oracle.py, emulate_bf16) agree to 2e-3 (test_rna_inference_matches_bf16_emulating_oracle);
+2e-2 is the bound against the fp32 reference."""
 import numpy as np
 import pytest
 import torch
@@ -45,6 +51,22 @@ def test_rna_inference_matches_reference_golden(golden):
     assert mlp._ENGINES, "the fused inference engine did not run"
     _close(feat[:, :64], torch.tensor(g["rna_feat_head"]), 2e-2, "rna features")
     _close(y, torch.tensor(g["rna_out"]), 2e-2, "rna output")
+
+
+def test_rna_inference_matches_bf16_emulating_oracle():
+    """Against an oracle that rounds the same operands to bf16 (weights, inputs, hidden activations; fp32 accumulation)
+    the kernels agree to accumulation-order noise: this is the tight check, the golden comparison above bounds the bf16
+    storage itself."""
+    from multimodalbrainsurvival_b200 import models
+    rna, head = _rna(1111)
+    model = models.RNAOnlyModel(rna, head).to(DEV).eval()
+    x = torch.tensor(det_input((6, 12778), a=0.11), device=DEV)
+    with torch.no_grad():
+        feat = model.extract(x)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ref = mlp_oracle.mlp_forward(x.cpu(), mlp_oracle.rna_layers(sd), emulate_bf16=True)[-1]
+    rel = float((feat.cpu().double() - ref.double()).norm() / ref.double().norm())
+    assert rel < 2e-3, rel
 
 
 def test_early_fusion_inference_matches_reference_golden(golden):
