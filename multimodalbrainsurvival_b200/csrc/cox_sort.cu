@@ -453,7 +453,10 @@ __device__ __forceinline__ void for_rows(int cnt, int tid, F&& f) {
 // the sorted payloads [FS_CAP] | sorted s~ words [FS_CAP]) | s_cnt[S_SUB + 1]
 constexpr int S_SUB = 1 << FS_LOG_S;   // sub-buckets of the counting sort
 constexpr int S_PAD = 160;             // >= S_KU sentinels behind the bucket (the finish reads S_KU slots from a sub-bucket's start)
-constexpr int S_KU = 8;                // slots every sample compares unconditionally (largest sub-bucket of a typical block)
+#ifndef MMBS_S_KU
+#define MMBS_S_KU 8
+#endif
+constexpr int S_KU = MMBS_S_KU;        // slots every sample compares unconditionally
 constexpr int S_DYN_SMEM = (2 * (FS_CAP + S_PAD) + S_SUB + 8) * 4;
 static_assert(S_PAD >= S_KU, "sentinel padding must cover the unconditional compares");
 
@@ -529,13 +532,13 @@ __global__ void __launch_bounds__(B_THREADS, 2) fs_bucket_sort_kernel(
   uint32_t cmax;   // largest sub-bucket of the block
   {
     constexpr int PER = S_SUB / B_THREADS;
-    uint32_t c[PER], sum = 0, big = 0, sq = 0;
-#pragma unroll
+    uint32_t sum = 0, big = 0, sq = 0;   // (two passes over the thread's counters instead of a register array: the
+#pragma unroll                           //  48 sample registers stay live through this phase)
     for (int k = 0; k < PER; ++k) {
-      c[k] = s_cnt[tid * PER + k];
-      sum += c[k];
-      big = max(big, c[k]);
-      sq += c[k] > uint32_t(S_KU) ? c[k] * c[k] : 0u;   // (sizes add up to <= FS_CAP: the squares to < 2^27)
+      const uint32_t c = s_cnt[tid * PER + k];
+      sum += c;
+      big = max(big, c);
+      sq += c > uint32_t(S_KU) ? c * c : 0u;   // (sizes add up to <= FS_CAP: the squares to < 2^27)
     }
     big = __reduce_max_sync(0xffffffffu, big);
     sq = __reduce_add_sync(0xffffffffu, sq);
@@ -547,8 +550,9 @@ __global__ void __launch_bounds__(B_THREADS, 2) fs_bucket_sort_kernel(
     uint32_t run = sc.x - sum;
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
+      const uint32_t c = s_cnt[tid * PER + k];
       s_cnt[tid * PER + k] = run;
-      run += c[k];
+      run += c;
     }
     if (tid == 0) s_cnt[S_SUB] = uint32_t(cnt);
     cmax = 0;

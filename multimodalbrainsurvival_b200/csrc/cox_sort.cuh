@@ -11,7 +11,10 @@ constexpr int FS_BINS = 4096;              // histogram of the top 12 key bits
 constexpr int FS_MAX_BUCKETS = 4096;
 constexpr int FS_CAP = 8192;               // samples one block sorts in shared memory (= slots per bucket region)
 constexpr int FS_TARGET = 6144;            // aimed bucket size (12 of the 16 rows of a block): 1.33x head-room below FS_CAP
-constexpr int FS_LOG_S = 12;               // 4096 sub-buckets per bucket (~1.25 samples each)
+#ifndef MMBS_FS_LOG_S
+#define MMBS_FS_LOG_S 12
+#endif
+constexpr int FS_LOG_S = MMBS_FS_LOG_S;    // 2^12 = 4096 sub-buckets per bucket (~1.5 samples each)
 constexpr int FS_SQ_BUDGET = 1 << 20;      // rank-by-comparison finish: accepted sum of (sub-bucket size)^2 over the sub-buckets
                                            // of more than 8 samples (one run of ~1000 tied times, or the bucket that ends at
                                            // t -> 0 and spans a hundred binades); beyond: the LSD pipeline
