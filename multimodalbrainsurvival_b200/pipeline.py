@@ -11,14 +11,16 @@ import torch
 
 
 def prefetch_to_device(batches, device, depth: int = 2):
-    """Iterate over host tensors, yielding device tensors whose copy was issued ``depth`` steps
-    ahead.  A yielded tensor is only valid until the next one is requested (its buffer is reused)."""
+    """Iterate over host tensors - or tuples / lists of host tensors (e.g. (patch_bag, rna) of the joint-fusion loader:
+    copies that share the stream cannot queue behind each other's batches on the DMA engine) - yielding device tensors
+    (tuples) whose copy was issued ``depth`` steps ahead.  A yielded item is only valid until the next one is requested
+    (its buffers are reused)."""
     dev = torch.device(device)
     copy_stream = torch.cuda.Stream(device=dev)
     slots = depth + 1
-    ring = [None] * slots          # device staging buffers
+    ring = [None] * slots          # device staging buffers (a list per slot)
     ready = [None] * slots         # copy finished (recorded on the copy stream)
-    released = [None] * slots      # consumer finished with the buffer (recorded on its stream)
+    released = [None] * slots      # consumer finished with the buffers (recorded on its stream)
     it = iter(batches)
     head = 0                       # next slot to fill
     pending = []
@@ -26,34 +28,37 @@ def prefetch_to_device(batches, device, depth: int = 2):
     def issue():
         nonlocal head
         try:
-            host = next(it)
+            item = next(it)
         except StopIteration:
             return False
-        if not host.is_pinned():
-            host = host.pin_memory()
+        single = isinstance(item, torch.Tensor)
+        hosts = [item] if single else list(item)
+        hosts = [h if h.is_pinned() else h.pin_memory() for h in hosts]
         k = head
         head = (head + 1) % slots
-        if ring[k] is None or ring[k].shape != host.shape or ring[k].dtype != host.dtype:
-            ring[k] = torch.empty(host.shape, dtype=host.dtype, device=dev)
+        if ring[k] is None or len(ring[k]) != len(hosts) or any(
+                r.shape != h.shape or r.dtype != h.dtype for r, h in zip(ring[k], hosts)):
+            ring[k] = [torch.empty(h.shape, dtype=h.dtype, device=dev) for h in hosts]
         with torch.cuda.stream(copy_stream):
             if released[k] is not None:
                 copy_stream.wait_event(released[k])
-            ring[k].copy_(host, non_blocking=True)
+            for r, h in zip(ring[k], hosts):
+                r.copy_(h, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         ready[k] = ev
-        pending.append((k, host))   # keep the pinned source alive until its copy is consumed
+        pending.append((k, hosts, single))   # keep the pinned sources alive until their copies are consumed
         return True
 
     for _ in range(depth):
         if not issue():
             break
     while pending:
-        k, _host = pending.pop(0)
+        k, _hosts, single = pending.pop(0)
         cur = torch.cuda.current_stream(dev)
         cur.wait_event(ready[k])
         issue()
-        yield ring[k]
+        yield ring[k][0] if single else tuple(ring[k])
         rel = torch.cuda.Event()
         rel.record(torch.cuda.current_stream(dev))
         released[k] = rel
