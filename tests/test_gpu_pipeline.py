@@ -30,3 +30,13 @@ def test_host_writer_copies_on_a_side_stream():
     w.wait()
     assert [float(o[0, 0]) for o in outs] == [1.0, 4.0, 7.0, 10.0]
     assert all(bool((o == o[0, 0]).all()) for o in outs)
+
+
+def test_prefetch_to_device_takes_tuples():
+    """(patch_bag, rna) pairs of the joint-fusion loader travel in one slot, in order, on the copy stream."""
+    from multimodalbrainsurvival_b200 import pipeline
+    g = torch.Generator().manual_seed(0)
+    host = [(torch.randn(4, 3, 8, 8, generator=g), torch.randn(4, 17, generator=g)) for _ in range(5)]
+    for i, (x, r) in enumerate(pipeline.prefetch_to_device(iter(host), "cuda:0", depth=2)):
+        assert x.is_cuda and r.is_cuda
+        assert torch.equal(x.cpu(), host[i][0]) and torch.equal(r.cpu(), host[i][1])
