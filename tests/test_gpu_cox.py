@@ -256,3 +256,17 @@ def test_non_binary_status_weights():
     t = rng.integers(0, 40, n).astype(np.float32)
     e = rng.choice(np.array([0.0, 0.5, 1.0, 2.0], np.float32), n)
     _check(s, t, e, "non-binary status")
+
+
+def test_randomised_distributions_against_torch():
+    """tools/cox_fuzz.py: 40 random (distribution, size) cases - uniform, exponential, log-normal, bimodal, integer months,
+    mixed ties, denormal-sized, signed, a 90 % constant tail, power law; 2 K to 2 M samples - permutation bit-exact with
+    torch.sort(stable), loss / gradient against an fp64 evaluation of the reference's formula, on whichever pipeline the
+    input lands (bucketed, or the LSD pipeline after a device-side hand-over)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "cox_fuzz.py"), "40", "7"], capture_output=True,
+                       text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
