@@ -415,8 +415,13 @@ __global__ void __launch_bounds__(P_THREADS, 2) fs_partition_kernel(
   uint2* s_pairs = reinterpret_cast<uint2*>(s_dyn + 2 * nbp);
   float* s_sc = reinterpret_cast<float*>(s_dyn + 2 * nbp + 2 * P_TILE);
   if (tid < 8) reinterpret_cast<uint32_t*>(&s_E)[tid] = reinterpret_cast<const uint32_t*>(edge)[tid];
+  if (tid == 8) s_w[0] = (*reinterpret_cast<volatile int32_t*>(fallback) != 0) ? 1u : 0u;
   for (int i = tid; i < nbp; i += P_THREADS) s_cnt[i] = 0;
   __syncthreads();
+  // an earlier tile already gave the input up (a bucket overflowed: heavy ties): the LSD pipeline will redo everything,
+  // the remaining tiles have nothing to add (with 40 K copies per key the flag is up after a fifth of the tiles)
+  if (s_w[0] != 0u) return;
+  __syncthreads();   // (s_w is the scan scratch of partition_tile)
   const int64_t tile_base = int64_t(blockIdx.x) * P_TILE;
   const int n_valid = int(min((long long)P_TILE, (long long)(n - tile_base)));
   const bool full = n_valid == P_TILE && (reinterpret_cast<uintptr_t>(times) & 15) == 0 &&
