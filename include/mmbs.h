@@ -360,6 +360,16 @@ int mmbs_nll_surv_backward(const float* grad_unit, const float* grad_loss, int64
  * threads <= 0: one per hardware thread (at most 64). */
 int mmbs_write_matrix_csv(const double* data, int64_t rows, int64_t cols, const char* path, int32_t threads);
 
+/* Large cohorts: the same three counts as a 2-D dominance problem (O(n * 2^block_shift) instead of O(n^2)).  The caller
+ * sorts the deaths by exit time and by prediction and passes: perm[s] = time position of the s-th smallest prediction, inv =
+ * its inverse, table[(nb + 1) x (nb + 1)] = exclusive 2-D prefix of the (s / S, perm[s] / S) histogram (S = 2^block_shift, nb
+ * = ceil(n_deaths / S)), and per subject: admissible[i] = number of admissible deaths (a prefix of the time order), lo[i] /
+ * hi[i] = deaths with a smaller / smaller-or-equal prediction.  Adds correct to counts_out[1] and tied to counts_out[2]
+ * (the caller owns counts_out[0] = sum of admissible). */
+int mmbs_concordance_dominance(const int32_t* perm, const int32_t* inv, const int64_t* table, int64_t n_deaths,
+                               int block_shift, const int64_t* lo, const int64_t* hi, const int64_t* admissible, int64_t n,
+                               unsigned long long* counts_out, void* stream);
+
 /* ------------------------------------------------------- attention aggregation
  * Tail of TanhAttention.forward (/root/reference/1_HistoPathology/models.py:22-33; 5_JointFusion/models.py, same text):
  *   attn[b, p] = softmax_p( tanh(h[b, p, :]) . vector ),  h = x W^T (fp32, from a linear plan)

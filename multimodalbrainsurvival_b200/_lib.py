@@ -90,6 +90,8 @@ SIGNATURES = {
     "mmbs_stem_pack_weight": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
     "mmbs_stem_pack_input_c": (ctypes.c_int, [c_void_p, c_void_p, c_i64, ctypes.c_int, c_void_p]),
     "mmbs_stem_pack_weight_c": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, c_void_p]),
+    "mmbs_concordance_dominance": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, ctypes.c_int, c_void_p, c_void_p,
+                                                  c_void_p, c_i64, c_void_p, c_void_p]),
     "mmbs_attention_pool": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, ctypes.c_int, ctypes.c_int, c_void_p,
                                            c_void_p, c_void_p, c_void_p]),
     "mmbs_tanh_inplace_f32": (ctypes.c_int, [c_void_p, c_i64, c_void_p]),

@@ -91,6 +91,47 @@ def survival_grouping(output_list, ids_list, survival_months, vital_status):
     return ids_unique, mean[:, 0].cpu().numpy(), sm, vs
 
 
+PAIRWISE_MAX_N = 50_000     # above: the O(n S) dominance count instead of the O(n^2) pair kernel
+_DOMINANCE_SHIFT = 11       # S = 2048 deaths per table block
+
+
+def _concordance_counts_dominance(t, p, e):
+    """The same exact counts for large cohorts (csrc/cindex.cu, cindex_dominance_kernel).  torch does the preparatory
+    sorts / binary searches / prefix sums of the index arrays; the pair counting itself is the kernel's."""
+    n = t.numel()
+    dev = t.device
+    d = e != 0
+    nd = int(d.sum())
+    if nd == 0:
+        return 0, 0, 0
+    td, order = torch.sort(t[d], stable=True)                     # deaths by exit time: time position k
+    pd_ = p[d][order]
+    # admissible deaths of subject i = a prefix of that order: strictly earlier deaths, plus - for a censored subject -
+    # the deaths at its own exit time
+    adm = torch.where(d, torch.searchsorted(td, t, right=False), torch.searchsorted(td, t, right=True))
+    pr, perm = torch.sort(pd_, stable=True)                       # deaths by prediction: perm[s] = time position
+    lo = torch.searchsorted(pr, p, right=False)
+    hi = torch.searchsorted(pr, p, right=True)
+    perm32 = perm.to(torch.int32).contiguous()
+    inv32 = torch.empty_like(perm32)
+    inv32[perm] = torch.arange(nd, device=dev, dtype=torch.int32)
+    S = 1 << _DOMINANCE_SHIFT
+    nb = (nd + S - 1) // S
+    cell = (torch.arange(nd, device=dev) >> _DOMINANCE_SHIFT) * nb + (perm >> _DOMINANCE_SHIFT)
+    hist = torch.bincount(cell, minlength=nb * nb).view(nb, nb)
+    table = torch.zeros((nb + 1, nb + 1), dtype=torch.int64, device=dev)
+    table[1:, 1:] = hist.cumsum(0).cumsum(1)                      # exclusive 2-D prefix: #{s < bs S, perm[s] < bv S}
+    out = torch.zeros(3, dtype=torch.int64, device=dev)
+    out[0] = adm.sum()
+    with _lib.on_device(dev):
+        _lib.check(_lib.lib().mmbs_concordance_dominance(_lib.ptr(perm32), _lib.ptr(inv32), _lib.ptr(table), nd,
+                                                         _DOMINANCE_SHIFT, _lib.ptr(lo.contiguous()), _lib.ptr(hi.contiguous()),
+                                                         _lib.ptr(adm.contiguous()), n, _lib.ptr(out), _lib.stream_ptr()),
+                   "mmbs_concordance_dominance")
+    pairs, correct, tied = (int(v) for v in out.cpu().tolist())
+    return pairs, correct, tied
+
+
 def concordance_counts(event_times, predicted_scores, event_observed, device=None):
     """(admissible pairs, correct, tied) of Harrell's C, counted exactly on the GPU (csrc/cindex.cu).
     Inputs: array-likes / tensors of length n; compared in float64 like the reference's pandas columns."""
@@ -109,6 +150,8 @@ def concordance_counts(event_times, predicted_scores, event_observed, device=Non
     dev = next((x.device for x in (t, p) if x.is_cuda), None) or torch.device("cuda", torch.cuda.current_device()
                                                                              if device is None else device)
     t, p, e = t.to(dev).contiguous(), p.to(dev).contiguous(), e.to(dev).to(torch.uint8).contiguous()
+    if n > PAIRWISE_MAX_N:
+        return _concordance_counts_dominance(t, p, e)
     out = torch.empty(3, dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().mmbs_concordance_counts(_lib.ptr(t), _lib.ptr(p), _lib.ptr(e), n, _lib.ptr(out),

@@ -70,9 +70,68 @@ __global__ void __launch_bounds__(CI_THREADS) cindex_count_kernel(const double* 
   }
 }
 
+// ---- large cohorts: the same counts as a 2-D dominance problem, O(n * S) instead of O(n^2).
+// With the deaths sorted by exit time (position k) and, separately, by prediction (perm[s] = time position of the s-th
+// smallest prediction, inv = its inverse), a subject with L admissible deaths (a prefix of the time order) and lo / hi =
+// number of deaths with a smaller / smaller-or-equal prediction has
+//     correct = F(lo, L),   tied = F(hi, L) - F(lo, L),   F(m, L) = #{ s < m : perm[s] < L }.
+// F is evaluated from a table of block corners T[bs][bv] = #{ s < bs S : perm[s] < bv S } (built by the caller: a 2-D
+// histogram and two prefix sums) plus two partial scans of at most S entries: the tail of the row block in perm and the
+// tail of the column block in inv.  One warp per subject, coalesced scans.
+constexpr int CI_DOM_THREADS = 256;
+
+__device__ __forceinline__ unsigned long long dominance_count(const int32_t* __restrict__ perm, const int32_t* __restrict__ inv,
+                                                              const int64_t* __restrict__ table, int row_len, int shift,
+                                                              int64_t m, int64_t l, int lane) {
+  const int64_t bs = m >> shift, bv = l >> shift;
+  const int64_t s0 = bs << shift, v0 = bv << shift;
+  uint32_t cnt = 0;
+  for (int64_t s = s0 + lane; s < m; s += 32) cnt += (int64_t(__ldg(perm + s)) < l) ? 1u : 0u;
+  for (int64_t v = v0 + lane; v < l; v += 32) cnt += (int64_t(__ldg(inv + v)) < s0) ? 1u : 0u;
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  return static_cast<unsigned long long>(__ldg(table + bs * row_len + bv)) + cnt;
+}
+
+__global__ void __launch_bounds__(CI_DOM_THREADS) cindex_dominance_kernel(
+    const int32_t* __restrict__ perm, const int32_t* __restrict__ inv, const int64_t* __restrict__ table, int row_len, int shift,
+    const int64_t* __restrict__ lo, const int64_t* __restrict__ hi, const int64_t* __restrict__ adm, int64_t n,
+    unsigned long long* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = int64_t(gridDim.x) * (CI_DOM_THREADS / 32);
+  unsigned long long correct = 0, tied = 0;
+  for (int64_t q = int64_t(blockIdx.x) * (CI_DOM_THREADS / 32) + (threadIdx.x >> 5); q < n; q += warps) {
+    const int64_t l = __ldg(adm + q), a = __ldg(lo + q), b = __ldg(hi + q);
+    if (l == 0) continue;   // (warp-uniform)
+    const unsigned long long fa = dominance_count(perm, inv, table, row_len, shift, a, l, lane);
+    const unsigned long long fb = (b == a) ? fa : dominance_count(perm, inv, table, row_len, shift, b, l, lane);
+    correct += fa;
+    tied += fb - fa;
+  }
+  if (lane == 0) {
+    if (correct) atomicAdd(out + 1, correct);
+    if (tied) atomicAdd(out + 2, tied);
+  }
+}
+
 }  // namespace mmbs
 
 using namespace mmbs;
+
+extern "C" int mmbs_concordance_dominance(const int32_t* perm, const int32_t* inv, const int64_t* table, int64_t n_deaths,
+                                          int block_shift, const int64_t* lo, const int64_t* hi, const int64_t* admissible,
+                                          int64_t n, unsigned long long* counts_out, void* stream_) {
+  if (int rc = mmbs_device_check()) return rc;
+  MMBS_REQUIRE(perm && inv && table && lo && hi && admissible && counts_out, "mmbs_concordance_dominance: null pointer");
+  MMBS_REQUIRE(n >= 1 && n_deaths >= 1 && n_deaths < (int64_t(1) << 31) && block_shift >= 4 && block_shift <= 20,
+               "mmbs_concordance_dominance: bad argument");
+  const int row_len = int(((n_deaths + (int64_t(1) << block_shift) - 1) >> block_shift) + 1);
+  const int64_t warps = ceil_div(n, 1);
+  const unsigned grid = unsigned(std::min<int64_t>(ceil_div(warps, CI_DOM_THREADS / 32), int64_t(sm_count()) * 16));
+  cindex_dominance_kernel<<<grid, CI_DOM_THREADS, 0, static_cast<cudaStream_t>(stream_)>>>(
+      perm, inv, table, row_len, block_shift, lo, hi, admissible, n, counts_out);
+  MMBS_LAUNCH_CHECK();
+  return MMBS_OK;
+}
 
 extern "C" int mmbs_concordance_counts(const double* event_times, const double* predicted, const uint8_t* event_observed,
                                        int64_t n, unsigned long long* counts_out, void* stream_) {

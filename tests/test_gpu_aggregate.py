@@ -124,3 +124,27 @@ def test_concordance_index_edge_cases_and_get_survival_ci():
     ci, df = aggregate.get_survival_CI(out, ids, sm, vs)
     ref = cindex_oracle.concordance_index(df["survival_months"], -df["score"], df["vital_status"])
     assert ci == ref and 0.0 <= ci <= 1.0
+
+
+@pytest.mark.parametrize("ties", [False, True])
+def test_concordance_dominance_path_matches_pair_kernel(ties, monkeypatch):
+    """Large cohorts take the O(n S) dominance count (cindex_dominance_kernel): the three integer counts must equal the
+    O(n^2) pair kernel's, which is bit-exact with the oracle (ties in time and in prediction included)."""
+    from multimodalbrainsurvival_b200 import aggregate
+    from oracle import cindex_oracle
+    rng = np.random.default_rng(5 + int(ties))
+    n = 30_000
+    t = np.floor(rng.uniform(0, 200, n)) if ties else rng.uniform(0, 200, n)
+    p = np.round(rng.standard_normal(n), 1) if ties else rng.standard_normal(n)
+    e = (rng.uniform(size=n) < 0.6).astype(np.int64)
+    want = aggregate.concordance_counts(t, p, e)                      # n <= PAIRWISE_MAX_N: the pair kernel
+    monkeypatch.setattr(aggregate, "PAIRWISE_MAX_N", 1000)
+    got = aggregate.concordance_counts(t, p, e)
+    assert got == want and want[0] > 0
+    small = slice(0, 700)                                              # and the oracle itself on a small slice
+    monkeypatch.setattr(aggregate, "PAIRWISE_MAX_N", 100)
+    assert aggregate.concordance_counts(t[small], p[small], e[small]) == \
+        cindex_oracle.concordance_counts(t[small], p[small], e[small])
+    # degenerate inputs: nobody died / everybody died at the same time
+    assert aggregate.concordance_counts(t[small], p[small], np.zeros(700)) == (0, 0, 0)
+    assert aggregate.concordance_counts(np.ones(700), p[small], np.ones(700)) == (0, 0, 0)
