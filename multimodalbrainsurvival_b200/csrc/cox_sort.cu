@@ -37,9 +37,10 @@
 namespace mmbs {
 
 constexpr int FS_HIST_THREADS = 256;
-constexpr int P_THREADS = 512;
+constexpr int P_THREADS = 1024;
 constexpr int P_ITEMS = 16;
-constexpr int P_TILE = P_THREADS * P_ITEMS;        // 8192
+constexpr int P_TILE = P_THREADS * P_ITEMS;        // 16384: ~10 samples per (tile, bucket) run (8192-sample tiles at two
+                                                   // blocks per SM: 119 us at 10 M, 4096 at three: 165 us, this: 111 us)
 constexpr int B_THREADS = 512;
 constexpr int B_ITEMS = FS_CAP / B_THREADS;        // 16 (the skew below assumes 16)
 constexpr float FS_EPS = 1e-5f;
@@ -259,10 +260,11 @@ __global__ void __launch_bounds__(FS_HIST_THREADS, 6) fs_hist_kernel(
 
 // ------------------------------------------------------------------------------------------ partition
 // dynamic shared memory: s_cnt[nbp] (re-used for the slot deltas) | s_start[nbp] | staged pairs[P_TILE] | staged scores[P_TILE]
-// (nbp = nb rounded up to a multiple of the block size).  A staged pair is (key, e | event << 13 | bucket << 14) with e the
+// (nbp = nb rounded up to a multiple of the block size).  A staged pair is (key, e | event << 14 | bucket << 15) with e the
 // sample's position inside the tile: the write-out pass needs no separate bucket-id array.
 constexpr uint32_t P_E_MASK = P_TILE - 1;
-static_assert(P_TILE == 8192 && FS_MAX_BUCKETS <= 4096, "staged payload packs 13 + 1 + 12 bits");
+constexpr int P_E_BITS = 14;
+static_assert(P_TILE == (1 << P_E_BITS) && FS_MAX_BUCKETS <= 4096, "staged payload packs 14 + 1 + 12 bits");
 
 template <bool FULL>   // FULL: the tile holds P_TILE samples and `times` / `status` / `scores` are 16-byte aligned
 __device__ __forceinline__ void partition_tile(const float* __restrict__ times, const float* __restrict__ status,
@@ -363,7 +365,7 @@ __device__ __forceinline__ void partition_tile(const float* __restrict__ times, 
         if (FULL || br[j] != 0xffffffffu) {
           const uint32_t b = br[j] >> 16;
           const uint32_t pos = s_start[b] + (br[j] & 0xffffu);
-          s_pairs[pos] = make_uint2(key[j], uint32_t(e0 + k) | (((ev >> j) & 1u) << 13) | (b << 14));
+          s_pairs[pos] = make_uint2(key[j], uint32_t(e0 + k) | (((ev >> j) & 1u) << P_E_BITS) | (b << (P_E_BITS + 1)));
           s_sc[pos] = s4[k];
         }
       }
@@ -384,12 +386,12 @@ __device__ __forceinline__ void partition_tile(const float* __restrict__ times, 
     const int i = j * P_THREADS + tid;
     if (FULL || i < n_valid) {
       const uint2 pr = s_pairs[i];
-      const uint32_t b = pr.y >> 14;
+      const uint32_t b = pr.y >> (P_E_BITS + 1);
       const uint32_t dst = uint32_t(i) + s_delta[b];
       // (3 slots stay free: the blocked 16-byte loads of the loss / backward kernels start at base & ~3)
       if (dst < uint32_t(FS_CAP - 3)) {
         const size_t o = size_t(b) * FS_CAP + dst;
-        pairs_out[o] = make_uint2(pr.x, uint32_t(tile_base + (pr.y & P_E_MASK)) | (((pr.y >> 13) & 1u) << 31));
+        pairs_out[o] = make_uint2(pr.x, uint32_t(tile_base + (pr.y & P_E_MASK)) | (((pr.y >> P_E_BITS) & 1u) << 31));
         if (scores != nullptr) sc_out[o] = s_sc[i];
       } else {
         overflow = true;
@@ -399,7 +401,7 @@ __device__ __forceinline__ void partition_tile(const float* __restrict__ times, 
   if (overflow) atomicOr(fallback, 1);
 }
 
-__global__ void __launch_bounds__(P_THREADS, 2) fs_partition_kernel(
+__global__ void __launch_bounds__(P_THREADS, 1) fs_partition_kernel(
     const float* __restrict__ times, const float* __restrict__ status, const float* __restrict__ scores, int do_max,
     uint32_t* __restrict__ max_enc, int32_t* __restrict__ nan_flag, int64_t n, const uint2* __restrict__ lut,
     const FsEdge* __restrict__ edge, int nb, uint32_t* __restrict__ cursor, uint2* __restrict__ pairs_out,
